@@ -1,0 +1,124 @@
+/*
+ * uno_b200 -- C ABI of the B200-native U-NO integral-operator path.
+ *
+ * The reference (ashiq24/UNO) is pure Python on PyTorch and has no FFI of its own: its boundary for
+ * this path is the nn.Module API of integral_operators.py.  Each entry point below replaces the body
+ * of one reference forward (or its autograd-generated backward); uno_b200/integral_operators.py keeps
+ * the reference's module classes / signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - every tensor argument is a DEVICE pointer to a dense, contiguous fp32 buffer in the reference's
+ *     layout: activations [B, C, d1(, d2(, d3))]; spectral weights complex64 interleaved (re,im)
+ *     [Ci, Co, m1(, m2(, m3))] -- exactly the memory of torch.view_as_real(weightsN);
+ *     Conv{n}d(k=1) weight [Co, Ci], bias [Co]; InstanceNorm gamma/beta [Co].
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - `ws` is caller-owned scratch of at least *_workspace_bytes(desc); contents are undefined after.
+ *   - return value 0 = ok; non-zero = error, message in uno_last_error() (thread-local).
+ *       1 invalid argument / unsupported shape (the reference raises RuntimeError for these)
+ *       2 workspace too small      3 CUDA runtime error
+ *   - plan constants (twiddle matrices, resample bands) are built on first use of a shape and cached
+ *     for the life of the process; the first call of a new shape therefore allocates device memory
+ *     and must not happen inside CUDA-graph capture.
+ */
+#ifndef UNO_B200_H
+#define UNO_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNO_OK 0
+#define UNO_EINVAL 1
+#define UNO_EWORKSPACE 2
+#define UNO_ECUDA 3
+
+/* Shape of one SpectralConv{1,2,3}d_Uno / pointwise_op_{2,3}D / OperatorBlock call.
+ * Unused trailing dims must be 1 (in_dim/out_dim) or 0 (modes).                          */
+typedef struct uno_conv_desc {
+    int ndim;        /* 1, 2 or 3 */
+    int batch;       /* B */
+    int in_ch;       /* in_codim  */
+    int out_ch;      /* out_codim */
+    int in_dim[3];   /* input grid  */
+    int out_dim[3];  /* output grid (dim1, dim2, dim3 of the forward call) */
+    int modes[3];    /* modes1, modes2, modes3 (ignored by the pointwise entry points) */
+} uno_conv_desc;
+
+typedef struct uno_block_desc {
+    uno_conv_desc conv;
+    int normalize;   /* OperatorBlock(Normalize=...) : InstanceNorm(affine) on conv(x)+w(x) */
+    int non_lin;     /* OperatorBlock(Non_Lin=...)   : exact-erf GELU                       */
+    float eps;       /* InstanceNorm eps (1e-5)                                             */
+} uno_block_desc;
+
+const char* uno_last_error(void);
+int uno_version(void);
+const char* uno_backend_name(void);   /* "cuda-sm100a" for the product library */
+void uno_clear_plans(void);
+
+/* ---- SpectralConv{1,2,3}d_Uno -------------------------------------------------------------------
+ * fwd replaces integral_operators.py:47-72 (1-D), :181-207 (2-D), :385-427 (3-D).
+ *   x  [B,Ci,*in]   w[nW] (nW = 1,2,4 = weights1..)   y [B,Co,*out]
+ *   xhat: optional out, the kept-mode input spectrum (complex64, uno_spectral_conv_xhat_elems()
+ *         complex elements) that bwd needs; pass NULL for inference.
+ * bwd is the autograd backward of the same lines:
+ *   gy [B,Co,*out], xhat from fwd -> gx [B,Ci,*in] (overwritten, or += when accumulate_gx),
+ *   gw[nW] like w (overwritten; torch convention dL/dRe + i dL/dIm).  gx or gw may be NULL to skip. */
+int uno_spectral_conv_check(const uno_conv_desc* d);
+size_t uno_spectral_conv_workspace_bytes(const uno_conv_desc* d);
+size_t uno_spectral_conv_xhat_elems(const uno_conv_desc* d);
+int uno_spectral_conv_fwd(const uno_conv_desc* d, const float* x, const float* const* w, float* y,
+                          float* xhat, void* ws, size_t ws_bytes, void* stream);
+int uno_spectral_conv_bwd(const uno_conv_desc* d, const float* gy, const float* xhat,
+                          const float* const* w, float* gx, float* const* gw, int accumulate_gx,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ---- pointwise_op_2D / pointwise_op_3D ----------------------------------------------------------
+ * fwd replaces integral_operators.py:224-243 (2-D: Conv2d(k=1) + bicubic anti-aliased resample,
+ * align_corners=True) and :438-468 (3-D: Conv3d(k=1) + rfftn / corner copy / irfftn(s=out)).
+ *   saved: optional out of uno_pointwise_saved_elems() floats (the resampled input when the resample
+ *          runs before the channel mix); bwd recomputes it when NULL.
+ * bwd: gz [B,Co,*out] -> gx [B,Ci,*in] (overwritten), gconv_w [Co,Ci], gconv_b [Co] (overwritten). */
+size_t uno_pointwise_workspace_bytes(const uno_conv_desc* d);
+size_t uno_pointwise_saved_elems(const uno_conv_desc* d);
+int uno_pointwise_fwd(const uno_conv_desc* d, const float* x, const float* conv_w,
+                      const float* conv_b, float* z, float* saved, void* ws, size_t ws_bytes,
+                      void* stream);
+int uno_pointwise_bwd(const uno_conv_desc* d, const float* gz, const float* x, const float* saved,
+                      const float* conv_w, float* gx, float* gconv_w, float* gconv_b, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* ---- OperatorBlock_2D / OperatorBlock_3D ---------------------------------------------------------
+ * fwd replaces integral_operators.py:272-284 / :501-513:  y = gelu?( IN?( conv(x) + w(x) ) ).
+ *   pre  : optional out [B,Co,*out]: the tensor bwd needs -- conv(x)+w(x) (pre-norm sum when
+ *          normalize, else the pre-activation).  NULL for inference.
+ *   stats: [B*Co, 2] (mean, rstd) out, required when normalize and pre != NULL.
+ * bwd: gy -> gx, gw[nW], gconv_w, gconv_b, ggamma, gbeta (all overwritten).                          */
+size_t uno_operator_block_workspace_bytes(const uno_block_desc* d);
+int uno_operator_block_fwd(const uno_block_desc* d, const float* x, const float* const* w,
+                           const float* conv_w, const float* conv_b, const float* gamma,
+                           const float* beta, float* y, float* xhat, float* pw_saved, float* pre,
+                           float* stats, void* ws, size_t ws_bytes, void* stream);
+int uno_operator_block_bwd(const uno_block_desc* d, const float* gy, const float* x,
+                           const float* xhat, const float* pw_saved, const float* pre,
+                           const float* stats, const float* const* w, const float* conv_w,
+                           const float* gamma, const float* beta, float* gx, float* const* gw,
+                           float* gconv_w, float* gconv_b, float* ggamma, float* gbeta, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ---- host-only planning helpers (no GPU touched; exercised by the CPU test-suite) ----------------
+ * Each writes the dense fp32 matrix the kernels multiply by.  Sizes: see uno_b200/csrc/plan.h.      */
+int uno_plan_dft_last_analysis(int n, int m, double scale, float* out /* [n, 2m] */);
+int uno_plan_dft_last_synthesis(int n, int m, double scale, int hermitian, float* out /* [2m, n] */);
+int uno_plan_dft_mid_analysis(int n, int m, float* out /* [2m, n] complex */);
+int uno_plan_dft_mid_synthesis(int n, int m, float* out /* [n, 2m] complex */);
+int uno_plan_sr_mid(int n_in, int n_out, float* out /* [n_out, n_in] complex */);
+int uno_plan_sr_last_modes(int n_in, int n_out);
+int uno_plan_bicubic_aa(int n_in, int n_out, int transpose, float* out /* dense [n_out,n_in] or its transpose */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNO_B200_H */

@@ -1,0 +1,193 @@
+// TEST INFRASTRUCTURE ONLY.  Plain-loop implementation of uno_b200/csrc/backend.h so that the
+// orchestration in uno_api.cpp (plan matrices, strides, corner maps, adjoints, epilogue selection)
+// can be exercised by the CPU test-suite on a machine with no GPU.  Built by tests/hostemu/build.py
+// into tests/hostemu/libuno_hostemu.so; the product (uno_b200/_lib.py) never loads it and
+// uno_backend_name() of this build returns "host-emulation".
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../uno_b200/csrc/backend.h"
+
+namespace uno {
+
+int be_upload(void** dptr, const void* host, size_t bytes) {
+    *dptr = malloc(bytes ? bytes : 1);
+    if (!*dptr) return 1;
+    memcpy(*dptr, host, bytes);
+    return 0;
+}
+void be_free(void* d) { free(d); }
+int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); return 0; }
+const char* be_name() { return "host-emulation"; }
+const char* be_error_string(int) { return "host emulation error"; }
+
+static inline float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+static inline float gelu_grad_f(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+
+int be_gemm(const GemmArgs& a, stream_t) {
+    for (int b = 0; b < a.batch; ++b) {
+        const float* A = a.A + b * a.sA;
+        const float* B = a.B + b * a.sB;
+        float* C = a.C + b * a.sC;
+        float* C2 = a.C2 ? a.C2 + b * a.sC : nullptr;
+        for (int m = 0; m < a.M; ++m)
+            for (int n = 0; n < a.N; ++n) {
+                double acc = 0;
+                for (int k = 0; k < a.K; ++k) acc += (double)A[m * a.a_rs + k * a.a_cs] * B[k * a.ldb + n];
+                float v = (float)acc;
+                float* c = &C[m * a.ldc + n];
+                switch (a.epi) {
+                    case EPI_STORE: *c = v + (a.bias ? a.bias[m] : 0.0f); break;
+                    case EPI_ACCUM: *c += v; break;
+                    case EPI_ACCUM_GELU: *c += v; C2[m * a.ldc + n] = gelu_f(*c); break;
+                    case EPI_ACCUM_GELU_INPLACE: *c = gelu_f(*c + v); break;
+                    default: return 1;
+                }
+            }
+    }
+    return 0;
+}
+
+int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t) {
+    for (int m = 0; m < a.M; ++m)
+        for (int n = 0; n < a.N; ++n) {
+            double acc = 0;
+            for (int b = 0; b < a.batch; ++b) {
+                const float* A = a.A + b * a.sA + m * a.lda;
+                const float* B = a.B + b * a.sB + n * a.ldb;
+                for (int k = 0; k < a.K; ++k) acc += (double)A[k] * B[k];
+            }
+            a.C[m * a.ldc + n] += (float)acc;
+        }
+    return 0;
+}
+
+int be_mid(const MidArgs& a, stream_t) {
+    for (long o = 0; o < a.O; ++o)
+        for (int j = 0; j < a.J; ++j)
+            for (int i = 0; i < a.I; ++i) {
+                double re = 0, im = 0;
+                for (int h = 0; h < a.H; ++h) {
+                    const float mr = a.Mat[((long)j * a.H + h) * 2], mi = a.Mat[((long)j * a.H + h) * 2 + 1];
+                    const float* x = a.X + ((o * a.H + h) * a.I + i) * 2;
+                    re += (double)mr * x[0] - (double)mi * x[1];
+                    im += (double)mr * x[1] + (double)mi * x[0];
+                }
+                float* y = a.Y + ((o * a.J + j) * a.I + i) * 2;
+                y[0] = (float)re;
+                y[1] = (float)im;
+            }
+    return 0;
+}
+
+int be_cmm(const CmmArgs& a, stream_t) {
+    for (int m = 0; m < a.M; ++m)
+        for (int n = 0; n < a.N; ++n)
+            for (int qo = 0; qo < a.q_outer; ++qo)
+                for (int qi = 0; qi < a.q_inner; ++qi) {
+                    double re = 0, im = 0;
+                    for (int k = 0; k < a.K; ++k) {
+                        const float* pa = a.A + 2 * (m * a.a_sm + k * a.a_sk + qo * a.a_sqo + qi);
+                        const float* pb = a.B + 2 * (k * a.b_sk + n * a.b_sn + qo * a.b_sqo + qi);
+                        const double ar = pa[0], ai = a.conjA ? -pa[1] : pa[1];
+                        const double br = pb[0], bi = a.conjB ? -pb[1] : pb[1];
+                        re += ar * br - ai * bi;
+                        im += ar * bi + ai * br;
+                    }
+                    float* pc = a.C + 2 * (m * a.c_sm + n * a.c_sn + qo * a.c_sqo + qi);
+                    pc[0] = (float)re;
+                    pc[1] = (float)im;
+                }
+    return 0;
+}
+
+int be_banded(const BandedArgs& a, stream_t) {
+    for (long o = 0; o < a.outer; ++o)
+        for (int j = 0; j < a.n_out; ++j)
+            for (int i = 0; i < a.inner; ++i) {
+                double acc = 0;
+                for (int t = 0; t < a.taps; ++t)
+                    acc += (double)a.w[(long)j * a.taps + t] * a.x[(o * a.n_in + a.start[j] + t) * a.inner + i];
+                a.y[(o * a.n_out + j) * a.inner + i] = (float)acc;
+            }
+    return 0;
+}
+
+int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t) {
+    for (size_t i = 0; i < n; ++i) y[i] = gelu_f(pre[i]);
+    return 0;
+}
+int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t) {
+    for (size_t i = 0; i < n; ++i) g[i] = gy[i] * gelu_grad_f(pre[i]);
+    return 0;
+}
+
+int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t) {
+    for (long p = 0; p < planes; ++p) {
+        double s = 0;
+        for (long i = 0; i < L; ++i) s += x[p * L + i];
+        const double mu = s / L;
+        double v = 0;
+        for (long i = 0; i < L; ++i) { double d = x[p * L + i] - mu; v += d * d; }
+        stats[2 * p] = (float)mu;
+        stats[2 * p + 1] = (float)(1.0 / std::sqrt(v / L + eps));
+    }
+    return 0;
+}
+
+int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
+                    float* y, long planes, int C, long L, int non_lin, stream_t) {
+    for (long p = 0; p < planes; ++p) {
+        const int c = (int)(p % C);
+        for (long i = 0; i < L; ++i) {
+            float n = (x[p * L + i] - stats[2 * p]) * stats[2 * p + 1] * gamma[c] + beta[c];
+            y[p * L + i] = non_lin ? gelu_f(n) : n;
+        }
+    }
+    return 0;
+}
+
+int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
+                    const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
+                    long L, int non_lin, stream_t) {
+    for (long p = 0; p < planes; ++p) {
+        const int c = (int)(p % C);
+        const float mu = stats[2 * p], rstd = stats[2 * p + 1];
+        double s1 = 0, s2 = 0;
+        for (long i = 0; i < L; ++i) {
+            const float xh = (x[p * L + i] - mu) * rstd;
+            const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
+            s1 += gn;
+            s2 += (double)gn * xh;
+        }
+        ggamma[c] += (float)s2;
+        gbeta[c] += (float)s1;
+        const float m1 = (float)(s1 / L), m2 = (float)(s2 / L);
+        for (long i = 0; i < L; ++i) {
+            const float xh = (x[p * L + i] - mu) * rstd;
+            const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
+            g[p * L + i] = gamma[c] * rstd * (gn - m1 - xh * m2);
+        }
+    }
+    return 0;
+}
+
+int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t) {
+    for (long p = 0; p < planes; ++p) {
+        double s = 0;
+        for (long i = 0; i < L; ++i) s += x[p * L + i];
+        out[p % C] += alpha * (float)s;
+    }
+    return 0;
+}
+
+int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t) {
+    for (long p = 0; p < planes; ++p)
+        for (long i = 0; i < L; ++i) y[p * L + i] += v[p % C] * alpha;
+    return 0;
+}
+
+}  // namespace uno

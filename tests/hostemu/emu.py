@@ -1,0 +1,169 @@
+"""TEST INFRASTRUCTURE ONLY: numpy front-end to the host-emulation build of the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from uno_b200 import _capi  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        sys.path.insert(0, HERE)
+        import build as _build  # tests/hostemu/build.py
+
+        _lib = _capi.bind(_build.build())
+        assert _lib.uno_backend_name() == b"host-emulation"
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.complex64)
+
+
+def _ws(nbytes):
+    return np.empty(max(nbytes, 8) // 4 + 64, np.float32)
+
+
+def spectral_fwd(x, weights, out_dims, modes, want_xhat=True):
+    L = lib()
+    x = _f32(x)
+    ws_ = [_c64(w) for w in weights]
+    B, Ci = x.shape[:2]
+    Co = ws_[0].shape[1]
+    d = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims, modes)
+    _capi.check(L, L.uno_spectral_conv_check(C.byref(d)))
+    y = np.empty((B, Co) + tuple(out_dims), np.float32)
+    xhat = np.empty(L.uno_spectral_conv_xhat_elems(C.byref(d)), np.complex64) if want_xhat else None
+    ws = _ws(L.uno_spectral_conv_workspace_bytes(C.byref(d)))
+    wp = _capi.ptr_array([w.ctypes.data for w in ws_])
+    _capi.check(L, L.uno_spectral_conv_fwd(C.byref(d), _p(x), wp, _p(y), _p(xhat), _p(ws), ws.nbytes, None))
+    return (y, xhat) if want_xhat else y
+
+
+def spectral_bwd(x_shape, weights, out_dims, modes, gy, xhat):
+    L = lib()
+    ws_ = [_c64(w) for w in weights]
+    B, Ci = x_shape[:2]
+    Co = ws_[0].shape[1]
+    d = _capi.conv_desc(B, Ci, Co, x_shape[2:], out_dims, modes)
+    gy = _f32(gy)
+    gx = np.empty(x_shape, np.float32)
+    gws = [np.empty_like(w) for w in ws_]
+    ws = _ws(L.uno_spectral_conv_workspace_bytes(C.byref(d)))
+    wp = _capi.ptr_array([w.ctypes.data for w in ws_])
+    gwp = _capi.ptr_array([w.ctypes.data for w in gws])
+    _capi.check(L, L.uno_spectral_conv_bwd(C.byref(d), _p(gy), _p(xhat), wp, _p(gx), gwp, 0, _p(ws), ws.nbytes, None))
+    return gx, gws
+
+
+def pointwise_fwd(x, conv_w, conv_b, out_dims, want_saved=True):
+    L = lib()
+    x = _f32(x)
+    cw = _f32(conv_w).reshape(conv_w.shape[0], conv_w.shape[1])
+    cb = _f32(conv_b)
+    B, Ci = x.shape[:2]
+    Co = cw.shape[0]
+    d = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims)
+    z = np.empty((B, Co) + tuple(out_dims), np.float32)
+    n = L.uno_pointwise_saved_elems(C.byref(d))
+    saved = np.empty(n, np.float32) if (want_saved and n) else None
+    ws = _ws(L.uno_pointwise_workspace_bytes(C.byref(d)))
+    _capi.check(L, L.uno_pointwise_fwd(C.byref(d), _p(x), _p(cw), _p(cb), _p(z), _p(saved), _p(ws), ws.nbytes, None))
+    return z, saved
+
+
+def pointwise_bwd(x, conv_w, out_dims, gz, saved):
+    L = lib()
+    x = _f32(x)
+    cw = _f32(conv_w).reshape(conv_w.shape[0], conv_w.shape[1])
+    B, Ci = x.shape[:2]
+    Co = cw.shape[0]
+    d = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims)
+    gz = _f32(gz)
+    gx = np.empty_like(x)
+    gw = np.empty_like(cw)
+    gb = np.empty(Co, np.float32)
+    ws = _ws(L.uno_pointwise_workspace_bytes(C.byref(d)))
+    _capi.check(L, L.uno_pointwise_bwd(C.byref(d), _p(gz), _p(x), _p(saved), _p(cw), _p(gx), _p(gw), _p(gb), _p(ws), ws.nbytes, None))
+    return gx, gw, gb
+
+
+def block_fwd(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None, non_lin=True, train=True):
+    L = lib()
+    x = _f32(x)
+    ws_ = [_c64(w) for w in weights]
+    cw = _f32(conv_w).reshape(conv_w.shape[0], conv_w.shape[1])
+    cb = _f32(conv_b)
+    B, Ci = x.shape[:2]
+    Co = cw.shape[0]
+    normalize = gamma is not None
+    g = _f32(gamma) if normalize else None
+    bt = _f32(beta) if normalize else None
+    cd = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims, modes)
+    bd = _capi.block_desc(cd, normalize, non_lin)
+    y = np.empty((B, Co) + tuple(out_dims), np.float32)
+    need_pre = train and (normalize or non_lin)
+    pre = np.empty_like(y) if need_pre else None
+    stats = np.empty((B * Co, 2), np.float32) if (need_pre and normalize) else None
+    xhat = np.empty(L.uno_spectral_conv_xhat_elems(C.byref(cd)), np.complex64) if train else None
+    n = L.uno_pointwise_saved_elems(C.byref(cd))
+    saved = np.empty(n, np.float32) if (train and n) else None
+    ws = _ws(L.uno_operator_block_workspace_bytes(C.byref(bd)))
+    wp = _capi.ptr_array([w.ctypes.data for w in ws_])
+    _capi.check(
+        L,
+        L.uno_operator_block_fwd(C.byref(bd), _p(x), wp, _p(cw), _p(cb), _p(g), _p(bt), _p(y), _p(xhat), _p(saved), _p(pre), _p(stats), _p(ws), ws.nbytes, None),
+    )
+    return y, dict(xhat=xhat, saved=saved, pre=pre, stats=stats)
+
+
+def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=None, non_lin=True):
+    L = lib()
+    x = _f32(x)
+    ws_ = [_c64(w) for w in weights]
+    cw = _f32(conv_w).reshape(conv_w.shape[0], conv_w.shape[1])
+    B, Ci = x.shape[:2]
+    Co = cw.shape[0]
+    normalize = gamma is not None
+    g = _f32(gamma) if normalize else None
+    bt = _f32(beta) if normalize else None
+    cd = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims, modes)
+    bd = _capi.block_desc(cd, normalize, non_lin)
+    gy = _f32(gy)
+    gx = np.empty_like(x)
+    gws = [np.empty_like(w) for w in ws_]
+    gcw = np.empty_like(cw)
+    gcb = np.empty(Co, np.float32)
+    gg = np.empty(Co, np.float32) if normalize else None
+    gb = np.empty(Co, np.float32) if normalize else None
+    ws = _ws(L.uno_operator_block_workspace_bytes(C.byref(bd)))
+    wp = _capi.ptr_array([w.ctypes.data for w in ws_])
+    gwp = _capi.ptr_array([w.ctypes.data for w in gws])
+    _capi.check(
+        L,
+        L.uno_operator_block_bwd(
+            C.byref(bd), _p(gy), _p(x), _p(ctx["xhat"]), _p(ctx["saved"]), _p(ctx["pre"]), _p(ctx["stats"]), wp, _p(cw), _p(g), _p(bt),
+            _p(gx), gwp, _p(gcw), _p(gcb), _p(gg), _p(gb), _p(ws), ws.nbytes, None,
+        ),
+    )
+    return gx, gws, gcw, gcb, gg, gb

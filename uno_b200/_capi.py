@@ -1,0 +1,109 @@
+"""ctypes prototypes for the C ABI declared in include/uno_b200.h.
+
+``bind(path)`` loads a shared library exporting that ABI and attaches argument / return types.
+The product loads exactly one library through ``uno_b200._lib`` (the nvcc-built
+``uno_b200/csrc/libuno_b200.so``); the CPU test-suite also binds the host-emulation build under
+``tests/hostemu`` with the same prototypes to check the orchestration without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int),
+        ("batch", C.c_int),
+        ("in_ch", C.c_int),
+        ("out_ch", C.c_int),
+        ("in_dim", C.c_int * 3),
+        ("out_dim", C.c_int * 3),
+        ("modes", C.c_int * 3),
+    ]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("conv", ConvDesc), ("normalize", C.c_int), ("non_lin", C.c_int), ("eps", C.c_float)]
+
+
+# every symbol include/uno_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_DESC = C.POINTER(ConvDesc)
+_BDESC = C.POINTER(BlockDesc)
+_PP = C.POINTER(C.c_void_p)
+SYMBOLS = {
+    "uno_last_error": (C.c_char_p, []),
+    "uno_version": (C.c_int, []),
+    "uno_backend_name": (C.c_char_p, []),
+    "uno_clear_plans": (None, []),
+    "uno_spectral_conv_check": (C.c_int, [_DESC]),
+    "uno_spectral_conv_workspace_bytes": (C.c_size_t, [_DESC]),
+    "uno_spectral_conv_xhat_elems": (C.c_size_t, [_DESC]),
+    "uno_spectral_conv_fwd": (C.c_int, [_DESC, _P, _PP, _P, _P, _P, C.c_size_t, _P]),
+    "uno_spectral_conv_bwd": (C.c_int, [_DESC, _P, _P, _PP, _P, _PP, C.c_int, _P, C.c_size_t, _P]),
+    "uno_pointwise_workspace_bytes": (C.c_size_t, [_DESC]),
+    "uno_pointwise_saved_elems": (C.c_size_t, [_DESC]),
+    "uno_pointwise_fwd": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "uno_pointwise_bwd": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "uno_operator_block_workspace_bytes": (C.c_size_t, [_BDESC]),
+    "uno_operator_block_fwd": (C.c_int, [_BDESC, _P, _PP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "uno_operator_block_bwd": (
+        C.c_int,
+        [_BDESC, _P, _P, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P, C.c_size_t, _P],
+    ),
+    "uno_plan_dft_last_analysis": (C.c_int, [C.c_int, C.c_int, C.c_double, _P]),
+    "uno_plan_dft_last_synthesis": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, _P]),
+    "uno_plan_dft_mid_analysis": (C.c_int, [C.c_int, C.c_int, _P]),
+    "uno_plan_dft_mid_synthesis": (C.c_int, [C.c_int, C.c_int, _P]),
+    "uno_plan_sr_mid": (C.c_int, [C.c_int, C.c_int, _P]),
+    "uno_plan_sr_last_modes": (C.c_int, [C.c_int, C.c_int]),
+    "uno_plan_bicubic_aa": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
+}
+
+
+def bind(path: str) -> C.CDLL:
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def conv_desc(batch: int, in_ch: int, out_ch: int, in_dims: Sequence[int], out_dims: Sequence[int], modes: Sequence[int] = ()) -> ConvDesc:
+    d = ConvDesc()
+    d.ndim = len(in_dims)
+    d.batch, d.in_ch, d.out_ch = int(batch), int(in_ch), int(out_ch)
+    for a in range(3):
+        d.in_dim[a] = int(in_dims[a]) if a < len(in_dims) else 1
+        d.out_dim[a] = int(out_dims[a]) if a < len(out_dims) else 1
+        d.modes[a] = int(modes[a]) if a < len(modes) else 0
+    return d
+
+
+def block_desc(conv: ConvDesc, normalize: bool, non_lin: bool, eps: float = 1e-5) -> BlockDesc:
+    b = BlockDesc()
+    b.conv = conv
+    b.normalize, b.non_lin, b.eps = int(bool(normalize)), int(bool(non_lin)), float(eps)
+    return b
+
+
+def ptr_array(ptrs: Sequence[int]):
+    """void*[n] from integer addresses (0 -> NULL)."""
+    arr = (C.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p if p else None
+    return arr
+
+
+class UnoError(RuntimeError):
+    """Non-zero status from the C ABI (message from uno_last_error())."""
+
+
+def check(lib: C.CDLL, rc: int) -> None:
+    if rc != 0:
+        msg = lib.uno_last_error()
+        raise UnoError((msg.decode() if msg else "unknown error") + f" [uno status {rc}]")

@@ -1,0 +1,97 @@
+// Primitive-kernel interface between the orchestration (uno_api.cpp) and the device code
+// (backend_cuda.cu: hand-written sm_100a kernels).  tests/hostemu/backend_host.cpp implements the
+// same interface with plain loops so the orchestration (matrices, strides, corner maps, adjoints)
+// can be checked on a machine without a GPU; that build is test infrastructure and is never loaded
+// by the product.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace uno {
+
+typedef void* stream_t;
+
+// ---- persistent constants (plan matrices) ---------------------------------------------------------
+int be_upload(void** dptr, const void* host, size_t bytes);   // allocate + copy, synchronous
+void be_free(void* dptr);
+int be_memset(void* d, int v, size_t bytes, stream_t s);
+const char* be_name();
+const char* be_error_string(int code);   // message for a non-zero return of any be_* call
+
+// ---- C[M,N] = A[M,K] * B[K,N]  (fp32, row-major B and C, strided A), optionally batched -----------
+enum GemmEpi {
+    EPI_STORE = 0,        // C = acc (+ bias[m])
+    EPI_ACCUM = 1,        // C = C + acc
+    EPI_ACCUM_GELU = 2,   // C = C + acc ; C2 = gelu(C)
+    EPI_ACCUM_GELU_INPLACE = 3,   // C = gelu(C + acc)
+};
+struct GemmArgs {
+    const float* A = nullptr; long a_rs = 0, a_cs = 1;   // A(m,k) = A[m*a_rs + k*a_cs]
+    const float* B = nullptr; long ldb = 0;              // B(k,n) = B[k*ldb + n]
+    float* C = nullptr; long ldc = 0;                    // C(m,n) = C[m*ldc + n]
+    float* C2 = nullptr;                                 // second output (same ldc / batch stride)
+    const float* bias = nullptr;                         // per-row bias [M] (EPI_STORE only)
+    int M = 0, N = 0, K = 0;
+    int batch = 1; long sA = 0, sB = 0, sC = 0;          // batch strides in elements
+    int epi = EPI_STORE;
+};
+int be_gemm(const GemmArgs& a, stream_t s);
+
+// ---- C[M,N] (+)= sum_batch A_b[M,K] * B_b[N,K]^T   (weight-gradient reduction; C pre-zeroed) -------
+struct GemmNtArgs {
+    const float* A = nullptr; long lda = 0, sA = 0;
+    const float* B = nullptr; long ldb = 0, sB = 0;
+    float* C = nullptr; long ldc = 0;
+    int M = 0, N = 0, K = 0, batch = 1;
+};
+int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s);
+
+// ---- complex transform along a middle axis: Y[o,j,i] = sum_h Mat[j,h] * X[o,h,i] --------------------
+struct MidArgs {
+    const float* X = nullptr;    // complex64 interleaved [O, H, I]
+    const float* Mat = nullptr;  // complex64 interleaved [J, H]
+    float* Y = nullptr;          // complex64 interleaved [O, J, I]
+    int O = 0, H = 0, J = 0, I = 0;
+};
+int be_mid(const MidArgs& a, stream_t s);
+
+// ---- per-mode complex contraction: C[m,n,q] = sum_k opA(A[m,k,q]) * opB(B[k,n,q]) -----------------
+// q = (qo, qi): qi contiguous (length q_inner), qo strided.  All strides in complex elements.
+struct CmmArgs {
+    const float* A = nullptr; long a_sm = 0, a_sk = 0, a_sqo = 0; int conjA = 0;
+    const float* B = nullptr; long b_sk = 0, b_sn = 0, b_sqo = 0; int conjB = 0;
+    float* C = nullptr; long c_sm = 0, c_sn = 0, c_sqo = 0;
+    int M = 0, N = 0, K = 0, q_outer = 1, q_inner = 0;
+};
+int be_cmm(const CmmArgs& a, stream_t s);
+
+// ---- banded (resample) operators -------------------------------------------------------------------
+// last axis : y[r, j]    = sum_t w[j,t] * x[r, start[j]+t]          x [R, n_in]     y [R, n_out]
+// mid axis  : y[o, j, i] = sum_t w[j,t] * x[o, start[j]+t, i]       x [O, n_in, I]  y [O, n_out, I]
+struct BandedArgs {
+    const float* x = nullptr; float* y = nullptr;
+    const int* start = nullptr; const float* w = nullptr;
+    int n_in = 0, n_out = 0, taps = 0;
+    long outer = 0;    // R or O
+    int inner = 1;     // I (1 for the last-axis form)
+};
+int be_banded(const BandedArgs& a, stream_t s);
+
+// ---- elementwise / reductions ----------------------------------------------------------------------
+int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s);
+int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s);
+// per-plane mean / rstd over L contiguous elements: stats[p] = (mean, rstd)
+int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s);
+// y = [gelu]( (x-mean)*rstd*gamma[c] + beta[c] ), plane p -> channel p % C
+int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
+                    float* y, long planes, int C, long L, int non_lin, stream_t s);
+// backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller)
+int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
+                    const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
+                    long L, int non_lin, stream_t s);
+// out[c] += alpha * sum over planes p with p % C == c and over the plane's L elements  (out pre-zeroed)
+int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t s);
+// y[p, :] += v[p % C] * alpha
+int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t s);
+
+}  // namespace uno

@@ -1,0 +1,617 @@
+// Hand-written sm_100a kernels behind uno_b200/csrc/backend.h.
+//
+// Kernel inventory (DESIGN.md has the roofline each one is bound by):
+//   gemm_kernel        C = A*B (+epilogue)   truncated-DFT analysis/synthesis along the last axis,
+//                                             1x1 channel mix, weight-gradient reduction (split-K, atomics)
+//   mid_kernel         complex [J x H] transform along a middle axis, batched
+//   cmm_kernel         per-mode complex channel contraction (mode index on the lanes)
+//   banded_kernel      anti-aliased bicubic resample bands (and their transposes)
+//   elementwise / plane reductions: GELU fwd/bwd, InstanceNorm stats / apply / backward, bias sums
+//
+// Everything here is fp32 FMA on the SIMT pipes with fp32 accumulation; the tensor-core variants of
+// the GEMM-shaped stages live in gemm_tc.cuh and are selected by be_gemm when the shape qualifies.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "backend.h"
+
+namespace uno {
+
+namespace {
+
+inline cudaStream_t S(stream_t s) { return (cudaStream_t)s; }
+
+#define CU_LAUNCH_CHECK()                          \
+    do {                                           \
+        cudaError_t _e = cudaGetLastError();       \
+        if (_e != cudaSuccess) return (int)_e;     \
+    } while (0)
+
+__device__ __forceinline__ float gelu_f(float x) {
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) +
+           x * 0.39894228040143267794f * expf(-0.5f * x * x);
+}
+
+// =====================================================================================================
+// GEMM: C[M,N] = A[M,K] * B[K,N], arbitrary element strides on A and B, row-major C.
+// 256 threads arranged TX (n) x 256/TX (m); thread tile TM x TN with columns interleaved by TX so
+// that a warp's store / B-fragment read covers consecutive columns.
+// =====================================================================================================
+struct GemmK {
+    const float* A; long a_rs, a_cs, sA;
+    const float* B; long b_rs, b_cs, sB;
+    float* C; long ldc, sC;
+    float* C2;
+    const float* bias;
+    int M, N, K;
+    int ksplit;      // number of K partitions (atomic epilogue when > 1 or epi == EPI_ATOMIC)
+    int kchunk;      // K elements per partition
+    int epi;
+};
+enum { EPI_ATOMIC = 100 };
+
+template <int BM, int BN, int BK, int TX>
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmK a) {
+    constexpr int TY = 256 / TX;
+    constexpr int TM = BM / TY;
+    constexpr int TN = BN / TX;
+    static_assert(TM >= 1 && TN >= 1, "tile");
+    constexpr int LDA_S = BM + 4;
+    __shared__ __align__(16) float As[2][BK][LDA_S];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % TX, ty = tid / TX;
+    const int zb = blockIdx.z / a.ksplit;          // batch index
+    const int zk = blockIdx.z - zb * a.ksplit;     // K partition
+    const int ntiles = (a.N + BN - 1) / BN;       // tiles linearised on grid.x, n fastest
+    const long m0 = (long)(blockIdx.x / ntiles) * BM;
+    const int n0 = (int)(blockIdx.x % ntiles) * BN;
+    const float* __restrict__ A = a.A + zb * a.sA;
+    const float* __restrict__ B = a.B + zb * a.sB;
+    const int k_begin = zk * a.kchunk;
+    const int k_end = min(a.K, k_begin + a.kchunk);
+
+    constexpr int A_PER = (BM * BK + 255) / 256;
+    constexpr int B_PER = (BK * BN + 255) / 256;
+    float ra[A_PER], rb[B_PER];
+    const bool a_kfast = (a.a_cs == 1);
+    const bool b_nfast = (a.b_cs == 1);
+
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (a_kfast) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
+            float v = 0.f;
+            if (idx < BM * BK && m0 + m < a.M && k0 + k < k_end)
+                v = __ldg(A + (m0 + m) * a.a_rs + (long)(k0 + k) * a.a_cs);
+            ra[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+            const int idx = tid + i * 256;
+            int n, k;
+            if (b_nfast) { n = idx % BN; k = idx / BN; } else { k = idx % BK; n = idx / BK; }
+            float v = 0.f;
+            if (idx < BK * BN && n0 + n < a.N && k0 + k < k_end)
+                v = __ldg(B + (long)(k0 + k) * a.b_rs + (long)(n0 + n) * a.b_cs);
+            rb[i] = v;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int idx = tid + i * 256;
+            int m, k;
+            if (a_kfast) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
+            if (idx < BM * BK) As[buf][k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+            const int idx = tid + i * 256;
+            int n, k;
+            if (b_nfast) { n = idx % BN; k = idx / BN; } else { k = idx % BK; n = idx / BK; }
+            if (idx < BK * BN) Bs[buf][k][n] = rb[i];
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    int buf = 0;
+    load_tiles(k_begin);
+    store_tiles(0);
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const bool more = k0 + BK < k_end;
+        if (more) load_tiles(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[TM], bv[TN];
+            if constexpr (TM % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM + i]);
+                    av[i] = t.x; av[i + 1] = t.y; av[i + 2] = t.z; av[i + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) av[i] = As[buf][k][ty * TM + i];
+            }
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[buf][k][tx + j * TX];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    float* __restrict__ C = a.C + zb * a.sC;
+    float* __restrict__ C2 = a.C2 ? a.C2 + zb * a.sC : nullptr;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long m = m0 + ty * TM + i;
+        if (m >= a.M) continue;
+        const float bm = a.bias ? __ldg(a.bias + m) : 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx + j * TX;
+            if (n >= a.N) continue;
+            const long off = m * a.ldc + n;
+            const float v = acc[i][j];
+            switch (a.epi) {
+                case EPI_STORE: C[off] = v + bm; break;
+                case EPI_ACCUM: C[off] += v; break;
+                case EPI_ACCUM_GELU: { const float s = C[off] + v; C[off] = s; C2[off] = gelu_f(s); } break;
+                case EPI_ACCUM_GELU_INPLACE: C[off] = gelu_f(C[off] + v); break;
+                case EPI_ATOMIC: atomicAdd(C + off, v); break;
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int BK, int TX>
+int launch_gemm(const GemmK& k, int batch, cudaStream_t st) {
+    const long tiles = (long)((k.M + BM - 1) / BM) * ((k.N + BN - 1) / BN);
+    dim3 grid((unsigned)tiles, 1, (unsigned)(batch * k.ksplit));
+    gemm_kernel<BM, BN, BK, TX><<<grid, 256, 0, st>>>(k);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+int dispatch_gemm(const GemmK& k, int batch, cudaStream_t st) {
+    if (k.M <= 0 || k.N <= 0 || batch <= 0) return 0;
+    const bool smallK = (k.kchunk <= 48);
+    if (k.N <= 56) {   // skinny output: narrow thread layout, BN tailored to N
+        const int N = k.N;
+#define UNO_NARROW(BN)                                                        \
+    return smallK ? launch_gemm<128, BN, 8, 16>(k, batch, st) : launch_gemm<128, BN, 16, 16>(k, batch, st)
+        if (N <= 16) { UNO_NARROW(16); }
+        if (N <= 32) { UNO_NARROW(32); }
+        UNO_NARROW(48);
+#undef UNO_NARROW
+    }
+    if (k.M <= 32) return smallK ? launch_gemm<32, 64, 8, 32>(k, batch, st) : launch_gemm<32, 64, 16, 32>(k, batch, st);
+    if (k.M <= 64 || (k.M <= 192 && k.M % 128 != 0 && k.M % 64 == 0))
+        return smallK ? launch_gemm<64, 64, 8, 32>(k, batch, st) : launch_gemm<64, 64, 16, 32>(k, batch, st);
+    return smallK ? launch_gemm<128, 64, 8, 32>(k, batch, st) : launch_gemm<128, 64, 16, 32>(k, batch, st);
+}
+
+// =====================================================================================================
+// complex transform along a middle axis: Y[o,j,i] = sum_h Mat[j,h] X[o,h,i]
+// CTA: one o, 32 j x TI i outputs, 128 threads, each 2 j x (TI/8) i complex accumulators.
+// =====================================================================================================
+template <int TI>
+__global__ void __launch_bounds__(128) mid_kernel(const float2* __restrict__ X, const float2* __restrict__ Mat,
+                                                  float2* __restrict__ Y, int O, int H, int J, int I,
+                                                  int tilesI, int tilesJ) {
+    constexpr int NI = TI / 8;
+    constexpr int HK = 16;
+    __shared__ float2 Ms[HK][32 + 1];
+    __shared__ float2 Xs[HK][TI];
+    long bid = blockIdx.x;
+    const int ti0 = (int)(bid % tilesI) * TI; bid /= tilesI;
+    const int tj0 = (int)(bid % tilesJ) * 32; bid /= tilesJ;
+    const long o = bid;
+    const int tid = threadIdx.x;
+    const int tj = tid / 8, ti = tid % 8;
+    float2 acc[2][NI];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NI; ++b) acc[a][b] = make_float2(0.f, 0.f);
+    const float2* Xo = X + o * (long)H * I;
+    for (int h0 = 0; h0 < H; h0 += HK) {
+        // Mat tile: 32 j x 16 h, h contiguous in memory
+        for (int idx = tid; idx < 32 * HK; idx += 128) {
+            const int h = idx % HK, j = idx / HK;
+            float2 v = make_float2(0.f, 0.f);
+            if (tj0 + j < J && h0 + h < H) v = __ldg(Mat + (long)(tj0 + j) * H + h0 + h);
+            Ms[h][j] = v;
+        }
+        for (int idx = tid; idx < HK * TI; idx += 128) {
+            const int i = idx % TI, h = idx / TI;
+            float2 v = make_float2(0.f, 0.f);
+            if (ti0 + i < I && h0 + h < H) v = __ldg(Xo + (long)(h0 + h) * I + ti0 + i);
+            Xs[h][i] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < HK; ++h) {
+            const float2 m0 = Ms[h][tj], m1 = Ms[h][tj + 16];
+#pragma unroll
+            for (int b = 0; b < NI; ++b) {
+                const float2 x = Xs[h][ti + 8 * b];
+                acc[0][b].x = fmaf(m0.x, x.x, acc[0][b].x); acc[0][b].x = fmaf(-m0.y, x.y, acc[0][b].x);
+                acc[0][b].y = fmaf(m0.x, x.y, acc[0][b].y); acc[0][b].y = fmaf(m0.y, x.x, acc[0][b].y);
+                acc[1][b].x = fmaf(m1.x, x.x, acc[1][b].x); acc[1][b].x = fmaf(-m1.y, x.y, acc[1][b].x);
+                acc[1][b].y = fmaf(m1.x, x.y, acc[1][b].y); acc[1][b].y = fmaf(m1.y, x.x, acc[1][b].y);
+            }
+        }
+        __syncthreads();
+    }
+    float2* Yo = Y + o * (long)J * I;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int j = tj0 + tj + 16 * a;
+        if (j >= J) continue;
+#pragma unroll
+        for (int b = 0; b < NI; ++b) {
+            const int i = ti0 + ti + 8 * b;
+            if (i < I) Yo[(long)j * I + i] = acc[a][b];
+        }
+    }
+}
+
+// =====================================================================================================
+// per-mode complex contraction, mode index on the lanes: C[m,n,q] = sum_k A[m,k,q] B[k,n,q]
+// block (32 q, 4 n-tiles); thread tile 4 m x 4 n.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) cmm_kernel(const CmmArgs a, int chunks_per_row) {
+    const int qo = blockIdx.x / chunks_per_row;
+    const int qi = (blockIdx.x - qo * chunks_per_row) * 32 + threadIdx.x;
+    const int m0 = blockIdx.y * 4;
+    const int n0 = (blockIdx.z * 4 + threadIdx.y) * 4;
+    if (qi >= a.q_inner || n0 >= a.N) return;
+    const float2* A = reinterpret_cast<const float2*>(a.A) + (long)qo * a.a_sqo + qi;
+    const float2* B = reinterpret_cast<const float2*>(a.B) + (long)qo * a.b_sqo + qi;
+    float2* C = reinterpret_cast<float2*>(a.C) + (long)qo * a.c_sqo + qi;
+    const float sa = a.conjA ? -1.f : 1.f, sb = a.conjB ? -1.f : 1.f;
+    float2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    int mi[4], nj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mi[i] = min(m0 + i, a.M - 1); nj[i] = min(n0 + i, a.N - 1); }
+    for (int k = 0; k < a.K; ++k) {
+        float2 av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            av[i] = __ldg(A + (long)mi[i] * a.a_sm + (long)k * a.a_sk);
+            av[i].y *= sa;
+            bv[i] = __ldg(B + (long)k * a.b_sk + (long)nj[i] * a.b_sn);
+            bv[i].y *= sb;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[i][j].x = fmaf(av[i].x, bv[j].x, acc[i][j].x);
+                acc[i][j].x = fmaf(-av[i].y, bv[j].y, acc[i][j].x);
+                acc[i][j].y = fmaf(av[i].x, bv[j].y, acc[i][j].y);
+                acc[i][j].y = fmaf(av[i].y, bv[j].x, acc[i][j].y);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (m0 + i >= a.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n0 + j < a.N) C[(long)(m0 + i) * a.c_sm + (long)(n0 + j) * a.c_sn] = acc[i][j];
+    }
+}
+
+// =====================================================================================================
+// banded resample
+// =====================================================================================================
+__global__ void __launch_bounds__(256) banded_kernel(const BandedArgs a, long total) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % a.inner);
+        long r = idx / a.inner;
+        const int j = (int)(r % a.n_out);
+        const long o = r / a.n_out;
+        const float* w = a.w + (long)j * a.taps;
+        const float* x = a.x + (o * a.n_in + __ldg(a.start + j)) * a.inner + i;
+        float acc = 0.f;
+        for (int t = 0; t < a.taps; ++t) acc = fmaf(__ldg(w + t), __ldg(x + (long)t * a.inner), acc);
+        a.y[idx] = acc;
+    }
+}
+
+// =====================================================================================================
+// elementwise and per-plane reductions
+// =====================================================================================================
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__ pre, float* __restrict__ y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = gelu_f(pre[i]);
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ pre,
+                                                       float* __restrict__ g, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        g[i] = gy[i] * gelu_grad_f(pre[i]);
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (l == 0) sh[0] = t;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(512) plane_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, long L, float eps) {
+    __shared__ double sh[32];
+    const float* p = x + (long)blockIdx.x * L;
+    float s = 0.f;
+    double sd = 0.0;
+    int cnt = 0;
+    for (long i = threadIdx.x; i < L; i += blockDim.x) {
+        s += p[i];
+        if (++cnt == 64) { sd += s; s = 0.f; cnt = 0; }
+    }
+    sd += s;
+    const double mu = block_sum(sd, sh) / (double)L;
+    const float muf = (float)mu;
+    s = 0.f; sd = 0.0; cnt = 0;
+    for (long i = threadIdx.x; i < L; i += blockDim.x) {
+        const float d = p[i] - muf;
+        s = fmaf(d, d, s);
+        if (++cnt == 64) { sd += s; s = 0.f; cnt = 0; }
+    }
+    sd += s;
+    const double var = block_sum(sd, sh) / (double)L;
+    if (threadIdx.x == 0) {
+        stats[2 * blockIdx.x] = muf;
+        stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* __restrict__ y, int C, long L, int non_lin) {
+    const long p = blockIdx.x;
+    const int c = (int)(p % C);
+    const float mu = stats[2 * p], rstd = stats[2 * p + 1];
+    const float g = gamma[c] * rstd, b = beta[c] - mu * rstd * gamma[c];
+    const float* xp = x + p * L;
+    float* yp = y + p * L;
+    for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < L; i += (long)gridDim.y * blockDim.x) {
+        const float n = fmaf(xp[i], g, b);
+        yp[i] = non_lin ? gelu_f(n) : n;
+    }
+}
+
+__global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                           const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ g,
+                                                           float* __restrict__ ggamma, float* __restrict__ gbeta, int C,
+                                                           long L, int non_lin) {
+    __shared__ double sh[32];
+    const long p = blockIdx.x;
+    const int c = (int)(p % C);
+    const float mu = stats[2 * p], rstd = stats[2 * p + 1];
+    const float ga = gamma[c], be = beta[c];
+    const float* xp = x + p * L;
+    const float* gp = gy + p * L;
+    float s1 = 0.f, s2 = 0.f;
+    double d1 = 0.0, d2 = 0.0;
+    int cnt = 0;
+    for (long i = threadIdx.x; i < L; i += blockDim.x) {
+        const float xh = (xp[i] - mu) * rstd;
+        const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
+        s1 += gn;
+        s2 = fmaf(gn, xh, s2);
+        if (++cnt == 64) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+    }
+    d1 += s1; d2 += s2;
+    const double t1 = block_sum(d1, sh);
+    const double t2 = block_sum(d2, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(ggamma + c, (float)t2);
+        atomicAdd(gbeta + c, (float)t1);
+    }
+    const float m1 = (float)(t1 / (double)L), m2 = (float)(t2 / (double)L);
+    const float k = ga * rstd;
+    float* op = g + p * L;
+    for (long i = threadIdx.x; i < L; i += blockDim.x) {
+        const float xh = (xp[i] - mu) * rstd;
+        const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
+        op[i] = k * (gn - m1 - xh * m2);
+    }
+}
+
+__global__ void __launch_bounds__(512) channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int C, long L, float alpha) {
+    __shared__ double sh[32];
+    const long p = blockIdx.x;
+    const float* xp = x + p * L;
+    float s = 0.f;
+    double sd = 0.0;
+    int cnt = 0;
+    for (long i = threadIdx.x; i < L; i += blockDim.x) {
+        s += xp[i];
+        if (++cnt == 64) { sd += s; s = 0.f; cnt = 0; }
+    }
+    sd += s;
+    const double t = block_sum(sd, sh);
+    if (threadIdx.x == 0) atomicAdd(out + (p % C), alpha * (float)t);
+}
+
+__global__ void __launch_bounds__(256) add_channel_const_kernel(float* __restrict__ y, const float* __restrict__ v, float alpha, int C, long L) {
+    const long p = blockIdx.x;
+    const float c = v[p % C] * alpha;
+    float* yp = y + p * L;
+    for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < L; i += (long)gridDim.y * blockDim.x) yp[i] += c;
+}
+
+inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
+    size_t g = (n + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// backend.h implementation
+// =====================================================================================================
+const char* be_name() { return "cuda-sm100a"; }
+const char* be_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+int be_upload(void** dptr, const void* host, size_t bytes) {
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice);
+    return (int)e;
+}
+void be_free(void* d) { cudaFree(d); }
+int be_memset(void* d, int v, size_t bytes, stream_t s) { return (int)cudaMemsetAsync(d, v, bytes, S(s)); }
+
+int be_gemm(const GemmArgs& a, stream_t s) {
+    GemmK k;
+    k.A = a.A; k.a_rs = a.a_rs; k.a_cs = a.a_cs; k.sA = a.sA;
+    k.B = a.B; k.b_rs = a.ldb; k.b_cs = 1; k.sB = a.sB;
+    k.C = a.C; k.ldc = a.ldc; k.sC = a.sC; k.C2 = a.C2; k.bias = a.bias;
+    k.M = a.M; k.N = a.N; k.K = a.K; k.ksplit = 1; k.kchunk = a.K; k.epi = a.epi;
+    return dispatch_gemm(k, a.batch, S(s));
+}
+
+int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
+    GemmK k;
+    k.A = a.A; k.a_rs = a.lda; k.a_cs = 1; k.sA = a.sA;
+    k.B = a.B; k.b_rs = 1; k.b_cs = a.ldb; k.sB = a.sB;
+    k.C = a.C; k.ldc = a.ldc; k.sC = 0; k.C2 = nullptr; k.bias = nullptr;
+    k.M = a.M; k.N = a.N; k.K = a.K; k.epi = EPI_ATOMIC;
+    // split K so that batch * ksplit CTAs per output tile fill the machine
+    const int tiles = ((a.M + 63) / 64) * ((a.N + 63) / 64);
+    int want = (148 * 4 + tiles * a.batch - 1) / (tiles * a.batch);
+    int kchunk = (a.K + want - 1) / want;
+    kchunk = ((kchunk + 63) / 64) * 64;
+    if (kchunk < 256) kchunk = 256;
+    k.kchunk = kchunk;
+    k.ksplit = (a.K + kchunk - 1) / kchunk;
+    return dispatch_gemm(k, a.batch, S(s));
+}
+
+int be_mid(const MidArgs& a, stream_t s) {
+    if (a.O <= 0 || a.J <= 0 || a.I <= 0) return 0;
+    const int pad8 = ((a.I + 7) / 8) * 8, pad16 = ((a.I + 15) / 16) * 16;
+    const int tilesJ = (a.J + 31) / 32;
+    const float2* X = reinterpret_cast<const float2*>(a.X);
+    const float2* M = reinterpret_cast<const float2*>(a.Mat);
+    float2* Y = reinterpret_cast<float2*>(a.Y);
+    if (pad8 < pad16) {
+        const int tilesI = pad8 / 8;
+        const long blocks = (long)a.O * tilesI * tilesJ;
+        mid_kernel<8><<<(unsigned)blocks, 128, 0, S(s)>>>(X, M, Y, a.O, a.H, a.J, a.I, tilesI, tilesJ);
+    } else {
+        const int tilesI = pad16 / 16;
+        const long blocks = (long)a.O * tilesI * tilesJ;
+        mid_kernel<16><<<(unsigned)blocks, 128, 0, S(s)>>>(X, M, Y, a.O, a.H, a.J, a.I, tilesI, tilesJ);
+    }
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+int be_cmm(const CmmArgs& a, stream_t s) {
+    if (a.M <= 0 || a.N <= 0 || a.q_inner <= 0 || a.q_outer <= 0) return 0;
+    const int chunks = (a.q_inner + 31) / 32;
+    dim3 grid((unsigned)(chunks * a.q_outer), (unsigned)((a.M + 3) / 4), (unsigned)((a.N + 15) / 16));
+    cmm_kernel<<<grid, dim3(32, 4), 0, S(s)>>>(a, chunks);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+int be_banded(const BandedArgs& a, stream_t s) {
+    const long total = a.outer * a.n_out * a.inner;
+    if (total <= 0) return 0;
+    banded_kernel<<<grid_for((size_t)total, 256, 148 * 32), 256, 0, S(s)>>>(a, total);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s) {
+    if (!n) return 0;
+    gelu_fwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(pre, y, n);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s) {
+    if (!n) return 0;
+    gelu_bwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(gy, pre, g, n);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s) {
+    if (planes <= 0) return 0;
+    plane_stats_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(x, stats, L, eps);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, float* y,
+                    long planes, int C, long L, int non_lin, stream_t s) {
+    if (planes <= 0) return 0;
+    unsigned gx = grid_for((size_t)L, 256, 64);
+    norm_act_fwd_kernel<<<dim3((unsigned)planes, gx), 256, 0, S(s)>>>(x, stats, gamma, beta, y, C, L, non_lin);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma, const float* beta,
+                    float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
+    if (planes <= 0) return 0;
+    norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t s) {
+    if (planes <= 0) return 0;
+    channel_sum_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(x, out, C, L, alpha);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t s) {
+    if (planes <= 0) return 0;
+    unsigned gx = grid_for((size_t)L, 256, 64);
+    add_channel_const_kernel<<<dim3((unsigned)planes, gx), 256, 0, S(s)>>>(y, v, alpha, C, L);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace uno

@@ -1,0 +1,229 @@
+"""torch.autograd.Function shims over the C ABI (include/uno_b200.h).
+
+torch is used here for device memory (the caching allocator), the current stream and autograd
+bookkeeping only: every FLOP of the operators is in ``csrc/`` behind the C ABI.  Inputs must be CUDA
+fp32 tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _capi
+from ._lib import get as _get_lib
+
+# number of kernels this process launched through the C ABI (bench.py reports it as gpu_launches)
+_launch_counter = {"calls": 0}
+
+
+def _check_input(x: torch.Tensor, name: str = "input") -> None:
+    if not x.is_cuda:
+        raise RuntimeError(
+            f"uno_b200: {name} must be a CUDA tensor (got device {x.device}); the operators are CUDA kernels and have no CPU fallback"
+        )
+    if x.dtype != torch.float32:
+        # the reference raises RuntimeError for fp64 / bf16 inputs as well (weights are cfloat)
+        raise RuntimeError(f"uno_b200: expected float32 {name} but found {x.dtype}")
+
+
+def _stream(x: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[C.c_void_p]:
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _cweights(weights: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    out = []
+    for w in weights:
+        if w.dtype != torch.complex64:
+            raise RuntimeError(f"uno_b200: spectral weights must be complex64 (got {w.dtype})")
+        out.append(w.detach().contiguous())
+    return out
+
+
+def _desc(x: torch.Tensor, out_ch: int, out_dims, modes=()) -> _capi.ConvDesc:
+    return _capi.conv_desc(x.shape[0], x.shape[1], out_ch, x.shape[2:], [int(v) for v in out_dims], [int(v) for v in modes])
+
+
+class SpectralConvFn(torch.autograd.Function):
+    """SpectralConv{1,2,3}d_Uno.forward and its backward (integral_operators.py:47-72, :181-207, :385-427)."""
+
+    @staticmethod
+    def forward(ctx, x, out_dims, modes, need_grad, *weights):
+        lib = _get_lib()
+        _check_input(x)
+        x = x.contiguous()
+        ws = _cweights(weights)
+        Co = ws[0].shape[1]
+        d = _desc(x, Co, out_dims, modes)
+        _capi.check(lib, lib.uno_spectral_conv_check(C.byref(d)))
+        y = torch.empty((x.shape[0], Co) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=x.device)
+        xhat = None
+        if need_grad:
+            xhat = torch.empty(lib.uno_spectral_conv_xhat_elems(C.byref(d)), dtype=torch.complex64, device=x.device)
+        wsb = _workspace(lib.uno_spectral_conv_workspace_bytes(C.byref(d)), x.device)
+        wp = _capi.ptr_array([w.data_ptr() for w in ws])
+        _capi.check(lib, lib.uno_spectral_conv_fwd(C.byref(d), _ptr(x), wp, _ptr(y), _ptr(xhat), _ptr(wsb), wsb.numel(), _stream(x)))
+        _launch_counter["calls"] += 1
+        ctx.desc = d
+        ctx.x_shape = x.shape
+        ctx.save_for_backward(xhat, *ws) if need_grad else None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _get_lib()
+        xhat, *ws = ctx.saved_tensors
+        d = ctx.desc
+        gy = gy.contiguous()
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[4:])
+        gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=gy.device) if need_x else None
+        gws = [torch.empty_like(w) for w in ws] if need_w else []
+        wsb = _workspace(lib.uno_spectral_conv_workspace_bytes(C.byref(d)), gy.device)
+        wp = _capi.ptr_array([w.data_ptr() for w in ws])
+        gwp = _capi.ptr_array([g.data_ptr() for g in gws]) if need_w else None
+        _capi.check(lib, lib.uno_spectral_conv_bwd(C.byref(d), _ptr(gy), _ptr(xhat), wp, _ptr(gx), gwp, 0, _ptr(wsb), wsb.numel(), _stream(gy)))
+        _launch_counter["calls"] += 1
+        return (gx, None, None, None) + (tuple(gws) if need_w else (None,) * len(ws))
+
+
+class PointwiseFn(torch.autograd.Function):
+    """pointwise_op_2D / pointwise_op_3D forward + backward (integral_operators.py:224-243, :438-468)."""
+
+    @staticmethod
+    def forward(ctx, x, out_dims, need_grad, conv_w, conv_b):
+        lib = _get_lib()
+        _check_input(x)
+        x = x.contiguous()
+        Co = conv_w.shape[0]
+        cw = conv_w.detach().reshape(Co, -1).contiguous()
+        cb = conv_b.detach().contiguous()
+        d = _desc(x, Co, out_dims)
+        z = torch.empty((x.shape[0], Co) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=x.device)
+        saved = None
+        n = lib.uno_pointwise_saved_elems(C.byref(d))
+        if need_grad and n:
+            saved = torch.empty(n, dtype=torch.float32, device=x.device)
+        wsb = _workspace(lib.uno_pointwise_workspace_bytes(C.byref(d)), x.device)
+        _capi.check(lib, lib.uno_pointwise_fwd(C.byref(d), _ptr(x), _ptr(cw), _ptr(cb), _ptr(z), _ptr(saved), _ptr(wsb), wsb.numel(), _stream(x)))
+        _launch_counter["calls"] += 1
+        ctx.desc = d
+        ctx.w_shape = conv_w.shape
+        if need_grad:
+            ctx.save_for_backward(x, saved, cw)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        lib = _get_lib()
+        x, saved, cw = ctx.saved_tensors
+        d = ctx.desc
+        gz = gz.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(cw)
+        gb = torch.empty(cw.shape[0], dtype=torch.float32, device=gz.device)
+        wsb = _workspace(lib.uno_pointwise_workspace_bytes(C.byref(d)), gz.device)
+        _capi.check(lib, lib.uno_pointwise_bwd(C.byref(d), _ptr(gz), _ptr(x), _ptr(saved), _ptr(cw), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(wsb), wsb.numel(), _stream(gz)))
+        _launch_counter["calls"] += 1
+        return gx, None, None, gw.reshape(ctx.w_shape), gb
+
+
+class OperatorBlockFn(torch.autograd.Function):
+    """OperatorBlock_{2,3}D.forward fused: gelu?(IN?(conv(x) + w(x))) (integral_operators.py:272-284, :501-513)."""
+
+    @staticmethod
+    def forward(ctx, x, out_dims, modes, normalize, non_lin, eps, need_grad, conv_w, conv_b, gamma, beta, *weights):
+        lib = _get_lib()
+        _check_input(x)
+        x = x.contiguous()
+        ws = _cweights(weights)
+        Co = ws[0].shape[1]
+        cw = conv_w.detach().reshape(conv_w.shape[0], -1).contiguous()
+        cb = conv_b.detach().contiguous()
+        ga = gamma.detach().contiguous() if normalize else None
+        be = beta.detach().contiguous() if normalize else None
+        cd = _desc(x, Co, out_dims, modes)
+        _capi.check(lib, lib.uno_spectral_conv_check(C.byref(cd)))
+        bd = _capi.block_desc(cd, normalize, non_lin, eps)
+        dev = x.device
+        y = torch.empty((x.shape[0], Co) + tuple(int(v) for v in out_dims), dtype=torch.float32, device=dev)
+        xhat = saved = pre = stats = None
+        if need_grad:
+            xhat = torch.empty(lib.uno_spectral_conv_xhat_elems(C.byref(cd)), dtype=torch.complex64, device=dev)
+            n = lib.uno_pointwise_saved_elems(C.byref(cd))
+            if n:
+                saved = torch.empty(n, dtype=torch.float32, device=dev)
+            if normalize or non_lin:
+                pre = torch.empty_like(y)
+            if normalize:
+                stats = torch.empty((x.shape[0] * Co, 2), dtype=torch.float32, device=dev)
+        wsb = _workspace(lib.uno_operator_block_workspace_bytes(C.byref(bd)), dev)
+        wp = _capi.ptr_array([w.data_ptr() for w in ws])
+        _capi.check(
+            lib,
+            lib.uno_operator_block_fwd(
+                C.byref(bd), _ptr(x), wp, _ptr(cw), _ptr(cb), _ptr(ga), _ptr(be), _ptr(y), _ptr(xhat), _ptr(saved), _ptr(pre), _ptr(stats),
+                _ptr(wsb), wsb.numel(), _stream(x),
+            ),
+        )
+        _launch_counter["calls"] += 1
+        ctx.bd = bd
+        ctx.w_shape = conv_w.shape
+        ctx.normalize = normalize
+        ctx.nw = len(ws)
+        if need_grad:
+            ctx.save_for_backward(x, xhat, saved, pre, stats, cw, ga, be, *ws)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _get_lib()
+        x, xhat, saved, pre, stats, cw, ga, be, *ws = ctx.saved_tensors
+        bd = ctx.bd
+        gy = gy.contiguous()
+        dev = gy.device
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gws = [torch.empty_like(w) for w in ws]
+        gcw = torch.empty_like(cw)
+        gcb = torch.empty(cw.shape[0], dtype=torch.float32, device=dev)
+        gg = torch.empty_like(ga) if ctx.normalize else None
+        gb = torch.empty_like(be) if ctx.normalize else None
+        wsb = _workspace(lib.uno_operator_block_workspace_bytes(C.byref(bd)), dev)
+        wp = _capi.ptr_array([w.data_ptr() for w in ws])
+        gwp = _capi.ptr_array([g.data_ptr() for g in gws])
+        _capi.check(
+            lib,
+            lib.uno_operator_block_bwd(
+                C.byref(bd), _ptr(gy), _ptr(x), _ptr(xhat), _ptr(saved), _ptr(pre), _ptr(stats), wp, _ptr(cw), _ptr(ga), _ptr(be),
+                _ptr(gx), gwp, _ptr(gcw), _ptr(gcb), _ptr(gg), _ptr(gb), _ptr(wsb), wsb.numel(), _stream(gy),
+            ),
+        )
+        _launch_counter["calls"] += 1
+        return (gx, None, None, None, None, None, None, gcw.reshape(ctx.w_shape), gcb, gg, gb) + tuple(gws)
+
+
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def spectral_conv(x, weights, out_dims, modes):
+    return SpectralConvFn.apply(x, tuple(out_dims), tuple(modes), _needs_grad(x, *weights), *weights)
+
+
+def pointwise_op(x, conv_w, conv_b, out_dims):
+    return PointwiseFn.apply(x, tuple(out_dims), _needs_grad(x, conv_w, conv_b), conv_w, conv_b)
+
+
+def operator_block(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None, non_lin=True, eps=1e-5):
+    normalize = gamma is not None
+    need = _needs_grad(x, conv_w, conv_b, gamma, beta, *weights)
+    return OperatorBlockFn.apply(x, tuple(out_dims), tuple(modes), normalize, bool(non_lin), float(eps), need, conv_w, conv_b, gamma, beta, *weights)

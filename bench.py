@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the U-NO hot path on B200 (contract: see the task prompt / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload darcy|ns2d|ns3d]
+
+Default workload = BASELINE.json configs[1]: UNO_9(3, 32, pad=12) (darcy_flow_main.py:95) on synthetic
+421x421 Darcy inputs, batch 32 per GPU, forward + rel-L2 loss + backward (train_darcy.py:50-54), no
+optimizer step.  One JSON line is printed by rank 0.
+
+  value      samples/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same step driven from pinned HOST buffers (H2D of x,y and D2H of the loss inside the timed region)
+  roofline   dominant kernel family of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline / --impl reference: the oracle torch port (same MKL/ATen calls as the reference's CPU path)
+             timed on the host cores on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # name: (model class, ctor args, ctor kwargs, input shape w/o batch, target shape w/o batch, default batch, cpu sample batch)
+    "darcy": ("UNO_9", (3, 32), dict(pad=12), (421, 421, 1), (421, 421), 32, 2),
+    "ns2d": ("UNO", (14, 32), {}, (64, 64, 10), (64, 64), 64, 8),
+    "ns3d": ("Uno3D_T10", (6, 8), dict(pad=3), (64, 64, 64, 1), (64, 64, 64), 8, 1),
+}
+WORKLOAD_DESC = {
+    "darcy": "UNO_9(3,32,pad=12) Darcy 421x421 fwd+loss+bwd",
+    "ns2d": "UNO(14,32) Navier-Stokes 64x64x10 single-call fwd+loss+bwd",
+    "ns3d": "Uno3D_T10(6,8,pad=3) Navier-Stokes 64x64x64 fwd+loss+bwd",
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
+    NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def finish(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def build_model(workload, ops=None, device="cuda"):
+    from uno_b200 import models
+
+    cls, args, kw, *_ = WORKLOADS[workload]
+    torch.manual_seed(0)
+    kw = dict(kw)
+    if ops is not None:
+        kw["ops"] = ops
+    return getattr(models, cls)(*args, **kw).to(device)
+
+
+def make_step(model, loss_fn, B, tshape, reducer=None):
+    def step(x, y):
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            model.zero_grad(set_to_none=True)
+        out = model(x).reshape(B, *tshape)
+        loss = loss_fn(out.reshape(B, -1), y.reshape(B, -1))
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    return step
+
+
+def cpu_reference_run(workload, steps, warmup, batch=None):
+    """The oracle torch port (kind "port") on the host cores: fwd + loss + bwd, bounded batch."""
+    from oracle import uno_torch_port as port
+    from uno_b200.losses import LpLoss
+
+    _, _, _, xshape, tshape, _, cpu_b = WORKLOADS[workload]
+    B = batch or cpu_b
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = build_model(workload, ops=port, device="cpu")
+    torch.manual_seed(1)
+    x = torch.randn(B, *xshape)
+    y = torch.randn(B, *tshape)
+    step = make_step(model, LpLoss(size_average=False), B, tshape)
+    for _ in range(warmup):
+        step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x, y)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"batch {B} of the same workload, {steps} steps after {warmup} warm-up, fp32 torch CPU (oracle/uno_torch_port.py)",
+            "ms_per_step": dt * 1e3, "batch": B}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="darcy", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the BASELINE config's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cls, cargs, ckw, xshape, tshape, def_b, _ = WORKLOADS[args.workload]
+    B = args.batch or def_b
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 5)
+        r = cpu_reference_run(args.workload, steps, min(args.warmup, 1))
+        line = {
+            "impl": "reference", "metric": "UNO samples/sec (fwd+bwd)", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "per_gpu_batch": B, "cpu_sample_batch": r["batch"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from uno_b200 import _lib, build as _build
+    from uno_b200.losses import LpLoss
+    from uno_b200.parallel import GradReducer
+
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    lib = _lib.get()
+
+    model = build_model(args.workload, device=dev)
+    reducer = GradReducer(model) if world > 1 else None
+    loss_fn = LpLoss(size_average=False)
+    step = make_step(model, loss_fn, B, tshape, reducer)
+
+    torch.manual_seed(1 + rank)
+    x_host = torch.randn(B, *xshape).pin_memory()
+    y_host = torch.randn(B, *tshape).pin_memory()
+    x = x_host.to(dev)
+    y = y_host.to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        sync_all()
+        return ms
+
+    for _ in range(args.warmup):
+        step(x, y)
+    # --- device-resident timing
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.uno_launch_count()
+    total_ms = timed(lambda: step(x, y), args.steps)
+    launches = lib.uno_launch_count() - l0
+    clocks = sampler.finish()
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # --- end to end from pinned host memory
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        return float(step(xd, yd).item())
+
+    e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s",
+           "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms}
+
+    # --- per-kernel roofline, CUDA events around every launch of OUR kernels (separate steps so the
+    #     event records do not perturb `value`)
+    roofline, breakdown = None, None
+    if not args.no_profile and rank == 0:
+        hbm, how = peaks()
+        torch.cuda.synchronize()
+        lib.uno_profile_enable(1)
+        nprof = 2
+        for _ in range(nprof):
+            step(x, y)
+        torch.cuda.synchronize()
+        n = lib.uno_profile_report(None, 0)
+        buf = C.create_string_buffer(n + 16)
+        lib.uno_profile_report(buf, n + 16)
+        lib.uno_profile_enable(0)
+        prof = json.loads(buf.value.decode())
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        breakdown = {k: {"launches_per_step": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
+                         "share_of_uno_kernels": v["ms"] / tot,
+                         "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
+                         "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
+                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                    "traffic": None, "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
+                    "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                    "uno_kernel_ms_per_step": tot / nprof}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.workload, 3, 1)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "UNO samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[args.workload], "per_gpu_batch": B, "global_batch": B * world,
+                       "parallelism": f"dp{world} (batch shard, flat-buffer gradient all-reduce)" if world > 1 else "single GPU",
+                       "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -108,6 +108,16 @@ int uno_operator_block_bwd(const uno_block_desc* d, const float* gy, const float
                            float* gconv_w, float* gconv_b, float* ggamma, float* gbeta, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---- measurement hooks (bench.py) -----------------------------------------------------------------
+ * uno_launch_count: kernels this library has launched since it was loaded.
+ * uno_profile_enable(1) brackets every kernel launch with a CUDA-event pair on the launching stream;
+ * uno_profile_report synchronises the device and writes a JSON object
+ *   {"<kernel role>": {"launches": n, "ms": total, "bytes": algorithmic, "flops": algorithmic}, ...}
+ * into buf (truncated to cap) and returns the untruncated length.  Off by default.                   */
+long uno_launch_count(void);
+void uno_profile_enable(int on);
+size_t uno_profile_report(char* buf, size_t cap);
+
 /* ---- host-only planning helpers (no GPU touched; exercised by the CPU test-suite) ----------------
  * Each writes the dense fp32 matrix the kernels multiply by.  Sizes: see uno_b200/csrc/plan.h.      */
 int uno_plan_dft_last_analysis(int n, int m, double scale, float* out /* [n, 2m] */);

@@ -214,9 +214,9 @@ def _cubic_aa(t: np.float32) -> np.float32:
     a = f(-0.5)
     t = f(abs(t))
     if t < f(1.0):
-        return f(((a + f(2.0)) * t - (a + f(3.0))) * t * t + f(1.0))
+        return f(f(f(f(f(f(a + f(2.0)) * t) - f(a + f(3.0))) * t) * t) + f(1.0))
     if t < f(2.0):
-        return f((((t - f(5.0)) * t + f(8.0)) * t - f(4.0)) * a)
+        return f(f(f(f(f(a * t) - f(f(5.0) * a)) * t) + f(f(8.0) * a)) * t - f(f(4.0) * a))
     return f(0.0)
 
 

@@ -21,6 +21,9 @@ void be_free(void* d) { free(d); }
 int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); return 0; }
 const char* be_name() { return "host-emulation"; }
 const char* be_error_string(int) { return "host emulation error"; }
+void be_profile_enable(int) {}
+size_t be_profile_report(char* buf, size_t cap) { if (buf && cap > 2) { buf[0] = '{'; buf[1] = '}'; buf[2] = 0; } return 2; }
+long be_launch_count() { return 0; }
 
 static inline float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 static inline float gelu_grad_f(float x) {

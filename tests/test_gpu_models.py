@@ -1,0 +1,138 @@
+"""GPU: whole U-NO models on the CUDA blocks against the reference-generated golden outputs, plus the
+behavioural contract of the drop-in modules."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import BWD_TOL, FWD_TOL, rel_err
+from test_oracle import MODEL_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", list(MODEL_CASES))
+def test_models_match_reference_golden(tag, golden, cuda_lib):
+    from uno_b200 import models
+
+    cls, args, kw, xshape, tshape = MODEL_CASES[tag]
+    g = golden("models")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = getattr(models, cls)(*args, **kw)
+    assert list(model.state_dict().keys()) == [str(k) for k in g[f"{tag}.keys"]]
+    model = model.cuda()
+    torch.manual_seed(1)
+    x = torch.randn(*xshape)
+    tgt = torch.randn(*tshape)
+    y = model(x.cuda())
+    # end-to-end tolerance: rel-L2 <= 1e-4; observed far below
+    ref = g[f"{tag}.y"]
+    assert np.linalg.norm(y.detach().cpu().numpy() - ref) / np.linalg.norm(ref) < 1e-4
+    assert rel_err(y.detach().cpu().numpy(), ref) < 10 * FWD_TOL
+    B = xshape[0]
+    tg = tgt.cuda()
+    loss = torch.sum(torch.norm(y.reshape(B, -1) - tg.reshape(B, -1), 2, 1) / torch.norm(tg.reshape(B, -1), 2, 1))
+    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 1e-4 * abs(float(g[f"{tag}.loss"]))
+    loss.backward()
+    gfp = np.array([float(torch.view_as_real(p.grad).double().abs().sum()) if p.grad.is_complex() else float(p.grad.double().abs().sum()) for p in model.parameters()])
+    assert np.allclose(gfp, g[f"{tag}.grad_fp"], rtol=5e-3, atol=1e-6)
+
+
+def test_model_gradients_match_cpu_port(cuda_lib):
+    """Same weights on the CUDA blocks and on the CPU fp32 oracle port: every parameter gradient agrees."""
+    from oracle import uno_torch_port as port
+    from uno_b200 import models
+
+    torch.manual_seed(0)
+    ref = models.UNO(14, 8, ops=port)
+    torch.manual_seed(0)
+    ours = models.UNO(14, 8).cuda()
+    ours.load_state_dict(ref.state_dict())
+    torch.manual_seed(3)
+    x = torch.randn(2, 64, 64, 10)
+    (ref(x) ** 2).sum().backward()
+    (ours(x.cuda()) ** 2).sum().backward()
+    for (k, a), (_, b) in zip(ours.named_parameters(), ref.named_parameters()):
+        ga = torch.view_as_real(a.grad).cpu() if a.grad.is_complex() else a.grad.cpu()
+        gb = torch.view_as_real(b.grad) if b.grad.is_complex() else b.grad
+        assert float((ga - gb).abs().max()) < 4 * BWD_TOL * max(float(gb.abs().max()), 1e-6), k
+
+
+def test_sticky_dims_and_notebook_shapes(cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    c = ops.SpectralConv2d_Uno(2, 2, 16, 16, 4, 4).cuda()
+    x = torch.randn(1, 2, 16, 16, device="cuda")
+    assert c(x).shape == (1, 2, 16, 16)
+    assert c(x, 24, 20).shape == (1, 2, 24, 20)
+    assert c(x).shape == (1, 2, 24, 20)                       # sticky (integral_operators.py:182-184)
+    # UNO_Tutorial.ipynb:266 / :420 known shapes
+    blk = ops.OperatorBlock_2D(2, 4, 50, 50, 10, 10).cuda()
+    assert blk(torch.randn(1, 2, 100, 100, device="cuda")).shape == (1, 4, 50, 50)
+    assert blk(torch.randn(1, 2, 200, 200, device="cuda"), 100, 100).shape == (1, 4, 100, 100)
+    assert blk.conv.dim1 == 100 and blk.w.dim1 == 50         # conv mutated, pointwise not
+    # default modes (integral_operators.py:157-158, :331-333)
+    d = ops.SpectralConv2d_Uno(2, 2, 16, 16)
+    assert (d.modes1, d.modes2) == (7, 8)
+    e = ops.SpectralConv3d_Uno(1, 1, 4, 4, 6)
+    assert (e.modes1, e.modes2, e.modes3) == (4, 4, 4)
+    # float co-dimensions are int()-cast (models pass 2*factor*width with factor=3/4)
+    f = ops.OperatorBlock_2D(48.0, 96.0, 8, 8, 3, 3)
+    assert f.conv.weights1.shape == (48, 96, 3, 3) and f.w.conv.weight.shape == (96, 48, 1, 1)
+
+
+def test_error_contract(cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    c = ops.SpectralConv2d_Uno(2, 2, 8, 8, 3, 6).cuda()
+    with pytest.raises(RuntimeError):                         # modes2 > W//2+1 (reference: einsum size error)
+        c(torch.randn(1, 2, 8, 8, device="cuda"))
+    c = ops.SpectralConv2d_Uno(2, 2, 16, 16, 4, 4).cuda()
+    with pytest.raises(RuntimeError):                         # fp64 input (reference: ComplexDouble vs ComplexFloat)
+        c(torch.randn(1, 2, 16, 16, device="cuda", dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        c(torch.randn(1, 2, 16, 16, device="cuda", dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError, match="CUDA"):           # no CPU fallback
+        ops.SpectralConv2d_Uno(2, 2, 16, 16, 4, 4)(torch.randn(1, 2, 16, 16))
+    with pytest.raises(ValueError):                           # pointwise_op_1D raises on torch >= 1.11 upstream too
+        ops.OperatorBlock_1D(2, 2, 16, 4).cuda()(torch.randn(1, 2, 16, device="cuda"))
+
+
+def test_non_contiguous_and_no_grad(cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(0)
+    blk = ops.OperatorBlock_2D(3, 5, 12, 10, 4, 4, Normalize=True).cuda()
+    xc = torch.randn(2, 16, 20, 3, device="cuda")
+    x_nc = xc.permute(0, 3, 1, 2)                             # NCHW view of channels-last memory
+    y1 = blk(x_nc, 12, 10)
+    y2 = blk(x_nc.contiguous(), 12, 10)
+    assert torch.equal(y1, y2)
+    with torch.no_grad():
+        y3 = blk(x_nc, 12, 10)
+    assert rel_err(y3.cpu().numpy(), y1.detach().cpu().numpy()) < 1e-6
+    blk.eval()
+    assert torch.equal(blk(x_nc, 12, 10), y1)                 # no train/eval difference (B.1)
+
+
+def test_linearity_and_batch_independence_full_size(cuda_lib):
+    """Size-independent properties at a BASELINE-scale level (Darcy conv0: 32->64, 481^2 -> 240^2, 18 modes)."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(0)
+    c = ops.SpectralConv2d_Uno(32, 64, 240, 240, 18, 18).cuda()
+    x1 = torch.randn(2, 32, 481, 481, device="cuda")
+    x2 = torch.randn(2, 32, 481, 481, device="cuda")
+    with torch.no_grad():
+        y1, y2, y12 = c(x1), c(x2), c(2.0 * x1 - 3.0 * x2)
+        assert rel_err((2.0 * y1 - 3.0 * y2).cpu().numpy(), y12.cpu().numpy()) < FWD_TOL
+        ya = c(x1[:1])
+        assert rel_err(ya.cpu().numpy(), y1[:1].cpu().numpy()) < 1e-6
+        # a band-limited input is reproduced exactly by same-size identity weights
+        ident = ops.SpectralConv2d_Uno(1, 1, 64, 64, 8, 8).cuda()
+        ident.weights1.fill_(1.0)
+        ident.weights2.fill_(1.0)
+        n = torch.arange(64, device="cuda", dtype=torch.float32)
+        img = torch.cos(2 * torch.pi * 3 * n / 64)[:, None] * torch.sin(2 * torch.pi * 5 * n / 64)[None, :] + 0.5
+        out = ident(img[None, None])
+        assert rel_err(out[0, 0].cpu().numpy(), img.cpu().numpy()) < FWD_TOL

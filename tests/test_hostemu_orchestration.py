@@ -1,0 +1,82 @@
+"""CPU: the orchestration behind the C ABI (uno_api.cpp: plan matrices, strides, corner maps,
+adjoints, epilogue selection) run on the host-emulation backend, against the golden fixtures and the
+oracle.  The CUDA kernels themselves are covered by the -m gpu tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from cases import BLOCK_CASES, POINTWISE_CASES, SPECTRAL_CASES
+from conftest import BWD_TOL, FWD_TOL, ROOT, rel_err
+from oracle import uno_oracle as orc
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "hostemu"))
+import emu  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(SPECTRAL_CASES))
+def test_spectral(name, golden):
+    B, Ci, Co, idim, odim, modes = SPECTRAL_CASES[name]
+    g = golden("spectral")
+    ws = [g[f"{name}.w{i + 1}"] for i in range(2 ** (len(idim) - 1))]
+    y, xhat = emu.spectral_fwd(g[f"{name}.x"], ws, odim, modes)
+    assert rel_err(y, g[f"{name}.y"]) < FWD_TOL
+    gx, gws = emu.spectral_bwd(g[f"{name}.x"].shape, ws, odim, modes, g[f"{name}.gy"], xhat)
+    assert rel_err(gx, g[f"{name}.gx"]) < BWD_TOL
+    for i, gw in enumerate(gws):
+        assert rel_err(gw, g[f"{name}.gw{i + 1}"]) < BWD_TOL
+    # the saved spectrum is the reference's x_ft on the kept modes
+    _, x_ft = orc.spectral_conv_fwd(g[f"{name}.x"], ws, odim, modes, return_xhat=True)
+    nd = len(idim)
+    idx = [np.concatenate([np.arange(m), np.arange(n - m, n)]) for m, n in zip(modes[:-1], idim[:-1])] + [np.arange(modes[-1])]
+    kept = x_ft[(slice(None), slice(None)) + np.ix_(*idx)] if nd > 1 else x_ft[..., : modes[-1]]
+    assert rel_err(xhat.reshape(kept.shape), kept) < 1e-5
+
+
+@pytest.mark.parametrize("name", list(POINTWISE_CASES))
+def test_pointwise(name, golden):
+    B, Ci, Co, idim, odim = POINTWISE_CASES[name]
+    g = golden("pointwise")
+    for want_saved in (True, False):
+        z, saved = emu.pointwise_fwd(g[f"{name}.x"], g[f"{name}.cw"], g[f"{name}.cb"], odim, want_saved)
+        assert rel_err(z, g[f"{name}.y"]) < FWD_TOL
+        gx, gw, gb = emu.pointwise_bwd(g[f"{name}.x"], g[f"{name}.cw"], odim, g[f"{name}.gy"], saved)
+        assert rel_err(gx, g[f"{name}.gx"]) < BWD_TOL
+        assert rel_err(gw, g[f"{name}.gcw"].reshape(Co, Ci)) < BWD_TOL
+        assert rel_err(gb, g[f"{name}.gcb"]) < BWD_TOL
+
+
+@pytest.mark.parametrize("name", list(BLOCK_CASES))
+def test_block(name, golden):
+    B, Ci, Co, idim, odim, modes, norm, nl = BLOCK_CASES[name]
+    g = golden("blocks")
+    nd = len(idim)
+    P = lambda k: g[f"{name}.param.{k}"]
+    G = lambda k: g[f"{name}.grad.{k}"]
+    ws = [P(f"conv.weights{i + 1}") for i in range(2 ** (nd - 1))]
+    ga, be = (P("normalize_layer.weight"), P("normalize_layer.bias")) if norm else (None, None)
+    y, ctx = emu.block_fwd(g[f"{name}.x"], ws, P("w.conv.weight"), P("w.conv.bias"), odim, modes, ga, be, nl)
+    assert rel_err(y, g[f"{name}.y"]) < FWD_TOL
+    y_inf, _ = emu.block_fwd(g[f"{name}.x"], ws, P("w.conv.weight"), P("w.conv.bias"), odim, modes, ga, be, nl, train=False)
+    assert rel_err(y_inf, y) < 1e-6
+    gx, gws, gcw, gcb, gg, gb = emu.block_bwd(g[f"{name}.x"], ws, P("w.conv.weight"), odim, modes, g[f"{name}.gy"], ctx, ga, be, nl)
+    assert rel_err(gx, g[f"{name}.gx"]) < BWD_TOL
+    for i, gw in enumerate(gws):
+        assert rel_err(gw, G(f"conv.weights{i + 1}")) < BWD_TOL
+    assert rel_err(gcw, G("w.conv.weight").reshape(Co, Ci)) < BWD_TOL
+    scale = float(np.abs(gcw).max())
+    assert np.abs(gcb - G("w.conv.bias")).max() < BWD_TOL * max(float(np.abs(G("w.conv.bias")).max()), scale)
+    if norm:
+        assert rel_err(gg, G("normalize_layer.weight")) < BWD_TOL
+        assert rel_err(gb, G("normalize_layer.bias")) < BWD_TOL
+
+
+def test_error_codes():
+    x = np.zeros((1, 2, 8, 8), np.float32)
+    with pytest.raises(RuntimeError, match="exceeds the input spectrum"):
+        emu.spectral_fwd(x, [np.zeros((2, 2, 3, 6), np.complex64)] * 2, (8, 8), (3, 6))
+    with pytest.raises(RuntimeError, match="exceeds the output spectrum"):
+        emu.spectral_fwd(x, [np.zeros((2, 2, 5, 3), np.complex64)] * 2, (4, 8), (5, 3))
+    with pytest.raises(RuntimeError, match="pointwise_op_1D"):
+        emu.pointwise_fwd(np.zeros((1, 2, 8), np.float32), np.zeros((2, 2), np.float32), np.zeros(2, np.float32), (4,))

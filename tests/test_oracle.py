@@ -1,0 +1,165 @@
+"""CPU: the oracle (numpy fp64 restatement + torch functional port) against the golden fixtures that
+tests/golden/make_golden.py generated from the REAL reference.  This is what pins the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from cases import BLOCK_CASES, POINTWISE_CASES, RESAMPLE_PAIRS, SPECTRAL_CASES
+from conftest import rel_err
+from oracle import uno_oracle as orc
+from oracle import uno_torch_port as port
+
+# reference (fp32) vs oracle (fp64): the reference's own rounding noise
+REF_FWD = 3e-6
+REF_BWD = 2e-5
+
+
+def _weights(g, name, nd):
+    return [g[f"{name}.w{i + 1}"] for i in range(2 ** (nd - 1))]
+
+
+@pytest.mark.parametrize("name", list(SPECTRAL_CASES))
+def test_numpy_oracle_spectral(name, golden):
+    B, Ci, Co, idim, odim, modes = SPECTRAL_CASES[name]
+    g = golden("spectral")
+    ws = _weights(g, name, len(idim))
+    y = orc.spectral_conv_fwd(g[f"{name}.x"], ws, odim, modes)
+    assert rel_err(y, g[f"{name}.y"]) < REF_FWD
+    # the truncated-DFT form the kernels implement is the same operator
+    y2 = orc.spectral_conv_fwd_dft(g[f"{name}.x"], ws, odim, modes)
+    assert rel_err(y2, y) < 1e-12
+    gx, gws = orc.spectral_conv_bwd(g[f"{name}.x"], ws, odim, modes, g[f"{name}.gy"])
+    assert rel_err(gx, g[f"{name}.gx"]) < REF_BWD
+    for i, gw in enumerate(gws):
+        assert rel_err(gw, g[f"{name}.gw{i + 1}"]) < REF_BWD
+
+
+@pytest.mark.parametrize("name", list(SPECTRAL_CASES))
+def test_torch_port_spectral(name, golden):
+    B, Ci, Co, idim, odim, modes = SPECTRAL_CASES[name]
+    g = golden("spectral")
+    x = torch.tensor(g[f"{name}.x"], dtype=torch.float64, requires_grad=True)
+    ws = [torch.tensor(w, dtype=torch.complex128, requires_grad=True) for w in _weights(g, name, len(idim))]
+    y = port.spectral_conv(x, ws, odim, modes)
+    assert rel_err(y.detach().numpy(), g[f"{name}.y"]) < REF_FWD
+    y.backward(torch.tensor(g[f"{name}.gy"], dtype=torch.float64))
+    assert rel_err(x.grad.numpy(), g[f"{name}.gx"]) < REF_BWD
+    for i, w in enumerate(ws):
+        assert rel_err(w.grad.numpy(), g[f"{name}.gw{i + 1}"]) < REF_BWD
+
+
+@pytest.mark.parametrize("name", list(POINTWISE_CASES))
+def test_oracle_pointwise(name, golden):
+    B, Ci, Co, idim, odim = POINTWISE_CASES[name]
+    g = golden("pointwise")
+    fn = orc.pointwise_op_2d_fwd if len(idim) == 2 else orc.pointwise_op_3d_fwd
+    y = fn(g[f"{name}.x"], g[f"{name}.cw"], g[f"{name}.cb"], odim)
+    assert rel_err(y, g[f"{name}.y"]) < REF_FWD
+    # fp32 port reproduces forward and backward
+    x = torch.tensor(g[f"{name}.x"], requires_grad=True)
+    cw = torch.tensor(g[f"{name}.cw"], requires_grad=True)
+    cb = torch.tensor(g[f"{name}.cb"], requires_grad=True)
+    pf = port.pointwise_op_2d if len(idim) == 2 else port.pointwise_op_3d
+    yp = pf(x, cw, cb, odim)
+    assert rel_err(yp.detach().numpy(), g[f"{name}.y"]) < REF_FWD
+    yp.backward(torch.tensor(g[f"{name}.gy"]))
+    assert rel_err(x.grad.numpy(), g[f"{name}.gx"]) < REF_BWD
+    assert rel_err(cw.grad.numpy(), g[f"{name}.gcw"]) < REF_BWD
+    assert rel_err(cb.grad.numpy(), g[f"{name}.gcb"]) < REF_BWD
+
+
+@pytest.mark.parametrize("pair", RESAMPLE_PAIRS)
+def test_bicubic_matrix_matches_aten(pair, golden):
+    """The closed-form anti-aliased bicubic band equals what F.interpolate produced (fp32 weights)."""
+    a, b = pair
+    g = golden("pointwise")
+    R = orc.bicubic_aa_matrix(a, b)
+    start, band = g[f"R_{a}_{b}.start"], g[f"R_{a}_{b}.band"]
+    ref = np.zeros((b, a))
+    for i in range(b):
+        w = band[i][: a - start[i]]
+        ref[i, start[i] : start[i] + len(w)] = w
+    assert np.abs(R - ref).max() < 1e-6   # a few fp32 ulp on O(1) weights
+
+
+@pytest.mark.parametrize("name", list(BLOCK_CASES))
+def test_oracle_blocks(name, golden):
+    B, Ci, Co, idim, odim, modes, norm, nl = BLOCK_CASES[name]
+    g = golden("blocks")
+    nd = len(idim)
+    P = lambda k: g[f"{name}.param.{k}"]
+    ws = [P(f"conv.weights{i + 1}") for i in range(2 ** (nd - 1))]
+    nrm = (P("normalize_layer.weight"), P("normalize_layer.bias")) if norm else None
+    y = orc.operator_block_fwd(g[f"{name}.x"], ws, P("w.conv.weight"), P("w.conv.bias"), odim, modes, norm=nrm, non_lin=nl)
+    assert rel_err(y, g[f"{name}.y"]) < 5e-6
+    # torch port in fp64 incl. backward
+    T = lambda a, dt=torch.float64: torch.tensor(a, dtype=dt, requires_grad=True)
+    x = T(g[f"{name}.x"])
+    wst = [T(w, torch.complex128) for w in ws]
+    cw, cb = T(P("w.conv.weight")), T(P("w.conv.bias"))
+    ga, be = (T(nrm[0]), T(nrm[1])) if norm else (None, None)
+    yp = port.operator_block(x, wst, cw, cb, odim, modes, ga, be, nl)
+    assert rel_err(yp.detach().numpy(), g[f"{name}.y"]) < 5e-6
+    yp.backward(torch.tensor(g[f"{name}.gy"], dtype=torch.float64))
+    assert rel_err(x.grad.numpy(), g[f"{name}.gx"]) < REF_BWD
+    for i, w in enumerate(wst):
+        assert rel_err(w.grad.numpy(), g[f"{name}.grad.conv.weights{i + 1}"]) < REF_BWD
+    assert rel_err(cw.grad.numpy(), g[f"{name}.grad.w.conv.weight"]) < REF_BWD
+
+
+def test_config1_known_answer(golden):
+    """y.sum() = 365.5583, y[0,0,0,:3] = [0.0497660, 0.2998045, -0.3256869]."""
+    g = golden("config1")
+    assert abs(float(g["y_sum"]) - 365.5583) < 2e-3
+    assert np.abs(g["y_head"] - np.array([0.0497660, 0.2998045, -0.3256869], np.float32)).max() < 1e-6
+    torch.manual_seed(0)
+    m = port.SpectralConv2d_Uno(32, 32, 64, 64, 20, 20)
+    x = torch.randn(2, 32, 64, 64)
+    y = orc.spectral_conv_fwd(x.numpy(), [m.weights1.detach().numpy(), m.weights2.detach().numpy()], (64, 64), (20, 20))
+    assert abs(y.sum() - float(g["y_sum"])) < 2e-3
+    assert rel_err(y[:, ::4, ::4, ::4], g["y_sub"]) < REF_FWD
+
+
+def test_error_behaviour():
+    x = np.zeros((1, 2, 8, 8))
+    w = [np.zeros((2, 2, 3, 6), np.complex64)] * 2
+    with pytest.raises(ValueError):   # modes2 = 6 > 8//2+1 (reference: einsum size mismatch)
+        orc.spectral_conv_fwd(x, w, (8, 8), (3, 6))
+    w = [np.zeros((2, 2, 5, 3), np.complex64)] * 2
+    with pytest.raises(ValueError):   # modes1 = 5 > output rows 4
+        orc.spectral_conv_fwd(x, w, (4, 8), (5, 3))
+
+
+MODEL_CASES = {
+    "uno9_pad5": ("UNO_9", (3, 8), dict(pad=5), (1, 85, 85, 1), (1, 85, 85)),
+    "uno_ns2d": ("UNO", (14, 8), {}, (1, 64, 64, 10), (1, 64, 64)),
+    "uno_p_ns2d": ("UNO_P", (14, 8), {}, (1, 64, 64, 10), (1, 64, 64)),
+    "uno3d_t10": ("Uno3D_T10", (6, 4), dict(pad=3), (1, 64, 64, 10, 1), (1, 64, 64, 10)),
+}
+
+
+@pytest.mark.parametrize("tag", list(MODEL_CASES))
+def test_models_over_port_match_reference(tag, golden):
+    """uno_b200.models instantiated over the oracle port == the reference model files (same seed):
+    identical state_dict keys / init, same output, same loss, same gradient fingerprint."""
+    from uno_b200 import models
+
+    cls, args, kw, xshape, tshape = MODEL_CASES[tag]
+    g = golden("models")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = getattr(models, cls)(*args, **kw, ops=port)
+    assert list(model.state_dict().keys()) == [str(k) for k in g[f"{tag}.keys"]]
+    fp = np.array([float(torch.view_as_real(v).double().abs().sum()) if v.is_complex() else float(v.double().abs().sum()) for v in model.state_dict().values()])
+    assert np.allclose(fp, g[f"{tag}.state_fp"], rtol=1e-6)
+    torch.manual_seed(1)
+    x = torch.randn(*xshape)
+    y = model(x)
+    tgt = torch.randn(*tshape)
+    assert rel_err(y.detach().numpy(), g[f"{tag}.y"]) < 1e-5
+    B = xshape[0]
+    loss = torch.sum(torch.norm(y.reshape(B, -1) - tgt.reshape(B, -1), 2, 1) / torch.norm(tgt.reshape(B, -1), 2, 1))
+    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 1e-5 * abs(float(g[f"{tag}.loss"]))
+    loss.backward()
+    gfp = np.array([float(torch.view_as_real(p.grad).double().abs().sum()) if p.grad.is_complex() else float(p.grad.double().abs().sum()) for p in model.parameters()])
+    assert np.allclose(gfp, g[f"{tag}.grad_fp"], rtol=2e-3, atol=1e-7)

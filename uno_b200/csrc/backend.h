@@ -18,6 +18,14 @@ int be_memset(void* d, int v, size_t bytes, stream_t s);
 const char* be_name();
 const char* be_error_string(int code);   // message for a non-zero return of any be_* call
 
+// ---- optional per-launch timing (CUDA events on the launching stream), off by default --------------
+// While enabled every be_* launch is bracketed by an event pair and tagged with its role and its
+// algorithmic bytes / flops.  be_profile_report synchronises and writes one JSON object:
+//   {"tag": {"launches": n, "ms": total, "bytes": total, "flops": total}, ...}
+void be_profile_enable(int on);
+size_t be_profile_report(char* buf, size_t cap);
+long be_launch_count();                  // kernels launched by this library since load
+
 // ---- C[M,N] = A[M,K] * B[K,N]  (fp32, row-major B and C, strided A), optionally batched -----------
 enum GemmEpi {
     EPI_STORE = 0,        // C = acc (+ bias[m])
@@ -34,6 +42,7 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     int batch = 1; long sA = 0, sB = 0, sC = 0;          // batch strides in elements
     int epi = EPI_STORE;
+    const char* tag = "gemm";                            // role of this launch (profiling only)
 };
 int be_gemm(const GemmArgs& a, stream_t s);
 

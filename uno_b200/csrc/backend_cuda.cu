@@ -14,6 +14,11 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "backend.h"
 
@@ -22,6 +27,35 @@ namespace uno {
 namespace {
 
 inline cudaStream_t S(stream_t s) { return (cudaStream_t)s; }
+
+// ---- per-launch profiling (off by default) -----------------------------------------------------------
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };
+bool g_prof_on = false;
+long g_launches = 0;
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+
+struct ProfScope {
+    bool on;
+    cudaStream_t st;
+    size_t idx = 0;
+    ProfScope(const char* tag, double bytes, double flops, cudaStream_t s) : on(g_prof_on), st(s) {
+        ++g_launches;
+        if (!on) return;
+        ProfRec r{tag, nullptr, nullptr, bytes, flops};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        idx = g_prof.size();
+        g_prof.push_back(r);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        cudaEventRecord(g_prof[idx].e1, st);
+    }
+};
 
 #define CU_LAUNCH_CHECK()                          \
     do {                                           \
@@ -495,6 +529,46 @@ inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
 const char* be_name() { return "cuda-sm100a"; }
 const char* be_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
+void be_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (on && !g_prof_on) {
+        for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+        g_prof.clear();
+    }
+    g_prof_on = on != 0;
+}
+
+size_t be_profile_report(char* buf, size_t cap) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    struct Agg { long n = 0; double ms = 0, bytes = 0, flops = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+        Agg& a = agg[r.tag];
+        a.n += 1; a.ms += ms; a.bytes += r.bytes; a.flops += r.flops;
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof line, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"bytes\": %.0f, \"flops\": %.0f}",
+                 first ? "" : ", ", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if (buf && cap) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
+}
+
+long be_launch_count() { return g_launches; }
+
 int be_upload(void** dptr, const void* host, size_t bytes) {
     cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 4);
     if (e != cudaSuccess) return (int)e;
@@ -510,6 +584,13 @@ int be_gemm(const GemmArgs& a, stream_t s) {
     k.B = a.B; k.b_rs = a.ldb; k.b_cs = 1; k.sB = a.sB;
     k.C = a.C; k.ldc = a.ldc; k.sC = a.sC; k.C2 = a.C2; k.bias = a.bias;
     k.M = a.M; k.N = a.N; k.K = a.K; k.ksplit = 1; k.kchunk = a.K; k.epi = a.epi;
+    const double mn = (double)a.M * a.N * a.batch;
+    // algorithmic bytes: A and B read once (a batch-shared operand once), C written once (+ read when accumulating,
+    // + second output for the fused GELU)
+    double bytes = 4.0 * ((double)a.M * a.K * (a.sA ? a.batch : 1) + (double)a.K * a.N * (a.sB ? a.batch : 1) + mn);
+    if (a.epi != EPI_STORE) bytes += 4.0 * mn;
+    if (a.epi == EPI_ACCUM_GELU) bytes += 4.0 * mn;
+    ProfScope ps(a.tag, bytes, 2.0 * mn * a.K, S(s));
     return dispatch_gemm(k, a.batch, S(s));
 }
 
@@ -527,6 +608,8 @@ int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
     if (kchunk < 256) kchunk = 256;
     k.kchunk = kchunk;
     k.ksplit = (a.K + kchunk - 1) / kchunk;
+    ProfScope ps("conv1x1_wgrad", 4.0 * ((double)a.M * a.K + (double)a.N * a.K) * a.batch + 4.0 * a.M * a.N,
+                 2.0 * a.M * a.N * (double)a.K * a.batch, S(s));
     return dispatch_gemm(k, a.batch, S(s));
 }
 
@@ -537,6 +620,7 @@ int be_mid(const MidArgs& a, stream_t s) {
     const float2* X = reinterpret_cast<const float2*>(a.X);
     const float2* M = reinterpret_cast<const float2*>(a.Mat);
     float2* Y = reinterpret_cast<float2*>(a.Y);
+    ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
     if (pad8 < pad16) {
         const int tilesI = pad8 / 8;
         const long blocks = (long)a.O * tilesI * tilesJ;
@@ -553,6 +637,8 @@ int be_mid(const MidArgs& a, stream_t s) {
 int be_cmm(const CmmArgs& a, stream_t s) {
     if (a.M <= 0 || a.N <= 0 || a.q_inner <= 0 || a.q_outer <= 0) return 0;
     const int chunks = (a.q_inner + 31) / 32;
+    const double q = (double)a.q_inner * a.q_outer;
+    ProfScope ps("mode_contraction", 8.0 * q * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N), 8.0 * q * a.M * a.N * a.K, S(s));
     dim3 grid((unsigned)(chunks * a.q_outer), (unsigned)((a.M + 3) / 4), (unsigned)((a.N + 15) / 16));
     cmm_kernel<<<grid, dim3(32, 4), 0, S(s)>>>(a, chunks);
     CU_LAUNCH_CHECK();
@@ -562,6 +648,7 @@ int be_cmm(const CmmArgs& a, stream_t s) {
 int be_banded(const BandedArgs& a, stream_t s) {
     const long total = a.outer * a.n_out * a.inner;
     if (total <= 0) return 0;
+    ProfScope ps("resample_banded", 4.0 * ((double)a.outer * a.inner * (a.n_in + a.n_out)), 2.0 * total * a.taps, S(s));
     banded_kernel<<<grid_for((size_t)total, 256, 148 * 32), 256, 0, S(s)>>>(a, total);
     CU_LAUNCH_CHECK();
     return 0;
@@ -569,18 +656,21 @@ int be_banded(const BandedArgs& a, stream_t s) {
 
 int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s) {
     if (!n) return 0;
+    ProfScope ps("gelu_fwd", 8.0 * n, 0, S(s));
     gelu_fwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(pre, y, n);
     CU_LAUNCH_CHECK();
     return 0;
 }
 int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s) {
     if (!n) return 0;
+    ProfScope ps("gelu_bwd", 12.0 * n, 0, S(s));
     gelu_bwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(gy, pre, g, n);
     CU_LAUNCH_CHECK();
     return 0;
 }
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s) {
     if (planes <= 0) return 0;
+    ProfScope ps("instnorm_stats", 4.0 * planes * L, 0, S(s));
     plane_stats_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(x, stats, L, eps);
     CU_LAUNCH_CHECK();
     return 0;
@@ -589,6 +679,7 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
                     long planes, int C, long L, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
     unsigned gx = grid_for((size_t)L, 256, 64);
+    ProfScope ps("instnorm_gelu_fwd", 8.0 * planes * L, 0, S(s));
     norm_act_fwd_kernel<<<dim3((unsigned)planes, gx), 256, 0, S(s)>>>(x, stats, gamma, beta, y, C, L, non_lin);
     CU_LAUNCH_CHECK();
     return 0;
@@ -596,12 +687,14 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma, const float* beta,
                     float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
+    ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
     norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin);
     CU_LAUNCH_CHECK();
     return 0;
 }
 int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t s) {
     if (planes <= 0) return 0;
+    ProfScope ps("bias_grad", 4.0 * planes * L, 0, S(s));
     channel_sum_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(x, out, C, L, alpha);
     CU_LAUNCH_CHECK();
     return 0;
@@ -609,6 +702,7 @@ int be_channel_sum(const float* x, float* out, long planes, int C, long L, float
 int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t s) {
     if (planes <= 0) return 0;
     unsigned gx = grid_for((size_t)L, 256, 64);
+    ProfScope ps("bias_add", 8.0 * planes * L, 0, S(s));
     add_channel_const_kernel<<<dim3((unsigned)planes, gx), 256, 0, S(s)>>>(y, v, alpha, C, L);
     CU_LAUNCH_CHECK();
     return 0;

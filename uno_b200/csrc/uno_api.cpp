@@ -120,6 +120,7 @@ int analyse(const float* x, long P, int nmid, const MidOp* mids, int n_last, con
     g.B = last_mat; g.ldb = 2 * m;
     g.C = dst; g.ldc = 2 * m;
     g.M = (int)R; g.N = 2 * m; g.K = n_last;
+    g.tag = "dft_last_analysis";
     BE_TRY(be_gemm(g, st));
     const float* src = dst;
     for (int a = nmid - 1; a >= 0; --a) {
@@ -174,6 +175,7 @@ int synthesise(const float* in, long P, int nmid, const MidOp* mids, int m, cons
     g.C = y; g.ldc = n_last; g.C2 = y2;
     g.M = (int)R; g.N = n_last; g.K = 2 * m;
     g.epi = epi;
+    g.tag = "dft_last_synthesis";
     BE_TRY(be_gemm(g, st));
     return 0;
 }
@@ -564,6 +566,7 @@ int conv1x1(const float* wmat, long w_rs, long w_cs, const float* bias, const fl
     g.C = z; g.ldc = npix; g.sC = (long)Co * npix;
     g.bias = bias;
     g.M = Co; g.N = (int)npix; g.K = Ci; g.batch = batch; g.epi = epi;
+    g.tag = "conv1x1";
     return be_gemm(g, st);
 }
 
@@ -826,6 +829,10 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
     }
     return 0;
 }
+
+void uno_profile_enable(int on) { be_profile_enable(on); }
+size_t uno_profile_report(char* buf, size_t cap) { return be_profile_report(buf, cap); }
+long uno_launch_count(void) { return be_launch_count(); }
 
 // ---- host-only planning helpers -------------------------------------------------------------------
 int uno_plan_dft_last_analysis(int n, int m, double scale, float* out) {

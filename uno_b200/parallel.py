@@ -1,0 +1,103 @@
+"""Batch-sharded data parallelism for the U-NO models.
+
+Every operator on the path is independent across the batch index except the parameter gradients, so
+the only exchange is one SUM all-reduce of the gradients per step (the reference losses are SUMS over
+samples -- LpLoss(size_average=False), train_darcy.py:42 -- hence SUM, not mean).  >99.7 % of the
+payload is complex spectral weights; torch's DistributedDataParallel has no explicit complex support,
+so gradients live in ONE flat fp32 buffer (complex parameters as (re, im) pairs, each ``param.grad`` a
+view into it) that is all-reduced over NCCL / NVLink in buckets, launched from autograd hooks as soon
+as a bucket's gradients are final so the transfer overlaps the rest of backward.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradReducer:
+    def __init__(self, module: torch.nn.Module, process_group=None, bucket_mb: float = 32.0, overlap: bool = True):
+        self.group = process_group
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        dev = self.params[0].device
+        sizes = [p.numel() * (2 if p.is_complex() else 1) for p in self.params]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # gradients become final in roughly reverse registration order: lay the buffer out that way
+        order = list(range(len(self.params)))[::-1]
+        self._bucket_of = {}
+        self.buckets: List[List[int]] = []      # [start, end, n_params]
+        off, cur_start, cur_n = 0, 0, 0
+        limit = int(bucket_mb * (1 << 20) / 4)
+        for i in order:
+            p, n = self.params[i], sizes[i]
+            if p.dtype not in (torch.float32, torch.complex64):
+                raise TypeError(f"GradReducer supports float32 / complex64 parameters, got {p.dtype}")
+            view = self.flat[off : off + n]
+            p.grad = torch.view_as_complex(view.view(*p.shape, 2)) if p.is_complex() else view.view(p.shape)
+            self._bucket_of[i] = len(self.buckets)
+            off += n
+            cur_n += 1
+            if off - cur_start >= limit:
+                self.buckets.append([cur_start, off, cur_n])
+                cur_start, cur_n = off, 0
+        if cur_n:
+            self.buckets.append([cur_start, off, cur_n])
+        self._pending = [b[2] for b in self.buckets]
+        self._handles = []
+        self.overlap = overlap
+        if overlap:
+            for i, p in enumerate(self.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    # ------------------------------------------------------------------------------------------
+    def _enabled(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _make_hook(self, i):
+        def hook(_param):
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and self._enabled():
+                s, e, _ = self.buckets[b]
+                self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+        return hook
+
+    def zero_grad(self) -> None:
+        """Zero the flat buffer in place (keeps every param.grad a view of it)."""
+        self.flat.zero_()
+        self._pending = [b[2] for b in self.buckets]
+        self._handles = []
+
+    def finish(self) -> None:
+        """Call after backward(): wait for the bucket all-reduces (or run them now if hooks are off /
+        a bucket never completed, e.g. unused parameters)."""
+        if not self._enabled():
+            return
+        for b, left in enumerate(self._pending):
+            if left != 0 or not self.overlap:
+                s, e, _ = self.buckets[b]
+                self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    @property
+    def payload_bytes(self) -> int:
+        return self.flat.numel() * 4
+
+
+def shard_batch(x: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    """Rank r's contiguous slice [r*B/N, (r+1)*B/N) of a global batch."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    B = x.shape[0]
+    if B % world:
+        raise ValueError(f"global batch {B} is not divisible by world size {world}")
+    per = B // world
+    return x[rank * per : (rank + 1) * per]

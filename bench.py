@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
             self.ok = False
 
     def run(self):
-        while self.ok and not self._stop.is_set():
+        while self.ok and not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 try:
@@ -87,10 +87,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.05)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=2)
         s = sorted(self.samples)

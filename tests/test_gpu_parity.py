@@ -84,7 +84,8 @@ def test_operator_block_golden(name, golden, cuda_lib):
     for k, p in m.named_parameters():
         ref = g[f"{name}.grad.{k}"]
         # the conv bias in front of an InstanceNorm has an exactly-zero true gradient: compare absolutely
-        err = float(np.abs(_n(p.grad) - ref).max()) / max(float(np.abs(ref).max()), 1e-3 * scale)
+        den = scale if (norm and k == "w.conv.bias") else max(float(np.abs(ref).max()), 1e-3 * scale)
+        err = float(np.abs(_n(p.grad) - ref).max()) / den
         assert err < BWD_TOL, (k, err)
     with torch.no_grad():
         y2 = m(x.detach(), *odim)

@@ -1,0 +1,92 @@
+"""GPU: the tcgen05 (3xTF32) kernels against the SIMT fp32 kernels and the oracle, shape by shape."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import BWD_TOL, FWD_TOL, rel_err
+from oracle import uno_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fn, disable_tc):
+    old = os.environ.get("UNO_B200_DISABLE_TC")
+    os.environ["UNO_B200_DISABLE_TC"] = "1" if disable_tc else "0"
+    try:
+        out = fn()
+        torch.cuda.synchronize()
+        return out
+    finally:
+        if old is None:
+            os.environ.pop("UNO_B200_DISABLE_TC", None)
+        else:
+            os.environ["UNO_B200_DISABLE_TC"] = old
+
+
+# (B, Ci, Co, in, out, modes): output widths cover one/two N tiles, padded tiles, odd leading dims,
+# K = 2*modes2 with and without 16-byte aligned rows, and ragged row-tile tails
+SHAPES = [
+    (2, 3, 4, (40, 64), (30, 240), (6, 18)),
+    (1, 2, 3, (64, 64), (17, 481), (5, 18)),
+    (2, 2, 2, (32, 32), (50, 120), (8, 8)),
+    (1, 3, 2, (32, 32), (33, 31), (4, 5)),
+    (2, 2, 3, (32, 48), (9, 16), (3, 7)),
+    (1, 2, 2, (64, 64), (300, 64), (20, 22)),
+    (1, 1, 2, (96, 96), (130, 446), (9, 32)),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_rowgemm_tc_matches_simt_and_oracle(shape, cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    B, Ci, Co, idim, odim, modes = shape
+    torch.manual_seed(0)
+    m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
+    x = torch.randn(B, Ci, *idim, device="cuda")
+    gy = torch.randn(B, Co, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        y.backward(gy)
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy()
+
+    y_tc, gx_tc, gw_tc = _run(run, disable_tc=False)
+    y_si, gx_si, gw_si = _run(run, disable_tc=True)
+    ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
+    y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)
+    gx_or, gw_or = orc.spectral_conv_bwd(x.cpu().numpy(), ws, odim, modes, gy.cpu().numpy())
+    assert rel_err(y_si, y_or) < FWD_TOL
+    assert rel_err(y_tc, y_or) < FWD_TOL, rel_err(y_tc, y_or)
+    assert rel_err(gx_tc, gx_or) < BWD_TOL, rel_err(gx_tc, gx_or)
+    assert rel_err(gx_si, gx_or) < BWD_TOL
+    assert rel_err(gw_tc[..., 0] + 1j * gw_tc[..., 1], gw_or[0]) < BWD_TOL
+
+
+def test_block_epilogues_tc(cuda_lib):
+    """The fused accumulate / GELU epilogues of the tensor-core synthesis kernel."""
+    from oracle import uno_torch_port as port
+    from uno_b200 import integral_operators as ops
+
+    for norm, nl, odim in [(False, True, (24, 240)), (True, True, (24, 120)), (False, False, (10, 481)), (False, True, (12, 63))]:
+        torch.manual_seed(1)
+        blk = ops.OperatorBlock_2D(3, 4, *odim, 5, 9, Normalize=norm, Non_Lin=nl).cuda()
+        x = torch.randn(2, 3, 30, 100, device="cuda", requires_grad=True)
+        y = blk(x, *odim)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        with torch.no_grad():
+            y_inf = blk(x.detach(), *odim)
+        xr = x.detach().cpu().double().requires_grad_(True)
+        ws = [blk.conv.weights1.detach().cpu().to(torch.cdouble), blk.conv.weights2.detach().cpu().to(torch.cdouble)]
+        ga = blk.normalize_layer.weight.detach().cpu().double() if norm else None
+        be = blk.normalize_layer.bias.detach().cpu().double() if norm else None
+        yr = port.operator_block(xr, ws, blk.w.conv.weight.detach().cpu().double(), blk.w.conv.bias.detach().cpu().double(), odim, (5, 9), ga, be, nl)
+        yr.backward(gy.cpu().double())
+        assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < FWD_TOL
+        assert rel_err(y_inf.cpu().numpy(), yr.detach().numpy()) < FWD_TOL
+        assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy()) < BWD_TOL

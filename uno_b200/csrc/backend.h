@@ -43,6 +43,7 @@ struct GemmArgs {
     int batch = 1; long sA = 0, sB = 0, sC = 0;          // batch strides in elements
     int epi = EPI_STORE;
     const char* tag = "gemm";                            // role of this launch (profiling only)
+    bool b_const = false;                                // B is a persistent plan constant (its tensor-core image may be cached)
 };
 int be_gemm(const GemmArgs& a, stream_t s);
 

@@ -14,6 +14,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -21,6 +22,7 @@
 #include <vector>
 
 #include "backend.h"
+#include "tc_rowgemm.cuh"
 
 namespace uno {
 
@@ -521,6 +523,145 @@ inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
     return (unsigned)g;
 }
 
+
+// =====================================================================================================
+// tensor-core path: host-side operand images and dispatch
+// =====================================================================================================
+inline float tf32_rn(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+struct TcImage {
+    float* dev = nullptr;
+    int n_tiles = 0, N_t = 0, K_pad = 0;
+};
+struct TcKey {
+    const void* p; int K, N; long ldb;
+    bool operator<(const TcKey& o) const {
+        if (p != o.p) return p < o.p;
+        if (K != o.K) return K < o.K;
+        if (N != o.N) return N < o.N;
+        return ldb < o.ldb;
+    }
+};
+std::map<TcKey, TcImage> g_tc_images;
+std::mutex g_tc_mu;
+
+bool tc_enabled() {   // read every call so tests can flip UNO_B200_DISABLE_TC at run time
+    const char* e = getenv("UNO_B200_DISABLE_TC");
+    return !(e && e[0] && e[0] != '0');
+}
+
+// B [K x N] (device, row-major, ldb) -> per n-tile [hi | lo] images in the UMMA K-major interleave layout
+// of the transposed operand (N_t rows x K_pad): element (n, k) at float offset (k/4)*N_t*4 + n*4 + k%4.
+int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, TcImage* out) {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    TcKey key{B, K, N, ldb};
+    auto it = g_tc_images.find(key);
+    if (it != g_tc_images.end()) { *out = it->second; return 0; }
+    TcImage img;
+    img.K_pad = ((K + 7) / 8) * 8;
+    img.n_tiles = (N + 255) / 256;
+    const int per = (N + img.n_tiles - 1) / img.n_tiles;
+    img.N_t = ((per + 15) / 16) * 16;
+    std::vector<float> hB((size_t)K * N);
+    cudaError_t e = cudaMemcpy2D(hB.data(), (size_t)N * 4, B, (size_t)ldb * 4, (size_t)N * 4, K, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    const size_t half = (size_t)img.K_pad * img.N_t;
+    std::vector<float> h((size_t)img.n_tiles * 2 * half, 0.0f);
+    for (int t = 0; t < img.n_tiles; ++t)
+        for (int n = 0; n < img.N_t; ++n) {
+            const int gn = t * img.N_t + n;
+            if (gn >= N) continue;
+            for (int k = 0; k < K; ++k) {
+                const float b = hB[(size_t)k * N + gn];
+                const float hi = tf32_rn(b);
+                const float lo = tf32_rn(b - hi);
+                const size_t o = (size_t)(k / 4) * img.N_t * 4 + (size_t)n * 4 + (k % 4);
+                h[(size_t)t * 2 * half + o] = hi;
+                h[(size_t)t * 2 * half + half + o] = lo;
+            }
+        }
+    e = cudaMalloc(&img.dev, h.size() * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    g_tc_images[key] = img;
+    *out = img;
+    return 0;
+}
+
+void tc_forget(const void* p) {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    for (auto it = g_tc_images.begin(); it != g_tc_images.end();) {
+        if (it->first.p == p) { cudaFree(it->second.dev); it = g_tc_images.erase(it); } else ++it;
+    }
+}
+
+int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int EPI>
+int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int gx = num_sms() / p.n_tiles;
+    if (gx < 1) gx = 1;
+    if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
+    tc::rowgemm_smallk_kernel<EPI><<<dim3(gx, p.n_tiles), tc::kRowGemmThreads, smem, st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+// returns -1 when the shape does not qualify (caller falls back to the SIMT kernel)
+int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
+    if (!tc_enabled() || !a.b_const || a.batch != 1 || a.a_cs != 1 || a.bias || a.K > 64 || a.N < 16 || a.M < 1) return -1;
+    TcImage img;
+    const int K_pad = ((a.K + 7) / 8) * 8;
+    const int n_tiles = (a.N + 255) / 256;
+    const int N_t = ((((a.N + n_tiles - 1) / n_tiles) + 15) / 16) * 16;
+    const size_t smem = tc::rowgemm_smem_bytes(K_pad, N_t);
+    if (smem > 220 * 1024) return -1;
+    int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, &img);
+    if (rc) return rc;
+    tc::RowGemmParams p;
+    p.A = a.A; p.lda = a.a_rs; p.R = a.M;
+    p.Bimg = img.dev;
+    p.C = a.C; p.C2 = a.C2; p.ldc = a.ldc;
+    p.N = a.N; p.K = a.K; p.K_pad = img.K_pad; p.n_tiles = img.n_tiles; p.N_t = img.N_t;
+    p.m_tiles = ((long)a.M + 127) / 128;
+    p.epi = a.epi;
+    int cols = 32;
+    while (cols < 2 * img.N_t) cols *= 2;
+    p.tmem_cols = cols;
+    p.a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) && (a.K % 4 == 0);
+    switch (a.epi) {
+        case EPI_STORE: return launch_rowgemm<EPI_STORE>(p, smem, st);
+        case EPI_ACCUM: return launch_rowgemm<EPI_ACCUM>(p, smem, st);
+        case EPI_ACCUM_GELU: return launch_rowgemm<EPI_ACCUM_GELU>(p, smem, st);
+        case EPI_ACCUM_GELU_INPLACE: return launch_rowgemm<EPI_ACCUM_GELU_INPLACE>(p, smem, st);
+    }
+    return -1;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -575,7 +716,10 @@ int be_upload(void** dptr, const void* host, size_t bytes) {
     e = cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice);
     return (int)e;
 }
-void be_free(void* d) { cudaFree(d); }
+void be_free(void* d) {
+    tc_forget(d);
+    cudaFree(d);
+}
 int be_memset(void* d, int v, size_t bytes, stream_t s) { return (int)cudaMemsetAsync(d, v, bytes, S(s)); }
 
 int be_gemm(const GemmArgs& a, stream_t s) {
@@ -591,6 +735,8 @@ int be_gemm(const GemmArgs& a, stream_t s) {
     if (a.epi != EPI_STORE) bytes += 4.0 * mn;
     if (a.epi == EPI_ACCUM_GELU) bytes += 4.0 * mn;
     ProfScope ps(a.tag, bytes, 2.0 * mn * a.K, S(s));
+    const int rc = try_tc_rowgemm(a, S(s));
+    if (rc >= 0) return rc;
     return dispatch_gemm(k, a.batch, S(s));
 }
 

@@ -121,6 +121,7 @@ int analyse(const float* x, long P, int nmid, const MidOp* mids, int n_last, con
     g.C = dst; g.ldc = 2 * m;
     g.M = (int)R; g.N = 2 * m; g.K = n_last;
     g.tag = "dft_last_analysis";
+    g.b_const = true;
     BE_TRY(be_gemm(g, st));
     const float* src = dst;
     for (int a = nmid - 1; a >= 0; --a) {
@@ -176,6 +177,7 @@ int synthesise(const float* in, long P, int nmid, const MidOp* mids, int m, cons
     g.M = (int)R; g.N = n_last; g.K = 2 * m;
     g.epi = epi;
     g.tag = "dft_last_synthesis";
+    g.b_const = true;
     BE_TRY(be_gemm(g, st));
     return 0;
 }

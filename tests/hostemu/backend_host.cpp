@@ -119,6 +119,22 @@ int be_banded(const BandedArgs& a, stream_t) {
     return 0;
 }
 
+int be_banded2d(const Banded2DArgs& a, stream_t) {
+    for (long p = 0; p < a.planes; ++p)
+        for (int i = 0; i < a.n_out0; ++i)
+            for (int j = 0; j < a.n_out1; ++j) {
+                double acc = 0;
+                for (int t = 0; t < a.taps0; ++t) {
+                    double row = 0;
+                    const float* xr = a.x + (p * a.n_in0 + a.start0[i] + t) * a.n_in1 + a.start1[j];
+                    for (int u = 0; u < a.taps1; ++u) row += (double)a.w1[(long)j * a.taps1 + u] * xr[u];
+                    acc += (double)a.w0[(long)i * a.taps0 + t] * row;
+                }
+                a.y[(p * a.n_out0 + i) * a.n_out1 + j] = (float)acc;
+            }
+    return 0;
+}
+
 int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t) {
     for (size_t i = 0; i < n; ++i) y[i] = gelu_f(pre[i]);
     return 0;

@@ -35,6 +35,13 @@ SHAPES = [
     (2, 2, 3, (32, 48), (9, 16), (3, 7)),
     (1, 2, 2, (64, 64), (300, 64), (20, 22)),
     (1, 1, 2, (96, 96), (130, 446), (9, 32)),
+    # long contraction (K = input width > 64): K-pipelined kernel, 16-byte aligned and unaligned rows,
+    # ragged last chunk, several row tiles per CTA
+    (1, 2, 2, (20, 481), (10, 240), (5, 18)),
+    (2, 2, 3, (12, 240), (12, 120), (4, 8)),
+    (1, 2, 2, (9, 223), (9, 111), (3, 33)),
+    (1, 3, 2, (8, 130), (8, 64), (3, 5)),
+    (4, 8, 2, (1200, 100), (16, 16), (4, 6)),
 ]
 
 

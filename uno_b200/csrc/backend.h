@@ -87,6 +87,16 @@ struct BandedArgs {
 };
 int be_banded(const BandedArgs& a, stream_t s);
 
+// fused separable 2-D form: y[p] = R0 * x[p] * R1^T for every plane p   x [P, n_in0, n_in1] -> y [P, n_out0, n_out1]
+// span0 / span1: largest input extent (rows / cols) needed by any 32-row / 64-column output tile.
+struct Banded2DArgs {
+    const float* x = nullptr; float* y = nullptr; long planes = 0;
+    const int* start0 = nullptr; const float* w0 = nullptr; int n_in0 = 0, n_out0 = 0, taps0 = 0, span0 = 0;
+    const int* start1 = nullptr; const float* w1 = nullptr; int n_in1 = 0, n_out1 = 0, taps1 = 0, span1 = 0;
+    float* tmp = nullptr;   // scratch of planes * max(n_in0,n_out0) * max(n_in1,n_out1) floats for the two-pass fallback
+};
+int be_banded2d(const Banded2DArgs& a, stream_t s);
+
 // ---- elementwise / reductions ----------------------------------------------------------------------
 int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s);
 int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s);

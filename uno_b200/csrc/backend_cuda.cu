@@ -23,6 +23,7 @@
 
 #include "backend.h"
 #include "tc_rowgemm.cuh"
+#include "tc_kpipe.cuh"
 
 namespace uno {
 
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(128) cmm_kernel(const CmmArgs a, int chunks_pe
     int mi[4], nj[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { mi[i] = min(m0 + i, a.M - 1); nj[i] = min(n0 + i, a.N - 1); }
+#pragma unroll 4
     for (int k = 0; k < a.K; ++k) {
         float2 av[4], bv[4];
 #pragma unroll
@@ -379,6 +381,67 @@ __global__ void __launch_bounds__(256) banded_kernel(const BandedArgs a, long to
         float acc = 0.f;
         for (int t = 0; t < a.taps; ++t) acc = fmaf(__ldg(w + t), __ldg(x + (long)t * a.inner), acc);
         a.y[idx] = acc;
+    }
+}
+
+
+// fused separable 2-D resample: one CTA = one plane x (32 x 64) output tile.  The input window is staged
+// in shared memory, the column (last-axis) bands are applied into a second shared buffer, then the row
+// bands; x is read once and y written once.
+constexpr int kB2TH = 32, kB2TW = 64;
+__global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int tiles_h, int tiles_w, int RIN, int CIN) {
+    extern __shared__ float sm[];
+    const int ldin = CIN + 1;
+    float* in_s = sm;                                  // [RIN][CIN+1]
+    float* mid_s = in_s + (size_t)RIN * ldin;          // [RIN][TW]
+    float* w0s = mid_s + (size_t)RIN * kB2TW;          // [TH][taps0]
+    float* w1s = w0s + kB2TH * a.taps0;                // [TW][taps1]
+    int* st0s = reinterpret_cast<int*>(w1s + kB2TW * a.taps1);
+    int* st1s = st0s + kB2TH;
+    long bid = blockIdx.x;
+    const int tw = (int)(bid % tiles_w); bid /= tiles_w;
+    const int th = (int)(bid % tiles_h); bid /= tiles_h;
+    const long p = bid;
+    const int tid = threadIdx.x;
+    const int i0 = th * kB2TH, j0 = tw * kB2TW;
+    const int nh = min(kB2TH, a.n_out0 - i0), nw = min(kB2TW, a.n_out1 - j0);
+    const int r0 = __ldg(a.start0 + i0), c0 = __ldg(a.start1 + j0);
+    const int rin = min(__ldg(a.start0 + i0 + nh - 1) + a.taps0, a.n_in0) - r0;
+    const int cin = min(__ldg(a.start1 + j0 + nw - 1) + a.taps1, a.n_in1) - c0;
+    for (int i = tid; i < nh * a.taps0; i += 256) w0s[i] = __ldg(a.w0 + (long)i0 * a.taps0 + i);
+    for (int i = tid; i < nw * a.taps1; i += 256) w1s[i] = __ldg(a.w1 + (long)j0 * a.taps1 + i);
+    for (int i = tid; i < nh; i += 256) st0s[i] = __ldg(a.start0 + i0 + i) - r0;
+    for (int i = tid; i < nw; i += 256) st1s[i] = __ldg(a.start1 + j0 + i) - c0;
+    const float* xp = a.x + (p * a.n_in0 + r0) * (long)a.n_in1 + c0;
+    const int tx = tid & 63, ty = tid >> 6;   // 64 columns x 4 rows of threads: no integer division in the loops
+    for (int r = ty; r < rin; r += 4) {
+        const float* src = xp + (long)r * a.n_in1;
+        float* dst = in_s + r * ldin;
+        for (int c = tx; c < cin; c += 64) dst[c] = __ldg(src + c);
+    }
+    __syncthreads();
+    if (tx < nw) {
+        const float* w = w1s + tx * a.taps1;
+        const int off = st1s[tx];
+        for (int r = ty; r < rin; r += 4) {
+            const float* src = in_s + r * ldin + off;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int t = 0; t < a.taps1; ++t) acc = fmaf(w[t], src[t], acc);
+            mid_s[r * kB2TW + tx] = acc;
+        }
+    }
+    __syncthreads();
+    if (tx < nw) {
+        float* yp = a.y + (p * a.n_out0 + i0) * (long)a.n_out1 + j0 + tx;
+        for (int i = ty; i < nh; i += 4) {
+            const float* w = w0s + i * a.taps0;
+            const float* src = mid_s + st0s[i] * kB2TW + tx;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int t = 0; t < a.taps0; ++t) acc = fmaf(w[t], src[t * kB2TW], acc);
+            yp[(long)i * a.n_out1] = acc;
+        }
     }
 }
 
@@ -597,10 +660,16 @@ int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, TcImage* out) {
     return 0;
 }
 
+struct TcKpImage { float* dev = nullptr; int N_t = 0, n_chunks = 0; };
+std::map<TcKey, TcKpImage> g_tc_kp_images;
+
 void tc_forget(const void* p) {
     std::lock_guard<std::mutex> lk(g_tc_mu);
     for (auto it = g_tc_images.begin(); it != g_tc_images.end();) {
         if (it->first.p == p) { cudaFree(it->second.dev); it = g_tc_images.erase(it); } else ++it;
+    }
+    for (auto it = g_tc_kp_images.begin(); it != g_tc_kp_images.end();) {
+        if (it->first.p == p) { cudaFree(it->second.dev); it = g_tc_kp_images.erase(it); } else ++it;
     }
 }
 
@@ -627,6 +696,74 @@ int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
     if (gx < 1) gx = 1;
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     tc::rowgemm_smallk_kernel<EPI><<<dim3(gx, p.n_tiles), tc::kRowGemmThreads, smem, st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+// chunk-major image for the K-pipelined kernel: [chunk][hi | lo], half = (KC/4) x N_t x 16 bytes,
+// element (n, k) of chunk c at float offset ((k%32)/4)*N_t*4 + n*4 + k%4
+
+int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out) {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    TcKey key{B, K, N, ldb};
+    auto it = g_tc_kp_images.find(key);
+    if (it != g_tc_kp_images.end()) { *out = it->second; return 0; }
+    TcKpImage img;
+    img.N_t = ((N + 15) / 16) * 16;
+    img.n_chunks = (K + tc::kKC - 1) / tc::kKC;
+    std::vector<float> hB((size_t)K * N);
+    cudaError_t e = cudaMemcpy2D(hB.data(), (size_t)N * 4, B, (size_t)ldb * 4, (size_t)N * 4, K, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    const size_t half = (size_t)img.N_t * tc::kKC;
+    std::vector<float> h((size_t)img.n_chunks * 2 * half, 0.0f);
+    for (int k = 0; k < K; ++k) {
+        const int c = k / tc::kKC, kk = k % tc::kKC;
+        for (int n = 0; n < N; ++n) {
+            const float b = hB[(size_t)k * N + n];
+            const float hi = tf32_rn(b);
+            const float lo = tf32_rn(b - hi);
+            const size_t o = (size_t)(kk / 4) * img.N_t * 4 + (size_t)n * 4 + (kk % 4);
+            h[(size_t)c * 2 * half + o] = hi;
+            h[(size_t)c * 2 * half + half + o] = lo;
+        }
+    }
+    e = cudaMalloc(&img.dev, h.size() * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    g_tc_kp_images[key] = img;
+    *out = img;
+    return 0;
+}
+
+int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
+    if (!tc_enabled() || !a.b_const || a.batch != 1 || a.a_cs != 1 || a.bias || a.epi != EPI_STORE || a.K <= 64 || a.N < 8 || a.N > 256 || a.M < 1)
+        return -1;
+    const int N_t = ((a.N + 15) / 16) * 16;
+    int stages = (int)((200 * 1024) / tc::kpipe_stage_bytes(N_t));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return -1;
+    TcKpImage img;
+    int rc = tc_get_kpipe_image(a.B, a.ldb, a.K, a.N, &img);
+    if (rc) return rc;
+    tc::KPipeParams p;
+    p.A = a.A; p.lda = a.a_rs; p.R = a.M;
+    p.Bimg = img.dev; p.C = a.C; p.ldc = a.ldc;
+    p.N = a.N; p.K = a.K; p.N_t = img.N_t; p.n_chunks = img.n_chunks; p.stages = stages;
+    p.m_tiles = ((long)a.M + 127) / 128;
+    int cols = 32;
+    while (cols < 2 * img.N_t) cols *= 2;
+    p.tmem_cols = cols;
+    p.a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int gx = num_sms();
+    if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
+    tc::kpipe_kernel<<<gx, tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -735,7 +872,9 @@ int be_gemm(const GemmArgs& a, stream_t s) {
     if (a.epi != EPI_STORE) bytes += 4.0 * mn;
     if (a.epi == EPI_ACCUM_GELU) bytes += 4.0 * mn;
     ProfScope ps(a.tag, bytes, 2.0 * mn * a.K, S(s));
-    const int rc = try_tc_rowgemm(a, S(s));
+    int rc = try_tc_rowgemm(a, S(s));
+    if (rc >= 0) return rc;
+    rc = try_tc_kpipe(a, S(s));
     if (rc >= 0) return rc;
     return dispatch_gemm(k, a.batch, S(s));
 }
@@ -796,6 +935,40 @@ int be_banded(const BandedArgs& a, stream_t s) {
     if (total <= 0) return 0;
     ProfScope ps("resample_banded", 4.0 * ((double)a.outer * a.inner * (a.n_in + a.n_out)), 2.0 * total * a.taps, S(s));
     banded_kernel<<<grid_for((size_t)total, 256, 148 * 32), 256, 0, S(s)>>>(a, total);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+
+int be_banded2d(const Banded2DArgs& a, stream_t s) {
+    if (a.planes <= 0) return 0;
+    const int RIN = a.span0, CIN = a.span1;
+    const size_t smem = ((size_t)RIN * (CIN + 1) + (size_t)RIN * kB2TW + (size_t)kB2TH * a.taps0 + (size_t)kB2TW * a.taps1 + kB2TH + kB2TW) * 4;
+    if (smem > 200 * 1024) {
+        // very large scale factors: two passes through scratch (shrinking axis first)
+        BandedArgs l, m;
+        if (a.n_out1 <= a.n_in1) {
+            l.x = a.x; l.y = a.tmp; l.start = a.start1; l.w = a.w1; l.n_in = a.n_in1; l.n_out = a.n_out1; l.taps = a.taps1; l.outer = a.planes * a.n_in0; l.inner = 1;
+            m.x = a.tmp; m.y = a.y; m.start = a.start0; m.w = a.w0; m.n_in = a.n_in0; m.n_out = a.n_out0; m.taps = a.taps0; m.outer = a.planes; m.inner = a.n_out1;
+            int rc = be_banded(l, s);
+            return rc ? rc : be_banded(m, s);
+        }
+        m.x = a.x; m.y = a.tmp; m.start = a.start0; m.w = a.w0; m.n_in = a.n_in0; m.n_out = a.n_out0; m.taps = a.taps0; m.outer = a.planes; m.inner = a.n_in1;
+        l.x = a.tmp; l.y = a.y; l.start = a.start1; l.w = a.w1; l.n_in = a.n_in1; l.n_out = a.n_out1; l.taps = a.taps1; l.outer = a.planes * a.n_out0; l.inner = 1;
+        int rc = be_banded(m, s);
+        return rc ? rc : be_banded(l, s);
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(banded2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int tiles_h = (a.n_out0 + kB2TH - 1) / kB2TH, tiles_w = (a.n_out1 + kB2TW - 1) / kB2TW;
+    const long blocks = a.planes * tiles_h * tiles_w;
+    ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
+                 2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * a.taps1 + (double)a.n_out0 * a.n_out1 * a.taps0), S(s));
+    banded2d_kernel<<<(unsigned)blocks, 256, smem, S(s)>>>(a, tiles_h, tiles_w, RIN, CIN);
     CU_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,238 @@
+// tcgen05 GEMM with a long contraction dimension streamed from HBM:  C[R, N] = A[R, K] * B[K, N],
+// A row-major (K contiguous), N <= 256, K arbitrary.
+//
+// This is the analysis stage of the truncated DFT along the last axis (real samples -> kept modes:
+// K = grid width, N = 2*modes): x is read exactly once, 128 rows x 32 columns at a time.
+//
+//   * persistent CTAs (one per SM), static round-robin over 128-row tiles
+//   * a ring of S shared-memory stages; per stage the A chunk (tf32 hi and lo images, UMMA K-major
+//     "interleave" layout) written by 8 loader warps and the matching chunk of the constant B image
+//     (pre-split hi/lo, chunk-major in global memory, L2 resident) fetched by one bulk async copy
+//   * loader warps keep TWO chunks of global loads in flight per thread (registers double buffered), which
+//     is what keeps ~32 KB per SM outstanding even when rows are only 4-byte aligned (odd grid widths
+//     such as 481 rule out TMA tensor maps and 16-byte vector loads)
+//   * one lane issues 3 MMAs (hi*hi, hi*lo, lo*hi) per 8-wide k-step into one of two TMEM accumulators
+//   * 4 epilogue warps drain the other accumulator (tcgen05.ld 16x256b -> float2 stores)
+#pragma once
+#include "backend.h"
+#include "tc_common.cuh"
+#include "tc_rowgemm.cuh"
+
+namespace uno {
+namespace tc {
+
+struct KPipeParams {
+    const float* A; long lda; long R;
+    const float* Bimg;     // [n_chunks][hi | lo], each half (KC/4) x N_t x 16 bytes
+    float* C; long ldc;
+    int N, K, N_t, n_chunks, stages;
+    long m_tiles;
+    int tmem_cols;
+    int a_vec_ok;          // rows 16-byte aligned (lda % 4 == 0, base aligned)
+};
+
+constexpr int kKC = 32;                       // K elements per stage
+constexpr int kKpLoadWarps = 8;
+constexpr int kKpEpiWarps = 4;
+constexpr int kKpThreads = (kKpLoadWarps + kKpEpiWarps + 1) * 32;
+constexpr uint32_t kKpAHalf = (kKC / 4) * kLboA;   // bytes of one A image (hi or lo) per stage
+
+__host__ __device__ inline size_t kpipe_stage_bytes(int N_t) { return (size_t)2 * kKpAHalf + (size_t)2 * N_t * kKC * 4; }
+__host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return stages * kpipe_stage_bytes(N_t) + 32 * 8 + 16; }
+
+__global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t b_half = (uint32_t)p.N_t * kKC * 4;
+    const uint32_t stage_bytes = 2 * kKpAHalf + 2 * b_half;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    uint64_t* full = bars;            // [S] loaders (+ bulk copy bytes) -> mma
+    uint64_t* empty = bars + 8;       // [S] mma -> loaders
+    uint64_t* d_full = bars + 16;     // [2]
+    uint64_t* d_empty = bars + 18;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    constexpr int kMmaWarp = kKpLoadWarps + kKpEpiWarps;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], kKpLoadWarps * 32 + 1);   // +1: the arrive.expect_tx of the B copy
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], kKpEpiWarps * 32);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t buf_cols = (uint32_t)p.tmem_cols / 2;
+    const int NKC = p.n_chunks;
+
+    if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
+            const uint32_t lbo_b = (uint32_t)p.N_t * 16;
+            long g = 0;
+            int it = 0;
+            for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
+                for (int kc = 0; kc < NKC; ++kc, ++g) {
+                    const int s = (int)(g % S);
+                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t a_hi = base, a_lo = base + kKpAHalf;
+                    const uint32_t bh = base + 2 * kKpAHalf, bl = bh + b_half;
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        if (kc * kKC + ks * 8 >= p.K) break;
+                        const uint64_t da_hi = make_smem_desc(a_hi + ks * 2 * kLboA, kLboA, 128);
+                        const uint64_t da_lo = make_smem_desc(a_lo + ks * 2 * kLboA, kLboA, 128);
+                        const uint64_t db_hi = make_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128);
+                        const uint64_t db_lo = make_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
+                        mma_tf32(d_tmem, da_hi, db_hi, idesc, (kc | ks) ? 1u : 0u);
+                        mma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+                        mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&d_full[buf]);
+            }
+        }
+    } else if (warp < kKpLoadWarps) {
+        // ------------------------------------------------------------------ loaders: 256 threads, chunk = 128 rows x 32 k
+        const int ltid = threadIdx.x;
+        long n_my_tiles = 0;
+        for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) ++n_my_tiles;
+        const long total = n_my_tiles * NKC;   // chunks this CTA processes, in order
+        if (p.a_vec_ok) {
+            // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
+            const int kq = ltid & 7, rbase = ltid >> 3;
+            float4 cur[4], nxt[4];
+            auto issue = [&](long g, float4 (&v)[4]) {
+                const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
+                const int kc = (int)(g % NKC);
+                const int k0 = kc * kKC + kq * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long grow = tile * 128 + rbase + 32 * i;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (grow < p.R) {
+                        const float* src = p.A + grow * p.lda + k0;
+                        if (k0 + 4 <= p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                        else {
+                            if (k0 + 0 < p.K) v[i].x = __ldg(src + 0);
+                            if (k0 + 1 < p.K) v[i].y = __ldg(src + 1);
+                            if (k0 + 2 < p.K) v[i].z = __ldg(src + 2);
+                        }
+                    }
+                }
+            };
+            if (total > 0) issue(0, cur);
+            for (long g = 0; g < total; ++g) {
+                if (g + 1 < total) issue(g + 1, nxt);
+                const int s = (int)(g % S);
+                const uint32_t ph = (uint32_t)(g / S) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                if (ltid == 0) {
+                    mbar_arrive_expect_tx(&full[s], 2 * b_half);
+                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)(g % NKC) * (2 * b_half / 4), 2 * b_half, &full[s]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 hi, lo;
+                    split_tf32(cur[i].x, hi.x, lo.x);
+                    split_tf32(cur[i].y, hi.y, lo.y);
+                    split_tf32(cur[i].z, hi.z, lo.z);
+                    split_tf32(cur[i].w, hi.w, lo.w);
+                    const uint32_t o = (uint32_t)kq * kLboA + (uint32_t)(rbase + 32 * i) * 16;
+                    *reinterpret_cast<float4*>(st + o) = hi;
+                    *reinterpret_cast<float4*>(st + kKpAHalf + o) = lo;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[s]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            }
+        } else {
+            // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
+            float cur[16], nxt[16];
+            auto issue = [&](long g, float (&v)[16]) {
+                const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
+                const int k = (int)(g % NKC) * kKC + lane;
+                const bool kok = k < p.K;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const long grow = tile * 128 + warp + 8 * i;
+                    v[i] = (kok && grow < p.R) ? __ldg(p.A + grow * p.lda + k) : 0.f;
+                }
+            };
+            if (total > 0) issue(0, cur);
+            for (long g = 0; g < total; ++g) {
+                if (g + 1 < total) issue(g + 1, nxt);
+                const int s = (int)(g % S);
+                const uint32_t ph = (uint32_t)(g / S) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                if (ltid == 0) {
+                    mbar_arrive_expect_tx(&full[s], 2 * b_half);
+                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)(g % NKC) * (2 * b_half / 4), 2 * b_half, &full[s]);
+                }
+                const uint32_t ko = (uint32_t)(lane >> 2) * kLboA + (uint32_t)(lane & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float hi, lo;
+                    split_tf32(cur[i], hi, lo);
+                    const uint32_t o = ko + (uint32_t)(warp + 8 * i) * 16;
+                    *reinterpret_cast<float*>(st + o) = hi;
+                    *reinterpret_cast<float*>(st + kKpAHalf + o) = lo;
+                }
+                fence_proxy_async();
+                mbar_arrive(&full[s]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
+        const int q = warp - kKpLoadWarps;
+        RowGemmParams ep;
+        ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R;
+        const bool vec2 = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
+        int it = 0;
+        for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&d_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const long row0 = tile * 128 + q * 32;
+            const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
+            // both column "halves" handled by this warp
+            if (vec2) {
+                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, row0, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, row0, 0, 1, lane);
+            } else {
+                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, row0, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, row0, 0, 1, lane);
+            }
+            tc_fence_before();
+            mbar_arrive(&d_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace tc
+}  // namespace uno

@@ -79,11 +79,22 @@ struct DevMat {
 
 struct DevBand {
     int n_in = 0, n_out = 0, taps = 0;
+    int span32 = 0, span64 = 0;   // max input extent of a 32- / 64-output tile
     int* start = nullptr;
     float* w = nullptr;
     ~DevBand() { if (start) be_free(start); if (w) be_free(w); }
     int upload(const Banded& b) {
         n_in = b.n_in; n_out = b.n_out; taps = b.taps;
+        auto span = [&](int tile) {
+            int best = 0;
+            for (int i0 = 0; i0 < b.n_out; i0 += tile) {
+                const int last = std::min(i0 + tile, b.n_out) - 1;
+                best = std::max(best, b.start[last] + b.taps - b.start[i0]);
+            }
+            return best;
+        };
+        span32 = span(32);
+        span64 = span(64);
         void* p = nullptr;
         int rc = be_upload(&p, b.start.data(), b.start.size() * sizeof(int));
         start = (int*)p;
@@ -460,24 +471,12 @@ struct ResamplePlan {
     }
 
     int banded2(const float* x, long P, float* y, float* tmp, const DevBand* b, stream_t st) const {
-        // b[0] acts on axis 0 (rows), b[1] on axis 1 (last).  Shrinking axis first.
-        const int h_in = b[0].n_in, h_out = b[0].n_out, w_in = b[1].n_in, w_out = b[1].n_out;
-        BandedArgs l, m;
-        if (w_out <= w_in) {   // last axis first: [P,h_in,w_in] -> [P,h_in,w_out] -> [P,h_out,w_out]
-            l.x = x; l.y = tmp; l.start = b[1].start; l.w = b[1].w; l.n_in = w_in; l.n_out = w_out; l.taps = b[1].taps;
-            l.outer = P * h_in; l.inner = 1;
-            m.x = tmp; m.y = y; m.start = b[0].start; m.w = b[0].w; m.n_in = h_in; m.n_out = h_out; m.taps = b[0].taps;
-            m.outer = P; m.inner = w_out;
-            BE_TRY(be_banded(l, st));
-            BE_TRY(be_banded(m, st));
-        } else {               // row axis first: [P,h_in,w_in] -> [P,h_out,w_in] -> [P,h_out,w_out]
-            m.x = x; m.y = tmp; m.start = b[0].start; m.w = b[0].w; m.n_in = h_in; m.n_out = h_out; m.taps = b[0].taps;
-            m.outer = P; m.inner = w_in;
-            l.x = tmp; l.y = y; l.start = b[1].start; l.w = b[1].w; l.n_in = w_in; l.n_out = w_out; l.taps = b[1].taps;
-            l.outer = P * h_out; l.inner = 1;
-            BE_TRY(be_banded(m, st));
-            BE_TRY(be_banded(l, st));
-        }
+        // b[0] acts on axis 0 (rows), b[1] on axis 1 (last); one fused, shared-memory tiled kernel
+        Banded2DArgs a;
+        a.x = x; a.y = y; a.planes = P; a.tmp = tmp;
+        a.start0 = b[0].start; a.w0 = b[0].w; a.n_in0 = b[0].n_in; a.n_out0 = b[0].n_out; a.taps0 = b[0].taps; a.span0 = b[0].span32;
+        a.start1 = b[1].start; a.w1 = b[1].w; a.n_in1 = b[1].n_in; a.n_out1 = b[1].n_out; a.taps1 = b[1].taps; a.span1 = b[1].span64;
+        BE_TRY(be_banded2d(a, st));
         return 0;
     }
 

@@ -414,11 +414,14 @@ __global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int
     for (int i = tid; i < nw; i += 256) st1s[i] = __ldg(a.start1 + j0 + i) - c0;
     const float* xp = a.x + (p * a.n_in0 + r0) * (long)a.n_in1 + c0;
     const int tx = tid & 63, ty = tid >> 6;   // 64 columns x 4 rows of threads: no integer division in the loops
+    // asynchronous 4-byte copies (LDGSTS): the whole input window is in flight at once
     for (int r = ty; r < rin; r += 4) {
         const float* src = xp + (long)r * a.n_in1;
-        float* dst = in_s + r * ldin;
-        for (int c = tx; c < cin; c += 64) dst[c] = __ldg(src + c);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(in_s + r * ldin);
+        for (int c = tx; c < cin; c += 64)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + c) : "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (tx < nw) {
         const float* w = w1s + tx * a.taps1;

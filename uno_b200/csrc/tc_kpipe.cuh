@@ -138,9 +138,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                     }
                 }
             };
-            if (total > 0) issue(0, cur);
-            for (long g = 0; g < total; ++g) {
-                if (g + 1 < total) issue(g + 1, nxt);
+            auto process = [&](long g, const float4 (&v)[4]) {
                 const int s = (int)(g % S);
                 const uint32_t ph = (uint32_t)(g / S) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
@@ -152,18 +150,24 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float4 hi, lo;
-                    split_tf32(cur[i].x, hi.x, lo.x);
-                    split_tf32(cur[i].y, hi.y, lo.y);
-                    split_tf32(cur[i].z, hi.z, lo.z);
-                    split_tf32(cur[i].w, hi.w, lo.w);
+                    split_tf32(v[i].x, hi.x, lo.x);
+                    split_tf32(v[i].y, hi.y, lo.y);
+                    split_tf32(v[i].z, hi.z, lo.z);
+                    split_tf32(v[i].w, hi.w, lo.w);
                     const uint32_t o = (uint32_t)kq * kLboA + (uint32_t)(rbase + 32 * i) * 16;
                     *reinterpret_cast<float4*>(st + o) = hi;
                     *reinterpret_cast<float4*>(st + kKpAHalf + o) = lo;
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[s]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            };
+            // ping-pong register buffers: the loads of chunk g+1 are in flight while chunk g is split and stored
+            if (total > 0) issue(0, cur);
+            for (long g = 0; g < total; g += 2) {
+                if (g + 1 < total) issue(g + 1, nxt);
+                process(g, cur);
+                if (g + 2 < total) issue(g + 2, cur);
+                if (g + 1 < total) process(g + 1, nxt);
             }
         } else {
             // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
@@ -178,9 +182,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                     v[i] = (kok && grow < p.R) ? __ldg(p.A + grow * p.lda + k) : 0.f;
                 }
             };
-            if (total > 0) issue(0, cur);
-            for (long g = 0; g < total; ++g) {
-                if (g + 1 < total) issue(g + 1, nxt);
+            auto process = [&](long g, const float (&v)[16]) {
                 const int s = (int)(g % S);
                 const uint32_t ph = (uint32_t)(g / S) & 1u;
                 mbar_wait(&empty[s], ph ^ 1u);
@@ -193,15 +195,20 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float hi, lo;
-                    split_tf32(cur[i], hi, lo);
+                    split_tf32(v[i], hi, lo);
                     const uint32_t o = ko + (uint32_t)(warp + 8 * i) * 16;
                     *reinterpret_cast<float*>(st + o) = hi;
                     *reinterpret_cast<float*>(st + kKpAHalf + o) = lo;
                 }
                 fence_proxy_async();
                 mbar_arrive(&full[s]);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+            };
+            if (total > 0) issue(0, cur);
+            for (long g = 0; g < total; g += 2) {
+                if (g + 1 < total) issue(g + 1, nxt);
+                process(g, cur);
+                if (g + 2 < total) issue(g + 2, cur);
+                if (g + 1 < total) process(g + 1, nxt);
             }
         }
     } else {

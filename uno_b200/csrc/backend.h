@@ -44,6 +44,7 @@ struct GemmArgs {
     int epi = EPI_STORE;
     const char* tag = "gemm";                            // role of this launch (profiling only)
     bool b_const = false;                                // B is a persistent plan constant (its tensor-core image may be cached)
+    bool channel_mix = false;                            // A is a small weight matrix shared by the batch, B/C are [channels, pixels] per sample
 };
 int be_gemm(const GemmArgs& a, stream_t s);
 

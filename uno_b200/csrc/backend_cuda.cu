@@ -24,6 +24,7 @@
 #include "backend.h"
 #include "tc_rowgemm.cuh"
 #include "tc_kpipe.cuh"
+#include "tc_conv.cuh"
 
 namespace uno {
 
@@ -771,6 +772,58 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     return 0;
 }
 
+// per-stream scratch for the weight image of the tensor-core channel mix (stream order makes reuse safe)
+std::map<cudaStream_t, float*> g_conv_scratch;
+constexpr size_t kConvScratchBytes = 160 * 1024;
+
+int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
+    // GemmArgs view: C_b[M, N] = A[M, K] * B_b[K, N]  with M = out channels, N = pixels, K = in channels
+    if (!tc_enabled() || !a.channel_mix || a.sA != 0 || a.epi != EPI_STORE || a.N % 4 != 0 || a.N < 128 || a.M < 8 || a.M > 256 || a.K < 8)
+        return -1;
+    if (a.ldb != a.N || a.ldc != a.N || a.sB != (long)a.K * a.N || a.sC != (long)a.M * a.N) return -1;
+    if ((reinterpret_cast<uintptr_t>(a.B) & 15) || (reinterpret_cast<uintptr_t>(a.C) & 15)) return -1;
+    const int N_t = ((a.M + 15) / 16) * 16;
+    const int n_chunks = (a.K + tc::kKC - 1) / tc::kKC;
+    const size_t b_bytes = (size_t)2 * N_t * n_chunks * tc::kKC * 4;
+    if (b_bytes > kConvScratchBytes) return -1;
+    int stages = (int)((220 * 1024 - b_bytes - 512) / (2 * tc::kCvAHalf));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return -1;
+    float* img = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_tc_mu);
+        auto it = g_conv_scratch.find(st);
+        if (it == g_conv_scratch.end()) {
+            cudaError_t e = cudaMalloc(&img, kConvScratchBytes);
+            if (e != cudaSuccess) return (int)e;
+            g_conv_scratch[st] = img;
+        } else img = it->second;
+    }
+    const int K_pad = n_chunks * tc::kKC;
+    tc::conv_weight_image_kernel<<<(N_t * K_pad + 255) / 256, 256, 0, st>>>(a.A, a.a_rs, a.a_cs, a.M, a.K, N_t, K_pad, img);
+    CU_LAUNCH_CHECK();
+    tc::ConvTcParams p;
+    p.X = a.B; p.sXb = a.sB; p.npix = a.N;
+    p.Bimg = img; p.bias = a.bias; p.Y = a.C; p.sYb = a.sC;
+    p.K = a.K; p.N = a.M; p.N_t = N_t; p.n_chunks = n_chunks; p.stages = stages; p.batch = a.batch;
+    p.tiles_per_b = ((long)a.N + 127) / 128;
+    p.n_tiles = p.tiles_per_b * a.batch;
+    int cols = 32;
+    while (cols < 2 * N_t) cols *= 2;
+    p.tmem_cols = cols;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int gx = num_sms();
+    if ((long)gx > p.n_tiles) gx = (int)p.n_tiles;
+    tc::conv1x1_tc_kernel<<<gx, tc::kCvThreads, tc::conv_tc_smem_bytes(N_t, n_chunks, stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 // returns -1 when the shape does not qualify (caller falls back to the SIMT kernel)
 int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     if (!tc_enabled() || !a.b_const || a.batch != 1 || a.a_cs != 1 || a.bias || a.K > 64 || a.N < 16 || a.M < 1) return -1;
@@ -878,6 +931,8 @@ int be_gemm(const GemmArgs& a, stream_t s) {
     int rc = try_tc_rowgemm(a, S(s));
     if (rc >= 0) return rc;
     rc = try_tc_kpipe(a, S(s));
+    if (rc >= 0) return rc;
+    rc = try_tc_conv(a, S(s));
     if (rc >= 0) return rc;
     return dispatch_gemm(k, a.batch, S(s));
 }

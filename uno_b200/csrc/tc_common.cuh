@@ -97,13 +97,14 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 //             LBO = byte stride between core matrices adjacent along K (next 4 fp32 of K)
 //   MN-major: 8 k x 16 B (4 consecutive MN elements) core matrices; SBO = stride to the next 4 MN
 //             elements, LBO = stride to the next 8 k
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;   // descriptor version for sm_100
-    return d;                 // layout_type (bits 61-63) = 0: no swizzle
+    d |= (uint64_t)(layout_type & 7) << 61;   // 0 = no swizzle, 1 = 128B swizzle with 32-byte base (MN-major 32-bit operands)
+    return d;
 }
 
 // TMEM -> registers.  16x256b: a warp reads 16 lanes x 8 columns per repeat; thread t holds

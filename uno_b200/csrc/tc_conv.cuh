@@ -1,0 +1,234 @@
+// tcgen05 1x1 channel mix:  Y[b, n, p] = sum_k Wm[n, k] * X[b, k, p] (+ bias[n]),  p = pixel (contiguous).
+//
+// Used for Conv{2,3}d(k=1) forward (Wm = weight [Co,Ci]) and for its input gradient (Wm = weight^T).
+// UMMA view: D[128 pixels, N] = A[128 pixels, K] * B[K, N] with
+//   A = X_b^T : pixel index contiguous in memory  -> "MN-major" operand (no transpose pass needed)
+//   B = Wm    : [N, K] row-major                  -> K-major operand, tf32 hi/lo image resident in smem
+// The weights are parameters (they change every optimiser step), so their image is rebuilt on the fly by
+// conv_weight_image_kernel (a few KB) right before the main kernel.
+//
+//   * persistent CTAs, tiles = (sample, 128-pixel block), static round-robin
+//   * 8 loader warps stream 32-channel chunks of the tile (float4 along pixels, hi/lo split in registers,
+//     one 16-byte st.shared per value group into the MN-major interleave layout; register ping-pong keeps
+//     two chunks in flight)
+//   * one lane issues 3 MMAs per 8-channel k-step into one of two TMEM accumulators
+//   * 8 epilogue warps: tcgen05.ld 32x32b (lane = pixel) -> + bias -> stores that are 128 B contiguous per warp
+#pragma once
+#include "backend.h"
+#include "tc_common.cuh"
+#include "tc_kpipe.cuh"
+
+namespace uno {
+namespace tc {
+
+struct ConvTcParams {
+    const float* X; long sXb; long npix;
+    const float* Bimg;         // [hi | lo], each (K_pad/4) x N_t x 16 bytes
+    const float* bias;         // [N] or null
+    float* Y; long sYb;
+    int K, N, N_t, n_chunks, stages, batch;
+    long tiles_per_b, n_tiles;
+    int tmem_cols;
+};
+
+// MN-major tf32 operands must use the "128-byte swizzle with 32-byte base" canonical layout:
+//   atom = 32 pixels (128 B, contiguous) x 4 channels (rows 128 B apart); inside an atom the 32-byte granule g of
+//   channel row r sits at granule g ^ r.  Channel groups of 4 follow at SBO, pixel blocks of 32 at LBO.
+constexpr uint32_t kCvSbo = 512;                        // next group of 4 channels
+constexpr uint32_t kCvLbo = (kKC / 4) * kCvSbo;         // next block of 32 pixels (32 channels per stage)
+constexpr uint32_t kCvAHalf = 4 * kCvLbo;               // one A image (hi or lo) per stage: 32 channels x 128 pixels
+constexpr uint32_t kCvLayout = 1;                       // UMMA::LayoutType::SWIZZLE_128B_BASE32B
+constexpr int kCvLoadWarps = 8;
+constexpr int kCvEpiWarps = 8;
+constexpr int kCvThreads = (kCvLoadWarps + kCvEpiWarps + 1) * 32;
+
+__host__ __device__ inline size_t conv_tc_smem_bytes(int N_t, int n_chunks, int stages) {
+    return 1024 + (size_t)2 * N_t * n_chunks * kKC * 4 + (size_t)stages * 2 * kCvAHalf + 32 * 8 + 16;
+}
+
+// Wm(n, k) = W[n * w_rs + k * w_cs]  ->  resident K-major image (hi | lo), zero padded to N_t x K_pad
+__global__ void conv_weight_image_kernel(const float* __restrict__ W, long w_rs, long w_cs, int N, int K, int N_t, int K_pad,
+                                         float* __restrict__ img) {
+    const int total = N_t * K_pad;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx / K_pad, k = idx - n * K_pad;
+        float v = 0.f;
+        if (n < N && k < K) v = W[n * w_rs + k * w_cs];
+        // round hi to nearest tf32 (instead of truncating): the weights get the better split
+        const uint32_t u = __float_as_uint(v);
+        const float hi = __uint_as_float((u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u);
+        const float lo = v - hi;
+        const size_t o = (size_t)(k / 4) * N_t * 4 + (size_t)n * 4 + (k % 4);
+        img[o] = hi;
+        img[(size_t)N_t * K_pad + o] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const int K_pad = p.n_chunks * kKC;
+    const uint32_t b_half = (uint32_t)p.N_t * K_pad * 4;
+    uint8_t* sB = smem;
+    // the swizzled A stages must start on a 1024-byte boundary of the shared address space
+    uint8_t* sA = smem + 2 * b_half;
+    sA += (1024u - (smem_u32(sA) & 1023u)) & 1023u;
+    const uint32_t stage_bytes = 2 * kCvAHalf;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * stage_bytes);
+    uint64_t* full = bars;            // [S]
+    uint64_t* empty = bars + 8;       // [S]
+    uint64_t* d_full = bars + 16;     // [2]
+    uint64_t* d_empty = bars + 18;    // [2]
+    uint64_t* b_full = bars + 20;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    constexpr int kMmaWarp = kCvLoadWarps + kCvEpiWarps;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], kCvLoadWarps * 32);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&d_full[s], 1);
+            mbar_init(&d_empty[s], kCvEpiWarps * 32);
+        }
+        mbar_init(b_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t buf_cols = (uint32_t)p.tmem_cols / 2;
+    const int NKC = p.n_chunks;
+
+    if (warp == kMmaWarp) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // resident weight image, in pieces of <= 64 KB
+            mbar_arrive_expect_tx(b_full, 2 * b_half);
+            for (uint32_t off = 0; off < 2 * b_half; off += 65536u) {
+                const uint32_t n = min(65536u, 2 * b_half - off);
+                bulk_g2s(sB + off, reinterpret_cast<const uint8_t*>(p.Bimg) + off, n, b_full);
+            }
+            mbar_wait(b_full, 0);
+            const uint32_t idesc = make_idesc_tf32(128, p.N_t, /*a MN-major*/ 1, /*b K-major*/ 0);
+            const uint32_t lbo_b = (uint32_t)p.N_t * 16;
+            const uint32_t sB_addr = smem_u32(sB);
+            long g = 0;
+            int it = 0;
+            for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
+                for (int kc = 0; kc < NKC; ++kc, ++g) {
+                    const int s = (int)(g % S);
+                    mbar_wait(&full[s], (uint32_t)(g / S) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(sA + (size_t)s * stage_bytes), a_lo = a_hi + kCvAHalf;
+#pragma unroll
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        const int kglob = kc * (kKC / 8) + ks;      // global 8-channel step
+                        if (kglob * 8 >= p.K) break;
+                        const uint64_t da_hi = make_smem_desc(a_hi + ks * 2 * kCvSbo, kCvLbo, kCvSbo, kCvLayout);
+                        const uint64_t da_lo = make_smem_desc(a_lo + ks * 2 * kCvSbo, kCvLbo, kCvSbo, kCvLayout);
+                        const uint64_t db_hi = make_smem_desc(sB_addr + kglob * 2 * lbo_b, lbo_b, 128);
+                        const uint64_t db_lo = make_smem_desc(sB_addr + b_half + kglob * 2 * lbo_b, lbo_b, 128);
+                        mma_tf32(d_tmem, da_hi, db_hi, idesc, kglob ? 1u : 0u);
+                        mma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+                        mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&d_full[buf]);
+            }
+        }
+    } else if (warp < kCvLoadWarps) {
+        // ------------------------------------------------------------------ loaders: chunk = 32 channels x 128 pixels
+        const int ltid = threadIdx.x;
+        const int pg = ltid & 31, cb = ltid >> 5;      // pixel group (4 px), channel base
+        long n_my = 0;
+        for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_my;
+        const long total = n_my * NKC;
+        float4 cur[4], nxt[4];
+        auto issue = [&](long g, float4 (&v)[4]) {
+            const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
+            const int kc = (int)(g % NKC);
+            const long b = tile / p.tiles_per_b;
+            const long px = (tile - b * p.tiles_per_b) * 128 + pg * 4;
+            const float* xb = p.X + b * p.sXb;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ci = kc * kKC + cb + 8 * i;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ci < p.K && px < p.npix) v[i] = __ldg(reinterpret_cast<const float4*>(xb + (long)ci * p.npix + px));
+            }
+        };
+        auto process = [&](long g, const float4 (&v)[4]) {
+            const int s = (int)(g % S);
+            mbar_wait(&empty[s], ((uint32_t)(g / S) & 1u) ^ 1u);
+            uint8_t* st = sA + (size_t)s * stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cl = cb + 8 * i;                 // channel within the chunk
+                float4 hi, lo;
+                split_tf32(v[i].x, hi.x, lo.x);
+                split_tf32(v[i].y, hi.y, lo.y);
+                split_tf32(v[i].z, hi.z, lo.z);
+                split_tf32(v[i].w, hi.w, lo.w);
+                const uint32_t r4 = (uint32_t)cl & 3u;      // channel row inside its group of 4
+                const uint32_t o = (uint32_t)(pg >> 3) * kCvLbo + (uint32_t)(cl >> 2) * kCvSbo + r4 * 128u +
+                                   ((((uint32_t)(pg & 7) >> 1) ^ r4) << 5) + ((uint32_t)pg & 1u) * 16u;
+                *reinterpret_cast<float4*>(st + o) = hi;
+                *reinterpret_cast<float4*>(st + kCvAHalf + o) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full[s]);
+        };
+        if (total > 0) issue(0, cur);
+        for (long g = 0; g < total; g += 2) {
+            if (g + 1 < total) issue(g + 1, nxt);
+            process(g, cur);
+            if (g + 2 < total) issue(g + 2, cur);
+            if (g + 1 < total) process(g + 1, nxt);
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: warp e -> lane quarter e%4, column half e/4
+        const int e = warp - kCvLoadWarps;
+        const int q = e & 3, half = e >> 2;
+        int it = 0;
+        for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&d_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const long b = tile / p.tiles_per_b;
+            const long px = (tile - b * p.tiles_per_b) * 128 + q * 32 + lane;
+            float* yb = p.Y + b * p.sYb + px;
+            const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 16; c0 < p.N_t; c0 += 32) {
+                if (c0 >= p.N) break;
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(t_base + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (px < p.npix) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = c0 + j;
+                        if (n < p.N) yb[(long)n * p.npix] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&d_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+}  // namespace tc
+}  // namespace uno

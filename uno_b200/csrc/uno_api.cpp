@@ -568,6 +568,7 @@ int conv1x1(const float* wmat, long w_rs, long w_cs, const float* bias, const fl
     g.bias = bias;
     g.M = Co; g.N = (int)npix; g.K = Ci; g.batch = batch; g.epi = epi;
     g.tag = "conv1x1";
+    g.channel_mix = true;
     return be_gemm(g, st);
 }
 

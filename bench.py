@@ -264,31 +264,34 @@ def main():
     # --- per-kernel roofline, CUDA events around every launch of OUR kernels (separate steps so the
     #     event records do not perturb `value`)
     roofline, breakdown = None, None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile:
+        # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
         hbm, how = peaks()
-        torch.cuda.synchronize()
-        lib.uno_profile_enable(1)
+        sync_all()
+        if rank == 0:
+            lib.uno_profile_enable(1)
         nprof = 2
         for _ in range(nprof):
             step(x, y)
-        torch.cuda.synchronize()
-        n = lib.uno_profile_report(None, 0)
-        buf = C.create_string_buffer(n + 16)
-        lib.uno_profile_report(buf, n + 16)
-        lib.uno_profile_enable(0)
-        prof = json.loads(buf.value.decode())
-        tot = sum(v["ms"] for v in prof.values()) or 1.0
-        breakdown = {k: {"launches_per_step": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
-                         "share_of_uno_kernels": v["ms"] / tot,
-                         "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
-                         "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
-                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-        top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
-        achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
-        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": None, "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
-                    "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
-                    "uno_kernel_ms_per_step": tot / nprof}
+        sync_all()
+        if rank == 0:
+            n = lib.uno_profile_report(None, 0)
+            buf = C.create_string_buffer(n + 16)
+            lib.uno_profile_report(buf, n + 16)
+            lib.uno_profile_enable(0)
+            prof = json.loads(buf.value.decode())
+            tot = sum(v["ms"] for v in prof.values()) or 1.0
+            breakdown = {k: {"launches_per_step": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
+                             "share_of_uno_kernels": v["ms"] / tot,
+                             "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
+                             "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
+                         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+            top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
+            achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                        "traffic": None, "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
+                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                        "uno_kernel_ms_per_step": tot / nprof}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -24,7 +24,9 @@ class GradReducer:
             raise ValueError("module has no trainable parameters")
         dev = self.params[0].device
         sizes = [p.numel() * (2 if p.is_complex() else 1) for p in self.params]
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # every slot starts on a 16-byte boundary (complex views need an even element offset; vector kernels like 16 B)
+        slots = [(n + 3) // 4 * 4 for n in sizes]
+        self.flat = torch.zeros(sum(slots), dtype=torch.float32, device=dev)
         # gradients become final in roughly reverse registration order: lay the buffer out that way
         order = list(range(len(self.params)))[::-1]
         self._bucket_of = {}
@@ -38,7 +40,7 @@ class GradReducer:
             view = self.flat[off : off + n]
             p.grad = torch.view_as_complex(view.view(*p.shape, 2)) if p.is_complex() else view.view(p.shape)
             self._bucket_of[i] = len(self.buckets)
-            off += n
+            off += slots[i]
             cur_n += 1
             if off - cur_start >= limit:
                 self.buckets.append([cur_start, off, cur_n])

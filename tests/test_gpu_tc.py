@@ -128,4 +128,6 @@ def test_channel_mix_tc_matches_simt_and_fp64(shape, cuda_lib):
     assert rel_err(y_si, y_ref.numpy()) < FWD_TOL
     assert rel_err(y_tc, y_ref.numpy()) < FWD_TOL, rel_err(y_tc, y_ref.numpy())
     assert rel_err(gx_tc, gx_ref.numpy()) < BWD_TOL, rel_err(gx_tc, gx_ref.numpy())
-    assert rel_err(gw_tc, gw_si) < BWD_TOL
+    gw_ref = torch.einsum("bohw,bchw->oc", gy.cpu().double(), x.cpu().double()).reshape(Co, Ci, 1, 1)
+    assert rel_err(gw_si, gw_ref.numpy()) < BWD_TOL
+    assert rel_err(gw_tc, gw_ref.numpy()) < BWD_TOL, rel_err(gw_tc, gw_ref.numpy())

@@ -25,6 +25,7 @@
 #include "tc_rowgemm.cuh"
 #include "tc_kpipe.cuh"
 #include "tc_conv.cuh"
+#include "tc_wgrad.cuh"
 
 namespace uno {
 
@@ -389,15 +390,14 @@ __global__ void __launch_bounds__(256) banded_kernel(const BandedArgs a, long to
 // fused separable 2-D resample: one CTA = one plane x (32 x 64) output tile.  The input window is staged
 // in shared memory, the column (last-axis) bands are applied into a second shared buffer, then the row
 // bands; x is read once and y written once.
-constexpr int kB2TH = 32, kB2TW = 64;
-__global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int tiles_h, int tiles_w, int RIN, int CIN) {
+constexpr int kB2TH = 32, kB2TW = 64, kB2MidLd = 80;   // mid row pitch 80: rows r and r+1 of a warp land in disjoint banks
+__global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int tiles_h, int tiles_w, int RIN, int ldin) {
     extern __shared__ float sm[];
-    const int ldin = CIN + 1;
-    float* in_s = sm;                                  // [RIN][CIN+1]
-    float* mid_s = in_s + (size_t)RIN * ldin;          // [RIN][TW]
-    float* w0s = mid_s + (size_t)RIN * kB2TW;          // [TH][taps0]
-    float* w1s = w0s + kB2TH * a.taps0;                // [TW][taps1]
-    int* st0s = reinterpret_cast<int*>(w1s + kB2TW * a.taps1);
+    float* in_s = sm;                                  // [RIN][ldin], ldin odd
+    float* mid_s = in_s + (size_t)RIN * ldin;          // [RIN][kB2MidLd]
+    float* w0s = mid_s + (size_t)RIN * kB2MidLd;       // [TH][taps0]
+    float* w1t = w0s + kB2TH * a.taps0;                // [taps1][TW]  (transposed: conflict-free across columns)
+    int* st0s = reinterpret_cast<int*>(w1t + kB2TW * a.taps1);
     int* st1s = st0s + kB2TH;
     long bid = blockIdx.x;
     const int tw = (int)(bid % tiles_w); bid /= tiles_w;
@@ -409,12 +409,8 @@ __global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int
     const int r0 = __ldg(a.start0 + i0), c0 = __ldg(a.start1 + j0);
     const int rin = min(__ldg(a.start0 + i0 + nh - 1) + a.taps0, a.n_in0) - r0;
     const int cin = min(__ldg(a.start1 + j0 + nw - 1) + a.taps1, a.n_in1) - c0;
-    for (int i = tid; i < nh * a.taps0; i += 256) w0s[i] = __ldg(a.w0 + (long)i0 * a.taps0 + i);
-    for (int i = tid; i < nw * a.taps1; i += 256) w1s[i] = __ldg(a.w1 + (long)j0 * a.taps1 + i);
-    for (int i = tid; i < nh; i += 256) st0s[i] = __ldg(a.start0 + i0 + i) - r0;
-    for (int i = tid; i < nw; i += 256) st1s[i] = __ldg(a.start1 + j0 + i) - c0;
     const float* xp = a.x + (p * a.n_in0 + r0) * (long)a.n_in1 + c0;
-    const int tx = tid & 63, ty = tid >> 6;   // 64 columns x 4 rows of threads: no integer division in the loops
+    const int tx = tid & 63, ty = tid >> 6;
     // asynchronous 4-byte copies (LDGSTS): the whole input window is in flight at once
     for (int r = ty; r < rin; r += 4) {
         const float* src = xp + (long)r * a.n_in1;
@@ -422,17 +418,29 @@ __global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int
         for (int c = tx; c < cin; c += 64)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + c) : "memory");
     }
+    for (int i = tid; i < nh * a.taps0; i += 256) w0s[i] = __ldg(a.w0 + (long)i0 * a.taps0 + i);
+    if (tx < nw)
+        for (int t = ty; t < a.taps1; t += 4) w1t[t * kB2TW + tx] = __ldg(a.w1 + (long)(j0 + tx) * a.taps1 + t);
+    for (int i = tid; i < nh; i += 256) st0s[i] = __ldg(a.start0 + i0 + i) - r0;
+    for (int i = tid; i < nw; i += 256) st1s[i] = __ldg(a.start1 + j0 + i) - c0;
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    if (tx < nw) {
-        const float* w = w1s + tx * a.taps1;
-        const int off = st1s[tx];
-        for (int r = ty; r < rin; r += 4) {
-            const float* src = in_s + r * ldin + off;
-            float acc = 0.f;
+    {   // column bands: a warp covers 2 rows x 16 columns, so stride-2 (down-sampling) reads are conflict-free
+        const int hx = tid & 15, hy = tid >> 4;
+        for (int r = hy; r < rin; r += 16) {
+            const float* row = in_s + r * ldin;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = hx + 16 * jj;
+                if (j < nw) {
+                    const float* src = row + st1s[j];
+                    const float* w = w1t + j;
+                    float acc = 0.f;
 #pragma unroll 4
-            for (int t = 0; t < a.taps1; ++t) acc = fmaf(w[t], src[t], acc);
-            mid_s[r * kB2TW + tx] = acc;
+                    for (int t = 0; t < a.taps1; ++t) acc = fmaf(w[t * kB2TW], src[t], acc);
+                    mid_s[r * kB2MidLd + j] = acc;
+                }
+            }
         }
     }
     __syncthreads();
@@ -440,10 +448,10 @@ __global__ void __launch_bounds__(256) banded2d_kernel(const Banded2DArgs a, int
         float* yp = a.y + (p * a.n_out0 + i0) * (long)a.n_out1 + j0 + tx;
         for (int i = ty; i < nh; i += 4) {
             const float* w = w0s + i * a.taps0;
-            const float* src = mid_s + st0s[i] * kB2TW + tx;
+            const float* src = mid_s + st0s[i] * kB2MidLd + tx;
             float acc = 0.f;
 #pragma unroll 4
-            for (int t = 0; t < a.taps0; ++t) acc = fmaf(w[t], src[t * kB2TW], acc);
+            for (int t = 0; t < a.taps0; ++t) acc = fmaf(w[t], src[t * kB2MidLd], acc);
             yp[(long)i * a.n_out1] = acc;
         }
     }
@@ -824,6 +832,33 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     return 0;
 }
 
+int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
+    if (!tc_enabled() || a.M < 1 || a.N < 1 || a.M > 128 || a.N > 128 || a.K % 4 != 0 || a.K < 256) return -1;
+    if (a.lda != a.K || a.ldb != a.K || a.sA != (long)a.M * a.K || a.sB != (long)a.N * a.K) return -1;
+    if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15)) return -1;
+    tc::WgradParams p;
+    p.G = a.A; p.sGb = a.sA; p.X = a.B; p.sXb = a.sB; p.dW = a.C; p.ldw = a.ldc; p.npix = a.K;
+    p.M = a.M; p.N = a.N; p.N_t = ((a.N + 15) / 16) * 16; p.batch = a.batch;
+    p.stages = 3;
+    p.chunks_per_b = (int)((a.K + tc::kKC - 1) / tc::kKC);
+    p.total_chunks = (long)p.chunks_per_b * a.batch;
+    int cols = 32;
+    while (cols < p.N_t) cols *= 2;
+    p.tmem_cols = cols;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    long gx = num_sms();
+    if (gx > (p.total_chunks + 3) / 4) gx = (p.total_chunks + 3) / 4;
+    if (gx < 1) gx = 1;
+    tc::wgrad_tc_kernel<<<(unsigned)gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 // returns -1 when the shape does not qualify (caller falls back to the SIMT kernel)
 int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     if (!tc_enabled() || !a.b_const || a.batch != 1 || a.a_cs != 1 || a.bias || a.K > 64 || a.N < 16 || a.M < 1) return -1;
@@ -953,6 +988,8 @@ int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
     k.ksplit = (a.K + kchunk - 1) / kchunk;
     ProfScope ps("conv1x1_wgrad", 4.0 * ((double)a.M * a.K + (double)a.N * a.K) * a.batch + 4.0 * a.M * a.N,
                  2.0 * a.M * a.N * (double)a.K * a.batch, S(s));
+    const int rc = try_tc_wgrad(a, S(s));
+    if (rc >= 0) return rc;
     return dispatch_gemm(k, a.batch, S(s));
 }
 
@@ -1001,7 +1038,8 @@ int be_banded(const BandedArgs& a, stream_t s) {
 int be_banded2d(const Banded2DArgs& a, stream_t s) {
     if (a.planes <= 0) return 0;
     const int RIN = a.span0, CIN = a.span1;
-    const size_t smem = ((size_t)RIN * (CIN + 1) + (size_t)RIN * kB2TW + (size_t)kB2TH * a.taps0 + (size_t)kB2TW * a.taps1 + kB2TH + kB2TW) * 4;
+    const int ldin = CIN | 1;   // odd row pitch
+    const size_t smem = ((size_t)RIN * ldin + (size_t)RIN * kB2MidLd + (size_t)kB2TH * a.taps0 + (size_t)kB2TW * a.taps1 + kB2TH + kB2TW) * 4;
     if (smem > 200 * 1024) {
         // very large scale factors: two passes through scratch (shrinking axis first)
         BandedArgs l, m;
@@ -1026,7 +1064,7 @@ int be_banded2d(const Banded2DArgs& a, stream_t s) {
     const long blocks = a.planes * tiles_h * tiles_w;
     ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
                  2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * a.taps1 + (double)a.n_out0 * a.n_out1 * a.taps0), S(s));
-    banded2d_kernel<<<(unsigned)blocks, 256, smem, S(s)>>>(a, tiles_h, tiles_w, RIN, CIN);
+    banded2d_kernel<<<(unsigned)blocks, 256, smem, S(s)>>>(a, tiles_h, tiles_w, RIN, ldin);
     CU_LAUNCH_CHECK();
     return 0;
 }

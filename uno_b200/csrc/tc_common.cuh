@@ -42,6 +42,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// for roles whose wait is long (a whole tile): back off so the spinning warp does not steal issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
 
 // ---- async proxy ---------------------------------------------------------------------------------------
 // make generic-proxy st.shared visible to the async proxy (UMMA operand reads)

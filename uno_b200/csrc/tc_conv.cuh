@@ -117,16 +117,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, /*a MN-major*/ 1, /*b K-major*/ 0);
             const uint32_t lbo_b = (uint32_t)p.N_t * 16;
             const uint32_t sB_addr = smem_u32(sB);
-            long g = 0;
+            int s = 0;
+            uint32_t ph = 0;
             int it = 0;
             for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
-                for (int kc = 0; kc < NKC; ++kc, ++g) {
-                    const int s = (int)(g % S);
-                    mbar_wait(&full[s], (uint32_t)(g / S) & 1u);
+                for (int kc = 0; kc < NKC; ++kc) {
+                    mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(sA + (size_t)s * stage_bytes), a_lo = a_hi + kCvAHalf;
 #pragma unroll
@@ -142,82 +142,107 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
                         mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
                     }
                     tc_commit(&empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(&d_full[buf]);
             }
         }
     } else if (warp < kCvLoadWarps) {
         // ------------------------------------------------------------------ loaders: chunk = 32 channels x 128 pixels
+        // incremental cursors, one 32-bit division per TILE, one 64-bit multiply per chunk
         const int ltid = threadIdx.x;
         const int pg = ltid & 31, cb = ltid >> 5;      // pixel group (4 px), channel base
-        long n_my = 0;
-        for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_my;
-        const long total = n_my * NKC;
-        float4 cur[4], nxt[4];
-        auto issue = [&](long g, float4 (&v)[4]) {
-            const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
-            const int kc = (int)(g % NKC);
-            const long b = tile / p.tiles_per_b;
-            const long px = (tile - b * p.tiles_per_b) * 128 + pg * 4;
-            const float* xb = p.X + b * p.sXb;
+        const int n_tiles = (int)p.n_tiles, tpb = (int)p.tiles_per_b;
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_my;
+        const long total = (long)n_my * NKC;
+        const long stride8 = 8 * p.npix;
+        int i_tile = blockIdx.x, i_kc = 0;
+        const float* i_base = nullptr;                 // X + b*sXb + px of the issue cursor's tile
+        bool i_pxok = false;
+        auto retile = [&]() {
+            const int b = i_tile / tpb;
+            const long px = (long)(i_tile - b * tpb) * 128 + pg * 4;
+            i_pxok = px < p.npix;
+            i_base = p.X + (long)b * p.sXb + (i_pxok ? px : 0);
+        };
+        if (total > 0) retile();
+        int p_s = 0;
+        uint32_t p_ph = 0;
+        // swizzled MN-major destination of this thread inside a stage (channel cl = cb + 8*i -> group (cl>>2) = 2*i + (cb>>2), row r4 = cb&3)
+        const uint32_t r4 = (uint32_t)cb & 3u;
+        const uint32_t so = (uint32_t)(pg >> 3) * kCvLbo + (uint32_t)(cb >> 2) * kCvSbo + r4 * 128u + ((((uint32_t)(pg & 7) >> 1) ^ r4) << 5) +
+                            ((uint32_t)pg & 1u) * 16u;
+        float4 ring[kKpDepth][4];
+        auto issue = [&](float4 (&v)[4]) {
+            const int c0 = i_kc * kKC + cb;
+            const float* src = i_base + (long)c0 * p.npix;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int ci = kc * kKC + cb + 8 * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ci < p.K && px < p.npix) v[i] = __ldg(reinterpret_cast<const float4*>(xb + (long)ci * p.npix + px));
+                if (i_pxok && c0 + 8 * i < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * stride8));
+            }
+            if (++i_kc == NKC) {
+                i_kc = 0;
+                i_tile += gridDim.x;
+                if (i_tile < n_tiles) retile();
             }
         };
-        auto process = [&](long g, const float4 (&v)[4]) {
-            const int s = (int)(g % S);
-            mbar_wait(&empty[s], ((uint32_t)(g / S) & 1u) ^ 1u);
-            uint8_t* st = sA + (size_t)s * stage_bytes;
+        auto process = [&](const float4 (&v)[4]) {
+            mbar_wait(&empty[p_s], p_ph ^ 1u);
+            uint8_t* st = sA + (size_t)p_s * stage_bytes + so;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int cl = cb + 8 * i;                 // channel within the chunk
                 float4 hi, lo;
                 split_tf32(v[i].x, hi.x, lo.x);
                 split_tf32(v[i].y, hi.y, lo.y);
                 split_tf32(v[i].z, hi.z, lo.z);
                 split_tf32(v[i].w, hi.w, lo.w);
-                const uint32_t r4 = (uint32_t)cl & 3u;      // channel row inside its group of 4
-                const uint32_t o = (uint32_t)(pg >> 3) * kCvLbo + (uint32_t)(cl >> 2) * kCvSbo + r4 * 128u +
-                                   ((((uint32_t)(pg & 7) >> 1) ^ r4) << 5) + ((uint32_t)pg & 1u) * 16u;
-                *reinterpret_cast<float4*>(st + o) = hi;
-                *reinterpret_cast<float4*>(st + kCvAHalf + o) = lo;
+                *reinterpret_cast<float4*>(st + i * 2 * kCvSbo) = hi;
+                *reinterpret_cast<float4*>(st + kCvAHalf + i * 2 * kCvSbo) = lo;
             }
             fence_proxy_async();
-            mbar_arrive(&full[s]);
+            mbar_arrive(&full[p_s]);
+            if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
         };
-        if (total > 0) issue(0, cur);
-        for (long g = 0; g < total; g += 2) {
-            if (g + 1 < total) issue(g + 1, nxt);
-            process(g, cur);
-            if (g + 2 < total) issue(g + 2, cur);
-            if (g + 1 < total) process(g + 1, nxt);
+#pragma unroll
+        for (int d = 0; d < kKpDepth - 1; ++d)
+            if (d < total) issue(ring[d]);
+        for (long g = 0; g < total; g += kKpDepth) {
+#pragma unroll
+            for (int d = 0; d < kKpDepth; ++d) {
+                if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                if (g + d < total) process(ring[d]);
+            }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: warp e -> lane quarter e%4, column half e/4
         const int e = warp - kCvLoadWarps;
         const int q = e & 3, half = e >> 2;
+        const int n_tiles = (int)p.n_tiles, tpb = (int)p.tiles_per_b;
         int it = 0;
-        for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            mbar_wait(&d_full[buf], (uint32_t)(it >> 1) & 1u);
+            mbar_wait_relaxed(&d_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            const long b = tile / p.tiles_per_b;
-            const long px = (tile - b * p.tiles_per_b) * 128 + q * 32 + lane;
-            float* yb = p.Y + b * p.sYb + px;
+            const int b = tile / tpb;
+            const long px = (long)(tile - b * tpb) * 128 + q * 32 + lane;
+            const bool pxok = px < p.npix;
             const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
             for (int c0 = half * 16; c0 < p.N_t; c0 += 32) {
                 if (c0 >= p.N) break;
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(t_base + (uint32_t)c0, r);
+                float bv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bv[j] = (p.bias && c0 + j < p.N) ? __ldg(p.bias + c0 + j) : 0.f;
+                float* yp = p.Y + (long)b * p.sYb + (long)c0 * p.npix + (pxok ? px : 0);
                 tmem_ld_wait();
-                if (px < p.npix) {
+                if (pxok) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int n = c0 + j;
-                        if (n < p.N) yb[(long)n * p.npix] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n) : 0.f);
+                        if (c0 + j < p.N) *yp = __uint_as_float(r[j]) + bv[j];
+                        yp += p.npix;
                     }
                 }
             }

@@ -33,6 +33,7 @@ struct KPipeParams {
 
 constexpr int kKC = 32;                       // K elements per stage
 constexpr int kKpLoadWarps = 8;
+constexpr int kKpDepth = 4;                   // chunks of global loads kept in flight per loader thread
 constexpr int kKpEpiWarps = 4;
 constexpr int kKpThreads = (kKpLoadWarps + kKpEpiWarps + 1) * 32;
 constexpr uint32_t kKpAHalf = (kKC / 4) * kLboA;   // bytes of one A image (hi or lo) per stage
@@ -78,19 +79,19 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
             const uint32_t lbo_b = (uint32_t)p.N_t * 16;
-            long g = 0;
+            const uint32_t smem_base = smem_u32(smem);
+            int s = 0;
+            uint32_t ph = 0;
             int it = 0;
             for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
-                for (int kc = 0; kc < NKC; ++kc, ++g) {
-                    const int s = (int)(g % S);
-                    const uint32_t ph = (uint32_t)(g / S) & 1u;
+                for (int kc = 0; kc < NKC; ++kc) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
                     const uint32_t a_hi = base, a_lo = base + kKpAHalf;
                     const uint32_t bh = base + 2 * kKpAHalf, bl = bh + b_half;
 #pragma unroll
@@ -105,48 +106,69 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                         mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
                     }
                     tc_commit(&empty[s]);
+                    if (++s == S) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(&d_full[buf]);
             }
         }
     } else if (warp < kKpLoadWarps) {
         // ------------------------------------------------------------------ loaders: 256 threads, chunk = 128 rows x 32 k
+        // All indexing is incremental (no divisions, one 64-bit multiply per chunk): the loaders are the
+        // instruction-issue critical path of this kernel.
         const int ltid = threadIdx.x;
         long n_my_tiles = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) ++n_my_tiles;
         const long total = n_my_tiles * NKC;   // chunks this CTA processes, in order
+        // issue-side cursor (runs kKpDepth-1 chunks ahead) and process-side cursor
+        long i_tile = blockIdx.x;
+        int i_kc = 0;
+        int p_kc = 0, p_s = 0;
+        uint32_t p_ph = 0;
+        const uint32_t img_chunk_floats = 2 * b_half / 4;
+        auto stage_prologue = [&]() -> uint8_t* {
+            mbar_wait(&empty[p_s], p_ph ^ 1u);
+            uint8_t* st = smem + (size_t)p_s * stage_bytes;
+            if (ltid == 0) {
+                mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
+                bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
+            }
+            return st;
+        };
+        auto stage_epilogue = [&]() {
+            fence_proxy_async();
+            mbar_arrive(&full[p_s]);
+            if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
+            if (++p_kc == NKC) p_kc = 0;
+        };
         if (p.a_vec_ok) {
             // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
             const int kq = ltid & 7, rbase = ltid >> 3;
-            float4 cur[4], nxt[4];
-            auto issue = [&](long g, float4 (&v)[4]) {
-                const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
-                const int kc = (int)(g % NKC);
-                const int k0 = kc * kKC + kq * 4;
+            const long stride32 = 32 * p.lda;
+            const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
+            float4 ring[kKpDepth][4];
+            auto issue = [&](float4 (&v)[4]) {
+                const long row0 = i_tile * 128 + rbase;
+                const int k0 = i_kc * kKC + kq * 4;
+                const float* src = p.A + row0 * p.lda + k0;
+                const long rows_left = p.R - row0;            // row (32*i) valid iff 32*i < rows_left
+                const bool full4 = k0 + 4 <= p.K;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const long grow = tile * 128 + rbase + 32 * i;
                     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (grow < p.R) {
-                        const float* src = p.A + grow * p.lda + k0;
-                        if (k0 + 4 <= p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src));
+                    if (32 * i < rows_left) {
+                        const float* q = src + i * stride32;
+                        if (full4) v[i] = __ldg(reinterpret_cast<const float4*>(q));
                         else {
-                            if (k0 + 0 < p.K) v[i].x = __ldg(src + 0);
-                            if (k0 + 1 < p.K) v[i].y = __ldg(src + 1);
-                            if (k0 + 2 < p.K) v[i].z = __ldg(src + 2);
+                            if (k0 + 0 < p.K) v[i].x = __ldg(q + 0);
+                            if (k0 + 1 < p.K) v[i].y = __ldg(q + 1);
+                            if (k0 + 2 < p.K) v[i].z = __ldg(q + 2);
                         }
                     }
                 }
+                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
-            auto process = [&](long g, const float4 (&v)[4]) {
-                const int s = (int)(g % S);
-                const uint32_t ph = (uint32_t)(g / S) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                uint8_t* st = smem + (size_t)s * stage_bytes;
-                if (ltid == 0) {
-                    mbar_arrive_expect_tx(&full[s], 2 * b_half);
-                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)(g % NKC) * (2 * b_half / 4), 2 * b_half, &full[s]);
-                }
+            auto process = [&](const float4 (&v)[4]) {
+                uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float4 hi, lo;
@@ -154,61 +176,55 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                     split_tf32(v[i].y, hi.y, lo.y);
                     split_tf32(v[i].z, hi.z, lo.z);
                     split_tf32(v[i].w, hi.w, lo.w);
-                    const uint32_t o = (uint32_t)kq * kLboA + (uint32_t)(rbase + 32 * i) * 16;
-                    *reinterpret_cast<float4*>(st + o) = hi;
-                    *reinterpret_cast<float4*>(st + kKpAHalf + o) = lo;
+                    *reinterpret_cast<float4*>(st + i * 512) = hi;
+                    *reinterpret_cast<float4*>(st + kKpAHalf + i * 512) = lo;
                 }
-                fence_proxy_async();
-                mbar_arrive(&full[s]);
+                stage_epilogue();
             };
-            // ping-pong register buffers: the loads of chunk g+1 are in flight while chunk g is split and stored
-            if (total > 0) issue(0, cur);
-            for (long g = 0; g < total; g += 2) {
-                if (g + 1 < total) issue(g + 1, nxt);
-                process(g, cur);
-                if (g + 2 < total) issue(g + 2, cur);
-                if (g + 1 < total) process(g + 1, nxt);
+#pragma unroll
+            for (int d = 0; d < kKpDepth - 1; ++d)
+                if (d < total) issue(ring[d]);
+            for (long g = 0; g < total; g += kKpDepth) {
+#pragma unroll
+                for (int d = 0; d < kKpDepth; ++d) {
+                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                    if (g + d < total) process(ring[d]);
+                }
             }
         } else {
             // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
-            float cur[16], nxt[16];
-            auto issue = [&](long g, float (&v)[16]) {
-                const long tile = blockIdx.x + (g / NKC) * (long)gridDim.x;
-                const int k = (int)(g % NKC) * kKC + lane;
-                const bool kok = k < p.K;
+            const long stride8 = 8 * p.lda;
+            const uint32_t so = (uint32_t)(lane >> 2) * kLboA + (uint32_t)(lane & 3) * 4 + (uint32_t)warp * 16;
+            float ring[kKpDepth][16];
+            auto issue = [&](float (&v)[16]) {
+                const long row0 = i_tile * 128 + warp;
+                const int k = i_kc * kKC + lane;
+                const float* src = p.A + row0 * p.lda + k;
+                const long rows_left = (k < p.K) ? (p.R - row0) : 0;   // row (8*i) valid iff 8*i < rows_left
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const long grow = tile * 128 + warp + 8 * i;
-                    v[i] = (kok && grow < p.R) ? __ldg(p.A + grow * p.lda + k) : 0.f;
-                }
+                for (int i = 0; i < 16; ++i) v[i] = (8 * i < rows_left) ? __ldg(src + i * stride8) : 0.f;
+                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
-            auto process = [&](long g, const float (&v)[16]) {
-                const int s = (int)(g % S);
-                const uint32_t ph = (uint32_t)(g / S) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                uint8_t* st = smem + (size_t)s * stage_bytes;
-                if (ltid == 0) {
-                    mbar_arrive_expect_tx(&full[s], 2 * b_half);
-                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)(g % NKC) * (2 * b_half / 4), 2 * b_half, &full[s]);
-                }
-                const uint32_t ko = (uint32_t)(lane >> 2) * kLboA + (uint32_t)(lane & 3) * 4;
+            auto process = [&](const float (&v)[16]) {
+                uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float hi, lo;
                     split_tf32(v[i], hi, lo);
-                    const uint32_t o = ko + (uint32_t)(warp + 8 * i) * 16;
-                    *reinterpret_cast<float*>(st + o) = hi;
-                    *reinterpret_cast<float*>(st + kKpAHalf + o) = lo;
+                    *reinterpret_cast<float*>(st + i * 128) = hi;
+                    *reinterpret_cast<float*>(st + kKpAHalf + i * 128) = lo;
                 }
-                fence_proxy_async();
-                mbar_arrive(&full[s]);
+                stage_epilogue();
             };
-            if (total > 0) issue(0, cur);
-            for (long g = 0; g < total; g += 2) {
-                if (g + 1 < total) issue(g + 1, nxt);
-                process(g, cur);
-                if (g + 2 < total) issue(g + 2, cur);
-                if (g + 1 < total) process(g + 1, nxt);
+#pragma unroll
+            for (int d = 0; d < kKpDepth - 1; ++d)
+                if (d < total) issue(ring[d]);
+            for (long g = 0; g < total; g += kKpDepth) {
+#pragma unroll
+                for (int d = 0; d < kKpDepth; ++d) {
+                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                    if (g + d < total) process(ring[d]);
+                }
             }
         }
     } else {
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
         int it = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
-            mbar_wait(&d_full[buf], (uint32_t)(it >> 1) & 1u);
+            mbar_wait_relaxed(&d_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const long row0 = tile * 128 + q * 32;
             const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);

@@ -46,13 +46,21 @@ __host__ __device__ inline size_t rowgemm_smem_bytes(int K_pad, int N_t) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // Epilogue of one 128-row tile for one warp: TMEM lane quarter `q`, 16-column chunks c0 = 16*(2*i + half).
-// All loads of a 32-column group are issued before any store so that they are in flight together.
+// All loads of a 32-column group are issued before any store so that they are in flight together; the four
+// row pointers of a thread are formed once per tile (no 64-bit multiplies in the column loop).
 template <int EPI, bool VEC2>
 __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long row0, int n_base, int half, int lane) {
     constexpr bool kAccum = (EPI != EPI_STORE);
-    float* __restrict__ C = p.C;
-    float* __restrict__ C2 = p.C2;
-    // pairs of chunks: chunk indices (2*i + half) for i = 0.. ; process two chunks (i, i+1) per iteration
+    const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
+    float* rowp[4];          // index hh*2 + rr
+    bool rok[4];
+#pragma unroll
+    for (int hr = 0; hr < 4; ++hr) {
+        const long grow = row0 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2);
+        rok[hr] = grow < p.R;
+        rowp[hr] = p.C + (rok[hr] ? grow : 0) * p.ldc + n_base + 2 * (lane & 3);
+    }
+    const int ncol = p.N - n_base - 2 * (lane & 3);     // column c (relative) valid iff c < ncol
     for (int ci = half; ci * 16 < p.N_t; ci += 4) {
         const int c0a = ci * 16, c0b = (ci + 2) * 16;
         const bool has_b = c0b < p.N_t && n_base + c0b < p.N;
@@ -64,36 +72,22 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
             tmem_ld_16x256b_x2(t_base + (uint32_t)c0b, r[2]);
             tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0b, r[3]);
         }
-        // addresses: element pair e = (chunk j, half hh, repeat rep, row-pair rr)
-        long off[16];
-        bool ok0[16], ok1[16];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                for (int rep = 0; rep < 2; ++rep)
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int e = ((j * 2 + hh) * 2 + rep) * 2 + rr;
-                        const long grow = row0 + hh * 16 + rr * 8 + (lane >> 2);
-                        const int col = n_base + (j ? c0b : c0a) + rep * 8 + 2 * (lane & 3);
-                        const bool live = (j == 0 || has_b) && grow < p.R;
-                        ok0[e] = live && col < p.N;
-                        ok1[e] = live && col + 1 < p.N;
-                        off[e] = grow * p.ldc + col;
-                    }
+        // element pair e = (chunk j, half hh, repeat rep, row-pair rr)
         float2 cz[16];
         if (kAccum) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
+                const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
+                const int c = (j ? c0b : c0a) + rep * 8;
+                const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
+                const float* q = rowp[hh * 2 + rr] + c;
                 cz[e] = make_float2(0.f, 0.f);
                 if (VEC2) {
-                    if (ok1[e]) cz[e] = *reinterpret_cast<const float2*>(C + off[e]);
-                    else if (ok0[e]) cz[e].x = C[off[e]];
+                    if (live && c + 1 < ncol) cz[e] = *reinterpret_cast<const float2*>(q);
+                    else if (live && c < ncol) cz[e].x = q[0];
                 } else {
-                    if (ok0[e]) cz[e].x = C[off[e]];
-                    if (ok1[e]) cz[e].y = C[off[e] + 1];
+                    if (live && c < ncol) cz[e].x = q[0];
+                    if (live && c + 1 < ncol) cz[e].y = q[1];
                 }
             }
         }
@@ -101,17 +95,21 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
             const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
+            const int c = (j ? c0b : c0a) + rep * 8;
+            const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
+            const bool ok0 = live && c < ncol, ok1 = live && c + 1 < ncol;
+            float* q = rowp[hh * 2 + rr] + c;
             float2 acc = make_float2(__uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 0]), __uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 1]));
             if (kAccum) { acc.x += cz[e].x; acc.y += cz[e].y; }
             float2 act = acc;
             if (EPI == EPI_ACCUM_GELU || EPI == EPI_ACCUM_GELU_INPLACE) { act.x = gelu_erf(acc.x); act.y = gelu_erf(acc.y); }
             const float2 out1 = (EPI == EPI_ACCUM_GELU_INPLACE) ? act : acc;
-            if (VEC2 && ok1[e]) {
-                *reinterpret_cast<float2*>(C + off[e]) = out1;
-                if (EPI == EPI_ACCUM_GELU) *reinterpret_cast<float2*>(C2 + off[e]) = act;
+            if (VEC2 && ok1) {
+                *reinterpret_cast<float2*>(q) = out1;
+                if (EPI == EPI_ACCUM_GELU) *reinterpret_cast<float2*>(q + c2_delta) = act;
             } else {
-                if (ok0[e]) { C[off[e]] = out1.x; if (EPI == EPI_ACCUM_GELU) C2[off[e]] = act.x; }
-                if (ok1[e]) { C[off[e] + 1] = out1.y; if (EPI == EPI_ACCUM_GELU) C2[off[e] + 1] = act.y; }
+                if (ok0) { q[0] = out1.x; if (EPI == EPI_ACCUM_GELU) q[c2_delta] = act.x; }
+                if (ok1) { q[1] = out1.y; if (EPI == EPI_ACCUM_GELU) q[c2_delta + 1] = act.y; }
             }
         }
     }
@@ -186,11 +184,10 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
             }
         }
     } else if (warp >= kRowGemmEpiWarps) {
-        // ------------------------------------------------------------------ A loaders
+        // ------------------------------------------------------------------ A loaders: thread -> rows t and t+64, loop over the k chunks
         constexpr int NL = kRowGemmLoadWarps * 32;
-        constexpr int BATCH = 5;
+        constexpr int BATCH = 6;
         const int ltid = threadIdx.x - kRowGemmEpiWarps * 32;
-        const int total = 128 * CH;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
@@ -198,42 +195,44 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
             mbar_wait(&a_empty[s], ph ^ 1u);
             uint8_t* dst_hi = sA + (size_t)(s * 2 + 0) * a_bytes;
             uint8_t* dst_lo = sA + (size_t)(s * 2 + 1) * a_bytes;
-            const long row0 = tile * 128;
-            for (int cb = ltid; cb < total; cb += NL * BATCH) {
-                float4 v[BATCH];
-                uint32_t o[BATCH];
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) {
-                    const int c = cb + u * NL;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    o[u] = 0xFFFFFFFFu;
-                    if (c < total) {
-                        const int row = c / CH, kc = c - row * CH;
-                        o[u] = (uint32_t)kc * kLboA + (uint32_t)row * 16;
-                        const long grow = row0 + row;
-                        if (grow < p.R) {
-                            const float* src = p.A + grow * p.lda + kc * 4;
+            for (int rr = 0; rr < 128 / NL; ++rr) {
+                const int row = ltid + rr * NL;
+                const long grow = tile * 128 + row;
+                const bool rvalid = grow < p.R;
+                const float* src = p.A + (rvalid ? grow : 0) * p.lda;
+                const uint32_t ro = (uint32_t)row * 16;
+                for (int kc0 = 0; kc0 < CH; kc0 += BATCH) {
+                    float4 v[BATCH];
+#pragma unroll
+                    for (int u = 0; u < BATCH; ++u) {
+                        const int kc = kc0 + u;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (kc < CH && rvalid) {
+                            const float* q = src + kc * 4;
                             if (p.a_vec_ok && kc * 4 + 4 <= p.K) {
-                                v[u] = __ldg(reinterpret_cast<const float4*>(src));
+                                v[u] = __ldg(reinterpret_cast<const float4*>(q));
                             } else {
-                                if (kc * 4 + 0 < p.K) v[u].x = __ldg(src + 0);
-                                if (kc * 4 + 1 < p.K) v[u].y = __ldg(src + 1);
-                                if (kc * 4 + 2 < p.K) v[u].z = __ldg(src + 2);
-                                if (kc * 4 + 3 < p.K) v[u].w = __ldg(src + 3);
+                                if (kc * 4 + 0 < p.K) v[u].x = __ldg(q + 0);
+                                if (kc * 4 + 1 < p.K) v[u].y = __ldg(q + 1);
+                                if (kc * 4 + 2 < p.K) v[u].z = __ldg(q + 2);
+                                if (kc * 4 + 3 < p.K) v[u].w = __ldg(q + 3);
                             }
                         }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < BATCH; ++u) {
-                    if (o[u] == 0xFFFFFFFFu) continue;
-                    float4 hi, lo;
-                    split_tf32(v[u].x, hi.x, lo.x);
-                    split_tf32(v[u].y, hi.y, lo.y);
-                    split_tf32(v[u].z, hi.z, lo.z);
-                    split_tf32(v[u].w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(dst_hi + o[u]) = hi;
-                    *reinterpret_cast<float4*>(dst_lo + o[u]) = lo;
+                    for (int u = 0; u < BATCH; ++u) {
+                        const int kc = kc0 + u;
+                        if (kc >= CH) break;
+                        float4 hi, lo;
+                        split_tf32(v[u].x, hi.x, lo.x);
+                        split_tf32(v[u].y, hi.y, lo.y);
+                        split_tf32(v[u].z, hi.z, lo.z);
+                        split_tf32(v[u].w, hi.w, lo.w);
+                        const uint32_t o = (uint32_t)kc * kLboA + ro;
+                        *reinterpret_cast<float4*>(dst_hi + o) = hi;
+                        *reinterpret_cast<float4*>(dst_lo + o) = lo;
+                    }
                 }
             }
             fence_proxy_async();
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&d_full[s], ph);
+            mbar_wait_relaxed(&d_full[s], ph);
             tc_fence_after();
             const long row0 = tile * 128 + q * 32;
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);

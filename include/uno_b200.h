@@ -108,6 +108,56 @@ int uno_operator_block_bwd(const uno_block_desc* d, const float* gy, const float
                            float* gconv_w, float* gconv_b, float* ggamma, float* gbeta, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---- model glue around the blocks ------------------------------------
+ * The reference models wrap the operator blocks in two per-pixel MLPs whose permute / pad / cat / crop
+ * traffic dominates once the blocks are fused.  These entry points run each MLP as ONE kernel.
+ *
+ * lift   replaces  cat(a, grid) -> fc_n1/fc -> gelu -> fc0 -> gelu -> permute(0,3,1,2) -> F.pad
+ *        darcy_flow_uno2d.py:96-107, navier_stokes_uno2d.py:191-201, navier_stokes_uno3d.py:497-511
+ *   a    [B, *dim, raw_ch] channels-last      grid [*dim, grid_ch] (the positional features, built once)
+ *   w_a  [hidden, raw_ch+grid_ch], b_a [hidden], w_b [out_ch, hidden], b_b [out_ch]   (nn.Linear layout)
+ *   h    [B, out_ch, *(dim+pad_lo+pad_hi)] channels-first, zero in the padding
+ * project replaces torch.cat(src..., dim=1) -> crop -> permute(0,2,3,1) -> fc1 -> gelu -> fc2
+ *        darcy_flow_uno2d.py:121-131, navier_stokes_uno2d.py:215-225, navier_stokes_uno3d.py:551-575
+ *   src[s] [B, src_ch[s], *(dim+pad_lo+pad_hi)]   w1 [hidden, sum src_ch], w2 [out_ch, hidden]
+ *   out  [B, *dim, out_ch]
+ * The backward entry points recompute the hidden activations (forward saves nothing) and overwrite every
+ * gradient output; ga / gsrc[s] may be NULL to skip.  gsrc[s] is written over the whole padded grid
+ * (zero outside the crop).  Limits: raw_ch+grid_ch <= 16, lift hidden <= 32, lift out_ch <= 64,
+ * sum src_ch <= 64, project hidden <= 128, project out_ch <= 4 (uno_*_check reports UNO_EINVAL beyond). */
+typedef struct uno_pixel_desc {
+    int ndim;        /* 2 or 3 spatial axes */
+    int batch;
+    int dim[3];      /* un-padded / cropped grid (unused trailing entries 1) */
+    int pad_lo[3];   /* padding before / after each axis (unused trailing entries 0) */
+    int pad_hi[3];
+} uno_pixel_desc;
+
+typedef struct uno_lift_desc {
+    uno_pixel_desc px;
+    int raw_ch, grid_ch, hidden, out_ch;
+} uno_lift_desc;
+
+typedef struct uno_project_desc {
+    uno_pixel_desc px;
+    int nsrc;        /* 1..4 channel-first sources, concatenated along channels */
+    int src_ch[4];
+    int hidden, out_ch;
+} uno_project_desc;
+
+int uno_lift_check(const uno_lift_desc* d);
+int uno_lift_fwd(const uno_lift_desc* d, const float* a, const float* grid, const float* w_a,
+                 const float* b_a, const float* w_b, const float* b_b, float* h, void* stream);
+int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a, const float* grid,
+                 const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
+                 float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream);
+int uno_project_check(const uno_project_desc* d);
+int uno_project_fwd(const uno_project_desc* d, const float* const* src, const float* w1,
+                    const float* b1, const float* w2, const float* b2, float* out, void* stream);
+int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* const* src,
+                    const float* w1, const float* b1, const float* w2, float* const* gsrc, float* gw1,
+                    float* gb1, float* gw2, float* gb2, void* stream);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------------
  * uno_launch_count: kernels this library has launched since it was loaded.
  * uno_profile_enable(1) brackets every kernel launch with a CUDA-event pair on the launching stream;

@@ -187,3 +187,31 @@ class SpectralConv1d_Uno(_SpectralConvND):
         if modes1 is None:
             modes1 = dim1 // 2
         super().__init__(in_codim, out_codim, (dim1,), (modes1,))
+
+
+# ---- model glue (callers of the hot path) ----------------------------------
+def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
+    """darcy_flow_uno2d.py:96-107 / navier_stokes_uno2d.py:191-201 / navier_stokes_uno3d.py:497-511:
+    cat(a, grid) -> Linear -> gelu -> Linear -> gelu -> channels-first -> F.pad (zeros)."""
+    x = torch.cat((a, grid.expand(a.shape[0], *grid.shape)), dim=-1)
+    h = F.gelu(F.linear(F.gelu(F.linear(x, w_a, b_a)), w_b, b_b))
+    nd = h.dim() - 2
+    h = h.permute(0, nd + 1, *range(1, nd + 1))
+    pads = []
+    for lo, hi in reversed(list(zip(pad_lo, pad_hi))):
+        pads += [int(lo), int(hi)]
+    return F.pad(h, pads) if any(pads) else h.contiguous()
+
+
+def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
+    """darcy_flow_uno2d.py:121-131 / navier_stokes_uno2d.py:215-225 / navier_stokes_uno3d.py:551-575:
+    cat(srcs, dim=1) -> crop -> channels-last -> Linear -> gelu -> Linear."""
+    c = torch.cat(list(srcs), dim=1) if len(srcs) > 1 else srcs[0]
+    idx = [slice(None), slice(None)]
+    for a, (lo, hi) in enumerate(zip(crop_lo, crop_hi)):
+        n = c.shape[2 + a]
+        idx.append(slice(int(lo), n - int(hi)))
+    c = c[tuple(idx)]
+    nd = c.dim() - 2
+    c = c.permute(0, *range(2, nd + 2), 1)
+    return F.linear(F.gelu(F.linear(c, w1, b1)), w2, b2)

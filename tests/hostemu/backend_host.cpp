@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "../../uno_b200/csrc/backend.h"
 
@@ -206,6 +207,154 @@ int be_channel_sum(const float* x, float* out, long planes, int C, long L, float
 int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t) {
     for (long p = 0; p < planes; ++p)
         for (long i = 0; i < L; ++i) y[p * L + i] += v[p % C] * alpha;
+    return 0;
+}
+
+// ---- model glue: lift / project as plain loops (double accumulation) ------------------------------------
+namespace {
+struct Geo { long nraw, npad; };
+inline Geo geo(const int* n, const int* N) { return {(long)n[0] * n[1] * n[2], (long)N[0] * N[1] * N[2]}; }
+inline long padded_index(const int* n, const int* N, const int* lo, long rp) {
+    const int r2 = (int)(rp % n[2]);
+    const long t = rp / n[2];
+    const int r1 = (int)(t % n[1]), r0 = (int)(t / n[1]);
+    return ((long)(r0 + lo[0]) * N[1] + (r1 + lo[1])) * N[2] + (r2 + lo[2]);
+}
+}  // namespace
+
+int be_lift_supported(const LiftArgs& a) {
+    return a.raw_ch + a.grid_ch <= 16 && a.hid <= 32 && a.out_ch <= 64;
+}
+
+int be_lift_fwd(const LiftArgs& a, stream_t) {
+    const Geo g = geo(a.n, a.N);
+    const int cin = a.raw_ch + a.grid_ch;
+    memset(a.h, 0, sizeof(float) * a.batch * a.out_ch * g.npad);
+    for (long b = 0; b < a.batch; ++b)
+        for (long rp = 0; rp < g.nraw; ++rp) {
+            double in[64], a0[64];
+            for (int c = 0; c < cin; ++c)
+                in[c] = c < a.raw_ch ? a.a[(b * g.nraw + rp) * a.raw_ch + c] : a.grid[rp * a.grid_ch + (c - a.raw_ch)];
+            for (int k = 0; k < a.hid; ++k) {
+                double s = a.b_a[k];
+                for (int c = 0; c < cin; ++c) s += (double)a.w_a[k * cin + c] * in[c];
+                a0[k] = gelu_f((float)s);
+            }
+            const long pp = padded_index(a.n, a.N, a.lo, rp);
+            for (int o = 0; o < a.out_ch; ++o) {
+                double s = a.b_b[o];
+                for (int k = 0; k < a.hid; ++k) s += (double)a.w_b[o * a.hid + k] * a0[k];
+                a.h[(b * a.out_ch + o) * g.npad + pp] = gelu_f((float)s);
+            }
+        }
+    return 0;
+}
+
+int be_lift_bwd(const LiftArgs& a, stream_t) {
+    const Geo g = geo(a.n, a.N);
+    const int cin = a.raw_ch + a.grid_ch;
+    std::vector<double> gwa((size_t)a.hid * cin, 0.0), gba(a.hid, 0.0), gwb((size_t)a.out_ch * a.hid, 0.0), gbb(a.out_ch, 0.0);
+    for (long b = 0; b < a.batch; ++b)
+        for (long rp = 0; rp < g.nraw; ++rp) {
+            double in[64], pre0[64], a0[64], da0[64];
+            for (int c = 0; c < cin; ++c)
+                in[c] = c < a.raw_ch ? a.a[(b * g.nraw + rp) * a.raw_ch + c] : a.grid[rp * a.grid_ch + (c - a.raw_ch)];
+            for (int k = 0; k < a.hid; ++k) {
+                double s = a.b_a[k];
+                for (int c = 0; c < cin; ++c) s += (double)a.w_a[k * cin + c] * in[c];
+                pre0[k] = s; a0[k] = gelu_f((float)s); da0[k] = 0;
+            }
+            const long pp = padded_index(a.n, a.N, a.lo, rp);
+            for (int o = 0; o < a.out_ch; ++o) {
+                double s = a.b_b[o];
+                for (int k = 0; k < a.hid; ++k) s += (double)a.w_b[o * a.hid + k] * a0[k];
+                const double d1 = (double)a.gh[(b * a.out_ch + o) * g.npad + pp] * gelu_grad_f((float)s);
+                gbb[o] += d1;
+                for (int k = 0; k < a.hid; ++k) { gwb[o * a.hid + k] += d1 * a0[k]; da0[k] += d1 * a.w_b[o * a.hid + k]; }
+            }
+            for (int k = 0; k < a.hid; ++k) {
+                const double d0 = da0[k] * gelu_grad_f((float)pre0[k]);
+                da0[k] = d0;
+                gba[k] += d0;
+                for (int c = 0; c < cin; ++c) gwa[k * cin + c] += d0 * in[c];
+            }
+            if (a.ga)
+                for (int c = 0; c < a.raw_ch; ++c) {
+                    double s = 0;
+                    for (int k = 0; k < a.hid; ++k) s += da0[k] * a.w_a[k * cin + c];
+                    a.ga[(b * g.nraw + rp) * a.raw_ch + c] = (float)s;
+                }
+        }
+    for (size_t i = 0; i < gwa.size(); ++i) a.gw_a[i] += (float)gwa[i];
+    for (size_t i = 0; i < gba.size(); ++i) a.gb_a[i] += (float)gba[i];
+    for (size_t i = 0; i < gwb.size(); ++i) a.gw_b[i] += (float)gwb[i];
+    for (size_t i = 0; i < gbb.size(); ++i) a.gb_b[i] += (float)gbb[i];
+    return 0;
+}
+
+int be_proj_supported(const ProjArgs& a) {
+    int ctot = 0;
+    for (int s = 0; s < a.nsrc; ++s) ctot += a.src_ch[s];
+    return a.nsrc >= 1 && a.nsrc <= 4 && ctot <= 64 && a.hid <= 128 && a.out_ch <= 4;
+}
+
+int be_proj_fwd(const ProjArgs& a, stream_t) {
+    const Geo g = geo(a.n, a.N);
+    int ctot = 0;
+    for (int s = 0; s < a.nsrc; ++s) ctot += a.src_ch[s];
+    for (long b = 0; b < a.batch; ++b)
+        for (long rp = 0; rp < g.nraw; ++rp) {
+            const long pp = padded_index(a.n, a.N, a.lo, rp);
+            double in[64], o[4] = {0, 0, 0, 0};
+            int c = 0;
+            for (int s = 0; s < a.nsrc; ++s)
+                for (int cl = 0; cl < a.src_ch[s]; ++cl) in[c++] = a.src[s][(b * a.src_ch[s] + cl) * g.npad + pp];
+            for (int n = 0; n < a.hid; ++n) {
+                double s = a.b1[n];
+                for (int cc = 0; cc < ctot; ++cc) s += (double)a.w1[n * ctot + cc] * in[cc];
+                const double act = gelu_f((float)s);
+                for (int q = 0; q < a.out_ch; ++q) o[q] += (double)a.w2[q * a.hid + n] * act;
+            }
+            for (int q = 0; q < a.out_ch; ++q) a.out[(b * g.nraw + rp) * a.out_ch + q] = (float)(o[q] + a.b2[q]);
+        }
+    return 0;
+}
+
+int be_proj_bwd(const ProjArgs& a, stream_t) {
+    const Geo g = geo(a.n, a.N);
+    int ctot = 0;
+    for (int s = 0; s < a.nsrc; ++s) ctot += a.src_ch[s];
+    for (int s = 0; s < a.nsrc; ++s)
+        if (a.gsrc[s]) memset(a.gsrc[s], 0, sizeof(float) * a.batch * a.src_ch[s] * g.npad);
+    std::vector<double> gw1((size_t)a.hid * ctot, 0.0), gb1(a.hid, 0.0), gw2((size_t)a.out_ch * a.hid, 0.0), gb2(a.out_ch, 0.0);
+    for (long b = 0; b < a.batch; ++b)
+        for (long rp = 0; rp < g.nraw; ++rp) {
+            const long pp = padded_index(a.n, a.N, a.lo, rp);
+            double in[64], din[64];
+            int c = 0;
+            for (int s = 0; s < a.nsrc; ++s)
+                for (int cl = 0; cl < a.src_ch[s]; ++cl) { in[c] = a.src[s][(b * a.src_ch[s] + cl) * g.npad + pp]; din[c++] = 0; }
+            const float* go = a.gout + (b * g.nraw + rp) * a.out_ch;
+            for (int q = 0; q < a.out_ch; ++q) gb2[q] += go[q];
+            for (int n = 0; n < a.hid; ++n) {
+                double s = a.b1[n];
+                for (int cc = 0; cc < ctot; ++cc) s += (double)a.w1[n * ctot + cc] * in[cc];
+                const double act = gelu_f((float)s);
+                double t = 0;
+                for (int q = 0; q < a.out_ch; ++q) { t += (double)go[q] * a.w2[q * a.hid + n]; gw2[q * a.hid + n] += go[q] * act; }
+                const double dp = t * gelu_grad_f((float)s);
+                gb1[n] += dp;
+                for (int cc = 0; cc < ctot; ++cc) { gw1[n * ctot + cc] += dp * in[cc]; din[cc] += dp * a.w1[n * ctot + cc]; }
+            }
+            c = 0;
+            for (int s = 0; s < a.nsrc; ++s)
+                for (int cl = 0; cl < a.src_ch[s]; ++cl, ++c)
+                    if (a.gsrc[s]) a.gsrc[s][(b * a.src_ch[s] + cl) * g.npad + pp] = (float)din[c];
+        }
+    for (size_t i = 0; i < gw1.size(); ++i) a.gw1[i] += (float)gw1[i];
+    for (size_t i = 0; i < gb1.size(); ++i) a.gb1[i] += (float)gb1[i];
+    for (size_t i = 0; i < gw2.size(); ++i) a.gw2[i] += (float)gw2[i];
+    for (size_t i = 0; i < gb2.size(); ++i) a.gb2[i] += (float)gb2[i];
     return 0;
 }
 

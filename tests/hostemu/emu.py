@@ -167,3 +167,56 @@ def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=Non
         ),
     )
     return gx, gws, gcw, gcb, gg, gb
+
+
+# ---- model glue --------------------------------------------------------------------------------------
+def lift_fwd(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
+    L = lib()
+    a, grid, w_a, b_a, w_b, b_b = (_f32(t) for t in (a, grid, w_a, b_a, w_b, b_b))
+    dims = a.shape[1:-1]
+    d = _capi.lift_desc(a.shape[0], dims, pad_lo, pad_hi, a.shape[-1], grid.shape[-1], w_a.shape[0], w_b.shape[0])
+    _capi.check(L, L.uno_lift_check(C.byref(d)))
+    out_dims = tuple(n + lo + hi for n, lo, hi in zip(dims, pad_lo, pad_hi))
+    h = np.full((a.shape[0], w_b.shape[0]) + out_dims, np.nan, np.float32)
+    _capi.check(L, L.uno_lift_fwd(C.byref(d), _p(a), _p(grid), _p(w_a), _p(b_a), _p(w_b), _p(b_b), _p(h), None))
+    return h
+
+
+def lift_bwd(gh, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, want_ga=True):
+    L = lib()
+    gh, a, grid, w_a, b_a, w_b, b_b = (_f32(t) for t in (gh, a, grid, w_a, b_a, w_b, b_b))
+    d = _capi.lift_desc(a.shape[0], a.shape[1:-1], pad_lo, pad_hi, a.shape[-1], grid.shape[-1], w_a.shape[0], w_b.shape[0])
+    ga = np.full_like(a, np.nan) if want_ga else None
+    outs = [np.full_like(t, np.nan) for t in (w_a, b_a, w_b, b_b)]
+    _capi.check(L, L.uno_lift_bwd(C.byref(d), _p(gh), _p(a), _p(grid), _p(w_a), _p(b_a), _p(w_b), _p(b_b), _p(ga), *[_p(o) for o in outs], None))
+    return (ga, *outs)
+
+
+def project_fwd(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
+    L = lib()
+    srcs = [_f32(s) for s in srcs]
+    w1, b1, w2, b2 = (_f32(t) for t in (w1, b1, w2, b2))
+    full = srcs[0].shape[2:]
+    dims = tuple(n - lo - hi for n, lo, hi in zip(full, crop_lo, crop_hi))
+    d = _capi.project_desc(srcs[0].shape[0], dims, crop_lo, crop_hi, [s.shape[1] for s in srcs], w1.shape[0], w2.shape[0])
+    _capi.check(L, L.uno_project_check(C.byref(d)))
+    out = np.full((srcs[0].shape[0],) + dims + (w2.shape[0],), np.nan, np.float32)
+    sp = _capi.ptr_array([s.ctypes.data for s in srcs])
+    _capi.check(L, L.uno_project_fwd(C.byref(d), sp, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), None))
+    return out
+
+
+def project_bwd(gout, srcs, w1, b1, w2, crop_lo, crop_hi):
+    L = lib()
+    srcs = [_f32(s) for s in srcs]
+    gout, w1, b1, w2 = (_f32(t) for t in (gout, w1, b1, w2))
+    full = srcs[0].shape[2:]
+    dims = tuple(n - lo - hi for n, lo, hi in zip(full, crop_lo, crop_hi))
+    d = _capi.project_desc(srcs[0].shape[0], dims, crop_lo, crop_hi, [s.shape[1] for s in srcs], w1.shape[0], w2.shape[0])
+    gs = [np.full_like(s, np.nan) for s in srcs]
+    gw1, gb1, gw2 = np.full_like(w1, np.nan), np.full_like(b1, np.nan), np.full_like(w2, np.nan)
+    gb2 = np.full(w2.shape[0], np.nan, np.float32)
+    sp = _capi.ptr_array([s.ctypes.data for s in srcs])
+    gp = _capi.ptr_array([g.ctypes.data for g in gs])
+    _capi.check(L, L.uno_project_bwd(C.byref(d), _p(gout), sp, _p(w1), _p(b1), _p(w2), gp, _p(gw1), _p(gb1), _p(gw2), _p(gb2), None))
+    return gs, gw1, gb1, gw2, gb2

@@ -29,11 +29,25 @@ class BlockDesc(C.Structure):
     _fields_ = [("conv", ConvDesc), ("normalize", C.c_int), ("non_lin", C.c_int), ("eps", C.c_float)]
 
 
+class PixelDesc(C.Structure):
+    _fields_ = [("ndim", C.c_int), ("batch", C.c_int), ("dim", C.c_int * 3), ("pad_lo", C.c_int * 3), ("pad_hi", C.c_int * 3)]
+
+
+class LiftDesc(C.Structure):
+    _fields_ = [("px", PixelDesc), ("raw_ch", C.c_int), ("grid_ch", C.c_int), ("hidden", C.c_int), ("out_ch", C.c_int)]
+
+
+class ProjectDesc(C.Structure):
+    _fields_ = [("px", PixelDesc), ("nsrc", C.c_int), ("src_ch", C.c_int * 4), ("hidden", C.c_int), ("out_ch", C.c_int)]
+
+
 # every symbol include/uno_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _DESC = C.POINTER(ConvDesc)
 _BDESC = C.POINTER(BlockDesc)
 _PP = C.POINTER(C.c_void_p)
+_LDESC = C.POINTER(LiftDesc)
+_PDESC = C.POINTER(ProjectDesc)
 SYMBOLS = {
     "uno_last_error": (C.c_char_p, []),
     "uno_version": (C.c_int, []),
@@ -54,6 +68,12 @@ SYMBOLS = {
         C.c_int,
         [_BDESC, _P, _P, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P, C.c_size_t, _P],
     ),
+    "uno_lift_check": (C.c_int, [_LDESC]),
+    "uno_lift_fwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "uno_lift_bwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "uno_project_check": (C.c_int, [_PDESC]),
+    "uno_project_fwd": (C.c_int, [_PDESC, _PP, _P, _P, _P, _P, _P, _P]),
+    "uno_project_bwd": (C.c_int, [_PDESC, _P, _PP, _P, _P, _P, _PP, _P, _P, _P, _P, _P]),
     "uno_launch_count": (C.c_long, []),
     "uno_profile_enable": (None, [C.c_int]),
     "uno_profile_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),
@@ -92,6 +112,33 @@ def block_desc(conv: ConvDesc, normalize: bool, non_lin: bool, eps: float = 1e-5
     b.conv = conv
     b.normalize, b.non_lin, b.eps = int(bool(normalize)), int(bool(non_lin)), float(eps)
     return b
+
+
+def pixel_desc(batch: int, dims: Sequence[int], pad_lo: Sequence[int], pad_hi: Sequence[int]) -> PixelDesc:
+    p = PixelDesc()
+    p.ndim, p.batch = len(dims), int(batch)
+    for a in range(3):
+        p.dim[a] = int(dims[a]) if a < len(dims) else 1
+        p.pad_lo[a] = int(pad_lo[a]) if a < len(dims) else 0
+        p.pad_hi[a] = int(pad_hi[a]) if a < len(dims) else 0
+    return p
+
+
+def lift_desc(batch, dims, pad_lo, pad_hi, raw_ch, grid_ch, hidden, out_ch) -> LiftDesc:
+    d = LiftDesc()
+    d.px = pixel_desc(batch, dims, pad_lo, pad_hi)
+    d.raw_ch, d.grid_ch, d.hidden, d.out_ch = int(raw_ch), int(grid_ch), int(hidden), int(out_ch)
+    return d
+
+
+def project_desc(batch, dims, pad_lo, pad_hi, src_ch: Sequence[int], hidden, out_ch) -> ProjectDesc:
+    d = ProjectDesc()
+    d.px = pixel_desc(batch, dims, pad_lo, pad_hi)
+    d.nsrc = len(src_ch)
+    for i in range(4):
+        d.src_ch[i] = int(src_ch[i]) if i < len(src_ch) else 0
+    d.hidden, d.out_ch = int(hidden), int(out_ch)
+    return d
 
 
 def ptr_array(ptrs: Sequence[int]):

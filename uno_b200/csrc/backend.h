@@ -115,4 +115,39 @@ int be_channel_sum(const float* x, float* out, long planes, int C, long L, float
 // y[p, :] += v[p % C] * alpha
 int be_add_channel_const(float* y, const float* v, float alpha, long planes, int C, long L, stream_t s);
 
+// ---- model glue around the blocks: per-pixel MLPs, fused -----------------
+// Pixels live on up to three spatial axes; a "raw" grid n[] sits at offset lo[] inside a zero-padded grid N[]
+// (2-D callers pass n[0] = N[0] = 1).  Channels-last tensors: a [B, n.., raw_ch], grid [n.., grid_ch],
+// out [B, n.., out_ch]; channels-first tensors: h / src / gsrc [B, C, N..].
+//
+// lift:    h = pad( gelu( W_b * gelu( W_a * [a ; grid] + b_a ) + b_b ) )      W_a [hid, raw_ch+grid_ch], W_b [out_ch, hid]
+// project: out = W_2 * gelu( W_1 * crop(cat(src_0, src_1, ..)) + b_1 ) + b_2  W_1 [hid, sum src_ch],     W_2 [out_ch, hid]
+struct LiftArgs {
+    int batch = 0, n[3] = {1, 1, 1}, N[3] = {1, 1, 1}, lo[3] = {0, 0, 0};
+    int raw_ch = 0, grid_ch = 0, hid = 0, out_ch = 0;
+    const float* a = nullptr; const float* grid = nullptr;
+    const float* w_a = nullptr; const float* b_a = nullptr; const float* w_b = nullptr; const float* b_b = nullptr;
+    float* h = nullptr;                 // fwd output
+    const float* gh = nullptr;          // bwd input  [B, out_ch, N..]
+    float* ga = nullptr;                // bwd output [B, n.., raw_ch] (optional)
+    float* gw_a = nullptr; float* gb_a = nullptr; float* gw_b = nullptr; float* gb_b = nullptr;   // bwd outputs, PRE-ZEROED (accumulated with atomics)
+};
+int be_lift_supported(const LiftArgs& a);   // 1 if the kernels take this shape
+int be_lift_fwd(const LiftArgs& a, stream_t s);
+int be_lift_bwd(const LiftArgs& a, stream_t s);
+
+struct ProjArgs {
+    int batch = 0, n[3] = {1, 1, 1}, N[3] = {1, 1, 1}, lo[3] = {0, 0, 0};
+    int nsrc = 0, src_ch[4] = {0, 0, 0, 0}, hid = 0, out_ch = 0;
+    const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
+    const float* w1 = nullptr; const float* b1 = nullptr; const float* w2 = nullptr; const float* b2 = nullptr;
+    float* out = nullptr;               // fwd output [B, n.., out_ch]
+    const float* gout = nullptr;        // bwd input
+    float* gsrc[4] = {nullptr, nullptr, nullptr, nullptr};   // bwd outputs [B, src_ch, N..], fully written (zero outside the crop)
+    float* gw1 = nullptr; float* gb1 = nullptr; float* gw2 = nullptr; float* gb2 = nullptr;       // bwd outputs, PRE-ZEROED
+};
+int be_proj_supported(const ProjArgs& a);
+int be_proj_fwd(const ProjArgs& a, stream_t s);
+int be_proj_bwd(const ProjArgs& a, stream_t s);
+
 }  // namespace uno

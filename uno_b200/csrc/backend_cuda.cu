@@ -12,6 +12,7 @@
 // the GEMM-shaped stages live in gemm_tc.cuh and are selected by be_gemm when the shape qualifies.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -598,6 +599,8 @@ inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
     return (unsigned)g;
 }
 
+#include "pixel_mlp.cuh"
+
 
 // =====================================================================================================
 // tensor-core path: host-side operand images and dispatch
@@ -1121,6 +1124,151 @@ int be_add_channel_const(float* y, const float* v, float alpha, long planes, int
     add_channel_const_kernel<<<dim3((unsigned)planes, gx), 256, 0, S(s)>>>(y, v, alpha, C, L);
     CU_LAUNCH_CHECK();
     return 0;
+}
+
+// =====================================================================================================
+// model glue: fused lift / projection MLPs (pixel_mlp.cuh)
+// =====================================================================================================
+namespace {
+
+PixGeom pix_geom(const int* n, const int* N, const int* lo) {
+    PixGeom g;
+    g.n0 = n[0]; g.n1 = n[1]; g.n2 = n[2];
+    g.N0 = N[0]; g.N1 = N[1]; g.N2 = N[2];
+    g.lo0 = lo[0]; g.lo1 = lo[1]; g.lo2 = lo[2];
+    g.nraw = (long)n[0] * n[1] * n[2];
+    g.npad = (long)N[0] * N[1] * N[2];
+    return g;
+}
+
+LiftK lift_k(const LiftArgs& a) {
+    LiftK k;
+    k.g = pix_geom(a.n, a.N, a.lo);
+    k.batch = a.batch; k.raw_ch = a.raw_ch; k.grid_ch = a.grid_ch; k.cin = a.raw_ch + a.grid_ch; k.hid = a.hid; k.out_ch = a.out_ch;
+    k.a = a.a; k.grid = a.grid; k.w_a = a.w_a; k.b_a = a.b_a; k.w_b = a.w_b; k.b_b = a.b_b;
+    k.h = a.h; k.gh = a.gh; k.ga = a.ga; k.gw_a = a.gw_a; k.gb_a = a.gb_a; k.gw_b = a.gw_b; k.gb_b = a.gb_b;
+    return k;
+}
+
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+    // raise the dynamic shared-memory limit of this instantiation (idempotent, cheap)
+    if (bytes <= 48 * 1024) return 0;
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+template <int CIN, int HID>
+int launch_lift(const LiftK& k, bool bwd, cudaStream_t st) {
+    if (!bwd) {
+        const size_t smem = lift_fwd_smem(CIN, HID, k.out_ch);
+        int rc = ensure_smem(lift_fwd_kernel<CIN, HID>, smem);
+        if (rc) return rc;
+        const long total = (long)k.batch * k.g.npad;
+        const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
+        lift_fwd_kernel<CIN, HID><<<grid, kPixTP, smem, st>>>(k);
+    } else {
+        const size_t smem = lift_bwd_smem(CIN, HID, k.out_ch);
+        int rc = ensure_smem(lift_bwd_kernel<CIN, HID>, smem);
+        if (rc) return rc;
+        const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
+        const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * per_sm);
+        lift_bwd_kernel<CIN, HID><<<grid, kPixTP, smem, st>>>(k, ntiles);
+    }
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+int dispatch_lift(const LiftK& k, bool bwd, cudaStream_t st) {
+    const int ci = k.cin <= 4 ? 0 : (k.cin <= 8 ? 1 : 2);
+    const int hi = k.hid <= 16 ? 0 : 1;
+    switch (ci * 2 + hi) {
+        case 0: return launch_lift<4, 16>(k, bwd, st);
+        case 1: return launch_lift<4, 32>(k, bwd, st);
+        case 2: return launch_lift<8, 16>(k, bwd, st);
+        case 3: return launch_lift<8, 32>(k, bwd, st);
+        case 4: return launch_lift<16, 16>(k, bwd, st);
+        default: return launch_lift<16, 32>(k, bwd, st);
+    }
+}
+
+ProjK proj_k(const ProjArgs& a) {
+    ProjK k;
+    k.g = pix_geom(a.n, a.N, a.lo);
+    k.batch = a.batch; k.nsrc = a.nsrc; k.hid = a.hid; k.out_ch = a.out_ch;
+    k.ctot = 0;
+    for (int s = 0; s < 4; ++s) {
+        k.src[s] = s < a.nsrc ? a.src[s] : nullptr;
+        k.gsrc[s] = s < a.nsrc ? a.gsrc[s] : nullptr;
+        k.src_ch[s] = s < a.nsrc ? a.src_ch[s] : 0;
+        k.ctot += k.src_ch[s];
+    }
+    k.w1 = a.w1; k.b1 = a.b1; k.w2 = a.w2; k.b2 = a.b2; k.out = a.out; k.gout = a.gout;
+    k.gw1 = a.gw1; k.gb1 = a.gb1; k.gw2 = a.gw2; k.gb2 = a.gb2;
+    return k;
+}
+
+template <int CT>
+int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
+    if (!bwd) {
+        const size_t smem = proj_fwd_smem(CT, k.hid, k.out_ch);
+        int rc = ensure_smem(proj_fwd_kernel<CT>, smem);
+        if (rc) return rc;
+        const long total = (long)k.batch * k.g.nraw;
+        const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
+        proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k);
+    } else {
+        const size_t smem = proj_bwd_smem(CT, k.hid, k.out_ch);
+        int rc = ensure_smem(proj_bwd_kernel<CT>, smem);
+        if (rc) return rc;
+        const long ntiles = ((long)k.batch * k.g.npad + kPixTP - 1) / kPixTP;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * (smem > 110 * 1024 ? 1 : 2));
+        proj_bwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
+    }
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int be_lift_supported(const LiftArgs& a) {
+    const int cin = a.raw_ch + a.grid_ch;
+    return a.raw_ch >= 1 && a.grid_ch >= 0 && cin <= 16 && a.hid >= 1 && a.hid <= 32 && a.out_ch >= 1 && a.out_ch <= 64;
+}
+int be_lift_fwd(const LiftArgs& a, stream_t s) {
+    if (!be_lift_supported(a)) return (int)cudaErrorInvalidValue;
+    const LiftK k = lift_k(a);
+    const double px = (double)a.batch * k.g.nraw, ppx = (double)a.batch * k.g.npad;
+    ProfScope ps("lift_fwd", 4.0 * (px * a.raw_ch + ppx * a.out_ch), 2.0 * px * (k.cin * a.hid + a.hid * a.out_ch), S(s));
+    return dispatch_lift(k, false, S(s));
+}
+int be_lift_bwd(const LiftArgs& a, stream_t s) {
+    if (!be_lift_supported(a)) return (int)cudaErrorInvalidValue;
+    const LiftK k = lift_k(a);
+    const double px = (double)a.batch * k.g.nraw;
+    ProfScope ps("lift_bwd", 4.0 * px * (a.raw_ch * (a.ga ? 2 : 1) + a.out_ch), 2.0 * px * (2 * k.cin * a.hid + 3 * a.hid * a.out_ch), S(s));
+    return dispatch_lift(k, true, S(s));
+}
+
+int be_proj_supported(const ProjArgs& a) {
+    int ctot = 0;
+    if (a.nsrc < 1 || a.nsrc > 4) return 0;
+    for (int s = 0; s < a.nsrc; ++s) { if (a.src_ch[s] < 1) return 0; ctot += a.src_ch[s]; }
+    return ctot <= 64 && a.hid >= 1 && a.hid <= 128 && a.out_ch >= 1 && a.out_ch <= kProjMaxOut;
+}
+int be_proj_fwd(const ProjArgs& a, stream_t s) {
+    if (!be_proj_supported(a)) return (int)cudaErrorInvalidValue;
+    const ProjK k = proj_k(a);
+    const double px = (double)a.batch * k.g.nraw;
+    ProfScope ps("project_fwd", 4.0 * px * (k.ctot + a.out_ch), 2.0 * px * (k.ctot * a.hid + a.hid * a.out_ch), S(s));
+    return k.ctot <= 32 ? launch_proj<32>(k, false, S(s)) : launch_proj<64>(k, false, S(s));
+}
+int be_proj_bwd(const ProjArgs& a, stream_t s) {
+    if (!be_proj_supported(a)) return (int)cudaErrorInvalidValue;
+    const ProjK k = proj_k(a);
+    const double px = (double)a.batch * k.g.nraw, ppx = (double)a.batch * k.g.npad;
+    ProfScope ps("project_bwd", 4.0 * (px * (k.ctot + a.out_ch) + ppx * k.ctot), 2.0 * px * (3 * k.ctot * a.hid + 2 * a.hid * a.out_ch), S(s));
+    return k.ctot <= 32 ? launch_proj<32>(k, true, S(s)) : launch_proj<64>(k, true, S(s));
 }
 
 }  // namespace uno

@@ -1,0 +1,528 @@
+// Fused per-pixel MLP kernels for the model glue around the operator blocks.
+// Included by backend_cuda.cu inside namespace uno::{anonymous}, after gelu_f / gelu_grad_f.
+//
+//   lift    (darcy_flow_uno2d.py:96-107, navier_stokes_uno2d.py:191-201, navier_stokes_uno3d.py:497-511)
+//           cat(a, grid) -> Linear -> GELU -> Linear -> GELU -> permute to channels-first -> zero pad
+//           x is read once (channels-last), h written once (channels-first, padded); nothing else touches HBM.
+//   project (darcy_flow_uno2d.py:121-131, navier_stokes_uno2d.py:215-225, navier_stokes_uno3d.py:551-575)
+//           cat(src_0, src_1, ..) -> crop -> permute to channels-last -> Linear -> GELU -> Linear
+//           the concatenated / cropped / permuted tensors are never materialised.
+//
+// Backward kernels recompute the hidden activations from the inputs (nothing is saved by forward), write the
+// input gradients, and reduce the weight gradients over pixels in two levels: a 256-pixel tile is staged in
+// shared memory and contracted by all threads ("phase 2", a [rows x 256] * [256 x cols] product), accumulated
+// in shared memory across the tiles of a persistent CTA, then flushed with one atomicAdd per element per CTA.
+//
+// Bound: fwd kernels are HBM-bound (lift writes 4*out_ch B/pixel, project reads 4*sum(src_ch) B/pixel);
+// the backward kernels are fp32-FMA-bound on the SIMT pipes (3x the forward MACs).
+#pragma once
+
+struct PixGeom {
+    int n0, n1, n2;      // raw grid
+    int N0, N1, N2;      // padded grid
+    int lo0, lo1, lo2;   // raw origin inside the padded grid
+    long nraw, npad;     // pixels per sample
+};
+
+constexpr int kPixTP = 256;        // pixels per tile = threads per CTA
+constexpr int kPixTPP = 260;       // padded row pitch of the staging buffers (floats, multiple of 4)
+constexpr int kProjHC = 64;        // hidden units staged per phase-2 round of the projection backward
+
+__device__ __forceinline__ void gelu_both(float x, float& act, float& grad) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    act = x * cdf;
+    grad = fmaf(x * 0.39894228040143267794f, expf(-0.5f * x * x), cdf);
+}
+
+__device__ __forceinline__ float dot_tile(const float* __restrict__ r, const float* __restrict__ c) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < kPixTP; p += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(r + p);
+        const float4 b = *reinterpret_cast<const float4*>(c + p);
+        s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float sum_tile(const float* __restrict__ r) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < kPixTP; p += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(r + p);
+        s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__host__ __device__ inline int round4(int n) { return (n + 3) & ~3; }
+
+// =====================================================================================================
+// lift
+// =====================================================================================================
+struct LiftK {
+    PixGeom g;
+    int batch, raw_ch, grid_ch, cin, hid, out_ch;
+    const float *a, *grid, *w_a, *b_a, *w_b, *b_b;
+    float* h;
+    const float* gh;
+    float *ga, *gw_a, *gb_a, *gw_b, *gb_b;
+};
+
+// weights into shared memory, zero-padded to the template sizes (padded hidden units output gelu(0) = 0)
+template <int CIN, int HID>
+__device__ __forceinline__ void lift_stage_weights(const LiftK& k, float* sWa, float* sba, float* sWb, float* sbb) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < HID * CIN; i += kPixTP) {
+        const int kk = i / CIN, ci = i % CIN;
+        sWa[i] = (kk < k.hid && ci < k.cin) ? __ldg(k.w_a + kk * k.cin + ci) : 0.f;
+    }
+    for (int i = tid; i < HID; i += kPixTP) sba[i] = i < k.hid ? __ldg(k.b_a + i) : 0.f;
+    for (int i = tid; i < k.out_ch * HID; i += kPixTP) {
+        const int c = i / HID, kk = i % HID;
+        sWb[i] = kk < k.hid ? __ldg(k.w_b + c * k.hid + kk) : 0.f;
+    }
+    for (int i = tid; i < k.out_ch; i += kPixTP) sbb[i] = __ldg(k.b_b + i);
+}
+
+template <int CIN>
+__device__ __forceinline__ void lift_load_in(const LiftK& k, long b, long rpix, bool valid, float (&in)[CIN]) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        float v = 0.f;
+        if (valid) {
+            if (ci < k.raw_ch) v = __ldg(k.a + (b * k.g.nraw + rpix) * k.raw_ch + ci);
+            else if (ci < k.cin) v = __ldg(k.grid + rpix * k.grid_ch + (ci - k.raw_ch));
+        }
+        in[ci] = v;
+    }
+}
+
+template <int CIN, int HID>
+__device__ __forceinline__ void lift_first_layer(const float* sWa, const float* sba, const float (&in)[CIN], float (&pre0)[HID]) {
+#pragma unroll
+    for (int kk = 0; kk < HID; ++kk) {
+        float acc = sba[kk];
+        const float4* w4 = reinterpret_cast<const float4*>(sWa + kk * CIN);
+#pragma unroll
+        for (int q = 0; q < CIN / 4; ++q) {
+            const float4 w = w4[q];
+            acc = fmaf(w.x, in[4 * q + 0], acc);
+            acc = fmaf(w.y, in[4 * q + 1], acc);
+            acc = fmaf(w.z, in[4 * q + 2], acc);
+            acc = fmaf(w.w, in[4 * q + 3], acc);
+        }
+        pre0[kk] = acc;
+    }
+}
+
+template <int HID>
+__device__ __forceinline__ float lift_second_layer_row(const float* sWb_row, float bias, const float (&a0)[HID]) {
+    float acc0 = bias, acc1 = 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(sWb_row);
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+        const float4 w = w4[q];
+        acc0 = fmaf(w.x, a0[4 * q + 0], acc0);
+        acc1 = fmaf(w.y, a0[4 * q + 1], acc1);
+        acc0 = fmaf(w.z, a0[4 * q + 2], acc0);
+        acc1 = fmaf(w.w, a0[4 * q + 3], acc1);
+    }
+    return acc0 + acc1;
+}
+
+template <int CIN, int HID>
+__global__ void __launch_bounds__(kPixTP) lift_fwd_kernel(const LiftK k) {
+    extern __shared__ __align__(16) float psm[];
+    float* sWa = psm;                         // [HID][CIN]
+    float* sba = sWa + HID * CIN;             // [HID]
+    float* sWb = sba + HID;                   // [out_ch][HID]
+    float* sbb = sWb + round4(k.out_ch) * HID;
+    lift_stage_weights<CIN, HID>(k, sWa, sba, sWb, sbb);
+    __syncthreads();
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.npad;
+    for (long idx = (long)blockIdx.x * kPixTP + threadIdx.x; idx < total; idx += (long)gridDim.x * kPixTP) {
+        const long b = idx / g.npad;
+        const long pp = idx - b * g.npad;
+        const int i2 = (int)(pp % g.N2);
+        const long t = pp / g.N2;
+        const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
+        const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
+        const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
+        float* hp = k.h + b * k.out_ch * g.npad + pp;
+        if (inside) {
+            const long rpix = ((long)r0 * g.n1 + r1) * g.n2 + r2;
+            float in[CIN], a0[HID];
+            lift_load_in<CIN>(k, b, rpix, true, in);
+            lift_first_layer<CIN, HID>(sWa, sba, in, a0);
+#pragma unroll
+            for (int kk = 0; kk < HID; ++kk) a0[kk] = gelu_f(a0[kk]);
+            for (int c = 0; c < k.out_ch; ++c)
+                hp[(long)c * g.npad] = gelu_f(lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0));
+        } else {
+            for (int c = 0; c < k.out_ch; ++c) hp[(long)c * g.npad] = 0.f;
+        }
+    }
+}
+
+inline size_t lift_fwd_smem(int CIN, int HID, int out_ch) {
+    return sizeof(float) * (size_t)(HID * CIN + HID + round4(out_ch) * HID + round4(out_ch));
+}
+
+template <int CIN, int HID>
+__global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long ntiles) {
+    extern __shared__ __align__(16) float psm[];
+    const int OC4 = round4(k.out_ch);
+    float* sWa = psm;                         // [HID][CIN]
+    float* sba = sWa + HID * CIN;             // [HID]
+    float* sWb = sba + HID;                   // [out_ch][HID]
+    float* sbb = sWb + OC4 * HID;             // [out_ch]
+    float* accWa = sbb + OC4;                 // same shapes, gradient accumulators
+    float* accba = accWa + HID * CIN;
+    float* accWb = accba + HID;
+    float* accbb = accWb + OC4 * HID;
+    float* D1 = accbb + OC4;                  // [out_ch][TPP]  dL/dpre1
+    float* A0 = D1 + (size_t)OC4 * kPixTPP;   // [HID][TPP]     hidden activations
+    float* D0 = A0 + HID * kPixTPP;           // [HID][TPP]     dL/dpre0
+    float* IN = D0 + HID * kPixTPP;           // [CIN][TPP]     layer-0 inputs
+    const int tid = threadIdx.x;
+    lift_stage_weights<CIN, HID>(k, sWa, sba, sWb, sbb);
+    for (int i = tid; i < HID * CIN + HID + OC4 * HID + OC4; i += kPixTP) accWa[i] = 0.f;
+    __syncthreads();
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.nraw;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long idx = tile * kPixTP + tid;
+        const bool valid = idx < total;
+        const long b = valid ? idx / g.nraw : 0;
+        const long rp = valid ? idx - b * g.nraw : 0;
+        const int r2 = (int)(rp % g.n2);
+        const long t = rp / g.n2;
+        const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
+        const long pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
+        float in[CIN], a0[HID], gp0[HID], da0[HID];
+        lift_load_in<CIN>(k, b, rp, valid, in);
+        lift_first_layer<CIN, HID>(sWa, sba, in, a0);
+#pragma unroll
+        for (int kk = 0; kk < HID; ++kk) {
+            float act, grad;
+            gelu_both(a0[kk], act, grad);
+            a0[kk] = act; gp0[kk] = grad; da0[kk] = 0.f;
+        }
+        const float* ghp = k.gh + b * k.out_ch * g.npad + pp;
+        for (int c = 0; c < k.out_ch; ++c) {
+            const float pre1 = lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0);
+            const float gv = valid ? __ldg(ghp + (long)c * g.npad) : 0.f;
+            const float d1 = gv * gelu_grad_f(pre1);
+            D1[c * kPixTPP + tid] = d1;
+            const float4* w4 = reinterpret_cast<const float4*>(sWb + c * HID);
+#pragma unroll
+            for (int q = 0; q < HID / 4; ++q) {
+                const float4 w = w4[q];
+                da0[4 * q + 0] = fmaf(w.x, d1, da0[4 * q + 0]);
+                da0[4 * q + 1] = fmaf(w.y, d1, da0[4 * q + 1]);
+                da0[4 * q + 2] = fmaf(w.z, d1, da0[4 * q + 2]);
+                da0[4 * q + 3] = fmaf(w.w, d1, da0[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < HID; ++kk) {
+            da0[kk] *= gp0[kk];                       // dL/dpre0
+            D0[kk * kPixTPP + tid] = da0[kk];
+            A0[kk * kPixTPP + tid] = a0[kk];
+        }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) IN[ci * kPixTPP + tid] = in[ci];
+        if (k.ga != nullptr && valid) {
+            float* gap = k.ga + (b * g.nraw + rp) * k.raw_ch;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+                if (ci < k.raw_ch) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < HID; ++kk) s = fmaf(sWa[kk * CIN + ci], da0[kk], s);
+                    gap[ci] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: contract the staged tile over its 256 pixels
+        for (int e = tid; e < k.out_ch * HID; e += kPixTP) {
+            const int c = e / HID, kk = e % HID;
+            accWb[e] += dot_tile(D1 + c * kPixTPP, A0 + kk * kPixTPP);
+        }
+        for (int e = tid; e < HID * CIN; e += kPixTP) {
+            const int kk = e / CIN, ci = e % CIN;
+            accWa[e] += dot_tile(D0 + kk * kPixTPP, IN + ci * kPixTPP);
+        }
+        if (tid < k.out_ch) accbb[tid] += sum_tile(D1 + tid * kPixTPP);
+        else if (tid >= 128 && tid < 128 + HID) accba[tid - 128] += sum_tile(D0 + (tid - 128) * kPixTPP);
+        __syncthreads();
+    }
+    // ---- flush: one atomic per element per CTA
+    for (int e = tid; e < k.out_ch * HID; e += kPixTP) {
+        const int c = e / HID, kk = e % HID;
+        if (kk < k.hid) atomicAdd(k.gw_b + c * k.hid + kk, accWb[e]);
+    }
+    for (int e = tid; e < HID * CIN; e += kPixTP) {
+        const int kk = e / CIN, ci = e % CIN;
+        if (kk < k.hid && ci < k.cin) atomicAdd(k.gw_a + kk * k.cin + ci, accWa[e]);
+    }
+    for (int e = tid; e < k.out_ch; e += kPixTP) atomicAdd(k.gb_b + e, accbb[e]);
+    for (int e = tid; e < k.hid; e += kPixTP) atomicAdd(k.gb_a + e, accba[e]);
+}
+
+inline size_t lift_bwd_smem(int CIN, int HID, int out_ch) {
+    const int OC4 = round4(out_ch);
+    return sizeof(float) * ((size_t)2 * (HID * CIN + HID + OC4 * HID + OC4) + (size_t)(OC4 + 2 * HID + CIN) * kPixTPP);
+}
+
+// =====================================================================================================
+// project
+// =====================================================================================================
+struct ProjK {
+    PixGeom g;
+    int batch, nsrc, ctot, hid, out_ch;
+    const float* src[4];
+    float* gsrc[4];
+    int src_ch[4];
+    const float *w1, *b1, *w2, *b2;
+    float* out;
+    const float* gout;
+    float *gw1, *gb1, *gw2, *gb2;
+};
+constexpr int kProjMaxOut = 4;
+
+// per-channel base pointers (channel c of the virtual concatenation) and batch strides
+template <int CT>
+__device__ __forceinline__ void proj_stage_tables(const ProjK& k, const float** sbase, float** gbase, long* sstride) {
+    for (int c = threadIdx.x; c < CT; c += kPixTP) {
+        int s = 0, cl = c;
+        while (s < k.nsrc && cl >= k.src_ch[s]) { cl -= k.src_ch[s]; ++s; }
+        if (s < k.nsrc) {
+            sbase[c] = k.src[s] + (long)cl * k.g.npad;
+            gbase[c] = k.gsrc[s] ? k.gsrc[s] + (long)cl * k.g.npad : nullptr;
+            sstride[c] = (long)k.src_ch[s] * k.g.npad;
+        } else {
+            sbase[c] = nullptr; gbase[c] = nullptr; sstride[c] = 0;
+        }
+    }
+}
+
+template <int CT>
+__device__ __forceinline__ void proj_stage_weights(const ProjK& k, float* sW1, float* sb1, float* sW2, float* sb2) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < k.hid * CT; i += kPixTP) {
+        const int n = i / CT, c = i % CT;
+        sW1[i] = c < k.ctot ? __ldg(k.w1 + n * k.ctot + c) : 0.f;
+    }
+    for (int i = tid; i < k.hid; i += kPixTP) sb1[i] = __ldg(k.b1 + i);
+    for (int i = tid; i < k.out_ch * k.hid; i += kPixTP) sW2[i] = __ldg(k.w2 + i);
+    if (sb2) for (int i = tid; i < k.out_ch; i += kPixTP) sb2[i] = __ldg(k.b2 + i);
+}
+
+template <int CT>
+__device__ __forceinline__ float proj_hidden_row(const float* sW1_row, float bias, const float (&in)[CT]) {
+    float acc0 = bias, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    const float4* w4 = reinterpret_cast<const float4*>(sW1_row);
+#pragma unroll
+    for (int q = 0; q < CT / 4; ++q) {
+        const float4 w = w4[q];
+        acc0 = fmaf(w.x, in[4 * q + 0], acc0);
+        acc1 = fmaf(w.y, in[4 * q + 1], acc1);
+        acc2 = fmaf(w.z, in[4 * q + 2], acc2);
+        acc3 = fmaf(w.w, in[4 * q + 3], acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+}
+
+inline size_t proj_table_bytes(int CT) { return (size_t)CT * (2 * sizeof(void*) + sizeof(long)); }
+
+template <int CT>
+__global__ void __launch_bounds__(kPixTP) proj_fwd_kernel(const ProjK k) {
+    extern __shared__ __align__(16) float psm[];
+    const float** sbase = reinterpret_cast<const float**>(psm);
+    float** gbase = reinterpret_cast<float**>(psm) + CT;
+    long* sstride = reinterpret_cast<long*>(gbase + CT);
+    float* sW1 = reinterpret_cast<float*>(sstride + CT);   // [hid][CT]
+    float* sb1 = sW1 + (size_t)k.hid * CT;                 // [hid]
+    float* sW2 = sb1 + round4(k.hid);                      // [out_ch][hid]
+    float* sb2 = sW2 + round4(k.out_ch * k.hid);           // [out_ch]
+    proj_stage_tables<CT>(k, sbase, gbase, sstride);
+    proj_stage_weights<CT>(k, sW1, sb1, sW2, sb2);
+    __syncthreads();
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.nraw;
+    for (long idx = (long)blockIdx.x * kPixTP + threadIdx.x; idx < total; idx += (long)gridDim.x * kPixTP) {
+        const long b = idx / g.nraw;
+        const long rp = idx - b * g.nraw;
+        const int r2 = (int)(rp % g.n2);
+        const long t = rp / g.n2;
+        const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
+        const long pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
+        float in[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) in[c] = c < k.ctot ? __ldg(sbase[c] + b * sstride[c] + pp) : 0.f;
+        float o[kProjMaxOut];
+#pragma unroll
+        for (int q = 0; q < kProjMaxOut; ++q) o[q] = 0.f;
+        for (int n = 0; n < k.hid; ++n) {
+            const float a = gelu_f(proj_hidden_row<CT>(sW1 + (size_t)n * CT, sb1[n], in));
+#pragma unroll
+            for (int q = 0; q < kProjMaxOut; ++q)
+                if (q < k.out_ch) o[q] = fmaf(sW2[q * k.hid + n], a, o[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < kProjMaxOut; ++q)
+            if (q < k.out_ch) k.out[idx * k.out_ch + q] = o[q] + sb2[q];
+    }
+}
+
+inline size_t proj_fwd_smem(int CT, int hid, int out_ch) {
+    return proj_table_bytes(CT) + sizeof(float) * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid) + round4(out_ch));
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long ntiles) {
+    extern __shared__ __align__(16) float psm[];
+    const float** sbase = reinterpret_cast<const float**>(psm);
+    float** gbase = reinterpret_cast<float**>(psm) + CT;
+    long* sstride = reinterpret_cast<long*>(gbase + CT);
+    const int H4 = round4(k.hid), OH4 = round4(k.out_ch * k.hid);
+    float* sW1 = reinterpret_cast<float*>(sstride + CT);   // [hid][CT]
+    float* sb1 = sW1 + (size_t)k.hid * CT;                 // [hid]
+    float* sW2 = sb1 + H4;                                 // [out_ch][hid]
+    float* accW1 = sW2 + OH4;                              // gradient accumulators, same shapes
+    float* accb1 = accW1 + (size_t)k.hid * CT;
+    float* accW2 = accb1 + H4;
+    float* accb2 = accW2 + OH4;                            // [4]
+    float* D = accb2 + 4;                                  // [kProjHC][TPP]  dL/dpre1 of the current hidden chunk
+    float* IN = D + (size_t)kProjHC * kPixTPP;             // [CT][TPP]       cropped inputs
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    proj_stage_tables<CT>(k, sbase, gbase, sstride);
+    proj_stage_weights<CT>(k, sW1, sb1, sW2, nullptr);
+    for (int i = tid; i < k.hid * CT + H4 + OH4 + 4; i += kPixTP) accW1[i] = 0.f;
+    __syncthreads();
+    // phase-2 thread map: a warp owns an 8 (hidden) x 32 (channel) patch, a thread 2 x 4 of it
+    constexpr int WC = CT / 32, WN = 8 / WC, RN = 8 * WN;
+    const int c_l = lane & 7, n_l = lane >> 3;
+    const int cbase = (warp % WC) * 32, nwarp = (warp / WC) * 8;
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.npad;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long idx = tile * kPixTP + tid;
+        const bool inb = idx < total;
+        const long b = inb ? idx / g.npad : 0;
+        const long pp = inb ? idx - b * g.npad : 0;
+        const int i2 = (int)(pp % g.N2);
+        const long t = pp / g.N2;
+        const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
+        const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
+        const bool valid = inb && (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
+        const long rp = ((long)r0 * g.n1 + r1) * g.n2 + r2;
+        float in[CT], din[CT], go[kProjMaxOut];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            in[c] = (valid && c < k.ctot) ? __ldg(sbase[c] + b * sstride[c] + pp) : 0.f;
+            din[c] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < kProjMaxOut; ++q) go[q] = (valid && q < k.out_ch) ? __ldg(k.gout + (b * g.nraw + rp) * k.out_ch + q) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) IN[c * kPixTPP + tid] = in[c];
+        for (int ch0 = 0; ch0 < k.hid; ch0 += kProjHC) {
+            const int nn = min(kProjHC, k.hid - ch0);
+            for (int j = 0; j < nn; ++j) {
+                const int n = ch0 + j;
+                const float* wrow = sW1 + (size_t)n * CT;
+                float a, gp;
+                gelu_both(proj_hidden_row<CT>(wrow, sb1[n], in), a, gp);
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < kProjMaxOut; ++q)
+                    if (q < k.out_ch) {
+                        s = fmaf(go[q], sW2[q * k.hid + n], s);
+                        const float v = warp_sum(go[q] * a);          // dW2[q][n] partial over the warp's 32 pixels
+                        if (lane == 0) atomicAdd(accW2 + q * k.hid + n, v);
+                    }
+                const float dp = s * gp;
+                D[j * kPixTPP + tid] = dp;
+                const float4* w4 = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+                for (int q = 0; q < CT / 4; ++q) {
+                    const float4 w = w4[q];
+                    din[4 * q + 0] = fmaf(w.x, dp, din[4 * q + 0]);
+                    din[4 * q + 1] = fmaf(w.y, dp, din[4 * q + 1]);
+                    din[4 * q + 2] = fmaf(w.z, dp, din[4 * q + 2]);
+                    din[4 * q + 3] = fmaf(w.w, dp, din[4 * q + 3]);
+                }
+            }
+            __syncthreads();
+            // ---- phase 2: dW1[ch0 + r][c] += sum_p D[r][p] * IN[c][p]
+            for (int n0 = 0; n0 < nn; n0 += RN) {
+                const int nb = n0 + nwarp;
+                if (nb < nn) {
+                    float acc[2][4];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+                    const float* drow0 = D + (size_t)(nb + n_l) * kPixTPP;
+                    const float* drow1 = D + (size_t)(nb + n_l + 4) * kPixTPP;
+                    const float* icol = IN + (size_t)(cbase + c_l) * kPixTPP;
+#pragma unroll 2
+                    for (int p = 0; p < kPixTP; p += 4) {
+                        const float4 d0 = *reinterpret_cast<const float4*>(drow0 + p);
+                        const float4 d1 = *reinterpret_cast<const float4*>(drow1 + p);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 x = *reinterpret_cast<const float4*>(icol + (size_t)(8 * j) * kPixTPP + p);
+                            acc[0][j] = fmaf(d0.x, x.x, acc[0][j]); acc[0][j] = fmaf(d0.y, x.y, acc[0][j]);
+                            acc[0][j] = fmaf(d0.z, x.z, acc[0][j]); acc[0][j] = fmaf(d0.w, x.w, acc[0][j]);
+                            acc[1][j] = fmaf(d1.x, x.x, acc[1][j]); acc[1][j] = fmaf(d1.y, x.y, acc[1][j]);
+                            acc[1][j] = fmaf(d1.z, x.z, acc[1][j]); acc[1][j] = fmaf(d1.w, x.w, acc[1][j]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int r = nb + n_l + 4 * i;
+                        if (r < nn) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) accW1[(size_t)(ch0 + r) * CT + cbase + c_l + 8 * j] += acc[i][j];
+                        }
+                    }
+                }
+            }
+            if (tid < nn) accb1[ch0 + tid] += sum_tile(D + (size_t)tid * kPixTPP);
+            __syncthreads();
+        }
+        if (inb) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (c < k.ctot && gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = din[c];
+        }
+#pragma unroll
+        for (int q = 0; q < kProjMaxOut; ++q)
+            if (q < k.out_ch) {
+                const float v = warp_sum(go[q]);
+                if (lane == 0) atomicAdd(accb2 + q, v);
+            }
+    }
+    __syncthreads();
+    for (int i = tid; i < k.hid * CT; i += kPixTP) {
+        const int n = i / CT, c = i % CT;
+        if (c < k.ctot) atomicAdd(k.gw1 + n * k.ctot + c, accW1[i]);
+    }
+    for (int i = tid; i < k.hid; i += kPixTP) atomicAdd(k.gb1 + i, accb1[i]);
+    for (int i = tid; i < k.out_ch * k.hid; i += kPixTP) atomicAdd(k.gw2 + i, accW2[i]);
+    for (int i = tid; i < k.out_ch; i += kPixTP) atomicAdd(k.gb2 + i, accb2[i]);
+}
+
+inline size_t proj_bwd_smem(int CT, int hid, int out_ch) {
+    return proj_table_bytes(CT) +
+           sizeof(float) * ((size_t)2 * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid)) + 4 + (size_t)(kProjHC + CT) * kPixTPP);
+}

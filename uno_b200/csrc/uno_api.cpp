@@ -654,6 +654,56 @@ size_t block_ws_floats(const uno_block_desc* bd) {
     return spectral_ws_floats(d) + pw_ws_floats(d) + act + align64((size_t)2 * d->batch * d->out_ch) + 256;
 }
 
+// ---- model glue: lift / project ------------------------------------------------------------------------
+int check_pixel_desc(const uno_pixel_desc* p) {
+    if (p->ndim != 2 && p->ndim != 3) return fail(UNO_EINVAL, "pixel desc: ndim must be 2 or 3 (got %d)", p->ndim);
+    if (p->batch < 1) return fail(UNO_EINVAL, "pixel desc: batch must be positive (got %d)", p->batch);
+    for (int a = 0; a < p->ndim; ++a)
+        if (p->dim[a] < 1 || p->pad_lo[a] < 0 || p->pad_hi[a] < 0)
+            return fail(UNO_EINVAL, "pixel desc: axis %d has dim %d pad (%d,%d)", a, p->dim[a], p->pad_lo[a], p->pad_hi[a]);
+    return 0;
+}
+
+// spatial axes right-aligned into three slots (2-D: slot 0 has extent 1)
+void pixel_geometry(const uno_pixel_desc* p, int* n, int* N, int* lo) {
+    const int shift = 3 - p->ndim;
+    for (int a = 0; a < 3; ++a) { n[a] = N[a] = 1; lo[a] = 0; }
+    for (int a = 0; a < p->ndim; ++a) {
+        n[a + shift] = p->dim[a];
+        N[a + shift] = p->dim[a] + p->pad_lo[a] + p->pad_hi[a];
+        lo[a + shift] = p->pad_lo[a];
+    }
+}
+
+int make_lift_args(const uno_lift_desc* d, LiftArgs* a) {
+    if (!d) return fail(UNO_EINVAL, "null descriptor");
+    UNO_TRY(check_pixel_desc(&d->px));
+    a->batch = d->px.batch;
+    pixel_geometry(&d->px, a->n, a->N, a->lo);
+    a->raw_ch = d->raw_ch; a->grid_ch = d->grid_ch; a->hid = d->hidden; a->out_ch = d->out_ch;
+    if (d->raw_ch < 1 || d->grid_ch < 0 || d->hidden < 1 || d->out_ch < 1)
+        return fail(UNO_EINVAL, "lift: raw_ch/grid_ch/hidden/out_ch = %d/%d/%d/%d", d->raw_ch, d->grid_ch, d->hidden, d->out_ch);
+    if (!be_lift_supported(*a))
+        return fail(UNO_EINVAL, "lift: unsupported widths (raw_ch+grid_ch=%d <= 16, hidden=%d <= 32, out_ch=%d <= 64 required)",
+                    d->raw_ch + d->grid_ch, d->hidden, d->out_ch);
+    return 0;
+}
+
+int make_proj_args(const uno_project_desc* d, ProjArgs* a) {
+    if (!d) return fail(UNO_EINVAL, "null descriptor");
+    UNO_TRY(check_pixel_desc(&d->px));
+    a->batch = d->px.batch;
+    pixel_geometry(&d->px, a->n, a->N, a->lo);
+    a->nsrc = d->nsrc; a->hid = d->hidden; a->out_ch = d->out_ch;
+    if (d->nsrc < 1 || d->nsrc > 4) return fail(UNO_EINVAL, "project: nsrc must be 1..4 (got %d)", d->nsrc);
+    int ctot = 0;
+    for (int s = 0; s < d->nsrc; ++s) { a->src_ch[s] = d->src_ch[s]; ctot += d->src_ch[s]; }
+    if (!be_proj_supported(*a))
+        return fail(UNO_EINVAL, "project: unsupported widths (sum src_ch=%d <= 64, hidden=%d <= 128, out_ch=%d <= 4 required)",
+                    ctot, d->hidden, d->out_ch);
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -829,6 +879,75 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
         Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
         UNO_TRY(spectral_bwd_impl(d, sp, gs, xhat, w, gx, gw, /*accumulate_gx=*/1, sub, stream));
     }
+    return 0;
+}
+
+// ---- model glue ------------------------------------------------------------------------------------
+int uno_lift_check(const uno_lift_desc* d) { LiftArgs a; return make_lift_args(d, &a); }
+
+int uno_lift_fwd(const uno_lift_desc* d, const float* a_, const float* grid, const float* w_a,
+                 const float* b_a, const float* w_b, const float* b_b, float* h, void* stream) {
+    LiftArgs a;
+    UNO_TRY(make_lift_args(d, &a));
+    if (!a_ || (!grid && d->grid_ch > 0) || !w_a || !b_a || !w_b || !b_b || !h) return fail(UNO_EINVAL, "null tensor pointer");
+    a.a = a_; a.grid = grid; a.w_a = w_a; a.b_a = b_a; a.w_b = w_b; a.b_b = b_b; a.h = h;
+    BE_TRY(be_lift_fwd(a, stream));
+    return 0;
+}
+
+int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a_, const float* grid,
+                 const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
+                 float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream) {
+    LiftArgs a;
+    UNO_TRY(make_lift_args(d, &a));
+    if (!gh || !a_ || (!grid && d->grid_ch > 0) || !w_a || !b_a || !w_b || !b_b || !gw_a || !gb_a || !gw_b || !gb_b)
+        return fail(UNO_EINVAL, "null tensor pointer");
+    a.a = a_; a.grid = grid; a.w_a = w_a; a.b_a = b_a; a.w_b = w_b; a.b_b = b_b;
+    a.gh = gh; a.ga = ga; a.gw_a = gw_a; a.gb_a = gb_a; a.gw_b = gw_b; a.gb_b = gb_b;
+    const int cin = d->raw_ch + d->grid_ch;
+    BE_TRY(be_memset(gw_a, 0, sizeof(float) * d->hidden * cin, stream));
+    BE_TRY(be_memset(gb_a, 0, sizeof(float) * d->hidden, stream));
+    BE_TRY(be_memset(gw_b, 0, sizeof(float) * d->out_ch * d->hidden, stream));
+    BE_TRY(be_memset(gb_b, 0, sizeof(float) * d->out_ch, stream));
+    BE_TRY(be_lift_bwd(a, stream));
+    return 0;
+}
+
+int uno_project_check(const uno_project_desc* d) { ProjArgs a; return make_proj_args(d, &a); }
+
+int uno_project_fwd(const uno_project_desc* d, const float* const* src, const float* w1,
+                    const float* b1, const float* w2, const float* b2, float* out, void* stream) {
+    ProjArgs a;
+    UNO_TRY(make_proj_args(d, &a));
+    if (!src || !w1 || !b1 || !w2 || !b2 || !out) return fail(UNO_EINVAL, "null tensor pointer");
+    for (int s = 0; s < d->nsrc; ++s) {
+        if (!src[s]) return fail(UNO_EINVAL, "null source pointer %d", s);
+        a.src[s] = src[s];
+    }
+    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.out = out;
+    BE_TRY(be_proj_fwd(a, stream));
+    return 0;
+}
+
+int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* const* src,
+                    const float* w1, const float* b1, const float* w2, float* const* gsrc, float* gw1,
+                    float* gb1, float* gw2, float* gb2, void* stream) {
+    ProjArgs a;
+    UNO_TRY(make_proj_args(d, &a));
+    if (!gout || !src || !w1 || !b1 || !w2 || !gw1 || !gb1 || !gw2 || !gb2) return fail(UNO_EINVAL, "null tensor pointer");
+    int ctot = 0;
+    for (int s = 0; s < d->nsrc; ++s) {
+        if (!src[s]) return fail(UNO_EINVAL, "null source pointer %d", s);
+        a.src[s] = src[s];
+        a.gsrc[s] = gsrc ? gsrc[s] : nullptr;
+        ctot += d->src_ch[s];
+    }
+    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.gout = gout; a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2;
+    BE_TRY(be_memset(gw1, 0, sizeof(float) * d->hidden * ctot, stream));
+    BE_TRY(be_memset(gb1, 0, sizeof(float) * d->hidden, stream));
+    BE_TRY(be_memset(gw2, 0, sizeof(float) * d->out_ch * d->hidden, stream));
+    BE_TRY(be_memset(gb2, 0, sizeof(float) * d->out_ch, stream));
+    BE_TRY(be_proj_bwd(a, stream));
     return 0;
 }
 

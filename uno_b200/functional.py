@@ -211,6 +211,94 @@ class OperatorBlockFn(torch.autograd.Function):
         return (gx, None, None, None, None, None, None, gcw.reshape(ctx.w_shape), gcb, gg, gb) + tuple(gws)
 
 
+class LiftFn(torch.autograd.Function):
+    """cat(a, grid) -> Linear -> GELU -> Linear -> GELU -> channels-first -> zero pad, one kernel
+    (darcy_flow_uno2d.py:96-107, navier_stokes_uno2d.py:191-201, navier_stokes_uno3d.py:497-511)."""
+
+    @staticmethod
+    def forward(ctx, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
+        lib = _get_lib()
+        _check_input(a)
+        a = a.contiguous()
+        grid = grid.contiguous()
+        dims = tuple(a.shape[1:-1])
+        if tuple(grid.shape[:-1]) != dims:
+            raise RuntimeError(f"uno_b200: grid features {tuple(grid.shape)} do not match the input grid {dims}")
+        wa, ba, wb, bb = (t.detach().contiguous() for t in (w_a, b_a, w_b, b_b))
+        d = _capi.lift_desc(a.shape[0], dims, pad_lo, pad_hi, a.shape[-1], grid.shape[-1], wa.shape[0], wb.shape[0])
+        if wa.shape[1] != a.shape[-1] + grid.shape[-1] or wb.shape[1] != wa.shape[0]:
+            raise RuntimeError("uno_b200: lift weight shapes do not match the input channels")
+        _capi.check(lib, lib.uno_lift_check(C.byref(d)))
+        out_dims = tuple(n + lo + hi for n, lo, hi in zip(dims, pad_lo, pad_hi))
+        h = torch.empty((a.shape[0], wb.shape[0]) + out_dims, dtype=torch.float32, device=a.device)
+        _capi.check(lib, lib.uno_lift_fwd(C.byref(d), _ptr(a), _ptr(grid), _ptr(wa), _ptr(ba), _ptr(wb), _ptr(bb), _ptr(h), _stream(a)))
+        _launch_counter["calls"] += 1
+        ctx.desc = d
+        ctx.save_for_backward(a, grid, wa, ba, wb, bb)
+        return h
+
+    @staticmethod
+    def backward(ctx, gh):
+        lib = _get_lib()
+        a, grid, wa, ba, wb, bb = ctx.saved_tensors
+        gh = gh.contiguous()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gwa, gba, gwb, gbb = (torch.empty_like(t) for t in (wa, ba, wb, bb))
+        _capi.check(
+            lib,
+            lib.uno_lift_bwd(C.byref(ctx.desc), _ptr(gh), _ptr(a), _ptr(grid), _ptr(wa), _ptr(ba), _ptr(wb), _ptr(bb),
+                             _ptr(ga), _ptr(gwa), _ptr(gba), _ptr(gwb), _ptr(gbb), _stream(gh)),
+        )
+        _launch_counter["calls"] += 1
+        return ga, None, gwa, gba, gwb, gbb, None, None
+
+
+class ProjectFn(torch.autograd.Function):
+    """cat(srcs, dim=1) -> crop -> channels-last -> Linear -> GELU -> Linear, one kernel
+    (darcy_flow_uno2d.py:121-131, navier_stokes_uno2d.py:215-225, navier_stokes_uno3d.py:551-575)."""
+
+    @staticmethod
+    def forward(ctx, w1, b1, w2, b2, crop_lo, crop_hi, *srcs):
+        lib = _get_lib()
+        for t in srcs:
+            _check_input(t)
+        srcs = [t.contiguous() for t in srcs]
+        full = tuple(srcs[0].shape[2:])
+        if any(tuple(t.shape[2:]) != full or t.shape[0] != srcs[0].shape[0] for t in srcs):
+            raise RuntimeError("uno_b200: projection sources must share batch and grid")
+        dims = tuple(n - lo - hi for n, lo, hi in zip(full, crop_lo, crop_hi))
+        w1c, b1c, w2c, b2c = (t.detach().contiguous() for t in (w1, b1, w2, b2))
+        d = _capi.project_desc(srcs[0].shape[0], dims, crop_lo, crop_hi, [t.shape[1] for t in srcs], w1c.shape[0], w2c.shape[0])
+        if w1c.shape[1] != sum(t.shape[1] for t in srcs) or w2c.shape[1] != w1c.shape[0]:
+            raise RuntimeError("uno_b200: projection weight shapes do not match the source channels")
+        _capi.check(lib, lib.uno_project_check(C.byref(d)))
+        out = torch.empty((srcs[0].shape[0],) + dims + (w2c.shape[0],), dtype=torch.float32, device=srcs[0].device)
+        sp = _capi.ptr_array([t.data_ptr() for t in srcs])
+        _capi.check(lib, lib.uno_project_fwd(C.byref(d), sp, _ptr(w1c), _ptr(b1c), _ptr(w2c), _ptr(b2c), _ptr(out), _stream(out)))
+        _launch_counter["calls"] += 1
+        ctx.desc = d
+        ctx.save_for_backward(w1c, b1c, w2c, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = _get_lib()
+        w1c, b1c, w2c, *srcs = ctx.saved_tensors
+        gout = gout.contiguous()
+        gsrcs = [torch.empty_like(t) if ctx.needs_input_grad[6 + i] else None for i, t in enumerate(srcs)]
+        gw1, gb1, gw2 = torch.empty_like(w1c), torch.empty_like(b1c), torch.empty_like(w2c)
+        gb2 = torch.empty(w2c.shape[0], dtype=torch.float32, device=gout.device)
+        sp = _capi.ptr_array([t.data_ptr() for t in srcs])
+        gp = _capi.ptr_array([g.data_ptr() if g is not None else 0 for g in gsrcs])
+        _capi.check(
+            lib,
+            lib.uno_project_bwd(C.byref(ctx.desc), _ptr(gout), sp, _ptr(w1c), _ptr(b1c), _ptr(w2c), gp, _ptr(gw1), _ptr(gb1), _ptr(gw2),
+                                _ptr(gb2), _stream(gout)),
+        )
+        _launch_counter["calls"] += 1
+        return (gw1, gb1, gw2, gb2, None, None) + tuple(gsrcs)
+
+
 def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -227,3 +315,13 @@ def operator_block(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta
     normalize = gamma is not None
     need = _needs_grad(x, conv_w, conv_b, gamma, beta, *weights)
     return OperatorBlockFn.apply(x, tuple(out_dims), tuple(modes), normalize, bool(non_lin), float(eps), need, conv_w, conv_b, gamma, beta, *weights)
+
+
+def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
+    """h[B, C, *padded] = pad(gelu(fc_b(gelu(fc_a(cat(a, grid))))))  -- a [B, *dims, raw_ch] channels-last, grid [*dims, G]."""
+    return LiftFn.apply(a, grid, w_a, b_a, w_b, b_b, tuple(int(v) for v in pad_lo), tuple(int(v) for v in pad_hi))
+
+
+def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
+    """out[B, *cropped, out_ch] = fc2(gelu(fc1(crop(cat(srcs, dim=1)) channels-last)))."""
+    return ProjectFn.apply(w1, b1, w2, b2, tuple(int(v) for v in crop_lo), tuple(int(v) for v in crop_hi), *srcs)

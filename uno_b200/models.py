@@ -29,6 +29,17 @@ def _default_ops():
     return integral_operators
 
 
+def _glue_of(ops):
+    """The module providing the fused model glue ``lift`` / ``project`` for an operator module: the CUDA
+    kernels behind the C ABI (``uno_b200.functional``) for the drop-in, or the operator module itself when
+    it brings its own (the CPU oracle port used by the tests)."""
+    if hasattr(ops, "lift") and hasattr(ops, "project"):
+        return ops
+    from . import functional
+
+    return functional
+
+
 class _GridCache:
     """The reference rebuilds its coordinate features with numpy on the host in every forward
     (darcy_flow_uno2d.py:135-141).  Same values, built once per (shape, device)."""
@@ -68,6 +79,7 @@ class UNO_9(nn.Module):
         self.fc1 = nn.Linear(2 * w, w)
         self.fc2 = nn.Linear(w, 1)
         self._grids = _GridCache()
+        self._glue = _glue_of(ops)
 
     def get_grid(self, shape, device):
         b, sx, sy = shape[0], shape[1], shape[2]
@@ -80,20 +92,18 @@ class UNO_9(nn.Module):
         return self._grids.get((sx, sy), device, build).expand(b, -1, -1, -1)
 
     def forward(self, x):
-        x = torch.cat((x, self.get_grid(x.shape, x.device)), dim=-1)
-        h = F.gelu(self.fc0(F.gelu(self.fc_n1(x)))).permute(0, 3, 1, 2)
-        grow = math.ceil(h.shape[-1] / 85) * self.padding
-        h = F.pad(h, [0, grow, 0, grow])
+        # lift + permute + pad (darcy_flow_uno2d.py:96-107) and cat + crop + permute + projection (:121-131) are one
+        # kernel each; the padding grows the grid to the right / bottom only
+        grid = self.get_grid(x.shape, x.device)[0]
+        grow = math.ceil(x.shape[2] / 85) * self.padding
+        h = self._glue.lift(x, grid, self.fc_n1.weight, self.fc_n1.bias, self.fc0.weight, self.fc0.bias, (0, 0), (grow, grow))
         D1, D2 = h.shape[-2], h.shape[-1]
         c0 = self.conv0(h, D1 // 2, D2 // 2)
         c1 = self.conv1(c0, D1 // 4, D2 // 4)
         c2 = self.conv2(c1, D1 // 4, D2 // 4)
         c4 = torch.cat([self.conv4(c2, D1 // 2, D2 // 2), c0], dim=1)
-        c5 = torch.cat([self.conv5(c4, D1, D2), h], dim=1)
-        if self.padding != 0:
-            c5 = c5[..., :-grow, :-grow]
-        c5 = c5.permute(0, 2, 3, 1)
-        return self.fc2(F.gelu(self.fc1(c5)))
+        c5 = self.conv5(c4, D1, D2)
+        return self._glue.project([c5, h], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, (0, 0), (grow, grow))
 
 
 class _NS2DBase(nn.Module):
@@ -108,15 +118,15 @@ class _NS2DBase(nn.Module):
         return self._grids.get((sx, sy), device, build).expand(b, -1, -1, -1)
 
     def _lift(self, x):
-        x = torch.cat((x, self.get_grid(x.shape, x.device)), dim=-1)
-        h = F.gelu(self.fc0(F.gelu(self.fc(x)))).permute(0, 3, 1, 2)
+        # navier_stokes_uno2d.py:191-201 -- F.pad on all four sides
+        grid = self.get_grid(x.shape, x.device)[0]
         p = self.padding
-        return F.pad(h, [p, p, p, p])
+        return self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (p, p), (p, p))
 
-    def _project(self, h):
-        if self.padding != 0:
-            h = h[..., : -self.padding, : -self.padding]
-        return self.fc2(F.gelu(self.fc1(h.permute(0, 2, 3, 1))))
+    def _project(self, srcs):
+        # navier_stokes_uno2d.py:215-225 -- the reference crops only the trailing edge ([..., :-p, :-p])
+        p = self.padding
+        return self._glue.project(srcs, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, (0, 0), (p, p))
 
 
 class UNO(_NS2DBase):
@@ -140,6 +150,7 @@ class UNO(_NS2DBase):
         self.fc1 = nn.Linear(2 * w, 4 * w)
         self.fc2 = nn.Linear(4 * w, 1)
         self._grids = _GridCache()
+        self._glue = _glue_of(ops)
 
     def forward(self, x):
         h = self._lift(x)
@@ -151,8 +162,7 @@ class UNO(_NS2DBase):
         c3 = self.L3(c2, D1 // 4, D2 // 4)
         c4 = torch.cat([self.L4(c3, D1 // 2, D2 // 2), c1], dim=1)
         c5 = torch.cat([self.L5(c4, int(D1 * f), int(D2 * f)), c0], dim=1)
-        c6 = torch.cat([self.L6(c5, D1, D2), h], dim=1)
-        return self._project(c6)
+        return self._project([self.L6(c5, D1, D2), h])
 
 
 class UNO_P(_NS2DBase):
@@ -219,6 +229,7 @@ class Uno3D_T10(nn.Module):
         self.fc1 = nn.Linear(3 * w, 4 * w)
         self.fc2 = nn.Linear(4 * w, 1)
         self._grids = _GridCache()
+        self._glue = _glue_of(ops)
 
     def get_grid(self, shape, device):
         b, sx, sy, sz = shape[0], shape[1], shape[2], shape[3]
@@ -233,13 +244,18 @@ class Uno3D_T10(nn.Module):
 
     @staticmethod
     def _skip(src, like):
+        # trilinear with align_corners=True onto an identical grid is the identity (source index == target index,
+        # interpolation weight exactly 0), which is the case for every skip of the shipped configurations
+        if tuple(src.shape[2:]) == tuple(like.shape[2:]):
+            return src
         return F.interpolate(src, size=tuple(like.shape[2:]), mode="trilinear", align_corners=True)
 
     def forward(self, x):
-        x = torch.cat((x, self.get_grid(x.shape, x.device)), dim=-1)
-        h = F.gelu(self.fc0(F.gelu(self.fc(x)))).permute(0, 4, 1, 2, 3)
-        self.padding = int(self.pad * 0.1 * h.shape[-1])
-        h = F.pad(h, [self.padding if self.pad_both else 0, self.padding, 0, 0, 0, 0], mode="constant")
+        # navier_stokes_uno3d.py:497-511: lift, channels-first, pad the time axis (trailing edge, or both)
+        grid = self.get_grid(x.shape, x.device)[0]
+        self.padding = int(self.pad * 0.1 * x.shape[3])
+        lo = self.padding if self.pad_both else 0
+        h = self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (0, 0, lo), (0, 0, self.padding))
         D1, D2, D3 = h.shape[-3], h.shape[-2], h.shape[-1]
         c0 = self.conv0(h, int(3 * D1 / 4), int(3 * D2 / 4), D3)
         c1 = self.conv1(c0, D1 // 2, D2 // 2, D3)
@@ -250,7 +266,6 @@ class Uno3D_T10(nn.Module):
         c7 = self.conv7(c6, int(3 * D1 / 4), int(3 * D2 / 4), D3)
         c7 = torch.cat([c7, self._skip(c0, c7)], dim=1)
         c8 = self.conv8(c7, D1, D2, D3)
-        c8 = torch.cat([c8, self._skip(h, c8)], dim=1)
-        if self.padding != 0:
-            c8 = c8[..., self.padding : -self.padding] if self.pad_both else c8[..., : -self.padding]
-        return self.fc2(F.gelu(self.fc1(c8.permute(0, 2, 3, 4, 1))))
+        # :551-575: cat with the lifted input, crop the time padding, project
+        return self._glue.project([c8, self._skip(h, c8)], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                  (0, 0, lo), (0, 0, self.padding))

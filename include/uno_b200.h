@@ -177,6 +177,9 @@ int uno_plan_dft_mid_synthesis(int n, int m, float* out /* [n, 2m] complex */);
 int uno_plan_sr_mid(int n_in, int n_out, float* out /* [n_out, n_in] complex */);
 int uno_plan_sr_last_modes(int n_in, int n_out);
 int uno_plan_bicubic_aa(int n_in, int n_out, int transpose, float* out /* dense [n_out,n_in] or its transpose */);
+/* the register-blocked image of the same band that the fused 2-D resample kernel consumes, expanded to dense;
+ * gw[0], gw[1] receive the chosen (outputs per group, window) or (0,0) when the band does not fit (generic kernel) */
+int uno_plan_band_groups(int n_in, int n_out, int transpose, float* out, int* gw);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ def lift_inputs(case, seed=0):
     t = dict(a=f(B, *dims, raw), grid=f(*dims, gch), w_a=f(hid, cin) / np.sqrt(cin), b_a=0.3 * f(hid),
              w_b=f(out, hid) / np.sqrt(hid), b_b=0.3 * f(out))
     t["gh"] = f(B, out, *[n + l + h for n, l, h in zip(dims, lo, hi)])
-    return t
+    return {k: v.astype(np.float32) for k, v in t.items()}   # (float32 / np.float64 scalar promotes to float64)
 
 
 def lift_oracle(case, t):
@@ -32,8 +32,9 @@ def project_inputs(case, seed=0):
     f = lambda *s: rng.standard_normal(s).astype(np.float32)
     full = [n + l + h for n, l, h in zip(dims, lo, hi)]
     ct = sum(src_ch)
-    return dict(srcs=[f(B, c, *full) for c in src_ch], w1=f(hid, ct) / np.sqrt(ct), b1=0.3 * f(hid), w2=f(out, hid) / np.sqrt(hid),
-                b2=0.3 * f(out), gout=f(B, *dims, out))
+    t = dict(srcs=[f(B, c, *full) for c in src_ch], w1=f(hid, ct) / np.sqrt(ct), b1=0.3 * f(hid), w2=f(out, hid) / np.sqrt(hid),
+             b2=0.3 * f(out), gout=f(B, *dims, out))
+    return {k: ([x.astype(np.float32) for x in v] if k == "srcs" else v.astype(np.float32)) for k, v in t.items()}
 
 
 def project_oracle(case, t):

@@ -121,3 +121,22 @@ def test_bicubic_bands(lib, pair):
     assert np.abs(R.sum(1) - 1).max() < 1e-6                          # rows sum to one -> bias passes through
     Rt = _call(lib.uno_plan_bicubic_aa, (a, b), a, b, 1)
     assert np.array_equal(Rt, R.T)
+
+
+@pytest.mark.parametrize("pair", RESAMPLE_PAIRS + ((7, 12), (12, 7), (30, 9), (9, 30), (5, 40), (300, 20)))
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_band_groups_reproduce_the_band(pair, transpose, lib):
+    """The register-blocked image the fused resample kernel consumes expands to exactly the banded matrix."""
+    L = lib
+    n_in, n_out = pair
+    shape = (n_in, n_out) if transpose else (n_out, n_in)
+    dense = np.zeros(shape, np.float32)
+    assert L.uno_plan_bicubic_aa(n_in, n_out, transpose, dense.ctypes.data_as(C.c_void_p)) == 0
+    grouped = np.zeros(shape, np.float32)
+    gw = (C.c_int * 2)()
+    assert L.uno_plan_band_groups(n_in, n_out, transpose, grouped.ctypes.data_as(C.c_void_p), gw) == 0
+    if gw[0] == 0:      # band too wide for the register-blocked kernel: the generic kernel takes it
+        assert max(n_in, n_out) / min(n_in, n_out) > 2.5 or min(shape) < 8
+        return
+    assert (gw[0], gw[1]) in ((8, 8), (4, 8), (4, 16))
+    assert np.array_equal(grouped, dense)

@@ -84,6 +84,7 @@ SYMBOLS = {
     "uno_plan_sr_mid": (C.c_int, [C.c_int, C.c_int, _P]),
     "uno_plan_sr_last_modes": (C.c_int, [C.c_int, C.c_int]),
     "uno_plan_bicubic_aa": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
+    "uno_plan_band_groups": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
 }
 
 

@@ -95,6 +95,10 @@ struct Banded2DArgs {
     const int* start0 = nullptr; const float* w0 = nullptr; int n_in0 = 0, n_out0 = 0, taps0 = 0, span0 = 0;
     const int* start1 = nullptr; const float* w1 = nullptr; int n_in1 = 0, n_out1 = 0, taps1 = 0, span1 = 0;
     float* tmp = nullptr;   // scratch of planes * max(n_in0,n_out0) * max(n_in1,n_out1) floats for the two-pass fallback
+    // optional register-blocked images of the same bands (plan.h BandGroups); when both axes have one the
+    // register-blocked kernel runs: G outputs share a window of W inputs starting at gs[g], weights D[g][W][G]
+    const int* gs0 = nullptr; const float* D0 = nullptr; int G0 = 0, W0 = 0, ng0 = 0, tile_groups0 = 0, tile_span0 = 0;
+    const int* gs1 = nullptr; const float* D1 = nullptr; int G1 = 0, W1 = 0, ng1 = 0, tile_span1 = 0;
 };
 int be_banded2d(const Banded2DArgs& a, stream_t s);
 

@@ -599,7 +599,15 @@ inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
     return (unsigned)g;
 }
 
+template <typename K>
+int ensure_smem(K kernel, size_t bytes) {
+    // raise the dynamic shared-memory limit of this instantiation (idempotent, cheap)
+    if (bytes <= 48 * 1024) return 0;
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 #include "pixel_mlp.cuh"
+#include "resample2d.cuh"
 
 
 // =====================================================================================================
@@ -1038,8 +1046,55 @@ int be_banded(const BandedArgs& a, stream_t s) {
 }
 
 
+namespace {
+template <int G0, int W0, int G1, int W1>
+int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
+    Resample2K k;
+    k.x = a.x; k.y = a.y; k.planes = a.planes;
+    k.n_in0 = a.n_in0; k.n_out0 = a.n_out0; k.n_in1 = a.n_in1; k.n_out1 = a.n_out1;
+    k.gs0 = a.gs0; k.D0 = a.D0; k.ng0 = a.ng0;
+    k.gs1 = a.gs1; k.D1 = a.D1; k.ng1 = a.ng1;
+    k.TH = a.tile_groups0 * G0;
+    k.RIN = (a.tile_span0 + 3) & ~3;          // multiple of 4 keeps the weight images 16-byte aligned
+    k.ldin = a.tile_span1 | 1;                // odd pitch: lanes sweeping rows hit distinct banks
+    k.tiles_h = (a.ng0 + a.tile_groups0 - 1) / a.tile_groups0;
+    k.tiles_w = (a.n_out1 + kRsTW - 1) / kRsTW;
+    const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
+    if (smem > 160 * 1024) return -1;
+    int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1>, smem);
+    if (rc) return rc;
+    ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
+                 2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
+    const long blocks = a.planes * k.tiles_h * k.tiles_w;
+    resample2d_kernel<G0, W0, G1, W1><<<(unsigned)blocks, 256, smem, st>>>(k);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+// returns -1 when the register-blocked kernel does not take the shape
+int try_resample2d(const Banded2DArgs& a, cudaStream_t st) {
+    if (!a.D0 || !a.D1 || a.tile_groups0 < 1) return -1;
+    const int c0 = a.G0 == 8 ? 0 : (a.W0 == 8 ? 1 : 2), c1 = a.G1 == 8 ? 0 : (a.W1 == 8 ? 1 : 2);
+    switch (c0 * 3 + c1) {
+        case 0: return launch_resample2d<8, 8, 8, 8>(a, st);
+        case 1: return launch_resample2d<8, 8, 4, 8>(a, st);
+        case 2: return launch_resample2d<8, 8, 4, 16>(a, st);
+        case 3: return launch_resample2d<4, 8, 8, 8>(a, st);
+        case 4: return launch_resample2d<4, 8, 4, 8>(a, st);
+        case 5: return launch_resample2d<4, 8, 4, 16>(a, st);
+        case 6: return launch_resample2d<4, 16, 8, 8>(a, st);
+        case 7: return launch_resample2d<4, 16, 4, 8>(a, st);
+        default: return launch_resample2d<4, 16, 4, 16>(a, st);
+    }
+}
+}  // namespace
+
 int be_banded2d(const Banded2DArgs& a, stream_t s) {
     if (a.planes <= 0) return 0;
+    {
+        const int rc = try_resample2d(a, S(s));
+        if (rc >= 0) return rc;
+    }
     const int RIN = a.span0, CIN = a.span1;
     const int ldin = CIN | 1;   // odd row pitch
     const size_t smem = ((size_t)RIN * ldin + (size_t)RIN * kB2MidLd + (size_t)kB2TH * a.taps0 + (size_t)kB2TW * a.taps1 + kB2TH + kB2TW) * 4;
@@ -1150,13 +1205,6 @@ LiftK lift_k(const LiftArgs& a) {
     return k;
 }
 
-template <typename K>
-int ensure_smem(K kernel, size_t bytes) {
-    // raise the dynamic shared-memory limit of this instantiation (idempotent, cheap)
-    if (bytes <= 48 * 1024) return 0;
-    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
 template <int CIN, int HID>
 int launch_lift(const LiftK& k, bool bwd, cudaStream_t st) {
     if (!bwd) {
@@ -1171,8 +1219,9 @@ int launch_lift(const LiftK& k, bool bwd, cudaStream_t st) {
         int rc = ensure_smem(lift_bwd_kernel<CIN, HID>, smem);
         if (rc) return rc;
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
-        const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
-        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * per_sm);
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lift_bwd_kernel<CIN, HID>, kPixTP, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * per_sm);   // persistent: every CTA resident
         lift_bwd_kernel<CIN, HID><<<grid, kPixTP, smem, st>>>(k, ntiles);
     }
     CU_LAUNCH_CHECK();
@@ -1221,8 +1270,8 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const size_t smem = proj_bwd_smem(CT, k.hid, k.out_ch);
         int rc = ensure_smem(proj_bwd_kernel<CT>, smem);
         if (rc) return rc;
-        const long ntiles = ((long)k.batch * k.g.npad + kPixTP - 1) / kPixTP;
-        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * (smem > 110 * 1024 ? 1 : 2));
+        const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;   // tiles of the cropped grid
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);            // persistent, one CTA per SM
         proj_bwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
     }
     CU_LAUNCH_CHECK();

@@ -205,6 +205,75 @@ std::vector<float> banded_dense(const Banded& b) {
     return d;
 }
 
+BandGroups band_groups(const Banded& b) {
+    // nonzero extent of every output row
+    std::vector<int> lo(b.n_out, 0), hi(b.n_out, 0);   // [lo, hi)
+    for (int i = 0; i < b.n_out; ++i) {
+        int f = -1, l = -1;
+        for (int t = 0; t < b.taps; ++t)
+            if (b.w[(size_t)i * b.taps + t] != 0.0f) { if (f < 0) f = t; l = t; }
+        if (f < 0) { lo[i] = hi[i] = std::min(std::max(b.start[i], 0), b.n_in); }
+        else { lo[i] = b.start[i] + f; hi[i] = b.start[i] + l + 1; }
+    }
+    static const int cfgs[3][2] = {{8, 8}, {4, 8}, {4, 16}};
+    for (const auto& cfg : cfgs) {
+        const int G = cfg[0], W = cfg[1];
+        if (W > b.n_in) continue;
+        const int ng = (b.n_out + G - 1) / G;
+        bool fits = true;
+        std::vector<int> gs(ng, 0);
+        for (int g = 0; g < ng && fits; ++g) {
+            int a = b.n_in, e = 0;
+            bool any = false;
+            for (int q = 0; q < G; ++q) {
+                const int i = g * G + q;
+                if (i >= b.n_out || hi[i] <= lo[i]) continue;
+                a = std::min(a, lo[i]); e = std::max(e, hi[i]); any = true;
+            }
+            if (!any) { a = 0; e = 0; }
+            if (e - a > W) { fits = false; break; }
+            gs[g] = std::max(0, std::min(a, b.n_in - W));
+            if (g > 0 && gs[g] < gs[g - 1]) fits = false;   // tiles assume monotone windows
+        }
+        if (!fits) continue;
+        BandGroups r;
+        r.ok = true; r.G = G; r.W = W; r.ng = ng; r.n_in = b.n_in; r.n_out = b.n_out;
+        r.gstart = gs;
+        r.D.assign((size_t)ng * W * G, 0.0f);
+        for (int i = 0; i < b.n_out; ++i) {
+            const int g = i / G, q = i % G;
+            for (int t = 0; t < b.taps; ++t) {
+                const float w = b.w[(size_t)i * b.taps + t];
+                if (w == 0.0f) continue;
+                const int u = b.start[i] + t - gs[g];   // in [0, W) by construction
+                r.D[((size_t)g * W + u) * G + q] += w;
+            }
+        }
+        return r;
+    }
+    return BandGroups();
+}
+
+int BandGroups::span(int groups_per_tile) const {
+    int best = 0;
+    for (int g0 = 0; g0 < ng; g0 += groups_per_tile) {
+        const int g1 = std::min(g0 + groups_per_tile, ng) - 1;
+        best = std::max(best, gstart[g1] + W - gstart[g0]);
+    }
+    return best;
+}
+
+std::vector<float> band_groups_dense(const BandGroups& g) {
+    std::vector<float> d((size_t)g.n_out * g.n_in, 0.0f);
+    for (int gi = 0; gi < g.ng; ++gi)
+        for (int u = 0; u < g.W; ++u)
+            for (int q = 0; q < g.G; ++q) {
+                const int i = gi * g.G + q;
+                if (i < g.n_out) d[(size_t)i * g.n_in + g.gstart[gi] + u] += g.D[((size_t)gi * g.W + u) * g.G + q];
+            }
+    return d;
+}
+
 Banded banded_transpose(const Banded& b) {
     Banded t;
     t.n_in = b.n_out;

@@ -54,4 +54,19 @@ Banded bicubic_aa(int n_in, int n_out);
 Banded banded_transpose(const Banded& b);   // [n_in x n_out] operator, also banded
 std::vector<float> banded_dense(const Banded& b);
 
+// Register-blocked image of a banded operator for the fused 2-D resample kernel: G consecutive output
+// rows share one input window of W samples starting at gstart[g] (always inside [0, n_in - W]), and
+// D[g][u][q] is the dense weight of window sample u for output 4g+q (zero outside the band, zero for
+// outputs past n_out).  One of (G,W) = (8,8), (4,8), (4,16) is chosen -- the first whose windows fit;
+// ok = false when none does (very large scale factors, or inputs shorter than the window).
+struct BandGroups {
+    bool ok = false;
+    int G = 0, W = 0, ng = 0, n_in = 0, n_out = 0;
+    std::vector<int> gstart;   // [ng]
+    std::vector<float> D;      // [ng][W][G]
+    int span(int groups_per_tile) const;   // largest input extent of a tile of that many groups
+};
+BandGroups band_groups(const Banded& b);
+std::vector<float> band_groups_dense(const BandGroups& g);   // [n_out x n_in], for testing
+
 }  // namespace uno

@@ -1,0 +1,131 @@
+// Fused separable 2-D banded resample, register-blocked (pointwise_op_2D's anti-aliased bicubic and its transpose;
+// integral_operators.py:240-242).  Included by backend_cuda.cu inside namespace uno::{anonymous}.
+//
+//   y[p] = R0 * x[p] * R1^T  for every plane p,     x [P, n_in0, n_in1] -> y [P, n_out0, n_out1]
+//
+// Both bands come as "group images" (plan.h BandGroups): G consecutive outputs share a window of W inputs and a
+// dense G x W weight block.  One CTA = one plane x (TH x 64) output tile:
+//   1. the input window [rin x cin] is staged in shared memory with 4-byte LDGSTS (rows of 481 floats are not
+//      16-byte aligned), every element of x is read once per tile;
+//   2. pass A (contiguous axis): a warp owns one column group (its G1 x W1 weights sit in registers), lanes run over
+//      the window rows -> odd row pitch makes every shared access conflict-free; W1 loads feed G1*W1 FMAs;
+//   3. pass B (row axis): a warp owns one row group (G0 x W0 weights in registers), lanes run over 32 output
+//      columns; W0 loads feed G0*W0 FMAs and G0 coalesced 128-byte row stores.
+// Bound: HBM (4 B read per input element + 4 B written per output element); the FMA work is
+// planes * (n_in0*n_out1*W1 + n_out0*n_out1*W0), 25-40 flop per byte of traffic for the 2x resamples of the U-NO levels.
+#pragma once
+
+struct Resample2K {
+    const float* x; float* y; long planes;
+    int n_in0, n_out0, n_in1, n_out1;
+    const int* gs0; const float* D0; int ng0;   // row band groups
+    const int* gs1; const float* D1; int ng1;   // column band groups
+    int TH;                                     // output rows per tile (multiple of G0); 64 output columns per tile
+    int RIN, ldin;                              // rows of the staged window, its (odd) pitch
+    int tiles_h, tiles_w;
+};
+constexpr int kRsTW = 64, kRsMidLd = 65;
+
+template <int G0, int W0, int G1, int W1>
+__global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) {
+    extern __shared__ __align__(16) float rsm[];
+    constexpr int NG1 = kRsTW / G1;                      // column groups per tile
+    const int NG0 = k.TH / G0;                           // row groups per tile
+    float* in_s = rsm;                                   // [RIN][ldin]
+    float* mid_s = in_s + (size_t)k.RIN * k.ldin;        // [RIN][kRsMidLd]
+    float* d1s = mid_s + (size_t)k.RIN * kRsMidLd;       // [NG1][W1][G1]   (16-byte aligned by construction of the sizes below)
+    float* d0s = d1s + NG1 * W1 * G1;                    // [NG0][W0][G0]
+    int* gs1s = reinterpret_cast<int*>(d0s + NG0 * W0 * G0);   // [NG1]
+    int* gs0s = gs1s + NG1;                              // [NG0]
+    long bid = blockIdx.x;
+    const int tw = (int)(bid % k.tiles_w); bid /= k.tiles_w;
+    const int th = (int)(bid % k.tiles_h); bid /= k.tiles_h;
+    const long p = bid;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ga0 = th * NG0, ga1 = tw * NG1;            // first row / column group of the tile
+    const int ngh = min(NG0, k.ng0 - ga0), ngw = min(NG1, k.ng1 - ga1);
+    const int r0 = __ldg(k.gs0 + ga0), c0 = __ldg(k.gs1 + ga1);
+    const int rin = __ldg(k.gs0 + ga0 + ngh - 1) + W0 - r0;   // windows never leave the input (plan guarantee)
+    const int cin = __ldg(k.gs1 + ga1 + ngw - 1) + W1 - c0;
+    // ---- stage the input window
+    {
+        const float* xp = k.x + (p * k.n_in0 + r0) * (long)k.n_in1 + c0;
+        for (int r = warp; r < rin; r += 8) {
+            const float* src = xp + (long)r * k.n_in1;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(in_s + r * k.ldin);
+            for (int c = lane; c < cin; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + c) : "memory");
+        }
+    }
+    for (int i = tid; i < ngw * W1 * G1; i += 256) d1s[i] = __ldg(k.D1 + (size_t)ga1 * W1 * G1 + i);
+    for (int i = tid; i < ngh * W0 * G0; i += 256) d0s[i] = __ldg(k.D0 + (size_t)ga0 * W0 * G0 + i);
+    if (tid < ngw) gs1s[tid] = __ldg(k.gs1 + ga1 + tid) - c0;
+    if (tid >= 64 && tid < 64 + ngh) gs0s[tid - 64] = __ldg(k.gs0 + ga0 + tid - 64) - r0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- pass A: mid[r][j] = sum_u D1[g][u][q] * in[r][gs1[g] + u],  j = g*G1 + q
+    for (int cg = warp; cg < ngw; cg += 8) {
+        float w[W1][G1];
+        const float4* wsrc = reinterpret_cast<const float4*>(d1s + cg * W1 * G1);
+#pragma unroll
+        for (int u = 0; u < W1; ++u)
+#pragma unroll
+            for (int q4 = 0; q4 < G1 / 4; ++q4) {
+                const float4 v = wsrc[u * (G1 / 4) + q4];
+                w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
+            }
+        const int cs = gs1s[cg];
+        for (int r = lane; r < rin; r += 32) {
+            const float* src = in_s + r * k.ldin + cs;
+            float acc[G1];
+#pragma unroll
+            for (int q = 0; q < G1; ++q) acc[q] = 0.f;
+#pragma unroll
+            for (int u = 0; u < W1; ++u) {
+                const float v = src[u];
+#pragma unroll
+                for (int q = 0; q < G1; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
+            }
+            float* dst = mid_s + r * kRsMidLd + cg * G1;
+#pragma unroll
+            for (int q = 0; q < G1; ++q) dst[q] = acc[q];
+        }
+    }
+    __syncthreads();
+    // ---- pass B: y[i][j] = sum_u D0[g][u][q] * mid[gs0[g] + u][j],  i = g*G0 + q
+    const int i0 = ga0 * G0, j0 = tw * kRsTW;
+    for (int it = warp; it < ngh * 2; it += 8) {
+        const int rg = it >> 1, jc = (it & 1) * 32 + lane;
+        float w[W0][G0];
+        const float4* wsrc = reinterpret_cast<const float4*>(d0s + rg * W0 * G0);
+#pragma unroll
+        for (int u = 0; u < W0; ++u)
+#pragma unroll
+            for (int q4 = 0; q4 < G0 / 4; ++q4) {
+                const float4 v = wsrc[u * (G0 / 4) + q4];
+                w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
+            }
+        const float* src = mid_s + gs0s[rg] * kRsMidLd + jc;
+        float acc[G0];
+#pragma unroll
+        for (int q = 0; q < G0; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int u = 0; u < W0; ++u) {
+            const float v = src[u * kRsMidLd];
+#pragma unroll
+            for (int q = 0; q < G0; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
+        }
+        const int j = j0 + jc;
+        if (j < k.n_out1) {
+            float* yp = k.y + (p * k.n_out0 + i0 + rg * G0) * (long)k.n_out1 + j;
+#pragma unroll
+            for (int q = 0; q < G0; ++q)
+                if (i0 + rg * G0 + q < k.n_out0) yp[(long)q * k.n_out1] = acc[q];
+        }
+    }
+}
+
+inline size_t resample2d_smem(int RIN, int ldin, int TH, int G0, int W0, int G1, int W1) {
+    return sizeof(float) * ((size_t)RIN * ldin + (size_t)RIN * kRsMidLd + (size_t)(kRsTW / G1) * W1 * G1 + (size_t)(TH / G0) * W0 * G0 +
+                            kRsTW / G1 + TH / G0);
+}

@@ -82,7 +82,38 @@ struct DevBand {
     int span32 = 0, span64 = 0;   // max input extent of a 32- / 64-output tile
     int* start = nullptr;
     float* w = nullptr;
-    ~DevBand() { if (start) be_free(start); if (w) be_free(w); }
+    // register-blocked image (plan.h BandGroups); G == 0 when the band does not fit one
+    int G = 0, W = 0, ng = 0;
+    int tile_groups_rows = 0, tile_span_rows = 0;   // tile height in groups when this band acts on rows, and its window
+    int tile_span_cols = 0;                         // window of a 64-column tile when it acts on columns
+    int* gstart = nullptr;
+    float* D = nullptr;
+    ~DevBand() {
+        if (start) be_free(start);
+        if (w) be_free(w);
+        if (gstart) be_free(gstart);
+        if (D) be_free(D);
+    }
+    int upload_groups(const Banded& b) {
+        const BandGroups g = band_groups(b);
+        if (!g.ok) return 0;
+        G = g.G; W = g.W; ng = g.ng;
+        // rows: the tile height (in groups, <= 8) that wastes the fewest lanes when a warp sweeps the window rows
+        double best = -1.0;
+        for (int n = std::min(8, ng); n >= 1; --n) {
+            const int sp = g.span(n);
+            const double eff = (double)(n * G) / (32.0 * ((sp + 31) / 32));
+            if (eff > best + 1e-9) { best = eff; tile_groups_rows = n; tile_span_rows = sp; }
+        }
+        tile_span_cols = g.span(64 / G);
+        void* p = nullptr;
+        int rc = be_upload(&p, g.gstart.data(), g.gstart.size() * sizeof(int));
+        gstart = (int*)p;
+        if (rc) return rc;
+        rc = be_upload(&p, g.D.data(), g.D.size() * sizeof(float));
+        D = (float*)p;
+        return rc;
+    }
     int upload(const Banded& b) {
         n_in = b.n_in; n_out = b.n_out; taps = b.taps;
         auto span = [&](int tile) {
@@ -101,7 +132,8 @@ struct DevBand {
         if (rc) return rc;
         rc = be_upload(&p, b.w.data(), b.w.size() * sizeof(float));
         w = (float*)p;
-        return rc;
+        if (rc) return rc;
+        return upload_groups(b);
     }
 };
 
@@ -476,6 +508,11 @@ struct ResamplePlan {
         a.x = x; a.y = y; a.planes = P; a.tmp = tmp;
         a.start0 = b[0].start; a.w0 = b[0].w; a.n_in0 = b[0].n_in; a.n_out0 = b[0].n_out; a.taps0 = b[0].taps; a.span0 = b[0].span32;
         a.start1 = b[1].start; a.w1 = b[1].w; a.n_in1 = b[1].n_in; a.n_out1 = b[1].n_out; a.taps1 = b[1].taps; a.span1 = b[1].span64;
+        if (b[0].G && b[1].G) {
+            a.gs0 = b[0].gstart; a.D0 = b[0].D; a.G0 = b[0].G; a.W0 = b[0].W; a.ng0 = b[0].ng;
+            a.tile_groups0 = b[0].tile_groups_rows; a.tile_span0 = b[0].tile_span_rows;
+            a.gs1 = b[1].gstart; a.D1 = b[1].D; a.G1 = b[1].G; a.W1 = b[1].W; a.ng1 = b[1].ng; a.tile_span1 = b[1].tile_span_cols;
+        }
         BE_TRY(be_banded2d(a, st));
         return 0;
     }
@@ -992,6 +1029,19 @@ int uno_plan_bicubic_aa(int n_in, int n_out, int transpose, float* out) {
     Banded b = bicubic_aa(n_in, n_out);
     if (transpose) b = banded_transpose(b);
     auto v = banded_dense(b);
+    memcpy(out, v.data(), v.size() * sizeof(float));
+    return 0;
+}
+
+int uno_plan_band_groups(int n_in, int n_out, int transpose, float* out, int* gw) {
+    if (n_in < 1 || n_out < 1 || !out || !gw) return fail(UNO_EINVAL, "bad arguments");
+    Banded b = bicubic_aa(n_in, n_out);
+    if (transpose) b = banded_transpose(b);
+    BandGroups g = band_groups(b);
+    gw[0] = g.ok ? g.G : 0;
+    gw[1] = g.ok ? g.W : 0;
+    if (!g.ok) return 0;
+    auto v = band_groups_dense(g);
     memcpy(out, v.data(), v.size() * sizeof(float));
     return 0;
 }

@@ -28,6 +28,13 @@ def _check_input(x: torch.Tensor, name: str = "input") -> None:
         raise RuntimeError(f"uno_b200: expected float32 {name} but found {x.dtype}")
 
 
+def _check_params(*params: torch.Tensor) -> None:
+    for p in params:
+        if not p.is_cuda or p.dtype != torch.float32:
+            # F.linear raises RuntimeError for mismatched dtypes / devices in the reference as well
+            raise RuntimeError(f"uno_b200: parameters must be CUDA float32 tensors (got {p.dtype} on {p.device})")
+
+
 def _stream(x: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
 
@@ -219,6 +226,8 @@ class LiftFn(torch.autograd.Function):
     def forward(ctx, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
         lib = _get_lib()
         _check_input(a)
+        _check_input(grid, "grid features")
+        _check_params(w_a, b_a, w_b, b_b)
         a = a.contiguous()
         grid = grid.contiguous()
         dims = tuple(a.shape[1:-1])
@@ -262,6 +271,7 @@ class ProjectFn(torch.autograd.Function):
         lib = _get_lib()
         for t in srcs:
             _check_input(t)
+        _check_params(w1, b1, w2, b2)
         srcs = [t.contiguous() for t in srcs]
         full = tuple(srcs[0].shape[2:])
         if any(tuple(t.shape[2:]) != full or t.shape[0] != srcs[0].shape[0] for t in srcs):

@@ -184,6 +184,14 @@ int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t)
     for (size_t i = 0; i < n; ++i) g[i] = gy[i] * gelu_grad_f(pre[i]);
     return 0;
 }
+int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha, stream_t) {
+    for (long p = 0; p < planes; ++p) {
+        double s = 0;
+        for (long i = 0; i < L; ++i) { g[p * L + i] = gy[p * L + i] * gelu_grad_f(pre[p * L + i]); s += g[p * L + i]; }
+        gbias[p % C] += alpha * (float)s;
+    }
+    return 0;
+}
 
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t) {
     for (long p = 0; p < planes; ++p) {
@@ -212,11 +220,11 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
 
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
-                    long L, int non_lin, stream_t) {
+                    long L, int non_lin, float* gbias, float alpha, stream_t) {
     for (long p = 0; p < planes; ++p) {
         const int c = (int)(p % C);
         const float mu = stats[2 * p], rstd = stats[2 * p + 1];
-        double s1 = 0, s2 = 0;
+        double s1 = 0, s2 = 0, sg = 0;
         for (long i = 0; i < L; ++i) {
             const float xh = (x[p * L + i] - mu) * rstd;
             const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
@@ -230,7 +238,9 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
             const float xh = (x[p * L + i] - mu) * rstd;
             const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
             g[p * L + i] = gamma[c] * rstd * (gn - m1 - xh * m2);
+            sg += g[p * L + i];
         }
+        if (gbias) gbias[c] += alpha * (float)sg;
     }
     return 0;
 }

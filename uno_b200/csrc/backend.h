@@ -105,15 +105,20 @@ int be_banded2d(const Banded2DArgs& a, stream_t s);
 // ---- elementwise / reductions ----------------------------------------------------------------------
 int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s);
 int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s);
+// same, plane-structured, with the per-channel sum of the result folded in:
+//   g = gy * gelu'(pre) ;  gbias[p % C] += alpha * sum over the plane's L elements of g   (gbias pre-zeroed)
+int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias,
+                     float alpha, stream_t s);
 // per-plane mean / rstd over L contiguous elements: stats[p] = (mean, rstd)
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s);
 // y = [gelu]( (x-mean)*rstd*gamma[c] + beta[c] ), plane p -> channel p % C
 int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
                     float* y, long planes, int C, long L, int non_lin, stream_t s);
-// backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller)
+// backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller);
+// optional gbias[c] += alpha * sum of g over the channel's planes (pre-zeroed; NULL to skip)
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
-                    long L, int non_lin, stream_t s);
+                    long L, int non_lin, float* gbias, float alpha, stream_t s);
 // out[c] += alpha * sum over planes p with p % C == c and over the plane's L elements  (out pre-zeroed)
 int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t s);
 // y[p, :] += v[p % C] * alpha

@@ -471,6 +471,27 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
         g[i] = gy[i] * gelu_grad_f(pre[i]);
 }
 
+__device__ __forceinline__ double block_sum(double v, double* sh);
+
+// plane-structured GELU backward with the conv-bias gradient folded in: grid (planes, chunks)
+__global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const float* __restrict__ gy, const float* __restrict__ pre,
+                                                            float* __restrict__ g, int C, long L, float* __restrict__ gbias,
+                                                            float alpha) {
+    __shared__ double sh[32];
+    const long p = blockIdx.x;
+    const float* gp = gy + p * L;
+    const float* pp = pre + p * L;
+    float* op = g + p * L;
+    float s = 0.f;
+    for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < L; i += (long)gridDim.y * blockDim.x) {
+        const float v = gp[i] * gelu_grad_f(pp[i]);
+        op[i] = v;
+        s += v;
+    }
+    const double t = block_sum((double)s, sh);
+    if (threadIdx.x == 0) atomicAdd(gbias + (p % C), alpha * (float)t);
+}
+
 __device__ __forceinline__ double block_sum(double v, double* sh) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -534,7 +555,7 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ g,
                                                            float* __restrict__ ggamma, float* __restrict__ gbeta, int C,
-                                                           long L, int non_lin) {
+                                                           long L, int non_lin, float* __restrict__ gbias, float alpha) {
     __shared__ double sh[32];
     const long p = blockIdx.x;
     const int c = (int)(p % C);
@@ -562,10 +583,17 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
     const float m1 = (float)(t1 / (double)L), m2 = (float)(t2 / (double)L);
     const float k = ga * rstd;
     float* op = g + p * L;
+    float sg = 0.f;
     for (long i = threadIdx.x; i < L; i += blockDim.x) {
         const float xh = (xp[i] - mu) * rstd;
         const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
-        op[i] = k * (gn - m1 - xh * m2);
+        const float v = k * (gn - m1 - xh * m2);
+        op[i] = v;
+        sg += v;
+    }
+    if (gbias != nullptr) {   // conv-bias gradient: the (rounding-level) sum of what flows through the norm
+        const double tg = block_sum((double)sg, sh);
+        if (threadIdx.x == 0) atomicAdd(gbias + c, alpha * (float)tg);
     }
 }
 
@@ -1141,6 +1169,16 @@ int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t 
     CU_LAUNCH_CHECK();
     return 0;
 }
+int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha,
+                     stream_t s) {
+    if (planes <= 0 || L <= 0) return 0;
+    ProfScope ps("gelu_bwd", 12.0 * planes * L, 0, S(s));
+    // enough CTAs per plane to fill the machine, few enough that the atomics stay negligible
+    unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 2047) / 2048, (148L * 8 + planes - 1) / planes));
+    gelu_bwd_bias_kernel<<<dim3((unsigned)planes, gy_), 256, 0, S(s)>>>(gy, pre, g, C, L, gbias, alpha);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s) {
     if (planes <= 0) return 0;
     ProfScope ps("instnorm_stats", 4.0 * planes * L, 0, S(s));
@@ -1158,10 +1196,11 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
     return 0;
 }
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma, const float* beta,
-                    float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
+                    float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, float* gbias, float alpha,
+                    stream_t s) {
     if (planes <= 0) return 0;
     ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
-    norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin);
+    norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin, gbias, alpha);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1267,12 +1306,14 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k);
     } else {
-        const size_t smem = proj_bwd_smem(CT, k.hid, k.out_ch);
+        // double-buffer the staged inputs when both copies fit beside the weights (hid <= 64 at 64 channels)
+        const int nbuf = proj_bwd_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;
+        const size_t smem = proj_bwd_smem(CT, k.hid, k.out_ch, nbuf);
         int rc = ensure_smem(proj_bwd_kernel<CT>, smem);
         if (rc) return rc;
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;   // tiles of the cropped grid
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);            // persistent, one CTA per SM
-        proj_bwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
+        proj_bwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles, nbuf);
     }
     CU_LAUNCH_CHECK();
     return 0;

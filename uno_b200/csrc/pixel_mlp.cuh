@@ -83,6 +83,27 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 __host__ __device__ inline int round4(int n) { return (n + 3) & ~3; }
 
+// linear index over [batch, raw grid] -> (sample, linear index inside the PADDED grid); 32-bit arithmetic when it fits
+__device__ __forceinline__ void raw_to_padded(const PixGeom& g, long idx, long& b, long& rp, long& pp) {
+    int r0, r1, r2;
+    if (idx < 0x7fffffffL) {
+        const unsigned i = (unsigned)idx, nraw = (unsigned)g.nraw;
+        const unsigned bb = i / nraw, r = i - bb * nraw;
+        const unsigned t = r / (unsigned)g.n2;
+        r2 = (int)(r - t * (unsigned)g.n2);
+        r0 = (int)(t / (unsigned)g.n1);
+        r1 = (int)(t - (unsigned)r0 * (unsigned)g.n1);
+        b = bb; rp = r;
+    } else {
+        b = idx / g.nraw;
+        rp = idx - b * g.nraw;
+        r2 = (int)(rp % g.n2);
+        const long t = rp / g.n2;
+        r1 = (int)(t % g.n1); r0 = (int)(t / g.n1);
+    }
+    pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
+}
+
 // =====================================================================================================
 // lift
 // =====================================================================================================
@@ -420,7 +441,7 @@ inline size_t proj_fwd_smem(int CT, int hid, int out_ch) {
 // with thread tiles 8x4, (CT/4)x4 and 2x4.  A thread's four pixels are tp, tp+64, tp+128, tp+192 so that every
 // shared / global access of a warp is to 32 consecutive pixels.
 template <int CT>
-__global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long ntiles) {
+__global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long ntiles, int nbuf) {
     extern __shared__ __align__(16) float psm[];
     const float** sbase = reinterpret_cast<const float**>(psm);
     float** gbase = reinterpret_cast<float**>(psm) + CT;
@@ -434,13 +455,31 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
     float* accW2 = accb1 + H4;
     float* accb2 = accW2 + OH4;                            // [4]
     float* D = accb2 + 4;                                  // [kProjHC][TPP]  dL/dpre1 of the current hidden chunk
-    float* IN = D + (size_t)kProjHC * kPixTPP;             // [CT][TPP]       cropped inputs of the tile
+    float* INbuf = D + (size_t)kProjHC * kPixTPP;          // nbuf x [CT][TPP] cropped inputs of a tile (double-buffered when it fits)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     proj_stage_tables<CT>(k, sbase, gbase, sstride);
     proj_stage_weights<CT>(k, sW1, sb1, sW2, nullptr);
     for (int i = tid; i < k.hid * CT + H4 + OH4 + 4; i += kPixTP) accW1[i] = 0.f;
     __syncthreads();
     const PixGeom g = k.g;
+    const long total = (long)k.batch * g.nraw;
+    // asynchronous staging of a tile's inputs (LDGSTS: no registers, every load of the tile in flight at once);
+    // thread t copies pixel t of the tile, all channels; missing pixels / channels are zero-filled (src-size 0)
+    auto stage_tile = [&](long tile, float* dstbuf) {
+        const long idx = tile * kPixTP + tid;
+        const bool valid = idx < total;
+        long b = 0, rp = 0, pp = 0;
+        if (valid) raw_to_padded(g, idx, b, rp, pp);
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(dstbuf + tid);
+#pragma unroll 8
+        for (int c = 0; c < CT; ++c) {
+            const bool on = valid && c < k.ctot;
+            const float* src = on ? sbase[c] + b * sstride[c] + pp : k.w1;
+            const int sz = on ? 4 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (uint32_t)(c * kPixTPP * 4)), "l"(src), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     // ---- the padding of the source gradients is zero (the crop has no gradient there)
     if (g.npad != g.nraw) {
         const long ptotal = (long)k.batch * g.npad;
@@ -462,22 +501,23 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
     const int tn = tid >> 6, tp = tid & 63;                // PRE / DIN products: hidden (channel) block, pixel lane
     const int c_l = lane & 7, n_l = lane >> 3;
     const int cbase = (warp % WC) * 32, nwarp = (warp / WC) * 8;
-    const long total = (long)k.batch * g.nraw;
+    int cur = 0;
+    if (nbuf == 2 && (long)blockIdx.x < ntiles) stage_tile(blockIdx.x, INbuf);
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long base = tile * kPixTP;
-        // ---- stage the tile's inputs: thread t loads pixel t of the tile, all channels
-        {
-            const long idx = base + tid;
-            const bool valid = idx < total;
-            const long b = valid ? idx / g.nraw : 0;
-            const long rp = valid ? idx - b * g.nraw : 0;
-            const int r2 = (int)(rp % g.n2);
-            const long t = rp / g.n2;
-            const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
-            const long pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
-#pragma unroll 8
-            for (int c = 0; c < CT; ++c)
-                IN[c * kPixTPP + tid] = (valid && c < k.ctot) ? __ldg(sbase[c] + b * sstride[c] + pp) : 0.f;
+        float* IN = INbuf + (size_t)cur * CT * kPixTPP;
+        if (nbuf == 2) {
+            const long next = tile + gridDim.x;
+            if (next < ntiles) {
+                stage_tile(next, INbuf + (size_t)(cur ^ 1) * CT * kPixTPP);   // overlaps this tile's arithmetic
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            cur ^= 1;
+        } else {
+            stage_tile(tile, IN);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         // ---- this thread's four pixels in the register-tiled products
         long pb[4], ppx[4];
@@ -486,13 +526,10 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
         for (int q = 0; q < 4; ++q) {
             const long idx = base + tp + 64 * q;
             const bool valid = idx < total;
-            const long b = valid ? idx / g.nraw : -1;
-            const long rp = valid ? idx - b * g.nraw : 0;
-            const int r2 = (int)(rp % g.n2);
-            const long t = rp / g.n2;
-            const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
+            long b = -1, rp = 0, pp = 0;
+            if (valid) raw_to_padded(g, idx, b, rp, pp);
             pb[q] = b;
-            ppx[q] = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
+            ppx[q] = pp;
 #pragma unroll
             for (int o = 0; o < kProjMaxOut; ++o) go[q][o] = (valid && o < k.out_ch) ? __ldg(k.gout + idx * k.out_ch + o) : 0.f;
         }
@@ -665,7 +702,7 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
     for (int i = tid; i < k.out_ch; i += kPixTP) atomicAdd(k.gb2 + i, accb2[i]);
 }
 
-inline size_t proj_bwd_smem(int CT, int hid, int out_ch) {
+inline size_t proj_bwd_smem(int CT, int hid, int out_ch, int nbuf) {
     return proj_table_bytes(CT) +
-           sizeof(float) * ((size_t)2 * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid)) + 4 + (size_t)(kProjHC + CT) * kPixTPP);
+           sizeof(float) * ((size_t)2 * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid)) + 4 + (size_t)(kProjHC + nbuf * CT) * kPixTPP);
 }

@@ -47,14 +47,19 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
     const int r0 = __ldg(k.gs0 + ga0), c0 = __ldg(k.gs1 + ga1);
     const int rin = __ldg(k.gs0 + ga0 + ngh - 1) + W0 - r0;   // windows never leave the input (plan guarantee)
     const int cin = __ldg(k.gs1 + ga1 + ngw - 1) + W1 - c0;
-    // ---- stage the input window
+    // ---- stage the input window: a warp per row, lanes over columns (up to 160 columns unrolled, predicated)
     {
-        const float* xp = k.x + (p * k.n_in0 + r0) * (long)k.n_in1 + c0;
+        const float* xp = k.x + (p * k.n_in0 + r0) * (long)k.n_in1 + c0 + lane;
+        const uint32_t in_base = (uint32_t)__cvta_generic_to_shared(in_s) + 4u * lane;
         for (int r = warp; r < rin; r += 8) {
             const float* src = xp + (long)r * k.n_in1;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(in_s + r * k.ldin);
-            for (int c = lane; c < cin; c += 32)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + c) : "memory");
+            const uint32_t dst = in_base + 4u * (uint32_t)(r * k.ldin);
+#pragma unroll
+            for (int it = 0; it < 5; ++it)
+                if (lane + 32 * it < cin)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * it), "l"(src + 32 * it) : "memory");
+            for (int c = lane + 160; c < cin; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (c - lane)), "l"(src + (c - lane)) : "memory");
         }
     }
     for (int i = tid; i < ngw * W1 * G1; i += 256) d1s[i] = __ldg(k.D1 + (size_t)ga1 * W1 * G1 + i);
@@ -75,7 +80,9 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
                 w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
             }
         const int cs = gs1s[cg];
-        for (int r = lane; r < rin; r += 32) {
+        for (int rb = 0; rb < rin; rb += 32) {
+            // uniform control flow: lanes past the window recompute its last row and skip the store
+            const int r = min(rb + lane, rin - 1);
             const float* src = in_s + r * k.ldin + cs;
             float acc[G1];
 #pragma unroll
@@ -86,16 +93,17 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
 #pragma unroll
                 for (int q = 0; q < G1; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
             }
-            float* dst = mid_s + r * kRsMidLd + cg * G1;
+            if (rb + lane < rin) {
+                float* dst = mid_s + r * kRsMidLd + cg * G1;
 #pragma unroll
-            for (int q = 0; q < G1; ++q) dst[q] = acc[q];
+                for (int q = 0; q < G1; ++q) dst[q] = acc[q];
+            }
         }
     }
     __syncthreads();
     // ---- pass B: y[i][j] = sum_u D0[g][u][q] * mid[gs0[g] + u][j],  i = g*G0 + q
     const int i0 = ga0 * G0, j0 = tw * kRsTW;
-    for (int it = warp; it < ngh * 2; it += 8) {
-        const int rg = it >> 1, jc = (it & 1) * 32 + lane;
+    for (int rg = warp; rg < ngh; rg += 8) {
         float w[W0][G0];
         const float4* wsrc = reinterpret_cast<const float4*>(d0s + rg * W0 * G0);
 #pragma unroll
@@ -105,22 +113,27 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
                 const float4 v = wsrc[u * (G0 / 4) + q4];
                 w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
             }
-        const float* src = mid_s + gs0s[rg] * kRsMidLd + jc;
-        float acc[G0];
+        const float* srow = mid_s + gs0s[rg] * kRsMidLd + lane;
+        float* yrow = k.y + (p * k.n_out0 + i0 + rg * G0) * (long)k.n_out1 + j0 + lane;
+        const int rows_left = k.n_out0 - (i0 + rg * G0);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {          // the two 32-column halves of the tile share the weights
+            const float* src = srow + 32 * half;
+            float acc[G0];
 #pragma unroll
-        for (int q = 0; q < G0; ++q) acc[q] = 0.f;
+            for (int q = 0; q < G0; ++q) acc[q] = 0.f;
 #pragma unroll
-        for (int u = 0; u < W0; ++u) {
-            const float v = src[u * kRsMidLd];
+            for (int u = 0; u < W0; ++u) {
+                const float v = src[u * kRsMidLd];
 #pragma unroll
-            for (int q = 0; q < G0; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
-        }
-        const int j = j0 + jc;
-        if (j < k.n_out1) {
-            float* yp = k.y + (p * k.n_out0 + i0 + rg * G0) * (long)k.n_out1 + j;
+                for (int q = 0; q < G0; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
+            }
+            if (j0 + 32 * half + lane < k.n_out1) {
+                float* yp = yrow + 32 * half;
 #pragma unroll
-            for (int q = 0; q < G0; ++q)
-                if (i0 + rg * G0 + q < k.n_out0) yp[(long)q * k.n_out1] = acc[q];
+                for (int q = 0; q < G0; ++q)
+                    if (q < rows_left) yp[(long)q * k.n_out1] = acc[q];
+            }
         }
     }
 }

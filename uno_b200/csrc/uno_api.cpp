@@ -633,6 +633,7 @@ int pointwise_fwd_impl(const uno_conv_desc* d, ResamplePlan* rp, const float* x,
     return rp->apply(t, P, z, scratch, st);
 }
 
+// gconv_b == NULL: the caller has already produced the bias gradient (fused into the activation backward)
 int pointwise_bwd_impl(const uno_conv_desc* d, ResamplePlan* rp, const float* gz, const float* x,
                        const float* saved, const float* conv_w, float* gx, float* gconv_w,
                        float* gconv_b, Arena& ar, stream_t st) {
@@ -895,22 +896,34 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
     const size_t nact = (size_t)planes * g.n_out;
     Arena ar(ws, ws_bytes);
     const float* gs = gy;   // gradient w.r.t. conv(x)+w(x)
+    // the conv-bias gradient (gain * per-channel sum of gs) is folded into the kernel that produces gs
+    const float bias_gain = g.identity ? 1.0f : (float)rp->gain;
+    bool bias_done = false;
     if (bd->normalize) {
         float* buf = ar.take(nact);
         if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for operator block backward");
         BE_TRY(be_memset(ggamma, 0, d->out_ch * sizeof(float), stream));
         BE_TRY(be_memset(gbeta, 0, d->out_ch * sizeof(float), stream));
-        BE_TRY(be_norm_act_bwd(gy, pre, stats, gamma, beta, buf, ggamma, gbeta, planes, d->out_ch, g.n_out, bd->non_lin, stream));
+        if (gconv_b) BE_TRY(be_memset(gconv_b, 0, d->out_ch * sizeof(float), stream));
+        BE_TRY(be_norm_act_bwd(gy, pre, stats, gamma, beta, buf, ggamma, gbeta, planes, d->out_ch, g.n_out, bd->non_lin, gconv_b,
+                               bias_gain, stream));
+        bias_done = true;
         gs = buf;
     } else if (bd->non_lin) {
         float* buf = ar.take(nact);
         if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for operator block backward");
-        BE_TRY(be_gelu_bwd(gy, pre, buf, nact, stream));
+        if (gconv_b) {
+            BE_TRY(be_memset(gconv_b, 0, d->out_ch * sizeof(float), stream));
+            BE_TRY(be_gelu_bwd_bias(gy, pre, buf, planes, d->out_ch, g.n_out, gconv_b, bias_gain, stream));
+            bias_done = true;
+        } else {
+            BE_TRY(be_gelu_bwd(gy, pre, buf, nact, stream));
+        }
         gs = buf;
     }
     {
         Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
-        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, gconv_b, sub, stream));
+        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, bias_done ? nullptr : gconv_b, sub, stream));
     }
     {
         Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));

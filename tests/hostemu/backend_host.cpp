@@ -89,20 +89,21 @@ int be_mid(const MidArgs& a, stream_t) {
 }
 
 int be_cmm(const CmmArgs& a, stream_t) {
+  for (int cr = 0; cr < a.ncorner; ++cr)
     for (int m = 0; m < a.M; ++m)
         for (int n = 0; n < a.N; ++n)
             for (int qo = 0; qo < a.q_outer; ++qo)
                 for (int qi = 0; qi < a.q_inner; ++qi) {
                     double re = 0, im = 0;
                     for (int k = 0; k < a.K; ++k) {
-                        const float* pa = a.A + 2 * (m * a.a_sm + k * a.a_sk + qo * a.a_sqo + qi);
-                        const float* pb = a.B + 2 * (k * a.b_sk + n * a.b_sn + qo * a.b_sqo + qi);
+                        const float* pa = a.A[cr] + 2 * (m * a.a_sm + k * a.a_sk + qo * a.a_sqo + qi);
+                        const float* pb = a.B[cr] + 2 * (k * a.b_sk + n * a.b_sn + qo * a.b_sqo + qi);
                         const double ar = pa[0], ai = a.conjA ? -pa[1] : pa[1];
                         const double br = pb[0], bi = a.conjB ? -pb[1] : pb[1];
                         re += ar * br - ai * bi;
                         im += ar * bi + ai * br;
                     }
-                    float* pc = a.C + 2 * (m * a.c_sm + n * a.c_sn + qo * a.c_sqo + qi);
+                    float* pc = a.C[cr] + 2 * (m * a.c_sm + n * a.c_sn + qo * a.c_sqo + qi);
                     pc[0] = (float)re;
                     pc[1] = (float)im;
                 }
@@ -220,11 +221,11 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
 
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
-                    long L, int non_lin, float* gbias, float alpha, stream_t) {
+                    long L, int non_lin, stream_t) {
     for (long p = 0; p < planes; ++p) {
         const int c = (int)(p % C);
         const float mu = stats[2 * p], rstd = stats[2 * p + 1];
-        double s1 = 0, s2 = 0, sg = 0;
+        double s1 = 0, s2 = 0;
         for (long i = 0; i < L; ++i) {
             const float xh = (x[p * L + i] - mu) * rstd;
             const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
@@ -238,9 +239,7 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
             const float xh = (x[p * L + i] - mu) * rstd;
             const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
             g[p * L + i] = gamma[c] * rstd * (gn - m1 - xh * m2);
-            sg += g[p * L + i];
         }
-        if (gbias) gbias[c] += alpha * (float)sg;
     }
     return 0;
 }

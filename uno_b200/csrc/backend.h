@@ -68,10 +68,15 @@ int be_mid(const MidArgs& a, stream_t s);
 
 // ---- per-mode complex contraction: C[m,n,q] = sum_k opA(A[m,k,q]) * opB(B[k,n,q]) -----------------
 // q = (qo, qi): qi contiguous (length q_inner), qo strided.  All strides in complex elements.
+// Up to four independent problems of identical shape (the spectrum corners weights1..4) run in one launch.
 struct CmmArgs {
-    const float* A = nullptr; long a_sm = 0, a_sk = 0, a_sqo = 0; int conjA = 0;
-    const float* B = nullptr; long b_sk = 0, b_sn = 0, b_sqo = 0; int conjB = 0;
-    float* C = nullptr; long c_sm = 0, c_sn = 0, c_sqo = 0;
+    int ncorner = 1;
+    const float* A[4] = {nullptr, nullptr, nullptr, nullptr};
+    const float* B[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* C[4] = {nullptr, nullptr, nullptr, nullptr};
+    long a_sm = 0, a_sk = 0, a_sqo = 0; int conjA = 0;
+    long b_sk = 0, b_sn = 0, b_sqo = 0; int conjB = 0;
+    long c_sm = 0, c_sn = 0, c_sqo = 0;
     int M = 0, N = 0, K = 0, q_outer = 1, q_inner = 0;
 };
 int be_cmm(const CmmArgs& a, stream_t s);
@@ -114,11 +119,11 @@ int be_plane_stats(const float* x, float* stats, long planes, long L, float eps,
 // y = [gelu]( (x-mean)*rstd*gamma[c] + beta[c] ), plane p -> channel p % C
 int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
                     float* y, long planes, int C, long L, int non_lin, stream_t s);
-// backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller);
-// optional gbias[c] += alpha * sum of g over the channel's planes (pre-zeroed; NULL to skip)
+// backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller).
+// Every plane of g sums to zero in exact arithmetic (the mean is projected out).
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
-                    long L, int non_lin, float* gbias, float alpha, stream_t s);
+                    long L, int non_lin, stream_t s);
 // out[c] += alpha * sum over planes p with p % C == c and over the plane's L elements  (out pre-zeroed)
 int be_channel_sum(const float* x, float* out, long planes, int C, long L, float alpha, stream_t s);
 // y[p, :] += v[p % C] * alpha

@@ -3,7 +3,7 @@
 // Kernel inventory (DESIGN.md has the roofline each one is bound by):
 //   gemm_kernel        C = A*B (+epilogue)   truncated-DFT analysis/synthesis along the last axis,
 //                                             1x1 channel mix, weight-gradient reduction (split-K, atomics)
-//   mid_kernel         complex [J x H] transform along a middle axis, batched
+//   mid2_kernel        complex [J x H] transform along a leading axis, batched, register-tiled
 //   cmm_kernel         per-mode complex channel contraction (mode index on the lanes)
 //   banded_kernel      anti-aliased bicubic resample bands (and their transposes)
 //   elementwise / plane reductions: GELU fwd/bwd, InstanceNorm stats / apply / backward, bias sums
@@ -254,67 +254,92 @@ int dispatch_gemm(const GemmK& k, int batch, cudaStream_t st) {
 }
 
 // =====================================================================================================
-// complex transform along a middle axis: Y[o,j,i] = sum_h Mat[j,h] X[o,h,i]
-// CTA: one o, 32 j x TI i outputs, 128 threads, each 2 j x (TI/8) i complex accumulators.
+// complex transform along a leading axis, batched over planes:  Y[o,j,i] = sum_h Mat[j,h] * X[o,h,i]
+// Register-tiled: a thread owns TJ x TI complex outputs of one plane; a CTA holds ppc planes x (nj x ni) threads
+// and walks h in chunks staged in shared memory (the Mat chunk is shared by the CTA's planes).  Per h a thread
+// issues TJ 8-byte + one (TI=2: 16-byte) shared loads for 4*TJ*TI FMAs.
 // =====================================================================================================
-template <int TI>
-__global__ void __launch_bounds__(128) mid_kernel(const float2* __restrict__ X, const float2* __restrict__ Mat,
-                                                  float2* __restrict__ Y, int O, int H, int J, int I,
-                                                  int tilesI, int tilesJ) {
-    constexpr int NI = TI / 8;
-    constexpr int HK = 16;
-    __shared__ float2 Ms[HK][32 + 1];
-    __shared__ float2 Xs[HK][TI];
-    long bid = blockIdx.x;
-    const int ti0 = (int)(bid % tilesI) * TI; bid /= tilesI;
-    const int tj0 = (int)(bid % tilesJ) * 32; bid /= tilesJ;
-    const long o = bid;
+struct Mid2K {
+    const float2* X; const float2* Mat; float2* Y;
+    int O, H, J, I;
+    int nj, ni, ppc, HK, tilesJ, tilesI;
+};
+
+template <int TJ, int TI>
+__global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
+    extern __shared__ __align__(16) float2 msm[];
+    const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
+    float2* Ms = msm;                                   // [HK][JTP]
+    float2* Xs = Ms + (size_t)k.HK * JTP + (((size_t)k.HK * JTP) & 1);   // [ppc][HK][IT], 16-byte aligned
     const int tid = threadIdx.x;
-    const int tj = tid / 8, ti = tid % 8;
-    float2 acc[2][NI];
+    const int tpp = k.nj * k.ni;
+    const int grp = tid / tpp, t = tid - grp * tpp;
+    const int tj = t / k.ni, ti = t - tj * k.ni;
+    const bool active = grp < k.ppc;
+    long bid = blockIdx.x;
+    const int it = (int)(bid % k.tilesI); bid /= k.tilesI;
+    const int jt = (int)(bid % k.tilesJ); bid /= k.tilesJ;
+    const long o0 = bid * k.ppc;
+    const int j0 = jt * JT, i0 = it * IT;
+    float2 acc[TJ][TI];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < TJ; ++a)
 #pragma unroll
-        for (int b = 0; b < NI; ++b) acc[a][b] = make_float2(0.f, 0.f);
-    const float2* Xo = X + o * (long)H * I;
-    for (int h0 = 0; h0 < H; h0 += HK) {
-        // Mat tile: 32 j x 16 h, h contiguous in memory
-        for (int idx = tid; idx < 32 * HK; idx += 128) {
-            const int h = idx % HK, j = idx / HK;
+        for (int b = 0; b < TI; ++b) acc[a][b] = make_float2(0.f, 0.f);
+    for (int h0 = 0; h0 < k.H; h0 += k.HK) {
+        const int hk = min(k.HK, k.H - h0);
+        for (int idx = tid; idx < JT * k.HK; idx += 256) {
+            const int h = idx % k.HK, j = idx / k.HK;
             float2 v = make_float2(0.f, 0.f);
-            if (tj0 + j < J && h0 + h < H) v = __ldg(Mat + (long)(tj0 + j) * H + h0 + h);
-            Ms[h][j] = v;
+            if (j0 + j < k.J && h < hk) v = __ldg(k.Mat + (long)(j0 + j) * k.H + h0 + h);
+            Ms[h * JTP + j] = v;
         }
-        for (int idx = tid; idx < HK * TI; idx += 128) {
-            const int i = idx % TI, h = idx / TI;
+        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
+            const int i = idx % IT;
+            const int r = idx / IT;
+            const int h = r % k.HK, g = r / k.HK;
             float2 v = make_float2(0.f, 0.f);
-            if (ti0 + i < I && h0 + h < H) v = __ldg(Xo + (long)(h0 + h) * I + ti0 + i);
-            Xs[h][i] = v;
+            if (o0 + g < k.O && h < hk && i0 + i < k.I) v = __ldg(k.X + ((o0 + g) * k.H + h0 + h) * (long)k.I + i0 + i);
+            Xs[idx] = v;
         }
         __syncthreads();
+        if (active) {
+            const float2* mp = Ms + tj * TJ;
+            const float2* xp = Xs + (size_t)grp * k.HK * IT + ti * TI;
+#pragma unroll 4
+            for (int h = 0; h < hk; ++h) {
+                float2 m[TJ], x[TI];
 #pragma unroll
-        for (int h = 0; h < HK; ++h) {
-            const float2 m0 = Ms[h][tj], m1 = Ms[h][tj + 16];
+                for (int a = 0; a < TJ; ++a) m[a] = mp[h * JTP + a];
+                if (TI == 2) {
+                    const float4 v = *reinterpret_cast<const float4*>(xp + (size_t)h * IT);
+                    x[0] = make_float2(v.x, v.y);
+                    x[TI - 1] = make_float2(v.z, v.w);
+                } else {
+                    x[0] = xp[(size_t)h * IT];
+                }
 #pragma unroll
-            for (int b = 0; b < NI; ++b) {
-                const float2 x = Xs[h][ti + 8 * b];
-                acc[0][b].x = fmaf(m0.x, x.x, acc[0][b].x); acc[0][b].x = fmaf(-m0.y, x.y, acc[0][b].x);
-                acc[0][b].y = fmaf(m0.x, x.y, acc[0][b].y); acc[0][b].y = fmaf(m0.y, x.x, acc[0][b].y);
-                acc[1][b].x = fmaf(m1.x, x.x, acc[1][b].x); acc[1][b].x = fmaf(-m1.y, x.y, acc[1][b].x);
-                acc[1][b].y = fmaf(m1.x, x.y, acc[1][b].y); acc[1][b].y = fmaf(m1.y, x.x, acc[1][b].y);
+                for (int a = 0; a < TJ; ++a)
+#pragma unroll
+                    for (int b = 0; b < TI; ++b) {
+                        acc[a][b].x = fmaf(m[a].x, x[b].x, acc[a][b].x); acc[a][b].x = fmaf(-m[a].y, x[b].y, acc[a][b].x);
+                        acc[a][b].y = fmaf(m[a].x, x[b].y, acc[a][b].y); acc[a][b].y = fmaf(m[a].y, x[b].x, acc[a][b].y);
+                    }
             }
         }
         __syncthreads();
     }
-    float2* Yo = Y + o * (long)J * I;
+    if (active && o0 + grp < k.O) {
+        float2* Yo = k.Y + (o0 + grp) * (long)k.J * k.I;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int j = tj0 + tj + 16 * a;
-        if (j >= J) continue;
+        for (int a = 0; a < TJ; ++a) {
+            const int j = j0 + tj * TJ + a;
+            if (j >= k.J) continue;
 #pragma unroll
-        for (int b = 0; b < NI; ++b) {
-            const int i = ti0 + ti + 8 * b;
-            if (i < I) Yo[(long)j * I + i] = acc[a][b];
+            for (int b = 0; b < TI; ++b) {
+                const int i = i0 + ti * TI + b;
+                if (i < k.I) Yo[(long)j * k.I + i] = acc[a][b];
+            }
         }
     }
 }
@@ -324,14 +349,17 @@ __global__ void __launch_bounds__(128) mid_kernel(const float2* __restrict__ X, 
 // block (32 q, 4 n-tiles); thread tile 4 m x 4 n.
 // =====================================================================================================
 __global__ void __launch_bounds__(128) cmm_kernel(const CmmArgs a, int chunks_per_row) {
-    const int qo = blockIdx.x / chunks_per_row;
-    const int qi = (blockIdx.x - qo * chunks_per_row) * 32 + threadIdx.x;
+    const int per_corner = chunks_per_row * a.q_outer;
+    const int corner = blockIdx.x / per_corner;
+    const int bx = blockIdx.x - corner * per_corner;
+    const int qo = bx / chunks_per_row;
+    const int qi = (bx - qo * chunks_per_row) * 32 + threadIdx.x;
     const int m0 = blockIdx.y * 4;
     const int n0 = (blockIdx.z * 4 + threadIdx.y) * 4;
     if (qi >= a.q_inner || n0 >= a.N) return;
-    const float2* A = reinterpret_cast<const float2*>(a.A) + (long)qo * a.a_sqo + qi;
-    const float2* B = reinterpret_cast<const float2*>(a.B) + (long)qo * a.b_sqo + qi;
-    float2* C = reinterpret_cast<float2*>(a.C) + (long)qo * a.c_sqo + qi;
+    const float2* A = reinterpret_cast<const float2*>(a.A[corner]) + (long)qo * a.a_sqo + qi;
+    const float2* B = reinterpret_cast<const float2*>(a.B[corner]) + (long)qo * a.b_sqo + qi;
+    float2* C = reinterpret_cast<float2*>(a.C[corner]) + (long)qo * a.c_sqo + qi;
     const float sa = a.conjA ? -1.f : 1.f, sb = a.conjB ? -1.f : 1.f;
     float2 acc[4][4];
 #pragma unroll
@@ -555,7 +583,7 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ g,
                                                            float* __restrict__ ggamma, float* __restrict__ gbeta, int C,
-                                                           long L, int non_lin, float* __restrict__ gbias, float alpha) {
+                                                           long L, int non_lin) {
     __shared__ double sh[32];
     const long p = blockIdx.x;
     const int c = (int)(p % C);
@@ -583,17 +611,10 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
     const float m1 = (float)(t1 / (double)L), m2 = (float)(t2 / (double)L);
     const float k = ga * rstd;
     float* op = g + p * L;
-    float sg = 0.f;
     for (long i = threadIdx.x; i < L; i += blockDim.x) {
         const float xh = (xp[i] - mu) * rstd;
         const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
-        const float v = k * (gn - m1 - xh * m2);
-        op[i] = v;
-        sg += v;
-    }
-    if (gbias != nullptr) {   // conv-bias gradient: the (rounding-level) sum of what flows through the norm
-        const double tg = block_sum((double)sg, sh);
-        if (threadIdx.x == 0) atomicAdd(gbias + c, alpha * (float)tg);
+        op[i] = k * (gn - m1 - xh * m2);
     }
 }
 
@@ -1032,33 +1053,63 @@ int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
     return dispatch_gemm(k, a.batch, S(s));
 }
 
-int be_mid(const MidArgs& a, stream_t s) {
-    if (a.O <= 0 || a.J <= 0 || a.I <= 0) return 0;
-    const int pad8 = ((a.I + 7) / 8) * 8, pad16 = ((a.I + 15) / 16) * 16;
-    const int tilesJ = (a.J + 31) / 32;
-    const float2* X = reinterpret_cast<const float2*>(a.X);
-    const float2* M = reinterpret_cast<const float2*>(a.Mat);
-    float2* Y = reinterpret_cast<float2*>(a.Y);
-    ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
-    if (pad8 < pad16) {
-        const int tilesI = pad8 / 8;
-        const long blocks = (long)a.O * tilesI * tilesJ;
-        mid_kernel<8><<<(unsigned)blocks, 128, 0, S(s)>>>(X, M, Y, a.O, a.H, a.J, a.I, tilesI, tilesJ);
-    } else {
-        const int tilesI = pad16 / 16;
-        const long blocks = (long)a.O * tilesI * tilesJ;
-        mid_kernel<16><<<(unsigned)blocks, 128, 0, S(s)>>>(X, M, Y, a.O, a.H, a.J, a.I, tilesI, tilesJ);
-    }
+namespace {
+template <int TJ, int TI>
+int launch_mid2(const Mid2K& k, size_t smem, long blocks, cudaStream_t st) {
+    int rc = ensure_smem(mid2_kernel<TJ, TI>, smem);
+    if (rc) return rc;
+    mid2_kernel<TJ, TI><<<(unsigned)blocks, 256, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;
+}
+}  // namespace
+
+int be_mid(const MidArgs& a, stream_t s) {
+    if (a.O <= 0 || a.J <= 0 || a.I <= 0) return 0;
+    Mid2K k;
+    k.X = reinterpret_cast<const float2*>(a.X);
+    k.Mat = reinterpret_cast<const float2*>(a.Mat);
+    k.Y = reinterpret_cast<float2*>(a.Y);
+    k.O = a.O; k.H = a.H; k.J = a.J; k.I = a.I;
+    // thread tile: TI = 2 columns when there are any to pair; TJ = the largest of 4, 3, 2 that pads J by <= 6 %
+    const int TI = a.I >= 2 ? 2 : 1;
+    int TJ = 2;
+    for (int cand = 4; cand >= 2; --cand) {
+        const int padded = (a.J + cand - 1) / cand * cand;
+        if (padded * 100 <= a.J * 106 || cand == 2) { TJ = cand; break; }
+    }
+    const int ni_all = (a.I + TI - 1) / TI;
+    k.ni = std::min(ni_all, 32);
+    k.tilesI = (ni_all + k.ni - 1) / k.ni;
+    const int nj_all = (a.J + TJ - 1) / TJ;
+    const int nj_cap = std::max(1, 256 / k.ni);
+    k.tilesJ = (nj_all + nj_cap - 1) / nj_cap;
+    k.nj = (nj_all + k.tilesJ - 1) / k.tilesJ;            // balanced tiles
+    k.ppc = std::max(1, 256 / (k.nj * k.ni));
+    if ((long)k.ppc > a.O) k.ppc = (int)a.O;
+    k.HK = a.H <= 48 ? a.H : 32;
+    const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
+    size_t ms = (size_t)k.HK * JTP;
+    ms += ms & 1;
+    const size_t smem = (ms + (size_t)k.ppc * k.HK * IT) * sizeof(float2);
+    const long blocks = (long)((a.O + k.ppc - 1) / k.ppc) * k.tilesJ * k.tilesI;
+    ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
+    switch (TJ * 10 + TI) {
+        case 42: return launch_mid2<4, 2>(k, smem, blocks, S(s));
+        case 32: return launch_mid2<3, 2>(k, smem, blocks, S(s));
+        case 22: return launch_mid2<2, 2>(k, smem, blocks, S(s));
+        case 41: return launch_mid2<4, 1>(k, smem, blocks, S(s));
+        case 31: return launch_mid2<3, 1>(k, smem, blocks, S(s));
+        default: return launch_mid2<2, 1>(k, smem, blocks, S(s));
+    }
 }
 
 int be_cmm(const CmmArgs& a, stream_t s) {
     if (a.M <= 0 || a.N <= 0 || a.q_inner <= 0 || a.q_outer <= 0) return 0;
     const int chunks = (a.q_inner + 31) / 32;
-    const double q = (double)a.q_inner * a.q_outer;
+    const double q = (double)a.q_inner * a.q_outer * a.ncorner;
     ProfScope ps("mode_contraction", 8.0 * q * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N), 8.0 * q * a.M * a.N * a.K, S(s));
-    dim3 grid((unsigned)(chunks * a.q_outer), (unsigned)((a.M + 3) / 4), (unsigned)((a.N + 15) / 16));
+    dim3 grid((unsigned)(chunks * a.q_outer * a.ncorner), (unsigned)((a.M + 3) / 4), (unsigned)((a.N + 15) / 16));
     cmm_kernel<<<grid, dim3(32, 4), 0, S(s)>>>(a, chunks);
     CU_LAUNCH_CHECK();
     return 0;
@@ -1091,10 +1142,10 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     if (smem > 160 * 1024) return -1;
     int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1>, smem);
     if (rc) return rc;
+    if (a.planes > 65535) return -1;          // planes ride on grid.z
     ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
                  2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
-    const long blocks = a.planes * k.tiles_h * k.tiles_w;
-    resample2d_kernel<G0, W0, G1, W1><<<(unsigned)blocks, 256, smem, st>>>(k);
+    resample2d_kernel<G0, W0, G1, W1><<<dim3((unsigned)k.tiles_w, (unsigned)k.tiles_h, (unsigned)a.planes), 256, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1196,11 +1247,10 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
     return 0;
 }
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma, const float* beta,
-                    float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, float* gbias, float alpha,
-                    stream_t s) {
+                    float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
     ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
-    norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin, gbias, alpha);
+    norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin);
     CU_LAUNCH_CHECK();
     return 0;
 }

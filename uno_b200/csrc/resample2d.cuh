@@ -37,10 +37,8 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
     float* d0s = d1s + NG1 * W1 * G1;                    // [NG0][W0][G0]
     int* gs1s = reinterpret_cast<int*>(d0s + NG0 * W0 * G0);   // [NG1]
     int* gs0s = gs1s + NG1;                              // [NG0]
-    long bid = blockIdx.x;
-    const int tw = (int)(bid % k.tiles_w); bid /= k.tiles_w;
-    const int th = (int)(bid % k.tiles_h); bid /= k.tiles_h;
-    const long p = bid;
+    const int tw = blockIdx.x, th = blockIdx.y;          // grid = (tiles_w, tiles_h, planes)
+    const long p = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ga0 = th * NG0, ga1 = tw * NG1;            // first row / column group of the tile
     const int ngh = min(NG0, k.ng0 - ga0), ngw = min(NG1, k.ng1 - ga1);
@@ -54,11 +52,12 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
         for (int r = warp; r < rin; r += 8) {
             const float* src = xp + (long)r * k.n_in1;
             const uint32_t dst = in_base + 4u * (uint32_t)(r * k.ldin);
+            constexpr int CIT = W1 == 16 ? 5 : 3;       // unrolled, predicated column chunks (wider windows: loop below)
 #pragma unroll
-            for (int it = 0; it < 5; ++it)
+            for (int it = 0; it < CIT; ++it)
                 if (lane + 32 * it < cin)
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * it), "l"(src + 32 * it) : "memory");
-            for (int c = lane + 160; c < cin; c += 32)
+            for (int c = lane + 32 * CIT; c < cin; c += 32)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (c - lane)), "l"(src + (c - lane)) : "memory");
         }
     }
@@ -128,11 +127,12 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
 #pragma unroll
                 for (int q = 0; q < G0; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
             }
-            if (j0 + 32 * half + lane < k.n_out1) {
-                float* yp = yrow + 32 * half;
+            const bool col_ok = j0 + 32 * half + lane < k.n_out1;
+            float* yp = yrow + 32 * half;
 #pragma unroll
-                for (int q = 0; q < G0; ++q)
-                    if (q < rows_left) yp[(long)q * k.n_out1] = acc[q];
+            for (int q = 0; q < G0; ++q) {              // running row pointer: one 64-bit add per store, predicated stores
+                if (col_ok && q < rows_left) *yp = acc[q];
+                yp += k.n_out1;
             }
         }
     }

@@ -52,6 +52,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(role, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `role`, from the committed ncu --set full capture of
+    one step of this workload (profiles/r01_traffic.json, made by tools/ncu_traffic.py); None when there is none."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if workload != "darcy" or not os.path.exists(path):
+        return None
+    try:
+        return float(json.load(open(path))["roles"][role]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
@@ -289,7 +301,7 @@ def main():
             top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
             achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
             roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                        "traffic": None, "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
+                        "traffic": measured_traffic(top, args.workload), "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
                         "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
                         "uno_kernel_ms_per_step": tot / nprof}
 

@@ -152,11 +152,14 @@ int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a, const 
                  const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
                  float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream);
 int uno_project_check(const uno_project_desc* d);
+/* hidden_pre: optional [hidden, B * prod(dim)] floats -- the fc1 pre-activations.  When fwd writes them and bwd gets
+ * them back, the backward skips recomputing fc1 (a third of its arithmetic); NULL on either side = recompute. */
 int uno_project_fwd(const uno_project_desc* d, const float* const* src, const float* w1,
-                    const float* b1, const float* w2, const float* b2, float* out, void* stream);
+                    const float* b1, const float* w2, const float* b2, float* out, float* hidden_pre,
+                    void* stream);
 int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* const* src,
-                    const float* w1, const float* b1, const float* w2, float* const* gsrc, float* gw1,
-                    float* gb1, float* gw2, float* gb2, void* stream);
+                    const float* hidden_pre, const float* w1, const float* b1, const float* w2,
+                    float* const* gsrc, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------------
  * uno_launch_count: kernels this library has launched since it was loaded.

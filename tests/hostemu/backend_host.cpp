@@ -23,6 +23,9 @@ void be_free(void* d) { free(d); }
 int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); return 0; }
 const char* be_name() { return "host-emulation"; }
 const char* be_error_string(int) { return "host emulation error"; }
+stream_t be_side_stream() { return nullptr; }
+int be_fork(stream_t, stream_t) { return 0; }
+int be_join(stream_t, stream_t) { return 0; }
 void be_profile_enable(int) {}
 size_t be_profile_report(char* buf, size_t cap) { if (buf && cap > 2) { buf[0] = '{'; buf[1] = '}'; buf[2] = 0; } return 2; }
 long be_launch_count() { return 0; }
@@ -361,6 +364,7 @@ int be_proj_fwd(const ProjArgs& a, stream_t) {
             for (int n = 0; n < a.hid; ++n) {
                 double s = a.b1[n];
                 for (int cc = 0; cc < ctot; ++cc) s += (double)a.w1[n * ctot + cc] * in[cc];
+                if (a.pre_out) a.pre_out[(size_t)n * a.batch * g.nraw + b * g.nraw + rp] = (float)s;
                 const double act = gelu_f((float)s);
                 for (int q = 0; q < a.out_ch; ++q) o[q] += (double)a.w2[q * a.hid + n] * act;
             }
@@ -388,6 +392,7 @@ int be_proj_bwd(const ProjArgs& a, stream_t) {
             for (int n = 0; n < a.hid; ++n) {
                 double s = a.b1[n];
                 for (int cc = 0; cc < ctot; ++cc) s += (double)a.w1[n * ctot + cc] * in[cc];
+                if (a.pre_in) s = a.pre_in[(size_t)n * a.batch * g.nraw + b * g.nraw + rp];   // what the forward pass saved
                 const double act = gelu_f((float)s);
                 double t = 0;
                 for (int q = 0; q < a.out_ch; ++q) { t += (double)go[q] * a.w2[q * a.hid + n]; gw2[q * a.hid + n] += go[q] * act; }

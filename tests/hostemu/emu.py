@@ -192,7 +192,7 @@ def lift_bwd(gh, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, want_ga=True):
     return (ga, *outs)
 
 
-def project_fwd(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
+def project_fwd(srcs, w1, b1, w2, b2, crop_lo, crop_hi, want_pre=False):
     L = lib()
     srcs = [_f32(s) for s in srcs]
     w1, b1, w2, b2 = (_f32(t) for t in (w1, b1, w2, b2))
@@ -202,11 +202,12 @@ def project_fwd(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
     _capi.check(L, L.uno_project_check(C.byref(d)))
     out = np.full((srcs[0].shape[0],) + dims + (w2.shape[0],), np.nan, np.float32)
     sp = _capi.ptr_array([s.ctypes.data for s in srcs])
-    _capi.check(L, L.uno_project_fwd(C.byref(d), sp, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), None))
-    return out
+    pre = np.full((w1.shape[0], out.size // w2.shape[0]), np.nan, np.float32) if want_pre else None
+    _capi.check(L, L.uno_project_fwd(C.byref(d), sp, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), _p(pre), None))
+    return (out, pre) if want_pre else out
 
 
-def project_bwd(gout, srcs, w1, b1, w2, crop_lo, crop_hi):
+def project_bwd(gout, srcs, w1, b1, w2, crop_lo, crop_hi, pre=None):
     L = lib()
     srcs = [_f32(s) for s in srcs]
     gout, w1, b1, w2 = (_f32(t) for t in (gout, w1, b1, w2))
@@ -218,5 +219,6 @@ def project_bwd(gout, srcs, w1, b1, w2, crop_lo, crop_hi):
     gb2 = np.full(w2.shape[0], np.nan, np.float32)
     sp = _capi.ptr_array([s.ctypes.data for s in srcs])
     gp = _capi.ptr_array([g.ctypes.data for g in gs])
-    _capi.check(L, L.uno_project_bwd(C.byref(d), _p(gout), sp, _p(w1), _p(b1), _p(w2), gp, _p(gw1), _p(gb1), _p(gw2), _p(gb2), None))
+    pre = _f32(pre) if pre is not None else None
+    _capi.check(L, L.uno_project_bwd(C.byref(d), _p(gout), sp, _p(pre), _p(w1), _p(b1), _p(w2), gp, _p(gw1), _p(gb1), _p(gw2), _p(gb2), None))
     return gs, gw1, gb1, gw2, gb2

@@ -35,13 +35,15 @@ def test_project(name):
     _, _, lo, hi, *_ = case
     t = project_inputs(case)
     ref = project_oracle(case, t)
-    out = emu.project_fwd(t["srcs"], t["w1"], t["b1"], t["w2"], t["b2"], lo, hi)
+    out, pre = emu.project_fwd(t["srcs"], t["w1"], t["b1"], t["w2"], t["b2"], lo, hi, want_pre=True)
     assert rel_err(out, ref["out"]) < FWD_TOL
-    gs, gw1, gb1, gw2, gb2 = emu.project_bwd(t["gout"], t["srcs"], t["w1"], t["b1"], t["w2"], lo, hi)
-    for g, r in zip(gs, ref["gsrcs"]):
-        assert rel_err(g, r) < BWD_TOL
-    for got, key in ((gw1, "gw1"), (gb1, "gb1"), (gw2, "gw2"), (gb2, "gb2")):
-        assert rel_err(got, ref[key]) < BWD_TOL, key
+    assert np.isfinite(pre).all()
+    for saved in (None, pre):       # backward recomputing fc1, and backward fed the saved pre-activations
+        gs, gw1, gb1, gw2, gb2 = emu.project_bwd(t["gout"], t["srcs"], t["w1"], t["b1"], t["w2"], lo, hi, pre=saved)
+        for g, r in zip(gs, ref["gsrcs"]):
+            assert rel_err(g, r) < BWD_TOL
+        for got, key in ((gw1, "gw1"), (gb1, "gb1"), (gw2, "gw2"), (gb2, "gb2")):
+            assert rel_err(got, ref[key]) < BWD_TOL, key
 
 
 def test_descriptor_errors():

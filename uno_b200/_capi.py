@@ -72,8 +72,8 @@ SYMBOLS = {
     "uno_lift_fwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uno_lift_bwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uno_project_check": (C.c_int, [_PDESC]),
-    "uno_project_fwd": (C.c_int, [_PDESC, _PP, _P, _P, _P, _P, _P, _P]),
-    "uno_project_bwd": (C.c_int, [_PDESC, _P, _PP, _P, _P, _P, _PP, _P, _P, _P, _P, _P]),
+    "uno_project_fwd": (C.c_int, [_PDESC, _PP, _P, _P, _P, _P, _P, _P, _P]),
+    "uno_project_bwd": (C.c_int, [_PDESC, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P]),
     "uno_launch_count": (C.c_long, []),
     "uno_profile_enable": (None, [C.c_int]),
     "uno_profile_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),

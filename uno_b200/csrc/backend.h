@@ -18,6 +18,15 @@ int be_memset(void* d, int v, size_t bytes, stream_t s);
 const char* be_name();
 const char* be_error_string(int code);   // message for a non-zero return of any be_* call
 
+// ---- fork / join of independent kernel sequences (the two branches of an operator block) -----------------
+// be_side_stream: a library-owned stream on the current device (created on first use).  be_fork makes `side` wait
+// for everything enqueued on `main` so far; be_join makes `main` wait for everything enqueued on `side` so far.
+// Both are event record + stream-wait pairs: asynchronous, capturable in a CUDA graph, and invisible to the caller,
+// whose stream still orders the whole call.  Returning NULL from be_side_stream disables the overlap.
+stream_t be_side_stream();
+int be_fork(stream_t main_stream, stream_t side);
+int be_join(stream_t main_stream, stream_t side);
+
 // ---- optional per-launch timing (CUDA events on the launching stream), off by default --------------
 // While enabled every be_* launch is bracketed by an event pair and tagged with its role and its
 // algorithmic bytes / flops.  be_profile_report synchronises and writes one JSON object:
@@ -156,6 +165,10 @@ struct ProjArgs {
     const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
     const float* w1 = nullptr; const float* b1 = nullptr; const float* w2 = nullptr; const float* b2 = nullptr;
     float* out = nullptr;               // fwd output [B, n.., out_ch]
+    // hidden pre-activations W_1*x + b_1, [hid, B * n..] (hidden unit major): optional fwd output / optional bwd input.
+    // With it the backward skips recomputing the first layer (a third of its arithmetic) for 4*hid bytes per pixel.
+    float* pre_out = nullptr;
+    const float* pre_in = nullptr;
     const float* gout = nullptr;        // bwd input
     float* gsrc[4] = {nullptr, nullptr, nullptr, nullptr};   // bwd outputs [B, src_ch, N..], fully written (zero outside the crop)
     float* gw1 = nullptr; float* gb1 = nullptr; float* gw2 = nullptr; float* gb2 = nullptr;       // bwd outputs, PRE-ZEROED

@@ -288,13 +288,13 @@ __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
         for (int b = 0; b < TI; ++b) acc[a][b] = make_float2(0.f, 0.f);
     for (int h0 = 0; h0 < k.H; h0 += k.HK) {
         const int hk = min(k.HK, k.H - h0);
-        for (int idx = tid; idx < JT * k.HK; idx += 256) {
+        for (int idx = tid; idx < JT * k.HK; idx += blockDim.x) {
             const int h = idx % k.HK, j = idx / k.HK;
             float2 v = make_float2(0.f, 0.f);
             if (j0 + j < k.J && h < hk) v = __ldg(k.Mat + (long)(j0 + j) * k.H + h0 + h);
             Ms[h * JTP + j] = v;
         }
-        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
+        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += blockDim.x) {
             const int i = idx % IT;
             const int r = idx / IT;
             const int h = r % k.HK, g = r / k.HK;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
 // per-mode complex contraction, mode index on the lanes: C[m,n,q] = sum_k A[m,k,q] B[k,n,q]
 // block (32 q, 4 n-tiles); thread tile 4 m x 4 n.
 // =====================================================================================================
-__global__ void __launch_bounds__(128) cmm_kernel(const CmmArgs a, int chunks_per_row) {
+__global__ void __launch_bounds__(128, 6) cmm_kernel(const CmmArgs a, int chunks_per_row) {
     const int per_corner = chunks_per_row * a.q_outer;
     const int corner = blockIdx.x / per_corner;
     const int bx = blockIdx.x - corner * per_corner;
@@ -998,6 +998,60 @@ size_t be_profile_report(char* buf, size_t cap) {
 
 long be_launch_count() { return g_launches; }
 
+// ---- side stream + event ring for fork / join -----------------------------------------------------------
+namespace {
+struct SideStreams {
+    std::mutex mu;
+    std::map<int, cudaStream_t> streams;       // one per device
+    std::map<int, std::vector<cudaEvent_t>> events;
+    std::map<int, unsigned> next;
+    bool disabled = false;
+} g_side;
+
+cudaEvent_t side_event(int dev) {
+    auto& ring = g_side.events[dev];
+    if (ring.empty()) {
+        ring.resize(32);
+        for (auto& e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    }
+    return ring[g_side.next[dev]++ % ring.size()];
+}
+}  // namespace
+
+stream_t be_side_stream() {
+    std::lock_guard<std::mutex> lk(g_side.mu);
+    if (g_side.disabled) return nullptr;
+    if (const char* env = getenv("UNO_B200_NO_OVERLAP")) {
+        if (env[0] == '1') { g_side.disabled = true; return nullptr; }
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    auto it = g_side.streams.find(dev);
+    if (it == g_side.streams.end()) {
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { g_side.disabled = true; return nullptr; }
+        it = g_side.streams.emplace(dev, st).first;
+    }
+    return (stream_t)it->second;
+}
+
+static int link_streams(cudaStream_t from, cudaStream_t to) {
+    // everything enqueued on `from` so far happens before anything enqueued on `to` from now on
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lk(g_side.mu);
+        ev = side_event(dev);
+    }
+    e = cudaEventRecord(ev, from);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaStreamWaitEvent(to, ev, 0);
+}
+int be_fork(stream_t main_stream, stream_t side) { return link_streams(S(main_stream), S(side)); }
+int be_join(stream_t main_stream, stream_t side) { return link_streams(S(side), S(main_stream)); }
+
 int be_upload(void** dptr, const void* host, size_t bytes) {
     cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 4);
     if (e != cudaSuccess) return (int)e;
@@ -1055,10 +1109,10 @@ int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
 
 namespace {
 template <int TJ, int TI>
-int launch_mid2(const Mid2K& k, size_t smem, long blocks, cudaStream_t st) {
+int launch_mid2(const Mid2K& k, size_t smem, long blocks, int threads, cudaStream_t st) {
     int rc = ensure_smem(mid2_kernel<TJ, TI>, smem);
     if (rc) return rc;
-    mid2_kernel<TJ, TI><<<(unsigned)blocks, 256, smem, st>>>(k);
+    mid2_kernel<TJ, TI><<<(unsigned)blocks, threads, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1087,6 +1141,9 @@ int be_mid(const MidArgs& a, stream_t s) {
     k.nj = (nj_all + k.tilesJ - 1) / k.tilesJ;            // balanced tiles
     k.ppc = std::max(1, 256 / (k.nj * k.ni));
     if ((long)k.ppc > a.O) k.ppc = (int)a.O;
+    // enough CTAs to fill the machine three times over before planes start sharing a CTA (and its Mat tile)
+    while (k.ppc > 1 && (long)((a.O + k.ppc - 1) / k.ppc) * k.tilesJ * k.tilesI < 148L * 3) --k.ppc;
+    const int threads = std::min(256, (k.ppc * k.nj * k.ni + 31) / 32 * 32);
     k.HK = a.H <= 48 ? a.H : 32;
     const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
     size_t ms = (size_t)k.HK * JTP;
@@ -1095,12 +1152,12 @@ int be_mid(const MidArgs& a, stream_t s) {
     const long blocks = (long)((a.O + k.ppc - 1) / k.ppc) * k.tilesJ * k.tilesI;
     ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
     switch (TJ * 10 + TI) {
-        case 42: return launch_mid2<4, 2>(k, smem, blocks, S(s));
-        case 32: return launch_mid2<3, 2>(k, smem, blocks, S(s));
-        case 22: return launch_mid2<2, 2>(k, smem, blocks, S(s));
-        case 41: return launch_mid2<4, 1>(k, smem, blocks, S(s));
-        case 31: return launch_mid2<3, 1>(k, smem, blocks, S(s));
-        default: return launch_mid2<2, 1>(k, smem, blocks, S(s));
+        case 42: return launch_mid2<4, 2>(k, smem, blocks, threads, S(s));
+        case 32: return launch_mid2<3, 2>(k, smem, blocks, threads, S(s));
+        case 22: return launch_mid2<2, 2>(k, smem, blocks, threads, S(s));
+        case 41: return launch_mid2<4, 1>(k, smem, blocks, threads, S(s));
+        case 31: return launch_mid2<3, 1>(k, smem, blocks, threads, S(s));
+        default: return launch_mid2<2, 1>(k, smem, blocks, threads, S(s));
     }
 }
 
@@ -1342,6 +1399,7 @@ ProjK proj_k(const ProjArgs& a) {
         k.ctot += k.src_ch[s];
     }
     k.w1 = a.w1; k.b1 = a.b1; k.w2 = a.w2; k.b2 = a.b2; k.out = a.out; k.gout = a.gout;
+    k.pre_out = a.pre_out; k.pre_in = a.pre_in;
     k.gw1 = a.gw1; k.gb1 = a.gb1; k.gw2 = a.gw2; k.gb2 = a.gb2;
     return k;
 }
@@ -1400,14 +1458,15 @@ int be_proj_fwd(const ProjArgs& a, stream_t s) {
     if (!be_proj_supported(a)) return (int)cudaErrorInvalidValue;
     const ProjK k = proj_k(a);
     const double px = (double)a.batch * k.g.nraw;
-    ProfScope ps("project_fwd", 4.0 * px * (k.ctot + a.out_ch), 2.0 * px * (k.ctot * a.hid + a.hid * a.out_ch), S(s));
+    ProfScope ps("project_fwd", 4.0 * px * (k.ctot + a.out_ch + (a.pre_out ? a.hid : 0)), 2.0 * px * (k.ctot * a.hid + a.hid * a.out_ch), S(s));
     return k.ctot <= 32 ? launch_proj<32>(k, false, S(s)) : launch_proj<64>(k, false, S(s));
 }
 int be_proj_bwd(const ProjArgs& a, stream_t s) {
     if (!be_proj_supported(a)) return (int)cudaErrorInvalidValue;
     const ProjK k = proj_k(a);
     const double px = (double)a.batch * k.g.nraw, ppx = (double)a.batch * k.g.npad;
-    ProfScope ps("project_bwd", 4.0 * (px * (k.ctot + a.out_ch) + ppx * k.ctot), 2.0 * px * (3 * k.ctot * a.hid + 2 * a.hid * a.out_ch), S(s));
+    ProfScope ps("project_bwd", 4.0 * (px * (k.ctot + a.out_ch + (a.pre_in ? a.hid : 0)) + ppx * k.ctot),
+                 2.0 * px * ((a.pre_in ? 2 : 3) * k.ctot * a.hid + 2 * a.hid * a.out_ch), S(s));
     return k.ctot <= 32 ? launch_proj<32>(k, true, S(s)) : launch_proj<64>(k, true, S(s));
 }
 

@@ -338,6 +338,8 @@ struct ProjK {
     int src_ch[4];
     const float *w1, *b1, *w2, *b2;
     float* out;
+    float* pre_out;          // optional [hid][batch * nraw]
+    const float* pre_in;     // optional, same layout
     const float* gout;
     float *gw1, *gb1, *gw2, *gb2;
 };
@@ -418,7 +420,9 @@ __global__ void __launch_bounds__(kPixTP) proj_fwd_kernel(const ProjK k) {
         for (int q = 0; q < kProjMaxOut; ++q) o[q] = 0.f;
 #pragma unroll 2
         for (int n = 0; n < k.hid; ++n) {
-            const float a = gelu_act(proj_hidden_row<CT>(sW1 + (size_t)n * CT, sb1[n], in));
+            const float pre = proj_hidden_row<CT>(sW1 + (size_t)n * CT, sb1[n], in);
+            if (k.pre_out != nullptr) k.pre_out[(size_t)n * total + idx] = pre;
+            const float a = gelu_act(pre);
 #pragma unroll
             for (int q = 0; q < kProjMaxOut; ++q)
                 if (q < k.out_ch) o[q] = fmaf(sW2[q * k.hid + n], a, o[q]);
@@ -544,32 +548,43 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
             // ---- PRE = W1[chunk] * IN for hidden units ch0 + 8 tn + i, then D = (W2^T gout) * gelu'(PRE)
             {
                 float acc[8][4];
-                const float* wrow[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n = min(ch0 + 8 * tn + i, k.hid - 1);     // rows past hid: computed on a clamped row, discarded below
-                    wrow[i] = sW1 + (size_t)n * CT;
-                    const float bv = sb1[n];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) acc[i][q] = bv;
-                }
-                const float* xin = IN + tp;
-#pragma unroll 2
-                for (int c4 = 0; c4 < CT; c4 += 4) {
-                    float x[4][4];
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) x[cc][q] = xin[(size_t)(c4 + cc) * kPixTPP + 64 * q];
+                if (k.pre_in != nullptr) {
+                    // saved by the forward pass: [hid][pixels], a warp reads 32 consecutive pixels of one hidden unit
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 w = *reinterpret_cast<const float4*>(wrow[i] + c4);
+                        const int n = min(ch0 + 8 * tn + i, k.hid - 1);
+                        const float* src = k.pre_in + (size_t)n * total + base + tp;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            acc[i][q] = fmaf(w.x, x[0][q], acc[i][q]);
-                            acc[i][q] = fmaf(w.y, x[1][q], acc[i][q]);
-                            acc[i][q] = fmaf(w.z, x[2][q], acc[i][q]);
-                            acc[i][q] = fmaf(w.w, x[3][q], acc[i][q]);
+                        for (int q = 0; q < 4; ++q) acc[i][q] = pb[q] >= 0 ? __ldg(src + 64 * q) : 0.f;
+                    }
+                } else {
+                    const float* wrow[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int n = min(ch0 + 8 * tn + i, k.hid - 1);     // rows past hid: computed on a clamped row, discarded below
+                        wrow[i] = sW1 + (size_t)n * CT;
+                        const float bv = sb1[n];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][q] = bv;
+                    }
+                    const float* xin = IN + tp;
+#pragma unroll 2
+                    for (int c4 = 0; c4 < CT; c4 += 4) {
+                        float x[4][4];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) x[cc][q] = xin[(size_t)(c4 + cc) * kPixTPP + 64 * q];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w = *reinterpret_cast<const float4*>(wrow[i] + c4);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                acc[i][q] = fmaf(w.x, x[0][q], acc[i][q]);
+                                acc[i][q] = fmaf(w.y, x[1][q], acc[i][q]);
+                                acc[i][q] = fmaf(w.z, x[2][q], acc[i][q]);
+                                acc[i][q] = fmaf(w.w, x[3][q], acc[i][q]);
+                            }
                         }
                     }
                 }

@@ -194,8 +194,11 @@ size_t synth_stage_floats(long P, int nmid, const MidOp* mids, int m) {
     return best;
 }
 
+// `join_side`: a side stream whose work (it produced the tensor the epilogue accumulates onto) must be complete
+// before the last stage runs; the leading-axis stages before it still overlap with that stream.
 int synthesise(const float* in, long P, int nmid, const MidOp* mids, int m, const float* last_mat,
-               int n_last, float* y, int epi, float* y2, float* ws0, float* ws1, stream_t st) {
+               int n_last, float* y, int epi, float* y2, float* ws0, float* ws1, stream_t st,
+               stream_t join_side = nullptr) {
     long cur[2] = {1, 1};
     for (int a = 0; a < nmid; ++a) cur[a] = mids[a].n_in;
     const float* src = in;
@@ -221,6 +224,7 @@ int synthesise(const float* in, long P, int nmid, const MidOp* mids, int m, cons
     g.epi = epi;
     g.tag = "dft_last_synthesis";
     g.b_const = true;
+    if (join_side) BE_TRY(be_join(st, join_side));
     BE_TRY(be_gemm(g, st));
     return 0;
 }
@@ -368,7 +372,7 @@ void corner_geometry(const SpectralPlan* p, int c, long* off, int* q_outer, int*
 }
 
 int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, const float* const* w,
-                      float* y, int epi, float* y2, float* xhat, Arena& ar, stream_t st) {
+                      float* y, int epi, float* y2, float* xhat, Arena& ar, stream_t st, stream_t join_side = nullptr) {
     const int nd = d->ndim, nmid = nd - 1, ml = d->modes[nd - 1];
     const long Pin = (long)d->batch * d->in_ch, Pout = (long)d->batch * d->out_ch;
     SpectralSizes sz = spectral_sizes(d);
@@ -398,13 +402,13 @@ int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, c
         ca.M = d->batch; ca.N = d->out_ch; ca.K = d->in_ch; ca.q_outer = qo; ca.q_inner = qi;
         BE_TRY(be_cmm(ca, st));
     }
-    UNO_TRY(synthesise(yhat, Pout, nmid, p->fs, ml, p->s_last.d, d->out_dim[nd - 1], y, epi, y2, ws0, ws1, st));
+    UNO_TRY(synthesise(yhat, Pout, nmid, p->fs, ml, p->s_last.d, d->out_dim[nd - 1], y, epi, y2, ws0, ws1, st, join_side));
     return 0;
 }
 
 int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, const float* xhat,
                       const float* const* w, float* gx, float* const* gw, int accumulate_gx, Arena& ar,
-                      stream_t st) {
+                      stream_t st, stream_t join_side = nullptr) {
     const int nd = d->ndim, nmid = nd - 1, ml = d->modes[nd - 1];
     const long Pin = (long)d->batch * d->in_ch, Pout = (long)d->batch * d->out_ch;
     SpectralSizes sz = spectral_sizes(d);
@@ -453,7 +457,9 @@ int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, 
     }
     if (gx)
         UNO_TRY(synthesise(dxhat, Pin, nmid, p->bs, ml, p->gs_last.d, d->in_dim[nd - 1], gx,
-                           accumulate_gx ? EPI_ACCUM : EPI_STORE, nullptr, ws0, ws1, st));
+                           accumulate_gx ? EPI_ACCUM : EPI_STORE, nullptr, ws0, ws1, st, join_side));
+    else if (join_side)
+        BE_TRY(be_join(st, join_side));
     return 0;
 }
 
@@ -872,9 +878,16 @@ int uno_operator_block_fwd(const uno_block_desc* bd, const float* x, const float
     if (!acc) acc = bd->normalize ? ar.take((size_t)planes * g.n_out) : y;
     if (bd->normalize && !stats) stats = ar.take((size_t)2 * planes);
     if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for operator block forward");
+    // The two branches are independent until the last synthesis stage adds the spectral part onto w(x): the pointwise
+    // branch runs on the library's side stream, the spectral analysis / contraction / leading-axis synthesis on the
+    // caller's; they use disjoint halves of the workspace and meet again before the fused epilogue.
+    const size_t pw_floats = pw_ws_floats(d);
+    if (ar.off + pw_floats > ar.cap) return fail(UNO_EWORKSPACE, "workspace too small for operator block forward");
+    stream_t side = be_side_stream();
+    if (side) BE_TRY(be_fork(stream, side));
     {
-        Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
-        UNO_TRY(pointwise_fwd_impl(d, rp, x, conv_w, conv_b, acc, pw_saved, sub, stream));
+        Arena sub(ar.base + ar.off, pw_floats * sizeof(float));
+        UNO_TRY(pointwise_fwd_impl(d, rp, x, conv_w, conv_b, acc, pw_saved, sub, side ? side : stream));
     }
     int epi = EPI_ACCUM;
     float* y2 = nullptr;
@@ -883,8 +896,8 @@ int uno_operator_block_fwd(const uno_block_desc* bd, const float* x, const float
         else { epi = EPI_ACCUM_GELU; y2 = y; }
     }
     {
-        Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
-        UNO_TRY(spectral_fwd_impl(d, sp, x, w, acc, epi, y2, xhat, sub, stream));
+        Arena sub(ar.base + ar.off + pw_floats, (ar.cap - ar.off - pw_floats) * sizeof(float));
+        UNO_TRY(spectral_fwd_impl(d, sp, x, w, acc, epi, y2, xhat, sub, stream, side));
     }
     if (bd->normalize) {
         BE_TRY(be_plane_stats(acc, stats, planes, g.n_out, bd->eps, stream));
@@ -942,13 +955,19 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
         }
         gs = buf;
     }
+    // as in forward: the pointwise backward (which overwrites gx) on the side stream, the spectral backward on the
+    // caller's stream up to its last stage, which accumulates onto gx after the join
+    const size_t pw_floats = pw_ws_floats(d);
+    if (ar.off + pw_floats > ar.cap) return fail(UNO_EWORKSPACE, "workspace too small for operator block backward");
+    stream_t side = be_side_stream();
+    if (side) BE_TRY(be_fork(stream, side));
     {
-        Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
-        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, bias_done ? nullptr : gconv_b, sub, stream));
+        Arena sub(ar.base + ar.off, pw_floats * sizeof(float));
+        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, bias_done ? nullptr : gconv_b, sub, side ? side : stream));
     }
     {
-        Arena sub(ar.base + ar.off, (ar.cap - ar.off) * sizeof(float));
-        UNO_TRY(spectral_bwd_impl(d, sp, gs, xhat, w, gx, gw, /*accumulate_gx=*/1, sub, stream));
+        Arena sub(ar.base + ar.off + pw_floats, (ar.cap - ar.off - pw_floats) * sizeof(float));
+        UNO_TRY(spectral_bwd_impl(d, sp, gs, xhat, w, gx, gw, /*accumulate_gx=*/1, sub, stream, side));
     }
     return 0;
 }
@@ -987,7 +1006,8 @@ int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a_, const
 int uno_project_check(const uno_project_desc* d) { ProjArgs a; return make_proj_args(d, &a); }
 
 int uno_project_fwd(const uno_project_desc* d, const float* const* src, const float* w1,
-                    const float* b1, const float* w2, const float* b2, float* out, void* stream) {
+                    const float* b1, const float* w2, const float* b2, float* out, float* hidden_pre,
+                    void* stream) {
     ProjArgs a;
     UNO_TRY(make_proj_args(d, &a));
     if (!src || !w1 || !b1 || !w2 || !b2 || !out) return fail(UNO_EINVAL, "null tensor pointer");
@@ -995,14 +1015,14 @@ int uno_project_fwd(const uno_project_desc* d, const float* const* src, const fl
         if (!src[s]) return fail(UNO_EINVAL, "null source pointer %d", s);
         a.src[s] = src[s];
     }
-    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.out = out;
+    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.out = out; a.pre_out = hidden_pre;
     BE_TRY(be_proj_fwd(a, stream));
     return 0;
 }
 
 int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* const* src,
-                    const float* w1, const float* b1, const float* w2, float* const* gsrc, float* gw1,
-                    float* gb1, float* gw2, float* gb2, void* stream) {
+                    const float* hidden_pre, const float* w1, const float* b1, const float* w2,
+                    float* const* gsrc, float* gw1, float* gb1, float* gw2, float* gb2, void* stream) {
     ProjArgs a;
     UNO_TRY(make_proj_args(d, &a));
     if (!gout || !src || !w1 || !b1 || !w2 || !gw1 || !gb1 || !gw2 || !gb2) return fail(UNO_EINVAL, "null tensor pointer");
@@ -1014,6 +1034,7 @@ int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* c
         ctot += d->src_ch[s];
     }
     a.w1 = w1; a.b1 = b1; a.w2 = w2; a.gout = gout; a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2;
+    a.pre_in = hidden_pre;
     BE_TRY(be_memset(gw1, 0, sizeof(float) * d->hidden * ctot, stream));
     BE_TRY(be_memset(gb1, 0, sizeof(float) * d->hidden, stream));
     BE_TRY(be_memset(gw2, 0, sizeof(float) * d->out_ch * d->hidden, stream));

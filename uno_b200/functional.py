@@ -267,7 +267,7 @@ class ProjectFn(torch.autograd.Function):
     (darcy_flow_uno2d.py:121-131, navier_stokes_uno2d.py:215-225, navier_stokes_uno3d.py:551-575)."""
 
     @staticmethod
-    def forward(ctx, w1, b1, w2, b2, crop_lo, crop_hi, *srcs):
+    def forward(ctx, w1, b1, w2, b2, crop_lo, crop_hi, need_grad, *srcs):
         lib = _get_lib()
         for t in srcs:
             _check_input(t)
@@ -284,29 +284,33 @@ class ProjectFn(torch.autograd.Function):
         _capi.check(lib, lib.uno_project_check(C.byref(d)))
         out = torch.empty((srcs[0].shape[0],) + dims + (w2c.shape[0],), dtype=torch.float32, device=srcs[0].device)
         sp = _capi.ptr_array([t.data_ptr() for t in srcs])
-        _capi.check(lib, lib.uno_project_fwd(C.byref(d), sp, _ptr(w1c), _ptr(b1c), _ptr(w2c), _ptr(b2c), _ptr(out), _stream(out)))
+        # the fc1 pre-activations are kept for backward (hidden-unit major): 4*hidden bytes per pixel buy back a third
+        # of the backward arithmetic
+        pre = torch.empty((w1c.shape[0], out.numel() // w2c.shape[0]), dtype=torch.float32, device=out.device) if need_grad else None
+        _capi.check(lib, lib.uno_project_fwd(C.byref(d), sp, _ptr(w1c), _ptr(b1c), _ptr(w2c), _ptr(b2c), _ptr(out), _ptr(pre), _stream(out)))
         _launch_counter["calls"] += 1
         ctx.desc = d
-        ctx.save_for_backward(w1c, b1c, w2c, *srcs)
+        if need_grad:
+            ctx.save_for_backward(w1c, b1c, w2c, pre, *srcs)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         lib = _get_lib()
-        w1c, b1c, w2c, *srcs = ctx.saved_tensors
+        w1c, b1c, w2c, pre, *srcs = ctx.saved_tensors
         gout = gout.contiguous()
-        gsrcs = [torch.empty_like(t) if ctx.needs_input_grad[6 + i] else None for i, t in enumerate(srcs)]
+        gsrcs = [torch.empty_like(t) if ctx.needs_input_grad[7 + i] else None for i, t in enumerate(srcs)]
         gw1, gb1, gw2 = torch.empty_like(w1c), torch.empty_like(b1c), torch.empty_like(w2c)
         gb2 = torch.empty(w2c.shape[0], dtype=torch.float32, device=gout.device)
         sp = _capi.ptr_array([t.data_ptr() for t in srcs])
         gp = _capi.ptr_array([g.data_ptr() if g is not None else 0 for g in gsrcs])
         _capi.check(
             lib,
-            lib.uno_project_bwd(C.byref(ctx.desc), _ptr(gout), sp, _ptr(w1c), _ptr(b1c), _ptr(w2c), gp, _ptr(gw1), _ptr(gb1), _ptr(gw2),
-                                _ptr(gb2), _stream(gout)),
+            lib.uno_project_bwd(C.byref(ctx.desc), _ptr(gout), sp, _ptr(pre), _ptr(w1c), _ptr(b1c), _ptr(w2c), gp, _ptr(gw1), _ptr(gb1),
+                                _ptr(gw2), _ptr(gb2), _stream(gout)),
         )
         _launch_counter["calls"] += 1
-        return (gw1, gb1, gw2, gb2, None, None) + tuple(gsrcs)
+        return (gw1, gb1, gw2, gb2, None, None, None) + tuple(gsrcs)
 
 
 def _needs_grad(*tensors) -> bool:
@@ -334,4 +338,5 @@ def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
 
 def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
     """out[B, *cropped, out_ch] = fc2(gelu(fc1(crop(cat(srcs, dim=1)) channels-last)))."""
-    return ProjectFn.apply(w1, b1, w2, b2, tuple(int(v) for v in crop_lo), tuple(int(v) for v in crop_hi), *srcs)
+    need = _needs_grad(w1, b1, w2, b2, *srcs)
+    return ProjectFn.apply(w1, b1, w2, b2, tuple(int(v) for v in crop_lo), tuple(int(v) for v in crop_hi), need, *srcs)

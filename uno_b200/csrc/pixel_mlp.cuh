@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
     float* accba = accWa + HID * CIN;
     float* accWb = accba + HID;
     float* accbb = accWb + OC4 * HID;
-    float* D1 = accbb + OC4;                  // [out_ch][TPP]  dL/dpre1
-    float* A0 = D1 + (size_t)OC4 * kPixTPP;   // [HID][TPP]     hidden activations
+    float* GH = accbb + OC4;                  // 2 x [out_ch][TPP]  staged dL/dh of a tile, turned in place into dL/dpre1
+    float* A0 = GH + (size_t)2 * OC4 * kPixTPP;   // [HID][TPP]     hidden activations
     float* D0 = A0 + HID * kPixTPP;           // [HID][TPP]     dL/dpre0
     float* IN = D0 + HID * kPixTPP;           // [CIN][TPP]     layer-0 inputs
     const int tid = threadIdx.x;
@@ -240,15 +240,43 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
     __syncthreads();
     const PixGeom g = k.g;
     const long total = (long)k.batch * g.nraw;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // the upstream gradient of a tile is copied asynchronously (LDGSTS) one tile ahead: thread t fetches pixel t, all
+    // channels (consecutive channels are npad elements apart), zero-filled past the end
+    auto stage_gh = [&](long tile, float* dstbuf) {
         const long idx = tile * kPixTP + tid;
         const bool valid = idx < total;
-        const long b = valid ? idx / g.nraw : 0;
-        const long rp = valid ? idx - b * g.nraw : 0;
-        const int r2 = (int)(rp % g.n2);
-        const long t = rp / g.n2;
-        const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
-        const long pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
+        long b = 0, rp = 0, pp = 0;
+        if (valid) raw_to_padded(g, idx, b, rp, pp);
+        const float* src = valid ? k.gh + b * k.out_ch * g.npad + pp : k.w_a;
+        const long step = valid ? g.npad : 0;
+        const int sz = valid ? 4 : 0;
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(dstbuf + tid);
+#pragma unroll 4
+        for (int c = 0; c < k.out_ch; ++c) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+            dst += (uint32_t)(kPixTPP * 4);
+            src += step;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if ((long)blockIdx.x < ntiles) stage_gh(blockIdx.x, GH);
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        float* D1 = GH + (size_t)cur * OC4 * kPixTPP;
+        {
+            const long next = tile + gridDim.x;
+            if (next < ntiles) {
+                stage_gh(next, GH + (size_t)(cur ^ 1) * OC4 * kPixTPP);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            cur ^= 1;
+        }
+        const long idx = tile * kPixTP + tid;
+        const bool valid = idx < total;
+        long b = 0, rp = 0, pp = 0;
+        if (valid) raw_to_padded(g, idx, b, rp, pp);
         float in[CIN], a0[HID], gp0[HID], da0[HID];
         lift_load_in<CIN>(k, b, rp, valid, in);
         lift_first_layer<CIN, HID>(sWa, sba, in, a0);
@@ -258,11 +286,10 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
             gelu_both(a0[kk], act, grad);
             a0[kk] = act; gp0[kk] = grad; da0[kk] = 0.f;
         }
-        const float* ghp = k.gh + b * k.out_ch * g.npad + pp;
 #pragma unroll 4
         for (int c = 0; c < k.out_ch; ++c) {
             const float pre1 = lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0);
-            const float gv = valid ? __ldg(ghp + (long)c * g.npad) : 0.f;
+            const float gv = D1[c * kPixTPP + tid];      // this thread's own asynchronous copy (complete after wait_group)
             const float d1 = gv * gelu_der(pre1);
             D1[c * kPixTPP + tid] = d1;
             const float4* w4 = reinterpret_cast<const float4*>(sWb + c * HID);
@@ -324,7 +351,7 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
 
 inline size_t lift_bwd_smem(int CIN, int HID, int out_ch) {
     const int OC4 = round4(out_ch);
-    return sizeof(float) * ((size_t)2 * (HID * CIN + HID + OC4 * HID + OC4) + (size_t)(OC4 + 2 * HID + CIN) * kPixTPP);
+    return sizeof(float) * ((size_t)2 * (HID * CIN + HID + OC4 * HID + OC4) + (size_t)(2 * OC4 + 2 * HID + CIN) * kPixTPP);
 }
 
 // =====================================================================================================
@@ -474,16 +501,30 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
         const bool valid = idx < total;
         long b = 0, rp = 0, pp = 0;
         if (valid) raw_to_padded(g, idx, b, rp, pp);
-        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(dstbuf + tid);
-#pragma unroll 8
-        for (int c = 0; c < CT; ++c) {
-            const bool on = valid && c < k.ctot;
-            const float* src = on ? sbase[c] + b * sstride[c] + pp : k.w1;
-            const int sz = on ? 4 : 0;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst0 + (uint32_t)(c * kPixTPP * 4)), "l"(src), "r"(sz) : "memory");
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(dstbuf + tid);
+        const int sz = valid ? 4 : 0;
+        const long step = valid ? g.npad : 0;
+        // source by source: consecutive channels of one source are npad elements apart, so the address is a running sum
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s < k.nsrc) {
+                const int nch = k.src_ch[s];
+                const float* src = valid ? k.src[s] + b * nch * g.npad + pp : k.w1;
+#pragma unroll 4
+                for (int cl = 0; cl < nch; ++cl) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                    dst += (uint32_t)(kPixTPP * 4);
+                    src += step;
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // rows of channels past ctot (template padding) stay zero for the whole kernel
+    for (int i = tid; i < (CT - k.ctot) * kPixTPP; i += kPixTP) {
+        INbuf[(size_t)k.ctot * kPixTPP + i] = 0.f;
+        if (nbuf == 2) INbuf[(size_t)(CT + k.ctot) * kPixTPP + i] = 0.f;
+    }
     // ---- the padding of the source gradients is zero (the crop has no gradient there)
     if (g.npad != g.nraw) {
         const long ptotal = (long)k.batch * g.npad;
@@ -632,7 +673,7 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
             {
                 const float* dcol = D + tp;
                 const float* wbase = sW1 + (size_t)ch0 * CT + tn * CB;
-#pragma unroll 2
+#pragma unroll 4
                 for (int j = 0; j < nn; ++j) {
                     float d[4];
 #pragma unroll
@@ -688,14 +729,27 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
             }
             __syncthreads();
         }
-        // ---- input gradients of the tile (a warp stores 32 consecutive pixels of one channel)
+        // ---- input gradients of the tile (a warp stores 32 consecutive pixels of one channel); the per-pixel offset
+        //      only depends on the batch stride of the channel's source, so it is recomputed when that changes
+        {
+            long cur_stride = -1, off[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < CB; ++i) {
-            const int c = tn * CB + i;
-            if (c < k.ctot && gbase[c] != nullptr) {
+            for (int i = 0; i < CB; ++i) {
+                const int c = tn * CB + i;
+                if (c < k.ctot) {
+                    float* gb = gbase[c];
+                    const long st = sstride[c];
+                    if (st != cur_stride) {
+                        cur_stride = st;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (pb[q] >= 0) gbase[c][pb[q] * sstride[c] + ppx[q]] = dacc[i][q];
+                        for (int q = 0; q < 4; ++q) off[q] = pb[q] * st + ppx[q];
+                    }
+                    if (gb != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (pb[q] >= 0) gb[off[q]] = dacc[i][q];
+                    }
+                }
             }
         }
         if (tn == 0) {

@@ -288,13 +288,13 @@ __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
         for (int b = 0; b < TI; ++b) acc[a][b] = make_float2(0.f, 0.f);
     for (int h0 = 0; h0 < k.H; h0 += k.HK) {
         const int hk = min(k.HK, k.H - h0);
-        for (int idx = tid; idx < JT * k.HK; idx += blockDim.x) {
+        for (int idx = tid; idx < JT * k.HK; idx += 256) {
             const int h = idx % k.HK, j = idx / k.HK;
             float2 v = make_float2(0.f, 0.f);
             if (j0 + j < k.J && h < hk) v = __ldg(k.Mat + (long)(j0 + j) * k.H + h0 + h);
             Ms[h * JTP + j] = v;
         }
-        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += blockDim.x) {
+        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
             const int i = idx % IT;
             const int r = idx / IT;
             const int h = r % k.HK, g = r / k.HK;
@@ -1146,7 +1146,7 @@ int be_mid(const MidArgs& a, stream_t s) {
     k.ppc = std::max(1, 256 / (k.nj * k.ni));
     if ((long)k.ppc > a.O) k.ppc = (int)a.O;
     // (planes sharing a CTA share its Mat tile: splitting them up for more CTAs measured slower, 2.2 vs 1.8 ms per step)
-    const int threads = std::min(256, (k.ppc * k.nj * k.ni + 31) / 32 * 32);
+    const int threads = 256;   // compile-time strides in the staging loops
     k.HK = a.H <= 48 ? a.H : 32;
     const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
     size_t ms = (size_t)k.HK * JTP;

@@ -222,6 +222,12 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
     return 0;
 }
 
+int be_norm_fused_fwd(const float* x, float* stats, const float* gamma, const float* beta, float* y, long planes, int C,
+                      long L, float eps, int non_lin, stream_t s) {
+    int rc = be_plane_stats(x, stats, planes, L, eps, s);
+    return rc ? rc : be_norm_act_fwd(x, stats, gamma, beta, y, planes, C, L, non_lin, s);
+}
+
 int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
                     long L, int non_lin, stream_t) {

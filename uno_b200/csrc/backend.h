@@ -125,6 +125,10 @@ int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, i
                      float alpha, stream_t s);
 // per-plane mean / rstd over L contiguous elements: stats[p] = (mean, rstd)
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s);
+// statistics + normalisation (+ GELU) in one call: stats[p] = (mean, rstd) out, y as below.  The CUDA backend keeps each
+// plane on chip between the two (thread-block clusters) when it fits, else runs be_plane_stats + be_norm_act_fwd.
+int be_norm_fused_fwd(const float* x, float* stats, const float* gamma, const float* beta, float* y, long planes, int C,
+                      long L, float eps, int non_lin, stream_t s);
 // y = [gelu]( (x-mean)*rstd*gamma[c] + beta[c] ), plane p -> channel p % C
 int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta,
                     float* y, long planes, int C, long L, int non_lin, stream_t s);

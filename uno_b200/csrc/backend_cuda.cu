@@ -11,6 +11,7 @@
 // Everything here is fp32 FMA on the SIMT pipes with fp32 accumulation; the tensor-core variants of
 // the GEMM-shaped stages live in gemm_tc.cuh and are selected by be_gemm when the shape qualifies.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -657,6 +658,7 @@ int ensure_smem(K kernel, size_t bytes) {
 
 #include "pixel_mlp.cuh"
 #include "resample2d.cuh"
+#include "norm_cluster.cuh"
 
 
 // =====================================================================================================
@@ -1285,7 +1287,7 @@ int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, i
     if (planes <= 0 || L <= 0) return 0;
     ProfScope ps("gelu_bwd", 12.0 * planes * L, 0, S(s));
     // enough CTAs per plane to fill the machine, few enough that the atomics stay negligible
-    unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 2047) / 2048, (148L * 8 + planes - 1) / planes));
+    unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 8191) / 8192, (148L * 8 + planes - 1) / planes));
     gelu_bwd_bias_kernel<<<dim3((unsigned)planes, gy_), 256, 0, S(s)>>>(gy, pre, g, C, L, gbias, alpha);
     CU_LAUNCH_CHECK();
     return 0;
@@ -1296,6 +1298,23 @@ int be_plane_stats(const float* x, float* stats, long planes, long L, float eps,
     plane_stats_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(x, stats, L, eps);
     CU_LAUNCH_CHECK();
     return 0;
+}
+int be_norm_fused_fwd(const float* x, float* stats, const float* gamma, const float* beta, float* y, long planes, int C,
+                      long L, float eps, int non_lin, stream_t s) {
+    if (planes <= 0) return 0;
+    int slice = 0;
+    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_size(L, 4, 72 * 1024, &slice) : 0;
+    if (cs > 0) {
+        // one sweep: the plane stays in the shared memory of a cluster of `cs` CTAs between statistics and normalisation
+        ProfScope ps("instnorm_gelu_fwd", 8.0 * planes * L, 0, S(s));
+        const int rc = launch_cluster(norm_fwd_cluster_kernel, planes, cs, (size_t)slice * 4, S(s), x, stats, gamma, beta, y, C, L, slice,
+                                      eps, non_lin);
+        if (rc) return rc;
+        CU_LAUNCH_CHECK();
+        return 0;
+    }
+    int rc = be_plane_stats(x, stats, planes, L, eps, s);
+    return rc ? rc : be_norm_act_fwd(x, stats, gamma, beta, y, planes, C, L, non_lin, s);
 }
 int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, const float* beta, float* y,
                     long planes, int C, long L, int non_lin, stream_t s) {
@@ -1310,6 +1329,15 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
                     float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
     ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
+    int slice = 0;
+    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_size(L, 8, 72 * 1024, &slice) : 0;
+    if (cs > 0) {
+        const int rc = launch_cluster(norm_bwd_cluster_kernel, planes, cs, (size_t)slice * 8, S(s), gy, x, stats, gamma, beta, g, ggamma,
+                                      gbeta, C, L, slice, non_lin);
+        if (rc) return rc;
+        CU_LAUNCH_CHECK();
+        return 0;
+    }
     norm_act_bwd_kernel<<<(unsigned)planes, 512, 0, S(s)>>>(gy, x, stats, gamma, beta, g, ggamma, gbeta, C, L, non_lin);
     CU_LAUNCH_CHECK();
     return 0;

@@ -900,8 +900,7 @@ int uno_operator_block_fwd(const uno_block_desc* bd, const float* x, const float
         UNO_TRY(spectral_fwd_impl(d, sp, x, w, acc, epi, y2, xhat, sub, stream, side));
     }
     if (bd->normalize) {
-        BE_TRY(be_plane_stats(acc, stats, planes, g.n_out, bd->eps, stream));
-        BE_TRY(be_norm_act_fwd(acc, stats, gamma, beta, y, planes, d->out_ch, g.n_out, bd->non_lin, stream));
+        BE_TRY(be_norm_fused_fwd(acc, stats, gamma, beta, y, planes, d->out_ch, g.n_out, bd->eps, bd->non_lin, stream));
     }
     return 0;
 }

@@ -140,8 +140,8 @@ def make_step(model, loss_fn, B, tshape, reducer=None):
 def cpu_reference_run(workload, steps, warmup, batch=None):
     """The oracle torch port (kind "port") on the host cores: fwd + loss + bwd, bounded batch."""
     from oracle import uno_torch_port as port
-    from uno_b200.losses import LpLoss
 
+    LpLoss = port.LpLoss          # the CPU arm runs no code of the product
     _, _, _, xshape, tshape, _, cpu_b = WORKLOADS[workload]
     B = batch or cpu_b
     threads = os.cpu_count() or 1

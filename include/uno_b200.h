@@ -161,6 +161,34 @@ int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* c
                     const float* hidden_pre, const float* w1, const float* b1, const float* w2,
                     float* const* gsrc, float* gw1, float* gb1, float* gw2, float* gb2, void* stream);
 
+/* ---- training-step ops next to the path ------------------------------------------------
+ * uno_adam_step replaces the per-tensor Python loop of Adam.py:23-52 (functional `adam`) with one kernel launch per 24
+ * tensors.  Semantics are the reference's, not torch.optim.Adam's: for a complex tensor the second moment is the running
+ * average of g*conj(g) = |g|^2, stored -- like upstream -- in a complex tensor as (v, 0), so the real and imaginary part
+ * of a weight share one denominator.  `numel` counts FLOATS (2 per complex element).  amsgrad on a complex tensor is
+ * rejected (upstream raises from torch.maximum).  All tensors of a call share the 1-based `step`.
+ * uno_lp_loss_* is utilities3.LpLoss.rel (utilities3.py:86-100) for p = 2 on x, y [B, N]:
+ *   reduction 0: loss[B] = ||x_b - y_b|| / ||y_b||;  1: their sum (size_average=False);  2: their mean.
+ *   norms [B, 2] (||x-y||, ||y||) is written by fwd and read by bwd; ws = 16*B bytes of scratch.                     */
+typedef struct uno_adam_tensor {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+    float* max_exp_avg_sq;   /* NULL unless amsgrad */
+    long numel;
+    int is_complex;
+} uno_adam_tensor;
+
+typedef struct uno_adam_hyper {
+    double lr, beta1, beta2, eps, weight_decay;   /* doubles: 1 - beta2 must be formed before rounding to fp32, as upstream does */
+    int amsgrad;
+    int step;
+} uno_adam_hyper;
+
+int uno_adam_step(const uno_adam_tensor* tensors, int n, const uno_adam_hyper* h, void* stream);
+int uno_lp_loss_fwd(const float* x, const float* y, int batch, long n, int reduction, float* loss, float* norms,
+                    void* ws, size_t ws_bytes, void* stream);
+int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gloss, int batch, long n,
+                    int reduction, float* gx, void* stream);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------------
  * uno_launch_count: kernels this library has launched since it was loaded.
  * uno_profile_enable(1) brackets every kernel launch with a CUDA-event pair on the launching stream;

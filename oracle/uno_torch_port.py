@@ -215,3 +215,37 @@ def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
     nd = c.dim() - 2
     c = c.permute(0, *range(2, nd + 2), 1)
     return F.linear(F.gelu(F.linear(c, w1, b1)), w2, b2)
+
+
+# ---- training-step ops --------------------------------------------------------------
+class LpLoss:
+    """utilities3.py:75-103: relative Lp error per sample, summed / averaged over the batch."""
+
+    def __init__(self, d=2, p=2, size_average=True, reduction=True):
+        assert d > 0 and p > 0
+        self.d, self.p, self.reduction, self.size_average = d, p, reduction, size_average
+
+    def rel(self, x, y):
+        b = x.size()[0]
+        ratio = torch.norm(x.reshape(b, -1) - y.reshape(b, -1), self.p, 1) / torch.norm(y.reshape(b, -1), self.p, 1)
+        if not self.reduction:
+            return ratio
+        return ratio.mean() if self.size_average else ratio.sum()
+
+    __call__ = rel
+
+
+def adam_step(param, grad, state, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False):
+    """One update of Adam.py:23-52 on a single tensor, out of place, any dtype (complex: second moment = |g|^2 kept as
+    a complex number with zero imaginary part).  state = dict(exp_avg, exp_avg_sq[, max_exp_avg_sq]); returns the new
+    parameter and updates `state` in place."""
+    b1, b2 = betas
+    g = grad + weight_decay * param if weight_decay != 0 else grad
+    state["exp_avg"] = b1 * state["exp_avg"] + (1 - b1) * g
+    state["exp_avg_sq"] = b2 * state["exp_avg_sq"] + (1 - b2) * (g * g.conj())
+    second = state["exp_avg_sq"]
+    if amsgrad:
+        state["max_exp_avg_sq"] = torch.maximum(state["max_exp_avg_sq"], second)
+        second = state["max_exp_avg_sq"]
+    denom = second.sqrt() / (1 - b2**step) ** 0.5 + eps
+    return param - (lr / (1 - b1**step)) * state["exp_avg"] / denom

@@ -209,7 +209,60 @@ def make_models():
     save("models.npz", **out)
 
 
+def make_training():
+    """The reference's optimiser (Adam.py, complex-aware second moment |g|^2) and loss (utilities3.LpLoss) on a mixed
+    set of real and complex tensors: parameters, seeded gradients, states after every one of 5 steps."""
+    import Adam as ref_adam
+    import utilities3 as ref_util
+
+    out = {}
+    for tag, kw in (("plain", dict(lr=1e-2)), ("wd", dict(lr=3e-3, weight_decay=1e-2, betas=(0.8, 0.95), eps=1e-6)),
+                    ("amsgrad", dict(lr=1e-2, amsgrad=True))):
+        torch.manual_seed(7)
+        shapes = [((5, 3), False), ((17,), False), ((2, 3, 4, 4), True), ((1,), False), ((3, 2, 5), True)]
+        if kw.get("amsgrad"):
+            shapes = [s for s in shapes if not s[1]]        # torch.maximum has no complex kernel: upstream raises
+        params = [torch.nn.Parameter(torch.randn(*sh, dtype=torch.cfloat if cx else torch.float)) for sh, cx in shapes]
+        opt = ref_adam.Adam(params, **kw)
+        out[f"{tag}.n"] = np.array(len(params))
+        for i, q in enumerate(params):
+            out[f"{tag}.p0.{i}"] = n(q).copy()          # (numpy() aliases the parameter, which is updated in place)
+        for step in range(5):
+            for i, q in enumerate(params):
+                q.grad = torch.randn_like(q) * (0.5 + step)
+                out[f"{tag}.g{step}.{i}"] = n(q.grad)
+            opt.step()
+            for i, q in enumerate(params):
+                out[f"{tag}.p{step + 1}.{i}"] = n(q).copy()
+        for i, q in enumerate(params):
+            st = opt.state[q]
+            out[f"{tag}.m.{i}"] = n(st["exp_avg"])
+            out[f"{tag}.v.{i}"] = n(st["exp_avg_sq"])
+    torch.manual_seed(11)
+    x = torch.randn(4, 9, 7, requires_grad=True)
+    y = torch.randn(4, 9, 7)
+    for tag, kw in (("sum", dict(size_average=False)), ("mean", dict(size_average=True)), ("none", dict(reduction=False))):
+        loss = ref_util.LpLoss(**kw)(x, y)
+        gl = torch.randn_like(loss)
+        (gx,) = torch.autograd.grad(loss, x, gl)
+        out[f"loss.{tag}"] = n(loss)
+        out[f"loss.{tag}.gl"] = n(gl)
+        out[f"loss.{tag}.gx"] = n(gx)
+    out["loss.x"] = n(x)
+    out["loss.y"] = n(y)
+    save("training.npz", **out)
+
+
 if __name__ == "__main__":
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None, help="regenerate a single fixture (e.g. training)")
+    only = ap.parse_args().only
+    if only:
+        globals()["make_" + only]()
+        sys.exit(0)
+    make_training()
     make_spectral()
     make_pointwise()
     make_blocks()

@@ -418,4 +418,58 @@ int be_proj_bwd(const ProjArgs& a, stream_t) {
     return 0;
 }
 
+// ---- training-step ops: plain loops following Adam.py:23-52 and utilities3.py:86-100 -------------------------------------
+int be_adam_step(const AdamTensor* t, int n, const AdamHyper& h, stream_t) {
+    const double bc1 = 1.0 - pow(h.beta1, (double)h.step), bc2 = 1.0 - pow(h.beta2, (double)h.step);
+    const float step_size = (float)(h.lr / bc1), s2 = (float)sqrt(bc2);
+    const float omb1 = (float)(1.0 - h.beta1), omb2 = (float)(1.0 - h.beta2);
+    const float beta1 = (float)h.beta1, beta2 = (float)h.beta2, eps = (float)h.eps, wd = (float)h.weight_decay;
+    for (int k = 0; k < n; ++k) {
+        const AdamTensor& a = t[k];
+        for (long i = 0; i < a.numel; i += (a.is_complex ? 2 : 1)) {
+            const int w = a.is_complex ? 2 : 1;
+            float g[2] = {0, 0};
+            float sq = 0;
+            for (int c = 0; c < w; ++c) {
+                g[c] = a.grad[i + c] + wd * a.param[i + c];
+                a.exp_avg[i + c] = a.exp_avg[i + c] * beta1 + omb1 * g[c];
+                sq += g[c] * g[c];
+            }
+            a.exp_avg_sq[i] = a.exp_avg_sq[i] * beta2 + omb2 * sq;
+            if (a.is_complex) a.exp_avg_sq[i + 1] *= beta2;
+            float vhat = a.exp_avg_sq[i];
+            if (h.amsgrad && !a.is_complex) { vhat = std::max(a.max_exp_avg_sq[i], vhat); a.max_exp_avg_sq[i] = vhat; }
+            const float denom = sqrtf(vhat) / s2 + eps;
+            for (int c = 0; c < w; ++c) a.param[i + c] -= step_size * (a.exp_avg[i + c] / denom);
+        }
+    }
+    return 0;
+}
+
+int be_lp_loss_fwd(const float* x, const float* y, int B, long N, int reduction, float* loss, float* norms, double*, stream_t) {
+    double tot = 0;
+    for (int b = 0; b < B; ++b) {
+        double d2 = 0, y2 = 0;
+        for (long i = 0; i < N; ++i) { const double d = (double)x[b * N + i] - y[b * N + i]; d2 += d * d; y2 += (double)y[b * N + i] * y[b * N + i]; }
+        norms[2 * b] = (float)sqrt(d2);
+        norms[2 * b + 1] = (float)sqrt(y2);
+        const float r = norms[2 * b] / norms[2 * b + 1];
+        if (reduction == 0) loss[b] = r;
+        tot += r;
+    }
+    if (reduction == 1) loss[0] = (float)tot;
+    if (reduction == 2) loss[0] = (float)(tot / B);
+    return 0;
+}
+int be_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gl, int B, long N, int reduction, float* gx,
+                   stream_t) {
+    for (int b = 0; b < B; ++b) {
+        float scale = reduction == 0 ? gl[b] : gl[0];
+        if (reduction == 2) scale /= (float)B;
+        scale /= norms[2 * b] * norms[2 * b + 1];
+        for (long i = 0; i < N; ++i) gx[b * N + i] = (x[b * N + i] - y[b * N + i]) * scale;
+    }
+    return 0;
+}
+
 }  // namespace uno

@@ -222,3 +222,36 @@ def project_bwd(gout, srcs, w1, b1, w2, crop_lo, crop_hi, pre=None):
     pre = _f32(pre) if pre is not None else None
     _capi.check(L, L.uno_project_bwd(C.byref(d), _p(gout), sp, _p(pre), _p(w1), _p(b1), _p(w2), gp, _p(gw1), _p(gb1), _p(gw2), _p(gb2), None))
     return gs, gw1, gb1, gw2, gb2
+
+
+# ---- training-step ops -------------------------------------------------------------------------------------
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, max_sqs, step, lr, betas, eps, weight_decay, amsgrad):
+    """In-place update of numpy arrays (float32 or complex64) through uno_adam_step."""
+    L = lib()
+    n = len(params)
+    arr = (_capi.AdamTensor * n)()
+    for i in range(n):
+        cx = np.iscomplexobj(params[i])
+        arr[i].param = params[i].ctypes.data
+        arr[i].grad = grads[i].ctypes.data
+        arr[i].exp_avg = exp_avgs[i].ctypes.data
+        arr[i].exp_avg_sq = exp_avg_sqs[i].ctypes.data
+        arr[i].max_exp_avg_sq = max_sqs[i].ctypes.data if max_sqs is not None else None
+        arr[i].numel = params[i].size * (2 if cx else 1)
+        arr[i].is_complex = int(cx)
+    h = _capi.AdamHyper(lr, betas[0], betas[1], eps, weight_decay, int(amsgrad), step)
+    _capi.check(L, L.uno_adam_step(arr, n, C.byref(h), None))
+
+
+def lp_loss(x, y, reduction, gl):
+    L = lib()
+    x, y, gl = _f32(x), _f32(y), _f32(gl).reshape(-1)
+    B = x.shape[0]
+    N = x.size // B
+    loss = np.full(B if reduction == 0 else 1, np.nan, np.float32)
+    norms = np.full((B, 2), np.nan, np.float32)
+    ws = np.empty(2 * B, np.float64)
+    _capi.check(L, L.uno_lp_loss_fwd(_p(x), _p(y), B, N, reduction, _p(loss), _p(norms), _p(ws), ws.nbytes, None))
+    gx = np.full_like(x, np.nan)
+    _capi.check(L, L.uno_lp_loss_bwd(_p(x), _p(y), _p(norms), _p(gl), B, N, reduction, _p(gx), None))
+    return loss, gx

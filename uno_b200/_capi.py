@@ -37,6 +37,16 @@ class LiftDesc(C.Structure):
     _fields_ = [("px", PixelDesc), ("raw_ch", C.c_int), ("grid_ch", C.c_int), ("hidden", C.c_int), ("out_ch", C.c_int)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("max_exp_avg_sq", C.c_void_p), ("numel", C.c_long), ("is_complex", C.c_int)]
+
+
+class AdamHyper(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+                ("amsgrad", C.c_int), ("step", C.c_int)]
+
+
 class ProjectDesc(C.Structure):
     _fields_ = [("px", PixelDesc), ("nsrc", C.c_int), ("src_ch", C.c_int * 4), ("hidden", C.c_int), ("out_ch", C.c_int)]
 
@@ -74,6 +84,9 @@ SYMBOLS = {
     "uno_project_check": (C.c_int, [_PDESC]),
     "uno_project_fwd": (C.c_int, [_PDESC, _PP, _P, _P, _P, _P, _P, _P, _P]),
     "uno_project_bwd": (C.c_int, [_PDESC, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P]),
+    "uno_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.POINTER(AdamHyper), _P]),
+    "uno_lp_loss_fwd": (C.c_int, [_P, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "uno_lp_loss_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_long, C.c_int, _P, _P]),
     "uno_launch_count": (C.c_long, []),
     "uno_profile_enable": (None, [C.c_int]),
     "uno_profile_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),

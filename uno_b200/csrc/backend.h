@@ -181,4 +181,26 @@ int be_proj_supported(const ProjArgs& a);
 int be_proj_fwd(const ProjArgs& a, stream_t s);
 int be_proj_bwd(const ProjArgs& a, stream_t s);
 
+// ---- training-step ops next to the path ---------------------------------------------
+// The reference's Adam (Adam.py:8-52) over a list of tensors in one launch per 24 tensors.  numel counts floats; a complex
+// tensor is (re, im) pairs whose second moment is |g|^2 stored as (v, 0).  vmax is used only when amsgrad (real tensors).
+struct AdamTensor {
+    float* param = nullptr; const float* grad = nullptr; float* exp_avg = nullptr; float* exp_avg_sq = nullptr;
+    float* max_exp_avg_sq = nullptr;
+    long numel = 0;
+    int is_complex = 0;
+};
+struct AdamHyper {
+    double lr = 1e-3, beta1 = 0.9, beta2 = 0.999, eps = 1e-8, weight_decay = 0.0;
+    int amsgrad = 0;
+    int step = 1;          // 1-based step count of every tensor in the call
+};
+int be_adam_step(const AdamTensor* t, int n, const AdamHyper& h, stream_t s);
+
+// relative L2 loss of utilities3.LpLoss (p = 2): x, y [B, N]; reduction 0 = none ([B] out), 1 = sum, 2 = mean.
+// norms [B, 2] = (||x-y||, ||y||) out of fwd / in to bwd; acc = scratch of 2*B doubles.
+int be_lp_loss_fwd(const float* x, const float* y, int B, long N, int reduction, float* loss, float* norms, double* acc, stream_t s);
+int be_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gl, int B, long N, int reduction, float* gx,
+                   stream_t s);
+
 }  // namespace uno

@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -659,6 +660,7 @@ int ensure_smem(K kernel, size_t bytes) {
 #include "pixel_mlp.cuh"
 #include "resample2d.cuh"
 #include "norm_cluster.cuh"
+#include "train_ops.cuh"
 
 
 // =====================================================================================================
@@ -1499,6 +1501,61 @@ int be_proj_bwd(const ProjArgs& a, stream_t s) {
     ProfScope ps("project_bwd", 4.0 * (px * (k.ctot + a.out_ch + (a.pre_in ? a.hid : 0)) + ppx * k.ctot),
                  2.0 * px * ((a.pre_in ? 2 : 3) * k.ctot * a.hid + 2 * a.hid * a.out_ch), S(s));
     return k.ctot <= 32 ? launch_proj<32>(k, true, S(s)) : launch_proj<64>(k, true, S(s));
+}
+
+// =====================================================================================================
+// training-step ops (train_ops.cuh)
+// =====================================================================================================
+int be_adam_step(const AdamTensor* t, int n, const AdamHyper& h, stream_t s) {
+    const double bc1 = 1.0 - pow(h.beta1, (double)h.step), bc2 = 1.0 - pow(h.beta2, (double)h.step);
+    for (int i0 = 0; i0 < n; i0 += kAdamMaxTensors) {
+        AdamBatch b;
+        memset(&b, 0, sizeof b);
+        b.n = std::min(kAdamMaxTensors, n - i0);
+        double floats = 0;
+        int chunks = 0;
+        for (int i = 0; i < b.n; ++i) {
+            const AdamTensor& a = t[i0 + i];
+            b.param[i] = a.param; b.grad[i] = a.grad; b.m[i] = a.exp_avg; b.v[i] = a.exp_avg_sq; b.vmax[i] = a.max_exp_avg_sq;
+            b.numel[i] = a.numel; b.is_complex[i] = a.is_complex;
+            b.chunk_start[i] = chunks;
+            chunks += (int)((a.numel + kAdamChunk - 1) / kAdamChunk);
+            floats += (double)a.numel;
+        }
+        b.chunk_start[b.n] = chunks;
+        b.beta1 = (float)h.beta1; b.one_minus_beta1 = (float)(1.0 - h.beta1);
+        b.beta2 = (float)h.beta2; b.one_minus_beta2 = (float)(1.0 - h.beta2);
+        b.eps = (float)h.eps; b.weight_decay = (float)h.weight_decay;
+        b.step_size = (float)(h.lr / bc1);
+        b.sqrt_bc2 = (float)sqrt(bc2);
+        b.amsgrad = h.amsgrad;
+        if (chunks == 0) continue;
+        ProfScope ps("adam", 4.0 * floats * (h.amsgrad ? 8 : 6), 0, S(s));
+        adam_kernel<<<(unsigned)chunks, 256, 0, S(s)>>>(b);
+        CU_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int be_lp_loss_fwd(const float* x, const float* y, int B, long N, int reduction, float* loss, float* norms, double* acc, stream_t s) {
+    if (B <= 0 || N <= 0) return 0;
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * 2 * B, S(s));
+    if (e != cudaSuccess) return (int)e;
+    const unsigned gy = (unsigned)std::max<long>(1, std::min<long>((N + 8191) / 8192, (148L * 8 + B - 1) / B));
+    ProfScope ps("lp_loss", 8.0 * B * N, 0, S(s));
+    lp_partial_kernel<<<dim3((unsigned)B, gy), 256, 0, S(s)>>>(x, y, N, acc);
+    lp_finish_kernel<<<1, 256, 0, S(s)>>>(acc, B, reduction, norms, loss);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+int be_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gl, int B, long N, int reduction, float* gx,
+                   stream_t s) {
+    if (B <= 0 || N <= 0) return 0;
+    const unsigned gy = (unsigned)std::max<long>(1, std::min<long>((N + 8191) / 8192, (148L * 8 + B - 1) / B));
+    ProfScope ps("lp_loss_bwd", 12.0 * B * N, 0, S(s));
+    lp_bwd_kernel<<<dim3((unsigned)B, gy), 256, 0, S(s)>>>(x, y, norms, gl, N, B, reduction, gx);
+    CU_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace uno

@@ -1042,6 +1042,49 @@ int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* c
     return 0;
 }
 
+// ---- training-step ops ---------------------------------------------------------------------------------
+int uno_adam_step(const uno_adam_tensor* tensors, int n, const uno_adam_hyper* h, void* stream) {
+    if (!h || n < 0 || (n > 0 && !tensors)) return fail(UNO_EINVAL, "null argument");
+    if (!(h->lr >= 0.0)) return fail(UNO_EINVAL, "Invalid learning rate: %g", h->lr);
+    if (!(h->eps >= 0.0)) return fail(UNO_EINVAL, "Invalid epsilon value: %g", h->eps);
+    if (!(h->beta1 >= 0.0 && h->beta1 < 1.0)) return fail(UNO_EINVAL, "Invalid beta parameter at index 0: %g", h->beta1);
+    if (!(h->beta2 >= 0.0 && h->beta2 < 1.0)) return fail(UNO_EINVAL, "Invalid beta parameter at index 1: %g", h->beta2);
+    if (!(h->weight_decay >= 0.0)) return fail(UNO_EINVAL, "Invalid weight_decay value: %g", h->weight_decay);
+    if (h->step < 1) return fail(UNO_EINVAL, "step must be >= 1 (got %d)", h->step);
+    std::vector<AdamTensor> v((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const uno_adam_tensor& a = tensors[i];
+        if (!a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq || a.numel < 0) return fail(UNO_EINVAL, "tensor %d: null pointer", i);
+        if (a.is_complex && (a.numel & 1)) return fail(UNO_EINVAL, "tensor %d: complex tensor with an odd float count", i);
+        if (h->amsgrad && a.is_complex) return fail(UNO_EINVAL, "tensor %d: amsgrad is not defined for complex parameters (torch.maximum)", i);
+        if (h->amsgrad && !a.max_exp_avg_sq) return fail(UNO_EINVAL, "tensor %d: amsgrad needs max_exp_avg_sq", i);
+        v[i].param = a.param; v[i].grad = a.grad; v[i].exp_avg = a.exp_avg; v[i].exp_avg_sq = a.exp_avg_sq;
+        v[i].max_exp_avg_sq = a.max_exp_avg_sq; v[i].numel = a.numel; v[i].is_complex = a.is_complex;
+    }
+    AdamHyper hh;
+    hh.lr = h->lr; hh.beta1 = h->beta1; hh.beta2 = h->beta2; hh.eps = h->eps; hh.weight_decay = h->weight_decay;
+    hh.amsgrad = h->amsgrad; hh.step = h->step;
+    BE_TRY(be_adam_step(v.data(), n, hh, stream));
+    return 0;
+}
+
+int uno_lp_loss_fwd(const float* x, const float* y, int batch, long n, int reduction, float* loss, float* norms,
+                    void* ws, size_t ws_bytes, void* stream) {
+    if (!x || !y || !loss || !norms || !ws) return fail(UNO_EINVAL, "null tensor pointer");
+    if (batch < 1 || n < 1 || reduction < 0 || reduction > 2) return fail(UNO_EINVAL, "bad shape / reduction");
+    if (ws_bytes < sizeof(double) * 2 * (size_t)batch) return fail(UNO_EWORKSPACE, "workspace too small for the loss");
+    BE_TRY(be_lp_loss_fwd(x, y, batch, n, reduction, loss, norms, (double*)ws, stream));
+    return 0;
+}
+
+int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gloss, int batch, long n,
+                    int reduction, float* gx, void* stream) {
+    if (!x || !y || !norms || !gloss || !gx) return fail(UNO_EINVAL, "null tensor pointer");
+    if (batch < 1 || n < 1 || reduction < 0 || reduction > 2) return fail(UNO_EINVAL, "bad shape / reduction");
+    BE_TRY(be_lp_loss_bwd(x, y, norms, gloss, batch, n, reduction, gx, stream));
+    return 0;
+}
+
 void uno_profile_enable(int on) { be_profile_enable(on); }
 size_t uno_profile_report(char* buf, size_t cap) { return be_profile_report(buf, cap); }
 long uno_launch_count(void) { return be_launch_count(); }

@@ -36,11 +36,15 @@ WORKLOADS = {
     "darcy": ("UNO_9", (3, 32), dict(pad=12), (421, 421, 1), (421, 421), 32, 2),
     "ns2d": ("UNO", (14, 32), {}, (64, 64, 10), (64, 64), 64, 8),
     "ns3d": ("Uno3D_T10", (6, 8), dict(pad=3), (64, 64, 64, 1), (64, 64, 64), 8, 1),
+    # BASELINE.json configs[2] exactly as ns_train_2d.py:46-67 trains it: 10 autoregressive model calls, summed loss, ONE backward
+    "ns2d_ar": ("UNO", (14, 32), {}, (64, 64, 10), (64, 64, 10), 64, 4),
 }
+AR_STEPS = {"ns2d_ar": 10}
 WORKLOAD_DESC = {
     "darcy": "UNO_9(3,32,pad=12) Darcy 421x421 fwd+loss+bwd",
     "ns2d": "UNO(14,32) Navier-Stokes 64x64x10 single-call fwd+loss+bwd",
     "ns3d": "Uno3D_T10(6,8,pad=3) Navier-Stokes 64x64x64 fwd+loss+bwd",
+    "ns2d_ar": "UNO(14,32) Navier-Stokes 64x64, 10-step autoregressive rollout + BPTT (ns_train_2d.py:46-67)",
 }
 
 
@@ -121,14 +125,22 @@ def build_model(workload, ops=None, device="cuda"):
     return getattr(models, cls)(*args, **kw).to(device)
 
 
-def make_step(model, loss_fn, B, tshape, reducer=None):
+def make_step(model, loss_fn, B, tshape, reducer=None, ar_steps=0):
     def step(x, y):
         if reducer is not None:
             reducer.zero_grad()
         else:
             model.zero_grad(set_to_none=True)
-        out = model(x).reshape(B, *tshape)
-        loss = loss_fn(out.reshape(B, -1), y.reshape(B, -1))
+        if ar_steps:
+            # ns_train_2d.py:52-67: feed each prediction back as the newest input frame, sum the per-step losses
+            loss, xx = 0, x
+            for t in range(ar_steps):
+                im = model(xx)
+                loss = loss + loss_fn(im.reshape(B, -1), y[..., t : t + 1].reshape(B, -1))
+                xx = torch.cat((xx[..., 1:], im), dim=-1)
+        else:
+            out = model(x).reshape(B, *tshape)
+            loss = loss_fn(out.reshape(B, -1), y.reshape(B, -1))
         loss.backward()
         if reducer is not None:
             reducer.finish()
@@ -150,7 +162,7 @@ def cpu_reference_run(workload, steps, warmup, batch=None):
     torch.manual_seed(1)
     x = torch.randn(B, *xshape)
     y = torch.randn(B, *tshape)
-    step = make_step(model, LpLoss(size_average=False), B, tshape)
+    step = make_step(model, LpLoss(size_average=False), B, tshape, ar_steps=AR_STEPS.get(workload, 0))
     for _ in range(warmup):
         step(x, y)
     t0 = time.perf_counter()
@@ -219,7 +231,7 @@ def main():
     model = build_model(args.workload, device=dev)
     reducer = GradReducer(model) if world > 1 else None
     loss_fn = LpLoss(size_average=False)
-    step = make_step(model, loss_fn, B, tshape, reducer)
+    step = make_step(model, loss_fn, B, tshape, reducer, ar_steps=AR_STEPS.get(args.workload, 0))
 
     torch.manual_seed(1 + rank)
     x_host = torch.randn(B, *xshape).pin_memory()

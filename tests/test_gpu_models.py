@@ -136,3 +136,29 @@ def test_linearity_and_batch_independence_full_size(cuda_lib):
         img = torch.cos(2 * torch.pi * 3 * n / 64)[:, None] * torch.sin(2 * torch.pi * 5 * n / 64)[None, :] + 0.5
         out = ident(img[None, None])
         assert rel_err(out[0, 0].cpu().numpy(), img.cpu().numpy()) < FWD_TOL
+
+
+def test_autoregressive_rollout_gradients_match_cpu_port(cuda_lib):
+    """BASELINE config 3 as the reference trains it (ns_train_2d.py:52-67): predictions are fed back as inputs, so the
+    backward pass runs through the lift kernel's input gradient at every step.  CUDA path vs the CPU fp32 oracle port."""
+    import bench
+    from oracle import uno_torch_port as port
+    from uno_b200 import models
+    from uno_b200.losses import LpLoss
+
+    torch.manual_seed(0)
+    ref = models.UNO(14, 8, ops=port)
+    torch.manual_seed(0)
+    ours = models.UNO(14, 8).cuda()
+    ours.load_state_dict(ref.state_dict())
+    torch.manual_seed(5)
+    B, T = 2, 3
+    x = torch.randn(B, 64, 64, 10)
+    y = torch.randn(B, 64, 64, T)
+    lr_ = bench.make_step(ref, port.LpLoss(size_average=False), B, (64, 64, T), ar_steps=T)(x, y)
+    lo = bench.make_step(ours, LpLoss(size_average=False), B, (64, 64, T), ar_steps=T)(x.cuda(), y.cuda())
+    assert abs(float(lo) - float(lr_)) < 1e-4 * abs(float(lr_))
+    for (k, a), (_, b) in zip(ours.named_parameters(), ref.named_parameters()):
+        ga = torch.view_as_real(a.grad).cpu() if a.grad.is_complex() else a.grad.cpu()
+        gb = torch.view_as_real(b.grad) if b.grad.is_complex() else b.grad
+        assert float((ga - gb).abs().max()) < 8 * BWD_TOL * max(float(gb.abs().max()), 1e-6), k

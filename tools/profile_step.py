@@ -22,7 +22,7 @@ args = ap.parse_args()
 cls, cargs, ckw, xshape, tshape, def_b, _ = bench.WORKLOADS[args.workload]
 B = args.batch or def_b
 model = bench.build_model(args.workload)
-step = bench.make_step(model, LpLoss(size_average=False), B, tshape)
+step = bench.make_step(model, LpLoss(size_average=False), B, tshape, ar_steps=bench.AR_STEPS.get(args.workload, 0))
 torch.manual_seed(1)
 x = torch.randn(B, *xshape, device="cuda")
 y = torch.randn(B, *tshape, device="cuda")

@@ -129,7 +129,8 @@ int be_banded2d(const Banded2DArgs& a, stream_t) {
     if (a.D0 && a.D1) {
         // the register-blocked images (what the CUDA kernel consumes): window of W inputs per group of G outputs.
         // Walks the same tiles as the kernel so that the tile geometry handed over by the plan is exercised too.
-        const int TH = a.tile_groups0 * a.G0, NG1 = 64 / a.G1;
+        const int TW = a.G1 == 8 ? 128 : 64;
+        const int TH = a.tile_groups0 * a.G0, NG1 = TW / a.G1;
         for (long p = 0; p < a.planes; ++p)
             for (int ga0 = 0; ga0 < a.ng0; ga0 += a.tile_groups0)
                 for (int ga1 = 0; ga1 < a.ng1; ga1 += NG1) {
@@ -137,7 +138,7 @@ int be_banded2d(const Banded2DArgs& a, stream_t) {
                     const int r0 = a.gs0[ga0], c0 = a.gs1[ga1];
                     const int rin = a.gs0[ga0 + ngh - 1] + a.W0 - r0, cin = a.gs1[ga1 + ngw - 1] + a.W1 - c0;
                     if (rin > a.tile_span0 || cin > a.tile_span1 || r0 + rin > a.n_in0 || c0 + cin > a.n_in1 || TH < 1) return 1;
-                    std::vector<double> mid((size_t)rin * 64, 0.0);
+                    std::vector<double> mid((size_t)rin * TW, 0.0);
                     for (int r = 0; r < rin; ++r)
                         for (int g = 0; g < ngw; ++g)
                             for (int q = 0; q < a.G1; ++q) {
@@ -146,7 +147,7 @@ int be_banded2d(const Banded2DArgs& a, stream_t) {
                                 if (cs < 0) return 1;
                                 for (int u = 0; u < a.W1; ++u)
                                     acc += (double)a.D1[((long)(ga1 + g) * a.W1 + u) * a.G1 + q] * a.x[(p * a.n_in0 + r0 + r) * a.n_in1 + c0 + cs + u];
-                                mid[(size_t)r * 64 + g * a.G1 + q] = acc;
+                                mid[(size_t)r * TW + g * a.G1 + q] = acc;
                             }
                     for (int g = 0; g < ngh; ++g)
                         for (int q = 0; q < a.G0; ++q) {
@@ -154,11 +155,11 @@ int be_banded2d(const Banded2DArgs& a, stream_t) {
                             if (i >= a.n_out0) continue;
                             const int rs = a.gs0[ga0 + g] - r0;
                             if (rs < 0) return 1;
-                            for (int jc = 0; jc < 64; ++jc) {
+                            for (int jc = 0; jc < TW; ++jc) {
                                 const int j = ga1 * a.G1 + jc;
                                 if (j >= a.n_out1) continue;
                                 double acc = 0;
-                                for (int u = 0; u < a.W0; ++u) acc += (double)a.D0[((long)(ga0 + g) * a.W0 + u) * a.G0 + q] * mid[(size_t)(rs + u) * 64 + jc];
+                                for (int u = 0; u < a.W0; ++u) acc += (double)a.D0[((long)(ga0 + g) * a.W0 + u) * a.G0 + q] * mid[(size_t)(rs + u) * TW + jc];
                                 a.y[(p * a.n_out0 + i) * a.n_out1 + j] = (float)acc;
                             }
                         }

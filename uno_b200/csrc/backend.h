@@ -103,7 +103,9 @@ struct BandedArgs {
 int be_banded(const BandedArgs& a, stream_t s);
 
 // fused separable 2-D form: y[p] = R0 * x[p] * R1^T for every plane p   x [P, n_in0, n_in1] -> y [P, n_out0, n_out1]
-// span0 / span1: largest input extent (rows / cols) needed by any 32-row / 64-column output tile.
+// span0 / span1: largest input extent (rows / cols) needed by any 32-row / 64-column output tile (generic kernel);
+// tile_span0 / tile_span1: the same for the register-blocked kernel's tiles (tile_groups0 row groups x 64 columns,
+// 128 columns when G1 == 8).
 struct Banded2DArgs {
     const float* x = nullptr; float* y = nullptr; long planes = 0;
     const int* start0 = nullptr; const float* w0 = nullptr; int n_in0 = 0, n_out0 = 0, taps0 = 0, span0 = 0;

@@ -271,8 +271,7 @@ template <int TJ, int TI>
 __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
     extern __shared__ __align__(16) float2 msm[];
     const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
-    float2* Ms = msm;                                   // [HK][JTP]
-    float2* Xs = Ms + (size_t)k.HK * JTP + (((size_t)k.HK * JTP) & 1);   // [ppc][HK][IT], 16-byte aligned
+    // shared memory: 2 x { Mat chunk [HK][JTP] (padded to an even count) ; X chunk [ppc][HK][IT] (16-byte aligned) }
     const int tid = threadIdx.x;
     const int tpp = k.nj * k.ni;
     const int grp = tid / tpp, t = tid - grp * tpp;
@@ -288,26 +287,46 @@ __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
     for (int a = 0; a < TJ; ++a)
 #pragma unroll
         for (int b = 0; b < TI; ++b) acc[a][b] = make_float2(0.f, 0.f);
-    for (int h0 = 0; h0 < k.H; h0 += k.HK) {
+    // chunks of HK rows of h are staged with 8-byte LDGSTS into a double buffer: the copy of chunk c+1 overlaps the
+    // arithmetic of chunk c (out-of-range elements are zero-filled through src-size 0)
+    const size_t ms_elems = (size_t)k.HK * JTP + (((size_t)k.HK * JTP) & 1);
+    const size_t buf_elems = ms_elems + (size_t)k.ppc * k.HK * IT;
+    auto stage = [&](int h0, int buf) {
+        float2* Mb = msm + (size_t)buf * buf_elems;
+        float2* Xb = Mb + ms_elems;
         const int hk = min(k.HK, k.H - h0);
         for (int idx = tid; idx < JT * k.HK; idx += 256) {
             const int h = idx % k.HK, j = idx / k.HK;
-            float2 v = make_float2(0.f, 0.f);
-            if (j0 + j < k.J && h < hk) v = __ldg(k.Mat + (long)(j0 + j) * k.H + h0 + h);
-            Ms[h * JTP + j] = v;
+            const bool on = j0 + j < k.J && h < hk;
+            const float2* src = on ? k.Mat + (long)(j0 + j) * k.H + h0 + h : k.Mat;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Mb + h * JTP + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
         }
         for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
             const int i = idx % IT;
             const int r = idx / IT;
             const int h = r % k.HK, g = r / k.HK;
-            float2 v = make_float2(0.f, 0.f);
-            if (o0 + g < k.O && h < hk && i0 + i < k.I) v = __ldg(k.X + ((o0 + g) * k.H + h0 + h) * (long)k.I + i0 + i);
-            Xs[idx] = v;
+            const bool on = o0 + g < k.O && h < hk && i0 + i < k.I;
+            const float2* src = on ? k.X + ((o0 + g) * k.H + h0 + h) * (long)k.I + i0 + i : k.X;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xb + idx);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
+    int cur = 0;
+    for (int h0 = 0; h0 < k.H; h0 += k.HK, cur ^= 1) {
+        const int hk = min(k.HK, k.H - h0);
+        if (h0 + k.HK < k.H) {
+            stage(h0 + k.HK, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         if (active) {
-            const float2* mp = Ms + tj * TJ;
-            const float2* xp = Xs + (size_t)grp * k.HK * IT + ti * TI;
+            const float2* mp = msm + (size_t)cur * buf_elems + tj * TJ;
+            const float2* xp = msm + (size_t)cur * buf_elems + ms_elems + (size_t)grp * k.HK * IT + ti * TI;
 #pragma unroll 4
             for (int h = 0; h < hk; ++h) {
                 float2 m[TJ], x[TI];
@@ -1155,7 +1174,7 @@ int be_mid(const MidArgs& a, stream_t s) {
     const int JT = k.nj * TJ, IT = k.ni * TI, JTP = JT | 1;
     size_t ms = (size_t)k.HK * JTP;
     ms += ms & 1;
-    const size_t smem = (ms + (size_t)k.ppc * k.HK * IT) * sizeof(float2);
+    const size_t smem = 2 * (ms + (size_t)k.ppc * k.HK * IT) * sizeof(float2);   // double buffered
     const long blocks = (long)((a.O + k.ppc - 1) / k.ppc) * k.tilesJ * k.tilesI;
     ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
     switch (TJ * 10 + TI) {
@@ -1201,7 +1220,7 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     k.RIN = (a.tile_span0 + 3) & ~3;          // multiple of 4 keeps the weight images 16-byte aligned
     k.ldin = a.tile_span1 | 1;                // odd pitch: lanes sweeping rows hit distinct banks
     k.tiles_h = (a.ng0 + a.tile_groups0 - 1) / a.tile_groups0;
-    k.tiles_w = (a.n_out1 + kRsTW - 1) / kRsTW;
+    k.tiles_w = (a.n_out1 + rs_tile_w(G1) - 1) / rs_tile_w(G1);
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
     int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1>, smem);

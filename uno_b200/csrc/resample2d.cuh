@@ -24,11 +24,14 @@ struct Resample2K {
     int RIN, ldin;                              // rows of the staged window, its (odd) pitch
     int tiles_h, tiles_w;
 };
-constexpr int kRsTW = 64, kRsMidLd = 65;
+// output columns per tile: 128 for the small-window (G = 8, up-sampling) image, whose tiles are otherwise dominated by
+// per-tile overheads, 64 for the others
+__host__ __device__ constexpr int rs_tile_w(int G1) { return G1 == 8 ? 128 : 64; }
 
 template <int G0, int W0, int G1, int W1>
 __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) {
     extern __shared__ __align__(16) float rsm[];
+    constexpr int kRsTW = rs_tile_w(G1), kRsMidLd = kRsTW + 1;
     constexpr int NG1 = kRsTW / G1;                      // column groups per tile
     const int NG0 = k.TH / G0;                           // row groups per tile
     float* in_s = rsm;                                   // [RIN][ldin]
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
         float* yrow = k.y + (p * k.n_out0 + i0 + rg * G0) * (long)k.n_out1 + j0 + lane;
         const int rows_left = k.n_out0 - (i0 + rg * G0);
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {          // the two 32-column halves of the tile share the weights
+        for (int half = 0; half < kRsTW / 32; ++half) { // the 32-column slices of the tile share the weights
             const float* src = srow + 32 * half;
             float acc[G0];
 #pragma unroll
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) 
 }
 
 inline size_t resample2d_smem(int RIN, int ldin, int TH, int G0, int W0, int G1, int W1) {
-    return sizeof(float) * ((size_t)RIN * ldin + (size_t)RIN * kRsMidLd + (size_t)(kRsTW / G1) * W1 * G1 + (size_t)(TH / G0) * W0 * G0 +
-                            kRsTW / G1 + TH / G0);
+    const int TW = rs_tile_w(G1);
+    return sizeof(float) * ((size_t)RIN * ldin + (size_t)RIN * (TW + 1) + (size_t)(TW / G1) * W1 * G1 + (size_t)(TH / G0) * W0 * G0 +
+                            TW / G1 + TH / G0);
 }

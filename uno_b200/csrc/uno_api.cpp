@@ -105,7 +105,7 @@ struct DevBand {
             const double eff = (double)(n * G) / (32.0 * ((sp + 31) / 32));
             if (eff > best + 1e-9) { best = eff; tile_groups_rows = n; tile_span_rows = sp; }
         }
-        tile_span_cols = g.span(64 / G);
+        tile_span_cols = g.span((G == 8 ? 128 : 64) / G);   // columns per tile: resample2d.cuh rs_tile_w
         void* p = nullptr;
         int rc = be_upload(&p, g.gstart.data(), g.gstart.size() * sizeof(int));
         gstart = (int*)p;

@@ -140,3 +140,33 @@ def test_resample_matches_aten_bicubic_aa(pair, cuda_lib):
     z.backward(g)
     zr.backward(g)
     assert float((x.grad - xr.grad).abs().max() / xr.grad.abs().max()) < BWD_TOL
+
+
+@pytest.mark.parametrize("case", [
+    # (B, Ci, Co, in_dims, out_dims, modes): shapes that take the TILED mode-contraction kernel (M, N >= 16) with ragged
+    # 32 x 32 tiles, a mode count that is not a multiple of the 4 modes a CTA owns, k tails, and a strided outer mode axis
+    (32, 24, 40, (20, 18), (16, 14), (5, 3)),
+    (17, 48, 33, (12, 12), (12, 12), (6, 6)),
+    (20, 16, 19, (10, 9, 8), (8, 9, 8), (3, 2, 3)),
+])
+def test_spectral_conv_tiled_contraction_vs_oracle(case, cuda_lib):
+    from oracle import uno_oracle as orc
+    from uno_b200 import functional as Fn
+
+    B, Ci, Co, idim, odim, modes = case
+    rng = np.random.default_rng(B * 100 + Ci)
+    x = rng.standard_normal((B, Ci) + idim).astype(np.float32)
+    nw = 2 ** (len(idim) - 1)
+    ws = [((rng.standard_normal((Ci, Co) + modes) + 1j * rng.standard_normal((Ci, Co) + modes)) / np.sqrt(2 * Ci)).astype(np.complex64)
+          for _ in range(nw)]
+    gy = rng.standard_normal((B, Co) + odim).astype(np.float32)
+    y_ref = orc.spectral_conv_fwd(x, ws, odim, modes)
+    gx_ref, gw_ref = orc.spectral_conv_bwd(x, ws, odim, modes, gy)
+    xt = _t(x, grad=True)
+    wt = [_t(w, grad=True) for w in ws]
+    y = Fn.spectral_conv(xt, wt, odim, modes)
+    assert rel_err(_n(y), y_ref) < FWD_TOL
+    y.backward(_t(gy))
+    assert rel_err(_n(xt.grad), gx_ref) < BWD_TOL
+    for w, r in zip(wt, gw_ref):
+        assert rel_err(_n(w.grad), r) < BWD_TOL

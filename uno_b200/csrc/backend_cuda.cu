@@ -420,6 +420,110 @@ __global__ void __launch_bounds__(128, 6) cmm_kernel(const CmmArgs a, int chunks
 }
 
 // =====================================================================================================
+// per-mode complex contraction, tiled: the regime of many channels (NS-2D inner levels: 64 x 192 x 192 per mode, 36 modes).
+// A CTA owns 4 consecutive modes x a 32 (m) x 32 (n) output tile; a thread one mode and a 4 x 4 complex register tile.
+// k runs in chunks of 16 staged with 8-byte LDGSTS into a double buffer (lanes run over the 4 modes first, so every
+// 32-byte sector fetched from L2 is used whole); per k a thread issues 4 16-byte shared loads for 64 FMAs.
+// =====================================================================================================
+constexpr int kC2Q = 4, kC2M = 32, kC2N = 32, kC2K = 16;
+constexpr int kC2QStrideA = kC2K * kC2M + 8, kC2QStrideB = kC2K * kC2N + 8;   // float2 elements; +8 keeps the 4 modes' stores apart
+constexpr int kC2BufElems = kC2Q * (kC2QStrideA + kC2QStrideB);
+
+__global__ void __launch_bounds__(256) cmm2_kernel(const CmmArgs a, int qchunks) {
+    extern __shared__ __align__(16) float2 csm[];
+    const int tid = threadIdx.x;
+    const int per_corner = qchunks * a.q_outer;
+    const int corner = blockIdx.x / per_corner;
+    const int bx = blockIdx.x - corner * per_corner;
+    const int qo = bx / qchunks;
+    const int q0 = (bx - qo * qchunks) * kC2Q;
+    const int m0 = blockIdx.y * kC2M, n0 = blockIdx.z * kC2N;
+    const float2* A = reinterpret_cast<const float2*>(a.A[corner]) + (long)qo * a.a_sqo;
+    const float2* B = reinterpret_cast<const float2*>(a.B[corner]) + (long)qo * a.b_sqo;
+    float2* C = reinterpret_cast<float2*>(a.C[corner]) + (long)qo * a.c_sqo;
+    // staging map: lane bits 0-1 = mode, the rest = (row, k) pair index
+    const int sq = tid & 3, sp = tid >> 2;
+    const bool q_ok = q0 + sq < a.q_inner;
+    auto stage = [&](int k0, int buf) {
+        float2* As = csm + (size_t)buf * kC2BufElems + sq * kC2QStrideA;
+        float2* Bs = csm + (size_t)buf * kC2BufElems + kC2Q * kC2QStrideA + sq * kC2QStrideB;
+#pragma unroll
+        for (int it = 0; it < kC2K * kC2M / 64; ++it) {
+            const int pr = sp + 64 * it;
+            const int m = pr % kC2M, kk = pr / kC2M;
+            const bool on = q_ok && m0 + m < a.M && k0 + kk < a.K;
+            const float2* src = on ? A + (long)(m0 + m) * a.a_sm + (long)(k0 + kk) * a.a_sk + q0 + sq : A;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(As + kk * kC2M + m);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+        }
+#pragma unroll
+        for (int it = 0; it < kC2K * kC2N / 64; ++it) {
+            const int pr = sp + 64 * it;
+            const int n = pr % kC2N, kk = pr / kC2N;
+            const bool on = q_ok && n0 + n < a.N && k0 + kk < a.K;
+            const float2* src = on ? B + (long)(k0 + kk) * a.b_sk + (long)(n0 + n) * a.b_sn + q0 + sq : B;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Bs + kk * kC2N + n);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // compute map: 64 threads per mode, 8 x 8 of them over the tile
+    const int cq = tid >> 6, ty = (tid >> 3) & 7, tx = tid & 7;
+    const float sa = a.conjA ? -1.f : 1.f, sb = a.conjB ? -1.f : 1.f;
+    float2 acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    stage(0, 0);
+    int cur = 0;
+    for (int k0 = 0; k0 < a.K; k0 += kC2K, cur ^= 1) {
+        if (k0 + kC2K < a.K) {
+            stage(k0 + kC2K, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float2* As = csm + (size_t)cur * kC2BufElems + cq * kC2QStrideA + ty * 4;
+        const float2* Bs = csm + (size_t)cur * kC2BufElems + kC2Q * kC2QStrideA + cq * kC2QStrideB + tx * 4;
+        const int kn = min(kC2K, a.K - k0);
+#pragma unroll 4
+        for (int kk = 0; kk < kn; ++kk) {
+            float2 av[4], bv[4];
+            const float4 a01 = *reinterpret_cast<const float4*>(As + kk * kC2M), a23 = *reinterpret_cast<const float4*>(As + kk * kC2M + 2);
+            const float4 b01 = *reinterpret_cast<const float4*>(Bs + kk * kC2N), b23 = *reinterpret_cast<const float4*>(Bs + kk * kC2N + 2);
+            av[0] = make_float2(a01.x, a01.y * sa); av[1] = make_float2(a01.z, a01.w * sa);
+            av[2] = make_float2(a23.x, a23.y * sa); av[3] = make_float2(a23.z, a23.w * sa);
+            bv[0] = make_float2(b01.x, b01.y * sb); bv[1] = make_float2(b01.z, b01.w * sb);
+            bv[2] = make_float2(b23.x, b23.y * sb); bv[3] = make_float2(b23.z, b23.w * sb);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j].x = fmaf(av[i].x, bv[j].x, acc[i][j].x);
+                    acc[i][j].x = fmaf(-av[i].y, bv[j].y, acc[i][j].x);
+                    acc[i][j].y = fmaf(av[i].x, bv[j].y, acc[i][j].y);
+                    acc[i][j].y = fmaf(av[i].y, bv[j].x, acc[i][j].y);
+                }
+        }
+        __syncthreads();
+    }
+    if (q0 + cq < a.q_inner) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m >= a.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < a.N) C[(long)m * a.c_sm + (long)n * a.c_sn + q0 + cq] = acc[i][j];
+            }
+        }
+    }
+}
+
+// =====================================================================================================
 // banded resample
 // =====================================================================================================
 __global__ void __launch_bounds__(256) banded_kernel(const BandedArgs a, long total) {
@@ -1192,6 +1296,17 @@ int be_cmm(const CmmArgs& a, stream_t s) {
     const int chunks = (a.q_inner + 31) / 32;
     const double q = (double)a.q_inner * a.q_outer * a.ncorner;
     ProfScope ps("mode_contraction", 8.0 * q * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N), 8.0 * q * a.M * a.N * a.K, S(s));
+    if (a.M >= 16 && a.N >= 16) {
+        // enough rows and columns to fill 32 x 32 tiles: the shared-memory tiled kernel (4 modes per CTA)
+        const int qchunks = (a.q_inner + kC2Q - 1) / kC2Q;
+        const size_t smem = (size_t)2 * kC2BufElems * sizeof(float2);
+        int rc = ensure_smem(cmm2_kernel, smem);
+        if (rc) return rc;
+        dim3 grid2((unsigned)(qchunks * a.q_outer * a.ncorner), (unsigned)((a.M + kC2M - 1) / kC2M), (unsigned)((a.N + kC2N - 1) / kC2N));
+        cmm2_kernel<<<grid2, 256, smem, S(s)>>>(a, qchunks);
+        CU_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((unsigned)(chunks * a.q_outer * a.ncorner), (unsigned)((a.M + 3) / 4), (unsigned)((a.N + 15) / 16));
     cmm_kernel<<<grid, dim3(32, 4), 0, S(s)>>>(a, chunks);
     CU_LAUNCH_CHECK();

@@ -71,3 +71,33 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 # the host-emulation library is only ever mentioned in comments / docstrings, never loaded
                 assert "libuno_hostemu" not in src, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_model_file_shims_overlay_the_reference():
+    """uno_b200/dropin in front of the reference on sys.path: `from darcy_flow_uno2d import UNO_9, UNO_11` (darcy_flow_main.py:9)
+    gets our fused-glue UNO_9 and the reference's own UNO_11 (built on the drop-in blocks); same for the Navier-Stokes files."""
+    import subprocess
+
+    code = r'''
+import sys, types
+for n in ("matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(n, types.ModuleType(n))
+sys.dont_write_bytecode = True
+from darcy_flow_uno2d import UNO_9, UNO_11
+from navier_stokes_uno2d import UNO, UNO_P, UNO_S256
+from navier_stokes_uno3d import Uno3D_T10, Uno3D_T40
+import uno_b200.models as M, uno_b200.integral_operators as ops
+assert UNO_9 is M.UNO_9 and UNO is M.UNO and UNO_P is M.UNO_P and Uno3D_T10 is M.Uno3D_T10
+assert UNO_11.__module__ != "uno_b200.models" and UNO_11.__init__.__code__.co_filename.startswith("/root/reference")
+m = UNO_S256(14, 8)                                        # (UNO_11 itself does not construct upstream: SURVEY.md B.4)
+assert isinstance(m.L0, ops.OperatorBlock_2D)             # the reference's own model, on the CUDA drop-in blocks
+import torch
+torch.manual_seed(0); a = UNO_9(3, 8, pad=5)
+assert [k for k in a.state_dict()][:4] == ["fc_n1.weight", "fc_n1.bias", "fc0.weight", "fc0.bias"]
+print("ok")
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "uno_b200", "dropin"), ROOT, "/root/reference"]),
+               PYTHONDONTWRITEBYTECODE="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -781,6 +781,7 @@ int ensure_smem(K kernel, size_t bytes) {
 }
 
 #include "pixel_mlp.cuh"
+#include "pixel_mlp_mma.cuh"
 #include "resample2d.cuh"
 #include "norm_cluster.cuh"
 #include "train_ops.cuh"
@@ -1580,6 +1581,15 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long total = (long)k.batch * k.g.nraw;
         const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k);
+    } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr) {
+        // tensor-core kernel (needs the pre-activations the forward pass saved)
+        const int nbuf = proj_bwd_mma_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;
+        const size_t smem = proj_bwd_mma_smem(CT, k.hid, k.out_ch, nbuf);
+        int rc = ensure_smem(proj_bwd_mma_kernel<CT>, smem);
+        if (rc) return rc;
+        const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
+        proj_bwd_mma_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles, nbuf);
     } else {
         // double-buffer the staged inputs when both copies fit beside the weights (hid <= 64 at 64 channels)
         const int nbuf = proj_bwd_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;

@@ -1581,8 +1581,9 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long total = (long)k.batch * k.g.nraw;
         const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k);
-    } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr) {
-        // tensor-core kernel (needs the pre-activations the forward pass saved)
+    } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_MMA") != nullptr) {
+        // warp-level mma.sync 3xTF32 variant, opt-in: measured on B200 it is SLOWER than the fp32 kernel (5.1 vs 3.5 ms at
+        // Darcy size) -- legacy mma.sync TF32 issues at ~1 instruction per 22 cycles per SM here, below the fp32 FMA pipe
         const int nbuf = proj_bwd_mma_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;
         const size_t smem = proj_bwd_mma_smem(CT, k.hid, k.out_ch, nbuf);
         int rc = ensure_smem(proj_bwd_mma_kernel<CT>, smem);

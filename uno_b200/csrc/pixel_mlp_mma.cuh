@@ -8,7 +8,12 @@
 // W1 is constant during the kernel and is split into tf32 hi / lo images once (row pitch CT+8: conflict-free B fragments);
 // D and IN fragments are split on the fly.  With a single hidden chunk (hid <= 32: the Darcy and 3-D models) every warp
 // keeps its dW1 partial sums in registers across ALL tiles of the persistent CTA and reduces them once at the end.
-// Requires the fc1 pre-activations saved by the forward pass (pre_in); the SIMT kernel is the fallback.
+// Requires the fc1 pre-activations saved by the forward pass (pre_in).
+//
+// MEASURED (B200, Darcy 421^2, batch 32): parity-green on all projection cases but 5.14 ms against 3.53 ms for the fp32
+// kernel: the 3072 mma.sync per tile issue at ~1 per 22 cycles per SM, i.e. legacy warp-level TF32 MMA runs below the
+// fp32 FMA pipe on sm_100a.  Kept as an opt-in (UNO_B200_PROJ_MMA=1) record of that experiment; the tensor-core route
+// for these products is tcgen05 (UMMA from shared memory into TMEM), as in the tc_*.cuh kernels.
 #pragma once
 
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {

@@ -214,6 +214,13 @@ def test_training_step_is_cuda_graph_capturable(cuda_lib):
         ga = torch.view_as_real(a.grad) if a.grad.is_complex() else a.grad
         gb = torch.view_as_real(b.grad) if b.grad.is_complex() else b.grad
         assert float((ga - gb).abs().max()) <= 1e-5 * max(float(gb.abs().max()), 1e-6), k
+        # Adam turns a gradient into a step of size ~lr whatever its magnitude, so elements whose gradient is at the
+        # round-off level (their value depends on the order of the atomics) may legitimately differ by a fraction of lr;
+        # the update is compared where the gradient is well above that level, and bounded by lr everywhere
         pa = torch.view_as_real(a.detach()) if a.is_complex() else a.detach()
         pb = torch.view_as_real(b.detach()) if b.is_complex() else b.detach()
-        assert float((pa - pb).abs().max()) <= 1e-5 * max(float(pb.abs().max()), 1e-6), k
+        mag = (gb[..., 0] ** 2 + gb[..., 1] ** 2).sqrt().unsqueeze(-1).expand_as(gb) if a.is_complex() else gb.abs()
+        solid = mag > 1e-3 * float(mag.max())
+        assert float((pa - pb).abs().max()) <= 1e-3, k
+        if bool(solid.any()):
+            assert float((pa - pb)[solid].abs().max()) <= 5e-6, k

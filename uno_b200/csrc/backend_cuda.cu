@@ -1578,9 +1578,9 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const size_t smem = proj_fwd_smem(CT, k.hid, k.out_ch);
         int rc = ensure_smem(proj_fwd_kernel<CT>, smem);
         if (rc) return rc;
-        const long total = (long)k.batch * k.g.nraw;
-        const unsigned grid = grid_for((size_t)total, kPixTP, 148 * 8);
-        proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k);
+        const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
+        proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
     } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_MMA") != nullptr) {
         // warp-level mma.sync 3xTF32 variant, opt-in: measured on B200 it is SLOWER than the fp32 kernel (5.1 vs 3.5 ms at
         // Darcy size) -- legacy mma.sync TF32 issues at ~1 instruction per 22 cycles per SM here, below the fp32 FMA pipe

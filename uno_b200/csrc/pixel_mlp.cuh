@@ -397,7 +397,7 @@ __device__ __forceinline__ void proj_stage_weights(const ProjK& k, float* sW1, f
     }
     for (int i = tid; i < k.hid; i += kPixTP) sb1[i] = __ldg(k.b1 + i);
     for (int i = tid; i < k.out_ch * k.hid; i += kPixTP) sW2[i] = __ldg(k.w2 + i);
-    if (sb2) for (int i = tid; i < k.out_ch; i += kPixTP) sb2[i] = __ldg(k.b2 + i);
+    if (sb2) for (int i = tid; i < kProjMaxOut; i += kPixTP) sb2[i] = i < k.out_ch ? __ldg(k.b2 + i) : 0.f;
 }
 
 template <int CT>
@@ -417,8 +417,13 @@ __device__ __forceinline__ float proj_hidden_row(const float* sW1_row, float bia
 
 inline size_t proj_table_bytes(int CT) { return (size_t)CT * (2 * sizeof(void*) + sizeof(long)); }
 
+// Forward of the projection: a CTA walks 256-pixel tiles of the cropped grid; the tile's inputs are staged with LDGSTS
+// (thread t copies pixel t, all channels) and the hidden layer is a register-tiled product out of shared memory,
+// PRE[32 x 256] = W1[chunk] * IN with 8 hidden x 4 pixel thread tiles (pixels tp, tp+64, tp+128, tp+192: every access
+// of a warp is to 32 consecutive pixels).  GELU and the fc2 dot product are applied to the thread tile; the four
+// hidden-block partial sums of a pixel meet in shared memory.  Optionally writes the pre-activations for backward.
 template <int CT>
-__global__ void __launch_bounds__(kPixTP) proj_fwd_kernel(const ProjK k) {
+__global__ void __launch_bounds__(kPixTP, 2) proj_fwd_kernel(const ProjK k, long ntiles) {
     extern __shared__ __align__(16) float psm[];
     const float** sbase = reinterpret_cast<const float**>(psm);
     float** gbase = reinterpret_cast<float**>(psm) + CT;
@@ -426,42 +431,124 @@ __global__ void __launch_bounds__(kPixTP) proj_fwd_kernel(const ProjK k) {
     float* sW1 = reinterpret_cast<float*>(sstride + CT);   // [hid][CT]
     float* sb1 = sW1 + (size_t)k.hid * CT;                 // [hid]
     float* sW2 = sb1 + round4(k.hid);                      // [out_ch][hid]
-    float* sb2 = sW2 + round4(k.out_ch * k.hid);           // [out_ch]
+    float* sb2 = sW2 + round4(k.out_ch * k.hid);           // [4]
+    float* OUTP = sb2 + 4;                                 // [4 hidden blocks][256 pixels][4 outputs] partial fc2 sums
+    float* IN = OUTP + 4 * kPixTP * kProjMaxOut;           // [CT][TPP]
+    const int tid = threadIdx.x;
     proj_stage_tables<CT>(k, sbase, gbase, sstride);
     proj_stage_weights<CT>(k, sW1, sb1, sW2, sb2);
+    for (int i = tid; i < (CT - k.ctot) * kPixTPP; i += kPixTP) IN[(size_t)k.ctot * kPixTPP + i] = 0.f;
     __syncthreads();
     const PixGeom g = k.g;
     const long total = (long)k.batch * g.nraw;
-    for (long idx = (long)blockIdx.x * kPixTP + threadIdx.x; idx < total; idx += (long)gridDim.x * kPixTP) {
-        const long b = idx / g.nraw;
-        const long rp = idx - b * g.nraw;
-        const int r2 = (int)(rp % g.n2);
-        const long t = rp / g.n2;
-        const int r1 = (int)(t % g.n1), r0 = (int)(t / g.n1);
-        const long pp = ((long)(r0 + g.lo0) * g.N1 + (r1 + g.lo1)) * g.N2 + (r2 + g.lo2);
-        float in[CT];
+    const int tn = tid >> 6, tp = tid & 63;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long base = tile * kPixTP;
+        {   // stage the tile (two CTAs per SM overlap each other's copies)
+            const long idx = base + tid;
+            const bool valid = idx < total;
+            long b = 0, rp = 0, pp = 0;
+            if (valid) raw_to_padded(g, idx, b, rp, pp);
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(IN + tid);
+            const int sz = valid ? 4 : 0;
+            const long step = valid ? g.npad : 0;
 #pragma unroll
-        for (int c = 0; c < CT; ++c) in[c] = c < k.ctot ? __ldg(sbase[c] + b * sstride[c] + pp) : 0.f;
-        float o[kProjMaxOut];
-#pragma unroll
-        for (int q = 0; q < kProjMaxOut; ++q) o[q] = 0.f;
-#pragma unroll 2
-        for (int n = 0; n < k.hid; ++n) {
-            const float pre = proj_hidden_row<CT>(sW1 + (size_t)n * CT, sb1[n], in);
-            if (k.pre_out != nullptr) k.pre_out[(size_t)n * total + idx] = pre;
-            const float a = gelu_act(pre);
-#pragma unroll
-            for (int q = 0; q < kProjMaxOut; ++q)
-                if (q < k.out_ch) o[q] = fmaf(sW2[q * k.hid + n], a, o[q]);
+            for (int s = 0; s < 4; ++s) {
+                if (s < k.nsrc) {
+                    const int nch = k.src_ch[s];
+                    const float* src = valid ? k.src[s] + b * nch * g.npad + pp : k.w1;
+#pragma unroll 4
+                    for (int cl = 0; cl < nch; ++cl) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                        dst += (uint32_t)(kPixTPP * 4);
+                        src += step;
+                    }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
+        __syncthreads();
+        float o[4][kProjMaxOut];
 #pragma unroll
-        for (int q = 0; q < kProjMaxOut; ++q)
-            if (q < k.out_ch) k.out[idx * k.out_ch + q] = o[q] + sb2[q];
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int u = 0; u < kProjMaxOut; ++u) o[q][u] = 0.f;
+        for (int ch0 = 0; ch0 < k.hid; ch0 += kProjHC) {
+            float acc[8][4];
+            const float* wrow[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = min(ch0 + 8 * tn + i, k.hid - 1);      // rows past hid run on a clamped row and are discarded
+                wrow[i] = sW1 + (size_t)n * CT;
+                const float bv = sb1[n];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[i][q] = bv;
+            }
+            const float* xin = IN + tp;
+#pragma unroll 2
+            for (int c4 = 0; c4 < CT; c4 += 4) {
+                float x[4][4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) x[cc][q] = xin[(size_t)(c4 + cc) * kPixTPP + 64 * q];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w = *reinterpret_cast<const float4*>(wrow[i] + c4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[i][q] = fmaf(w.x, x[0][q], acc[i][q]);
+                        acc[i][q] = fmaf(w.y, x[1][q], acc[i][q]);
+                        acc[i][q] = fmaf(w.z, x[2][q], acc[i][q]);
+                        acc[i][q] = fmaf(w.w, x[3][q], acc[i][q]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = ch0 + 8 * tn + i;
+                if (n < k.hid) {                                     // uniform over the warp (tn is)
+                    float w2v[kProjMaxOut];
+#pragma unroll
+                    for (int u = 0; u < kProjMaxOut; ++u) w2v[u] = u < k.out_ch ? sW2[u * k.hid + n] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long idx = base + tp + 64 * q;
+                        if (k.pre_out != nullptr && idx < total) k.pre_out[(size_t)n * total + idx] = acc[i][q];
+                        const float a = gelu_act(acc[i][q]);
+#pragma unroll
+                        for (int u = 0; u < kProjMaxOut; ++u) o[q][u] = fmaf(w2v[u], a, o[q][u]);
+                    }
+                }
+            }
+        }
+        // the four hidden blocks of a pixel meet in shared memory
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(OUTP + ((size_t)tn * kPixTP + tp + 64 * q) * kProjMaxOut) = make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
+        __syncthreads();
+        {
+            const long idx = base + tid;
+            if (idx < total) {
+                float4 r = make_float4(sb2[0], sb2[1], sb2[2], sb2[3]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float4 v = *reinterpret_cast<const float4*>(OUTP + ((size_t)t * kPixTP + tid) * kProjMaxOut);
+                    r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+                }
+                const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int u = 0; u < kProjMaxOut; ++u)
+                    if (u < k.out_ch) k.out[idx * k.out_ch + u] = rr[u];
+            }
+        }
+        __syncthreads();       // IN and OUTP are rewritten by the next tile
     }
 }
 
 inline size_t proj_fwd_smem(int CT, int hid, int out_ch) {
-    return proj_table_bytes(CT) + sizeof(float) * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid) + round4(out_ch));
+    return proj_table_bytes(CT) + sizeof(float) * ((size_t)hid * CT + round4(hid) + round4(out_ch * hid) + 4 + 4 * kPixTP * kProjMaxOut +
+                                                   (size_t)CT * kPixTPP);
 }
 
 // Backward of the projection.  A CTA walks 256-pixel tiles of the CROPPED grid; per tile and per chunk of 32 hidden

@@ -782,6 +782,7 @@ int ensure_smem(K kernel, size_t bytes) {
 
 #include "pixel_mlp.cuh"
 #include "pixel_mlp_mma.cuh"
+#include "pixel_mlp_tc.cuh"
 #include "resample2d.cuh"
 #include "norm_cluster.cuh"
 #include "train_ops.cuh"
@@ -1581,6 +1582,15 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
+    } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr &&
+               getenv("UNO_B200_PROJ_MMA") == nullptr && getenv("UNO_B200_DISABLE_TC") == nullptr) {
+        // tcgen05 kernel: both large products on the tensor cores (3xTF32), accumulators in TMEM
+        const size_t smem = proj_bwd_tc_smem(k.hid, k.out_ch);
+        int rc = ensure_smem(proj_bwd_tc_kernel, smem);
+        if (rc) return rc;
+        const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
+        proj_bwd_tc_kernel<<<grid, 256, smem, st>>>(k, ntiles);
     } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_MMA") != nullptr) {
         // warp-level mma.sync 3xTF32 variant, opt-in: measured on B200 it is SLOWER than the fp32 kernel (5.1 vs 3.5 ms at
         // Darcy size) -- legacy mma.sync TF32 issues at ~1 instruction per 22 cycles per SM here, below the fp32 FMA pipe

@@ -54,5 +54,7 @@ PROJECT_CASES = {
     "ns3d_both": (1, (6, 5, 7), (0, 0, 2), (0, 0, 2), (16, 8), 32, 1),
     "single": (1, (9, 33), (1, 0), (0, 2), (20,), 24, 1),
     "multi_out": (1, (9, 11), (0, 0), (0, 0), (8, 3, 5), 40, 3),
-    "ragged_hidden": (2, (7, 37), (0, 0), (2, 1), (40, 24), 96, 2),  # two hidden chunks (64 + 32)
+    "ragged_hidden": (2, (7, 37), (0, 0), (2, 1), (40, 24), 96, 2),  # three hidden chunks of 32: the fp32 kernel (hid > 64)
+    "tc_two_chunks": (2, (13, 29), (0, 0), (1, 2), (40, 24), 48, 2),  # 64 channels, hid <= 64: the tcgen05 kernel, chunks 32 + 16, ragged tiles
+    "tc_wide": (3, (31, 17), (2, 0), (0, 3), (64,), 64, 1),           # one 64-channel source, two full chunks
 }

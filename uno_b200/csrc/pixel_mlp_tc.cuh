@@ -164,15 +164,21 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
         for (int ch = 0; ch < nchunks; ++ch) {
             const int ch0 = ch * kProjHC;
             const int nn = min(kProjHC, k.hid - ch0);
-            // ---- activation phase: 8 hidden x 2 pixels per thread
+            // ---- activation phase: 8 hidden x 2 pixels per thread; all 16 pre-activations are requested before the first use
             float dp[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int nc = min(ch0 + 8 * tn + i, k.hid - 1);
+                const float* src = k.pre_in + (size_t)nc * total + base + tp;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) dp[i][q] = vq[q] ? __ldg(src + 64 * q) : 0.f;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int j = 8 * tn + i;
                 const int n = ch0 + j;
                 const bool live = j < nn;
                 const int nc = live ? n : k.hid - 1;
-                const float* src = k.pre_in + (size_t)nc * total + base + tp;
                 float w2v[kProjMaxOut];
 #pragma unroll
                 for (int o = 0; o < kProjMaxOut; ++o) w2v[o] = o < k.out_ch ? sW2[o * k.hid + nc] : 0.f;
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     float a, gp;
-                    gelu_both(vq[q] ? __ldg(src + 64 * q) : 0.f, a, gp);
+                    gelu_both(dp[i][q], a, gp);
                     float s = 0.f;
 #pragma unroll
                     for (int o = 0; o < kProjMaxOut; ++o) {

@@ -108,3 +108,31 @@ def test_glue_matches_torch_at_darcy_size(cuda_lib):
     for x, y in zip(g0, g1):
         assert float((x - y).abs().max() / y.abs().max()) < BWD_TOL
     assert float(g0[0][..., S:, :].abs().max()) == 0.0 and float(g0[1][..., :, S:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("env", ["UNO_B200_PROJ_TC", "UNO_B200_PROJ_MMA"])
+@pytest.mark.parametrize("name", ["darcy", "tc_two_chunks", "tc_wide"])
+def test_project_backward_tensor_core_variants(env, name, cuda_lib):
+    """The opt-in tensor-core variants of the projection backward (tcgen05 / UMMA with TMEM accumulators, and warp-level
+    mma.sync; both 3xTF32) against the fp64 oracle: same tolerance as the default fp32 kernel."""
+    import os
+
+    from uno_b200 import functional as Fn
+
+    case = PROJECT_CASES[name]
+    _, _, lo, hi, *_ = case
+    t = project_inputs(case, seed=2)
+    ref = project_oracle(case, t)
+    srcs = [_cu(s, True) for s in t["srcs"]]
+    w1, b1, w2, b2 = (_cu(t[k], True) for k in ("w1", "b1", "w2", "b2"))
+    os.environ[env] = "1"
+    try:
+        out = Fn.project(srcs, w1, b1, w2, b2, lo, hi)
+        out.backward(_cu(t["gout"]))
+        torch.cuda.synchronize()
+    finally:
+        del os.environ[env]
+    for s, r in zip(srcs, ref["gsrcs"]):
+        assert rel_err(s.grad.cpu().numpy(), r) < BWD_TOL
+    for got, key in ((w1, "gw1"), (b1, "gb1"), (w2, "gw2"), (b2, "gb2")):
+        assert rel_err(got.grad.cpu().numpy(), ref[key]) < BWD_TOL, key

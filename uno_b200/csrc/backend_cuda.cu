@@ -1582,9 +1582,12 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
-    } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr &&
-               getenv("UNO_B200_PROJ_MMA") == nullptr && getenv("UNO_B200_DISABLE_TC") == nullptr) {
-        // tcgen05 kernel: both large products on the tensor cores (3xTF32), accumulators in TMEM
+    } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TC") != nullptr &&
+               getenv("UNO_B200_DISABLE_TC") == nullptr) {
+        // tcgen05 kernel, opt-in: both large products on the tensor cores (3xTF32), accumulators in TMEM.  Parity-green, but
+        // its phases (stage -> split -> activation -> MMA -> epilogue) still run back to back on one CTA per SM: 4.07 ms
+        // at Darcy size against 3.53 ms for the fp32 kernel.  It needs the warp-specialised pipeline of the tc_*.cuh
+        // kernels (producer / MMA / epilogue warps over a ring of tiles) to pay off.
         const size_t smem = proj_bwd_tc_smem(k.hid, k.out_ch);
         int rc = ensure_smem(proj_bwd_tc_kernel, smem);
         if (rc) return rc;

@@ -816,16 +816,27 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
             }
             __syncthreads();
         }
-        // ---- input gradients of the tile (a warp stores 32 consecutive pixels of one channel)
+        // ---- input gradients of the tile (a warp stores 32 consecutive pixels of one channel); the per-pixel offset
+        //      only depends on the batch stride of the channel's source, so it is recomputed when that changes
+        {
+            long cur_stride = -1, off[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < CB; ++i) {
-            const int c = tn * CB + i;
-            float* gb = gbase[c];                                    // NULL for channels past ctot and skipped sources
-            if (gb != nullptr) {
-                const long st = sstride[c];
+            for (int i = 0; i < CB; ++i) {
+                const int c = tn * CB + i;
+                if (c < k.ctot) {
+                    float* gb = gbase[c];
+                    const long st = sstride[c];
+                    if (st != cur_stride) {
+                        cur_stride = st;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (pb[q] >= 0) gb[pb[q] * st + ppx[q]] = dacc[i][q];
+                        for (int q = 0; q < 4; ++q) off[q] = pb[q] * st + ppx[q];
+                    }
+                    if (gb != nullptr) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (pb[q] >= 0) gb[off[q]] = dacc[i][q];
+                    }
+                }
             }
         }
         if (tn == 0) {

@@ -265,9 +265,8 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
                 }
                 tc::tc_commit(bar);
             }
-            if (tid == 0) tc::mbar_wait(bar, phase);     // one poller; the images may then be rewritten, the accumulators read
+            tc::mbar_wait(bar, phase);                   // the images may be rewritten, the accumulators read
             phase ^= 1u;
-            __syncthreads();
             tc::tc_fence_after();
         }
         // ---- input gradients: warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = the tile's pixels
@@ -276,6 +275,7 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
             long b = 0, rp = 0, pp = 0;
             const bool valid = idx < total;
             if (valid) raw_to_padded(g, idx, b, rp, pp);
+            long cur_stride = -1, off = 0;
 #pragma unroll
             for (int c0 = 0; c0 < CT; c0 += 16) {
                 uint32_t r[16];
@@ -285,8 +285,12 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + j;
-                        float* gb = gbase[c];                        // NULL for channels past ctot and skipped sources
-                        if (gb != nullptr) gb[b * sstride[c] + pp] = __uint_as_float(r[j]);
+                        if (c < k.ctot) {
+                            float* gb = gbase[c];
+                            const long st = sstride[c];
+                            if (st != cur_stride) { cur_stride = st; off = b * st + pp; }
+                            if (gb != nullptr) gb[off] = __uint_as_float(r[j]);
+                        }
                     }
                 }
             }

@@ -57,4 +57,5 @@ PROJECT_CASES = {
     "ragged_hidden": (2, (7, 37), (0, 0), (2, 1), (40, 24), 96, 2),  # three hidden chunks of 32: the fp32 kernel (hid > 64)
     "tc_two_chunks": (2, (13, 29), (0, 0), (1, 2), (40, 24), 48, 2),  # 64 channels, hid <= 64: the tcgen05 kernel, chunks 32 + 16, ragged tiles
     "tc_wide": (3, (31, 17), (2, 0), (0, 3), (64,), 64, 1),           # one 64-channel source, two full chunks
+    "tc_one_chunk": (3, (29, 23), (1, 0), (0, 2), (40, 24), 20, 1),   # hid < 32, one output: the warp-specialised tcgen05 kernel
 }

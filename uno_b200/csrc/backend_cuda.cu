@@ -1582,6 +1582,15 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
+    } else if (CT == 64 && k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TCP") != nullptr &&
+               getenv("UNO_B200_DISABLE_TC") == nullptr) {
+        // warp-specialised tcgen05 kernel (one hidden chunk)
+        const size_t smem = proj_bwd_tcp_smem(k.hid, k.out_ch);
+        int rc = ensure_smem(proj_bwd_tcp_kernel, smem);
+        if (rc) return rc;
+        const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
+        proj_bwd_tcp_kernel<<<grid, 256, smem, st>>>(k, ntiles);
     } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TC") != nullptr &&
                getenv("UNO_B200_DISABLE_TC") == nullptr) {
         // tcgen05 kernel, opt-in: both large products on the tensor cores (3xTF32), accumulators in TMEM.  Parity-green, but

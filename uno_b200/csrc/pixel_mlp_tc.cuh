@@ -332,3 +332,275 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_base, kPtTmemCols);
 }
+
+// =====================================================================================================
+// Warp-specialised form (hid <= 32: one hidden chunk).  The same tensor-core products as above, but the fp32 phases of a
+// tile are split between two groups of four warps that only meet at two mbarriers:
+//   group A (warps 0-3, thread = pixel)   INPUT(t): its pixel's 64 channels, copied by LDGSTS one tile ahead, become the
+//                                         stacked tf32 image; then EPI(t-1): its TMEM lane (= pixel) of the DIN
+//                                         accumulator -> gsrc; then it issues the copies of tile t+1
+//   group B (warps 4-7, thread = pixel)   ACT(t): 32 pre-activations (prefetched into registers one tile ahead) ->
+//                                         D in both operand images; the sums over pixels (db1, dW2, db2) stay in
+//                                         registers for the whole kernel
+//   thread 128                            waits for all 256 arrivals (bar_full), issues the 12 + 32 MMAs of the tile and
+//                                         commits to bar_mma, which both groups wait on before touching the images again
+// No block-wide barrier in the loop; the only exposed latency per tile is the tensor core's.
+// =====================================================================================================
+__global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, long ntiles) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    constexpr int CT = 64;
+    uint8_t* p0 = tsm + ((128u - (tc::smem_u32(tsm) & 127u)) & 127u);
+    uint8_t* IMG = p0;
+    uint8_t* A1hi = IMG + kPtImgBytes;
+    uint8_t* A1lo = A1hi + kPtA1Bytes;
+    uint8_t* Dhi = A1lo + kPtA1Bytes;
+    uint8_t* Dlo = Dhi + kPtDBytes;
+    uint8_t* Wimg = Dlo + kPtDBytes;                     // [hi | lo] fc1 image (one chunk)
+    float* RAW = reinterpret_cast<float*>(Wimg + (size_t)2 * kPtWBytes);
+    const float** sbase = reinterpret_cast<const float**>(RAW + 64 * kPtPix);
+    float** gbase = reinterpret_cast<float**>(const_cast<float**>(sbase) + CT);
+    long* sstride = reinterpret_cast<long*>(gbase + CT);
+    const int OH4 = round4(k.out_ch * k.hid);
+    float* sW2 = reinterpret_cast<float*>(sstride + CT);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(sW2 + OH4);
+    uint64_t* bar_mma = bar_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool groupA = tid < 128;
+    const int px = tid & 127;                            // this thread's pixel of every tile
+
+    proj_stage_tables<CT>(k, sbase, gbase, sstride);
+    for (uint32_t i = tid; i < (kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes) / 16; i += 256)
+        reinterpret_cast<float4*>(IMG)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < kProjHC * CT; i += 256) {
+        const int c = i % CT, j = i / CT;
+        float hi = 0.f, lo = 0.f;
+        if (j < k.hid && c < k.ctot) tc::split_tf32(__ldg(k.w1 + j * k.ctot + c), hi, lo);
+        uint8_t* d = Wimg + (uint32_t)(j >> 2) * kPtLboW + (uint32_t)c * 16 + (uint32_t)(j & 3) * 4;
+        *reinterpret_cast<float*>(d) = hi;
+        *reinterpret_cast<float*>(d + kPtWBytes) = lo;
+    }
+    for (int i = tid; i < k.out_ch * k.hid; i += 256) sW2[i] = __ldg(k.w2 + i);
+    if (tid == 0) {
+        tc::mbar_init(bar_full, 256);
+        tc::mbar_init(bar_mma, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kPtTmemCols);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.nraw;
+    if (g.npad != g.nraw) {      // the padding of the source gradients is zero
+        const long ptotal = (long)k.batch * g.npad;
+        for (long idx = (long)blockIdx.x * 256 + tid; idx < ptotal; idx += (long)gridDim.x * 256) {
+            const long b = idx / g.npad;
+            const long pp = idx - b * g.npad;
+            const int i2 = (int)(pp % g.N2);
+            const long t = pp / g.N2;
+            const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
+            const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
+            const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
+            if (!inside)
+                for (int c = 0; c < k.ctot; ++c)
+                    if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = 0.f;
+        }
+    }
+    const long step_tiles = gridDim.x;
+    long it = 0;
+    if (groupA) {
+        // ------------------------------------------------------------------ group A: input image + gradient stores
+        long b_prev = 0, pp_prev = 0, b_cur = 0, pp_cur = 0;
+        bool v_prev = false, v_cur = false;
+        auto stage_raw = [&](long tile, long& b, long& pp, bool& valid) {
+            const long idx = tile * kPtPix + px;
+            valid = idx < total;
+            long rp = 0;
+            b = 0; pp = 0;
+            if (valid) raw_to_padded(g, idx, b, rp, pp);
+            uint32_t dst = tc::smem_u32(RAW + px);
+            const int sz = valid ? 4 : 0;
+            const long step = valid ? g.npad : 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                if (s < k.nsrc) {
+                    const int nch = k.src_ch[s];
+                    const float* src = valid ? k.src[s] + b * nch * g.npad + pp : k.w1;
+#pragma unroll 4
+                    for (int cl = 0; cl < nch; ++cl) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+                        dst += (uint32_t)(kPtPix * 4);
+                        src += step;
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto store_gradients = [&](long b, long pp, bool valid) {
+            long cur_stride = -1, off = 0;
+#pragma unroll
+            for (int c0 = 0; c0 < CT; c0 += 16) {
+                uint32_t r[16];
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+                tc::tmem_ld_wait();
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        if (c < k.ctot) {
+                            float* gb = gbase[c];
+                            const long st = sstride[c];
+                            if (st != cur_stride) { cur_stride = st; off = b * st + pp; }
+                            if (gb != nullptr) gb[off] = __uint_as_float(r[j]);
+                        }
+                    }
+                }
+            }
+        };
+        if ((long)blockIdx.x < ntiles) stage_raw(blockIdx.x, b_cur, pp_cur, v_cur);
+        for (long tile = blockIdx.x; tile < ntiles; tile += step_tiles, ++it) {
+            if (it > 0) {                                // MMA(t-1) complete: image free, DIN accumulator final
+                tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);
+                tc::tc_fence_after();
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");        // this thread's own copies of tile t
+            {
+                uint8_t* d = IMG + (uint32_t)(px >> 2) * kPtLboA + (uint32_t)(px & 3) * 4;
+#pragma unroll 8
+                for (int c = 0; c < CT; ++c) {
+                    float hi, lo;
+                    tc::split_tf32(RAW[c * kPtPix + px], hi, lo);
+                    *reinterpret_cast<float*>(d + (uint32_t)c * 16) = hi;
+                    *reinterpret_cast<float*>(d + (uint32_t)(64 + c) * 16) = lo;
+                }
+            }
+            const long b_t = b_cur, pp_t = pp_cur;
+            const bool v_t = v_cur;
+            if (tile + step_tiles < ntiles) stage_raw(tile + step_tiles, b_cur, pp_cur, v_cur);   // this thread's RAW column is free again
+            if (it > 0) store_gradients(b_prev, pp_prev, v_prev);                                 // EPI(t-1)
+            b_prev = b_t; pp_prev = pp_t; v_prev = v_t;
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            tc::mbar_arrive(bar_full);
+        }
+        if (it > 0) {
+            tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);
+            tc::tc_fence_after();
+            store_gradients(b_prev, pp_prev, v_prev);
+            // dW1: TMEM lanes 0-63 hold the hi-part rows (channel = lane), 64-127 the lo-part rows: both add into gw1
+            const int c = (32 * warp + lane) & 63;
+            for (int c0 = 0; c0 < kProjHC; c0 += 16) {
+                uint32_t r[16];
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + 64u + (uint32_t)c0, r);
+                tc::tmem_ld_wait();
+                if (c < k.ctot) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < k.hid) atomicAdd(k.gw1 + (c0 + j) * k.ctot + c, __uint_as_float(r[j]));
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ group B: activation backward + MMA issue
+        const uint32_t idesc_din = tc::make_idesc_tf32(128, 64, 0, 0), idesc_dw = tc::make_idesc_tf32(128, kProjHC, 0, 0);
+        const uint32_t img_a = tc::smem_u32(IMG), a1hi_a = tc::smem_u32(A1hi), a1lo_a = tc::smem_u32(A1lo), dhi_a = tc::smem_u32(Dhi),
+                       dlo_a = tc::smem_u32(Dlo), w_a = tc::smem_u32(Wimg);
+        // (single output channel: every shipped model projects to one field; other widths run the fp32 kernel)
+        float pre[kProjHC], go = 0.f;
+        float s_b1[kProjHC], s_w2[kProjHC], s_b2 = 0.f;      // sums over this thread's pixels, whole kernel
+#pragma unroll
+        for (int n = 0; n < kProjHC; ++n) { s_b1[n] = 0.f; s_w2[n] = 0.f; }
+        auto prefetch = [&](long tile) {
+            const long idx = tile * kPtPix + px;
+            const bool valid = tile < ntiles && idx < total;
+#pragma unroll
+            for (int n = 0; n < kProjHC; ++n) pre[n] = (valid && n < k.hid) ? __ldg(k.pre_in + (size_t)n * total + idx) : 0.f;
+            go = valid ? __ldg(k.gout + idx) : 0.f;
+        };
+        prefetch(blockIdx.x);
+        for (long tile = blockIdx.x; tile < ntiles; tile += step_tiles, ++it) {
+            float hi[kProjHC], lo[kProjHC];
+#pragma unroll
+            for (int n = 0; n < kProjHC; ++n) {
+                float a, gp;
+                gelu_both(pre[n], a, gp);
+                const float w2 = n < k.hid ? sW2[n] : 0.f;
+                s_w2[n] = fmaf(go, a, s_w2[n]);
+                const float dp = go * w2 * gp;
+                s_b1[n] += dp;
+                tc::split_tf32(dp, hi[n], lo[n]);
+            }
+            s_b2 += go;
+            prefetch(tile + step_tiles);                 // next tile's loads fly while this tile's images are written
+            if (it > 0) {                                // MMA(t-1) complete: the D images may be rewritten
+                tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);
+                tc::tc_fence_after();
+            }
+#pragma unroll
+            for (int m = 0; m < kProjHC / 4; ++m) {
+                const uint32_t oa = (uint32_t)m * kPtLboA + (uint32_t)px * 16;
+                *reinterpret_cast<float4*>(A1hi + oa) = make_float4(hi[4 * m], hi[4 * m + 1], hi[4 * m + 2], hi[4 * m + 3]);
+                *reinterpret_cast<float4*>(A1lo + oa) = make_float4(lo[4 * m], lo[4 * m + 1], lo[4 * m + 2], lo[4 * m + 3]);
+            }
+            const uint32_t od = (uint32_t)(px >> 2) * kPtLboD + (uint32_t)(px & 3) * 4;
+#pragma unroll
+            for (int n = 0; n < kProjHC; ++n) {
+                *reinterpret_cast<float*>(Dhi + od + n * 16) = hi[n];
+                *reinterpret_cast<float*>(Dlo + od + n * 16) = lo[n];
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_full);
+            if (tid == 128) {
+                tc::mbar_wait(bar_full, (uint32_t)it & 1u);
+                tc::tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < kProjHC / 8; ++ks) {
+                    const uint64_t da_hi = tc::make_smem_desc(a1hi_a + ks * 2 * kPtLboA, kPtLboA, 128);
+                    const uint64_t da_lo = tc::make_smem_desc(a1lo_a + ks * 2 * kPtLboA, kPtLboA, 128);
+                    const uint64_t db_hi = tc::make_smem_desc(w_a + ks * 2 * kPtLboW, kPtLboW, 128);
+                    const uint64_t db_lo = tc::make_smem_desc(w_a + kPtWBytes + ks * 2 * kPtLboW, kPtLboW, 128);
+                    tc::mma_tf32(tmem_base, da_hi, db_hi, idesc_din, ks ? 1u : 0u);
+                    tc::mma_tf32(tmem_base, da_hi, db_lo, idesc_din, 1u);
+                    tc::mma_tf32(tmem_base, da_lo, db_hi, idesc_din, 1u);
+                }
+#pragma unroll 4
+                for (int ks = 0; ks < kPtPix / 8; ++ks) {
+                    const uint64_t da = tc::make_smem_desc(img_a + ks * 2 * kPtLboA, kPtLboA, 128);
+                    const uint64_t db_hi = tc::make_smem_desc(dhi_a + ks * 2 * kPtLboD, kPtLboD, 128);
+                    const uint64_t db_lo = tc::make_smem_desc(dlo_a + ks * 2 * kPtLboD, kPtLboD, 128);
+                    tc::mma_tf32(tmem_base + 64u, da, db_hi, idesc_dw, (it | ks) ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + 64u, da, db_lo, idesc_dw, 1u);
+                }
+                tc::tc_commit(bar_mma);
+            }
+            __syncwarp();
+        }
+        // sums over pixels: reduce over the warp, one atomic per value per warp
+#pragma unroll
+        for (int n = 0; n < kProjHC; ++n) {
+            const float v = warp_sum(s_b1[n]);
+            const float w = warp_sum(s_w2[n]);
+            if (lane == 0 && n < k.hid) {
+                atomicAdd(k.gb1 + n, v);
+                atomicAdd(k.gw2 + n, w);
+            }
+        }
+        {
+            const float v = warp_sum(s_b2);
+            if (lane == 0) atomicAdd(k.gb2, v);
+        }
+        if (it > 0 && tid == 128) tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);   // nothing of this CTA may still be in flight
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kPtTmemCols);
+}
+
+__host__ __device__ inline size_t proj_bwd_tcp_smem(int hid, int out_ch) {
+    return 1024 + kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes + (size_t)2 * kPtWBytes + 64 * kPtPix * 4 + proj_table_bytes(64) +
+           sizeof(float) * round4(out_ch * hid) + 64;
+}

@@ -551,6 +551,30 @@ inline size_t proj_fwd_smem(int CT, int hid, int out_ch) {
                                                    (size_t)CT * kPixTPP);
 }
 
+// The crop has no gradient in the padding: zero it.  A warp takes one row (b, i0, i1) of the padded grid at a time and its
+// lanes the columns that lie outside the crop (all of them for a padded row), so only the padding is ever visited.
+__device__ __forceinline__ void proj_zero_padding(const ProjK& k, float* const* gbase, const long* sstride) {
+    const PixGeom g = k.g;
+    if (g.npad == g.nraw) return;
+    const int lane = threadIdx.x & 31;
+    const long warps = (long)gridDim.x * (blockDim.x >> 5), w = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long rows = (long)k.batch * g.N0 * g.N1;
+    for (long row = w; row < rows; row += warps) {
+        const long b = row / ((long)g.N0 * g.N1);
+        const int rr = (int)(row - b * (long)g.N0 * g.N1);
+        const int i0 = rr / g.N1, i1 = rr - i0 * g.N1;
+        const bool row_inside = (unsigned)(i0 - g.lo0) < (unsigned)g.n0 && (unsigned)(i1 - g.lo1) < (unsigned)g.n1;
+        const long pp0 = ((long)i0 * g.N1 + i1) * g.N2;
+        // columns outside [lo2, lo2 + n2) -- or every column of a padded row
+        const int left = row_inside ? g.lo2 : g.N2, right0 = g.lo2 + g.n2, nright = row_inside ? g.N2 - right0 : 0;
+        for (int j = lane; j < left + nright; j += 32) {
+            const int i2 = j < left ? j : right0 + (j - left);
+            for (int c = 0; c < k.ctot; ++c)
+                if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp0 + i2] = 0.f;
+        }
+    }
+}
+
 // Backward of the projection.  A CTA walks 256-pixel tiles of the CROPPED grid; per tile and per chunk of 32 hidden
 // units it runs three register-tiled products out of shared memory
 //     PRE [32 x 256] = W1[chunk] * IN            (+ GELU / GELU' and the fc2 back-substitution -> D = dL/dpre)
@@ -613,21 +637,7 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_kernel(const ProjK k, long
         if (nbuf == 2) INbuf[(size_t)(CT + k.ctot) * kPixTPP + i] = 0.f;
     }
     // ---- the padding of the source gradients is zero (the crop has no gradient there)
-    if (g.npad != g.nraw) {
-        const long ptotal = (long)k.batch * g.npad;
-        for (long idx = (long)blockIdx.x * kPixTP + tid; idx < ptotal; idx += (long)gridDim.x * kPixTP) {
-            const long b = idx / g.npad;
-            const long pp = idx - b * g.npad;
-            const int i2 = (int)(pp % g.N2);
-            const long t = pp / g.N2;
-            const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
-            const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
-            const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
-            if (!inside)
-                for (int c = 0; c < k.ctot; ++c)
-                    if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = 0.f;
-        }
-    }
+    proj_zero_padding(k, gbase, sstride);
     constexpr int CB = CT / 4;                             // channels per thread in the DIN product
     constexpr int WC = CT / 32, WN = 8 / WC;               // dW1 product: a warp owns 8 (hidden) x 32 (channel), a thread 2 x 4
     const int tn = tid >> 6, tp = tid & 63;                // PRE / DIN products: hidden (channel) block, pixel lane

@@ -87,21 +87,7 @@ __global__ void __launch_bounds__(kPixTP, 1) proj_bwd_mma_kernel(const ProjK k, 
         INbuf[(size_t)k.ctot * kPixTPP + i] = 0.f;
         if (nbuf == 2) INbuf[(size_t)(CT + k.ctot) * kPixTPP + i] = 0.f;
     }
-    if (g.npad != g.nraw) {      // the padding of the source gradients is zero
-        const long ptotal = (long)k.batch * g.npad;
-        for (long idx = (long)blockIdx.x * kPixTP + tid; idx < ptotal; idx += (long)gridDim.x * kPixTP) {
-            const long b = idx / g.npad;
-            const long pp = idx - b * g.npad;
-            const int i2 = (int)(pp % g.N2);
-            const long t = pp / g.N2;
-            const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
-            const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
-            const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
-            if (!inside)
-                for (int c = 0; c < k.ctot; ++c)
-                    if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = 0.f;
-        }
-    }
+    proj_zero_padding(k, gbase, sstride);
     const int tn = tid >> 6, tp = tid & 63;                // activation phase: hidden block, pixel lane (pixels tp + 64 q)
     const bool one_chunk = k.hid <= kProjHC;
     float wacc[2][NT][4];                                  // dW1 partial sums of this warp's pixel slices (registers across tiles)

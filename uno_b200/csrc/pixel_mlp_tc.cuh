@@ -92,21 +92,7 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
 
     const PixGeom g = k.g;
     const long total = (long)k.batch * g.nraw;
-    if (g.npad != g.nraw) {      // the padding of the source gradients is zero
-        const long ptotal = (long)k.batch * g.npad;
-        for (long idx = (long)blockIdx.x * 256 + tid; idx < ptotal; idx += (long)gridDim.x * 256) {
-            const long b = idx / g.npad;
-            const long pp = idx - b * g.npad;
-            const int i2 = (int)(pp % g.N2);
-            const long t = pp / g.N2;
-            const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
-            const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
-            const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
-            if (!inside)
-                for (int c = 0; c < k.ctot; ++c)
-                    if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = 0.f;
-        }
-    }
+    proj_zero_padding(k, gbase, sstride);
     // LDGSTS of a tile's inputs into RAW[c][p]: threads 0-127 copy one pixel each, all channels (zero-filled past the end)
     auto stage_raw = [&](long tile) {
         if (tid < kPtPix) {
@@ -395,21 +381,7 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
 
     const PixGeom g = k.g;
     const long total = (long)k.batch * g.nraw;
-    if (g.npad != g.nraw) {      // the padding of the source gradients is zero
-        const long ptotal = (long)k.batch * g.npad;
-        for (long idx = (long)blockIdx.x * 256 + tid; idx < ptotal; idx += (long)gridDim.x * 256) {
-            const long b = idx / g.npad;
-            const long pp = idx - b * g.npad;
-            const int i2 = (int)(pp % g.N2);
-            const long t = pp / g.N2;
-            const int i1 = (int)(t % g.N1), i0 = (int)(t / g.N1);
-            const int r0 = i0 - g.lo0, r1 = i1 - g.lo1, r2 = i2 - g.lo2;
-            const bool inside = (unsigned)r0 < (unsigned)g.n0 && (unsigned)r1 < (unsigned)g.n1 && (unsigned)r2 < (unsigned)g.n2;
-            if (!inside)
-                for (int c = 0; c < k.ctot; ++c)
-                    if (gbase[c] != nullptr) gbase[c][b * sstride[c] + pp] = 0.f;
-        }
-    }
+    proj_zero_padding(k, gbase, sstride);
     const long step_tiles = gridDim.x;
     long it = 0;
     if (groupA) {
@@ -440,6 +412,9 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // every source a multiple of 16 channels wide (the shipped models: 32 + 32): a 16-column TMEM read never straddles
+        // two sources, so its stores run on one pointer advanced by the plane size
+        const bool src16 = (k.src_ch[0] % 16 == 0) && (k.src_ch[1] % 16 == 0) && (k.src_ch[2] % 16 == 0) && (k.src_ch[3] % 16 == 0);
         auto store_gradients = [&](long b, long pp, bool valid) {
             long cur_stride = -1, off = 0;
 #pragma unroll
@@ -447,7 +422,18 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
                 uint32_t r[16];
                 tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
-                if (valid) {
+                if (!valid || c0 >= k.ctot) continue;
+                if (src16) {
+                    float* gb = gbase[c0];
+                    if (gb != nullptr) {
+                        gb += b * sstride[c0] + pp;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            *gb = __uint_as_float(r[j]);
+                            gb += g.npad;
+                        }
+                    }
+                } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + j;

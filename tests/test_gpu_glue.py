@@ -110,11 +110,12 @@ def test_glue_matches_torch_at_darcy_size(cuda_lib):
     assert float(g0[0][..., S:, :].abs().max()) == 0.0 and float(g0[1][..., :, S:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("env", ["UNO_B200_PROJ_TCP", "UNO_B200_PROJ_TC", "UNO_B200_PROJ_MMA"])
+@pytest.mark.parametrize("env", ["UNO_B200_PROJ_SIMT", "UNO_B200_PROJ_TC", "UNO_B200_PROJ_MMA"])
 @pytest.mark.parametrize("name", ["darcy", "tc_two_chunks", "tc_wide", "tc_one_chunk"])
 def test_project_backward_tensor_core_variants(env, name, cuda_lib):
-    """The opt-in tensor-core variants of the projection backward (tcgen05 / UMMA with TMEM accumulators, and warp-level
-    mma.sync; both 3xTF32) against the fp64 oracle: same tolerance as the default fp32 kernel."""
+    """The selectable variants of the projection backward against the fp64 oracle, same tolerance for all: the fp32 kernel
+    (forced with UNO_B200_PROJ_SIMT; the default is the warp-specialised tcgen05 kernel where the shape allows it, which
+    test_project covers), the first barrier-synchronised tcgen05 kernel, and the warp-level mma.sync kernel (both 3xTF32)."""
     import os
 
     from uno_b200 import functional as Fn

@@ -1582,9 +1582,10 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
-    } else if (CT == 64 && k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TCP") != nullptr &&
-               getenv("UNO_B200_DISABLE_TC") == nullptr) {
-        // warp-specialised tcgen05 kernel (one hidden chunk)
+    } else if (CT == 64 && k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr &&
+               getenv("UNO_B200_PROJ_TC") == nullptr && getenv("UNO_B200_PROJ_MMA") == nullptr && getenv("UNO_B200_DISABLE_TC") == nullptr) {
+        // DEFAULT for the shipped shapes (64 channels, hid <= 32, one output, pre-activations kept by forward):
+        // warp-specialised tcgen05 kernel, 2.1 ms at Darcy size against 3.4 ms for the fp32 kernel (UNO_B200_PROJ_SIMT=1)
         const size_t smem = proj_bwd_tcp_smem(k.hid, k.out_ch);
         int rc = ensure_smem(proj_bwd_tcp_kernel, smem);
         if (rc) return rc;
@@ -1593,10 +1594,9 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         proj_bwd_tcp_kernel<<<grid, 256, smem, st>>>(k, ntiles);
     } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TC") != nullptr &&
                getenv("UNO_B200_DISABLE_TC") == nullptr) {
-        // tcgen05 kernel, opt-in: both large products on the tensor cores (3xTF32), accumulators in TMEM.  Parity-green, but
-        // its phases (stage -> split -> activation -> MMA -> epilogue) still run back to back on one CTA per SM: 4.07 ms
-        // at Darcy size against 3.53 ms for the fp32 kernel.  It needs the warp-specialised pipeline of the tc_*.cuh
-        // kernels (producer / MMA / epilogue warps over a ring of tiles) to pay off.
+        // first tcgen05 version, opt-in: same products, but its phases (stage -> split -> activation -> MMA -> epilogue) run
+        // back to back behind block-wide barriers: 4.07 ms at Darcy size.  Superseded by the warp-specialised kernel above;
+        // kept because it also covers two hidden chunks (hid <= 64).
         const size_t smem = proj_bwd_tc_smem(k.hid, k.out_ch);
         int rc = ensure_smem(proj_bwd_tc_kernel, smem);
         if (rc) return rc;

@@ -15,11 +15,11 @@
 // for dW1).  One thread issues the MMAs; everybody waits on one mbarrier (tcgen05.commit) before the images are reused.
 // Takes: 64-channel template, hid <= 64, saved pre-activations.
 //
-// STATUS (measured on B200, Darcy 421^2, batch 32): parity-green on every projection case and on the full-size comparison,
-// 4.07 ms per launch against 3.53 ms for the fp32 kernel (pixel_mlp.cuh), so it is OPT-IN (UNO_B200_PROJ_TC=1).  The
-// tensor-core work itself is ~1 k cycles of a ~27 k-cycle tile; the rest is the fp32 phases running back to back on eight
-// warps with five block-wide barriers per tile.  The next step is the warp-specialised form of the tc_*.cuh kernels
-// (input / activation / MMA / epilogue warps over a ring of tiles), which removes the barriers from the critical path.
+// STATUS (measured on B200, Darcy 421^2, batch 32): this first, barrier-synchronised version (proj_bwd_tc_kernel) is
+// parity-green but takes 4.07 ms per launch against 3.4 ms for the fp32 kernel (pixel_mlp.cuh): the tensor-core work is ~1 k
+// cycles of a ~27 k-cycle tile, the rest is the fp32 phases running back to back with five block-wide barriers per tile.
+// It is opt-in (UNO_B200_PROJ_TC=1) and kept for hid in (32, 64].  The warp-specialised kernel at the end of this file
+// (proj_bwd_tcp_kernel) removes the barriers from the critical path: 2.1 ms, the default for the shipped shapes.
 #pragma once
 
 constexpr int kPtPix = 128;                          // pixels per tile

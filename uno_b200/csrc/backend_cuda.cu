@@ -1591,7 +1591,7 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         if (rc) return rc;
         const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
-        proj_bwd_tcp_kernel<<<grid, 256, smem, st>>>(k, ntiles);
+        proj_bwd_tcp_kernel<<<grid, kTcpThreads, smem, st>>>(k, ntiles);
     } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TC") != nullptr &&
                getenv("UNO_B200_DISABLE_TC") == nullptr) {
         // first tcgen05 version, opt-in: same products, but its phases (stage -> split -> activation -> MMA -> epilogue) run

@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long
 //                                         commits to bar_mma, which both groups wait on before touching the images again
 // No block-wide barrier in the loop; the only exposed latency per tile is the tensor core's.
 // =====================================================================================================
-__global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, long ntiles) {
+constexpr int kTcpThreads = 512;      // 8 warps per group: two threads per pixel (half the channels / hidden units each)
+__global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const ProjK k, long ntiles) {
     extern __shared__ __align__(128) uint8_t tsm[];
     constexpr int CT = 64;
     uint8_t* p0 = tsm + ((128u - (tc::smem_u32(tsm) & 127u)) & 127u);
@@ -352,13 +353,14 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
     uint64_t* bar_mma = bar_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool groupA = tid < 128;
+    const bool groupA = tid < 256;
     const int px = tid & 127;                            // this thread's pixel of every tile
+    const int half = (tid >> 7) & 1;                     // group A: channels 32 half .. +32; group B: hidden units 16 half .. +16
 
     proj_stage_tables<CT>(k, sbase, gbase, sstride);
-    for (uint32_t i = tid; i < (kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes) / 16; i += 256)
+    for (uint32_t i = tid; i < (kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes) / 16; i += kTcpThreads)
         reinterpret_cast<float4*>(IMG)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < kProjHC * CT; i += 256) {
+    for (int i = tid; i < kProjHC * CT; i += kTcpThreads) {
         const int c = i % CT, j = i / CT;
         float hi = 0.f, lo = 0.f;
         if (j < k.hid && c < k.ctot) tc::split_tf32(__ldg(k.w1 + j * k.ctot + c), hi, lo);
@@ -366,9 +368,9 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
         *reinterpret_cast<float*>(d) = hi;
         *reinterpret_cast<float*>(d + kPtWBytes) = lo;
     }
-    for (int i = tid; i < k.out_ch * k.hid; i += 256) sW2[i] = __ldg(k.w2 + i);
+    for (int i = tid; i < k.out_ch * k.hid; i += kTcpThreads) sW2[i] = __ldg(k.w2 + i);
     if (tid == 0) {
-        tc::mbar_init(bar_full, 256);
+        tc::mbar_init(bar_full, kTcpThreads);
         tc::mbar_init(bar_mma, 1);
         tc::fence_barrier_init();
     }
@@ -394,21 +396,13 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
             long rp = 0;
             b = 0; pp = 0;
             if (valid) raw_to_padded(g, idx, b, rp, pp);
-            uint32_t dst = tc::smem_u32(RAW + px);
-            const int sz = valid ? 4 : 0;
-            const long step = valid ? g.npad : 0;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (s < k.nsrc) {
-                    const int nch = k.src_ch[s];
-                    const float* src = valid ? k.src[s] + b * nch * g.npad + pp : k.w1;
+            uint32_t dst = tc::smem_u32(RAW + (32 * half) * kPtPix + px);
 #pragma unroll 4
-                    for (int cl = 0; cl < nch; ++cl) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-                        dst += (uint32_t)(kPtPix * 4);
-                        src += step;
-                    }
-                }
+            for (int c = 32 * half; c < 32 * half + 32; ++c) {
+                const bool on = valid && c < k.ctot;
+                const float* src = on ? sbase[c] + b * sstride[c] + pp : k.w1;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(on ? 4 : 0) : "memory");
+                dst += (uint32_t)(kPtPix * 4);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -418,9 +412,10 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
         auto store_gradients = [&](long b, long pp, bool valid) {
             long cur_stride = -1, off = 0;
 #pragma unroll
-            for (int c0 = 0; c0 < CT; c0 += 16) {
+            for (int cc = 0; cc < 32; cc += 16) {
+                const int c0 = 32 * half + cc;
                 uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
                 if (!valid || c0 >= k.ctot) continue;
                 if (src16) {
@@ -457,7 +452,7 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
             {
                 uint8_t* d = IMG + (uint32_t)(px >> 2) * kPtLboA + (uint32_t)(px & 3) * 4;
 #pragma unroll 8
-                for (int c = 0; c < CT; ++c) {
+                for (int c = 32 * half; c < 32 * half + 32; ++c) {
                     float hi, lo;
                     tc::split_tf32(RAW[c * kPtPix + px], hi, lo);
                     *reinterpret_cast<float*>(d + (uint32_t)c * 16) = hi;
@@ -478,10 +473,11 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
             tc::tc_fence_after();
             store_gradients(b_prev, pp_prev, v_prev);
             // dW1: TMEM lanes 0-63 hold the hi-part rows (channel = lane), 64-127 the lo-part rows: both add into gw1
-            const int c = (32 * warp + lane) & 63;
-            for (int c0 = 0; c0 < kProjHC; c0 += 16) {
+            const int c = (32 * (warp & 3) + lane) & 63;
+            {
+                const int c0 = 16 * half;
                 uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + 64u + (uint32_t)c0, r);
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 64u + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
                 if (c < k.ctot) {
 #pragma unroll
@@ -496,51 +492,53 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
         const uint32_t img_a = tc::smem_u32(IMG), a1hi_a = tc::smem_u32(A1hi), a1lo_a = tc::smem_u32(A1lo), dhi_a = tc::smem_u32(Dhi),
                        dlo_a = tc::smem_u32(Dlo), w_a = tc::smem_u32(Wimg);
         // (single output channel: every shipped model projects to one field; other widths run the fp32 kernel)
-        float pre[kProjHC], go = 0.f;
-        float s_b1[kProjHC], s_w2[kProjHC], s_b2 = 0.f;      // sums over this thread's pixels, whole kernel
+        constexpr int NH = kProjHC / 2;                       // hidden units per thread
+        const int n0 = NH * half;
+        float pre[NH], go = 0.f;
+        float s_b1[NH], s_w2[NH], s_b2 = 0.f;                 // sums over this thread's pixels, whole kernel
 #pragma unroll
-        for (int n = 0; n < kProjHC; ++n) { s_b1[n] = 0.f; s_w2[n] = 0.f; }
+        for (int n = 0; n < NH; ++n) { s_b1[n] = 0.f; s_w2[n] = 0.f; }
         auto prefetch = [&](long tile) {
             const long idx = tile * kPtPix + px;
             const bool valid = tile < ntiles && idx < total;
 #pragma unroll
-            for (int n = 0; n < kProjHC; ++n) pre[n] = (valid && n < k.hid) ? __ldg(k.pre_in + (size_t)n * total + idx) : 0.f;
+            for (int n = 0; n < NH; ++n) pre[n] = (valid && n0 + n < k.hid) ? __ldg(k.pre_in + (size_t)(n0 + n) * total + idx) : 0.f;
             go = valid ? __ldg(k.gout + idx) : 0.f;
         };
         prefetch(blockIdx.x);
         for (long tile = blockIdx.x; tile < ntiles; tile += step_tiles, ++it) {
-            float hi[kProjHC], lo[kProjHC];
+            float hi[NH], lo[NH];
 #pragma unroll
-            for (int n = 0; n < kProjHC; ++n) {
+            for (int n = 0; n < NH; ++n) {
                 float a, gp;
                 gelu_both(pre[n], a, gp);
-                const float w2 = n < k.hid ? sW2[n] : 0.f;
+                const float w2 = n0 + n < k.hid ? sW2[n0 + n] : 0.f;
                 s_w2[n] = fmaf(go, a, s_w2[n]);
                 const float dp = go * w2 * gp;
                 s_b1[n] += dp;
                 tc::split_tf32(dp, hi[n], lo[n]);
             }
-            s_b2 += go;
+            if (half == 0) s_b2 += go;
             prefetch(tile + step_tiles);                 // next tile's loads fly while this tile's images are written
             if (it > 0) {                                // MMA(t-1) complete: the D images may be rewritten
                 tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);
                 tc::tc_fence_after();
             }
 #pragma unroll
-            for (int m = 0; m < kProjHC / 4; ++m) {
-                const uint32_t oa = (uint32_t)m * kPtLboA + (uint32_t)px * 16;
+            for (int m = 0; m < NH / 4; ++m) {
+                const uint32_t oa = (uint32_t)(n0 / 4 + m) * kPtLboA + (uint32_t)px * 16;
                 *reinterpret_cast<float4*>(A1hi + oa) = make_float4(hi[4 * m], hi[4 * m + 1], hi[4 * m + 2], hi[4 * m + 3]);
                 *reinterpret_cast<float4*>(A1lo + oa) = make_float4(lo[4 * m], lo[4 * m + 1], lo[4 * m + 2], lo[4 * m + 3]);
             }
-            const uint32_t od = (uint32_t)(px >> 2) * kPtLboD + (uint32_t)(px & 3) * 4;
+            const uint32_t od = (uint32_t)(px >> 2) * kPtLboD + (uint32_t)(px & 3) * 4 + (uint32_t)n0 * 16;
 #pragma unroll
-            for (int n = 0; n < kProjHC; ++n) {
+            for (int n = 0; n < NH; ++n) {
                 *reinterpret_cast<float*>(Dhi + od + n * 16) = hi[n];
                 *reinterpret_cast<float*>(Dlo + od + n * 16) = lo[n];
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_full);
-            if (tid == 128) {
+            if (tid == 256) {
                 tc::mbar_wait(bar_full, (uint32_t)it & 1u);
                 tc::tc_fence_after();
 #pragma unroll
@@ -567,19 +565,19 @@ __global__ void __launch_bounds__(256, 1) proj_bwd_tcp_kernel(const ProjK k, lon
         }
         // sums over pixels: reduce over the warp, one atomic per value per warp
 #pragma unroll
-        for (int n = 0; n < kProjHC; ++n) {
+        for (int n = 0; n < NH; ++n) {
             const float v = warp_sum(s_b1[n]);
             const float w = warp_sum(s_w2[n]);
-            if (lane == 0 && n < k.hid) {
-                atomicAdd(k.gb1 + n, v);
-                atomicAdd(k.gw2 + n, w);
+            if (lane == 0 && n0 + n < k.hid) {
+                atomicAdd(k.gb1 + n0 + n, v);
+                atomicAdd(k.gw2 + n0 + n, w);
             }
         }
         {
             const float v = warp_sum(s_b2);
             if (lane == 0) atomicAdd(k.gb2, v);
         }
-        if (it > 0 && tid == 128) tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);   // nothing of this CTA may still be in flight
+        if (it > 0 && tid == 256) tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);   // nothing of this CTA may still be in flight
     }
     tc::tc_fence_before();
     __syncthreads();

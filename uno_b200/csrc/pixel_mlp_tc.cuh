@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
         tc::mbar_init(bar_mma, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kPtTmemCols);
+    constexpr uint32_t kCols = 256;       // DIN accumulators at columns 0 / 64 (alternating tiles), dW1 at 128
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kCols);
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -409,13 +410,13 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
         // every source a multiple of 16 channels wide (the shipped models: 32 + 32): a 16-column TMEM read never straddles
         // two sources, so its stores run on one pointer advanced by the plane size
         const bool src16 = (k.src_ch[0] % 16 == 0) && (k.src_ch[1] % 16 == 0) && (k.src_ch[2] % 16 == 0) && (k.src_ch[3] % 16 == 0);
-        auto store_gradients = [&](long b, long pp, bool valid) {
+        auto store_gradients = [&](long b, long pp, bool valid, uint32_t acc_col) {
             long cur_stride = -1, off = 0;
 #pragma unroll
             for (int cc = 0; cc < 32; cc += 16) {
                 const int c0 = 32 * half + cc;
                 uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, r);
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + acc_col + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
                 if (!valid || c0 >= k.ctot) continue;
                 if (src16) {
@@ -459,25 +460,29 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
                     *reinterpret_cast<float*>(d + (uint32_t)(64 + c) * 16) = lo;
                 }
             }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bar_full);                   // the image of tile t is ready: everything below is off the critical path
             const long b_t = b_cur, pp_t = pp_cur;
             const bool v_t = v_cur;
             if (tile + step_tiles < ntiles) stage_raw(tile + step_tiles, b_cur, pp_cur, v_cur);   // this thread's RAW column is free again
-            if (it > 0) store_gradients(b_prev, pp_prev, v_prev);                                 // EPI(t-1)
+            // EPI(t-1) reads the accumulator MMA(t) does not write (they alternate); it finishes before this thread arrives
+            // for tile t+1, hence before MMA(t+1) reuses that accumulator
+            if (it > 0) {
+                store_gradients(b_prev, pp_prev, v_prev, (uint32_t)((it - 1) & 1) * 64u);
+                tc::tc_fence_before();
+            }
             b_prev = b_t; pp_prev = pp_t; v_prev = v_t;
-            tc::fence_proxy_async();
-            tc::tc_fence_before();
-            tc::mbar_arrive(bar_full);
         }
         if (it > 0) {
             tc::mbar_wait(bar_mma, (uint32_t)(it - 1) & 1u);
             tc::tc_fence_after();
-            store_gradients(b_prev, pp_prev, v_prev);
+            store_gradients(b_prev, pp_prev, v_prev, (uint32_t)((it - 1) & 1) * 64u);
             // dW1: TMEM lanes 0-63 hold the hi-part rows (channel = lane), 64-127 the lo-part rows: both add into gw1
             const int c = (32 * (warp & 3) + lane) & 63;
             {
                 const int c0 = 16 * half;
                 uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 64u + (uint32_t)c0, r);
+                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + 128u + (uint32_t)c0, r);
                 tc::tmem_ld_wait();
                 if (c < k.ctot) {
 #pragma unroll
@@ -547,17 +552,18 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
                     const uint64_t da_lo = tc::make_smem_desc(a1lo_a + ks * 2 * kPtLboA, kPtLboA, 128);
                     const uint64_t db_hi = tc::make_smem_desc(w_a + ks * 2 * kPtLboW, kPtLboW, 128);
                     const uint64_t db_lo = tc::make_smem_desc(w_a + kPtWBytes + ks * 2 * kPtLboW, kPtLboW, 128);
-                    tc::mma_tf32(tmem_base, da_hi, db_hi, idesc_din, ks ? 1u : 0u);
-                    tc::mma_tf32(tmem_base, da_hi, db_lo, idesc_din, 1u);
-                    tc::mma_tf32(tmem_base, da_lo, db_hi, idesc_din, 1u);
+                    const uint32_t din = tmem_base + (uint32_t)(it & 1) * 64u;
+                    tc::mma_tf32(din, da_hi, db_hi, idesc_din, ks ? 1u : 0u);
+                    tc::mma_tf32(din, da_hi, db_lo, idesc_din, 1u);
+                    tc::mma_tf32(din, da_lo, db_hi, idesc_din, 1u);
                 }
 #pragma unroll 4
                 for (int ks = 0; ks < kPtPix / 8; ++ks) {
                     const uint64_t da = tc::make_smem_desc(img_a + ks * 2 * kPtLboA, kPtLboA, 128);
                     const uint64_t db_hi = tc::make_smem_desc(dhi_a + ks * 2 * kPtLboD, kPtLboD, 128);
                     const uint64_t db_lo = tc::make_smem_desc(dlo_a + ks * 2 * kPtLboD, kPtLboD, 128);
-                    tc::mma_tf32(tmem_base + 64u, da, db_hi, idesc_dw, (it | ks) ? 1u : 0u);
-                    tc::mma_tf32(tmem_base + 64u, da, db_lo, idesc_dw, 1u);
+                    tc::mma_tf32(tmem_base + 128u, da, db_hi, idesc_dw, (it | ks) ? 1u : 0u);
+                    tc::mma_tf32(tmem_base + 128u, da, db_lo, idesc_dw, 1u);
                 }
                 tc::tc_commit(bar_mma);
             }
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, kPtTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kCols);
 }
 
 __host__ __device__ inline size_t proj_bwd_tcp_smem(int hid, int out_ch) {

@@ -35,6 +35,10 @@ SHAPES = [
     (2, 2, 3, (32, 48), (9, 16), (3, 7)),
     (1, 2, 2, (64, 64), (300, 64), (20, 22)),
     (1, 1, 2, (96, 96), (130, 446), (9, 32)),
+    # odd row pitch -> row-parity tiles with the column-shifted twiddle image: several 256-row blocks with a ragged
+    # last one, two column tiles, and the float2 path of both parities
+    (3, 2, 3, (40, 40), (45, 301), (6, 20)),
+    (2, 2, 5, (32, 32), (131, 77), (7, 9)),
     # long contraction (K = input width > 64): K-pipelined kernel, 16-byte aligned and unaligned rows,
     # ragged last chunk, several row tiles per CTA
     (1, 2, 2, (20, 481), (10, 240), (5, 18)),
@@ -79,7 +83,8 @@ def test_block_epilogues_tc(cuda_lib):
     from oracle import uno_torch_port as port
     from uno_b200 import integral_operators as ops
 
-    for norm, nl, odim in [(False, True, (24, 240)), (True, True, (24, 120)), (False, False, (10, 481)), (False, True, (12, 63))]:
+    for norm, nl, odim in [(False, True, (24, 240)), (True, True, (24, 120)), (False, False, (10, 481)), (False, True, (12, 63)),
+                          (False, True, (45, 301)), (True, True, (70, 33))]:
         torch.manual_seed(1)
         blk = ops.OperatorBlock_2D(3, 4, *odim, 5, 9, Normalize=norm, Non_Lin=nl).cuda()
         x = torch.randn(2, 3, 30, 100, device="cuda", requires_grad=True)

@@ -626,23 +626,48 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__
 
 __device__ __forceinline__ double block_sum(double v, double* sh);
 
-// plane-structured GELU backward with the conv-bias gradient folded in: grid (planes, chunks)
+// plane-structured GELU backward with the conv-bias gradient folded in: grid (planes, chunks).
+// Planes of an odd grid (481 x 481) start at any 4-byte offset, so each plane is cut into a scalar head (up to the next
+// 16-byte boundary), a float4 body and a scalar tail; the three tensors share the cut when `vec_ok` (same shape, bases
+// 16-byte aligned).
 __global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const float* __restrict__ gy, const float* __restrict__ pre,
                                                             float* __restrict__ g, int C, long L, float* __restrict__ gbias,
-                                                            float alpha) {
+                                                            float alpha, int vec_ok) {
     __shared__ double sh[32];
     const long p = blockIdx.x;
     const float* gp = gy + p * L;
     const float* pp = pre + p * L;
     float* op = g + p * L;
+    const long t = (long)blockIdx.y * blockDim.x + threadIdx.x, stride = (long)gridDim.y * blockDim.x;
+    const long head = vec_ok ? min(L, (4 - ((p * L) & 3)) & 3) : L;
+    const long nv = (L - head) >> 2;
     float s = 0.f;
-    for (long i = (long)blockIdx.y * blockDim.x + threadIdx.x; i < L; i += (long)gridDim.y * blockDim.x) {
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(gp + head);
+        const float4* p4 = reinterpret_cast<const float4*>(pp + head);
+        float4* o4 = reinterpret_cast<float4*>(op + head);
+#pragma unroll 2
+        for (long j = t; j < nv; j += stride) {
+            const float4 a = __ldcs(g4 + j), b = __ldcs(p4 + j);
+            float4 v;
+            v.x = a.x * gelu_grad_f(b.x);
+            v.y = a.y * gelu_grad_f(b.y);
+            v.z = a.z * gelu_grad_f(b.z);
+            v.w = a.w * gelu_grad_f(b.w);
+            o4[j] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    }
+    // scalar remainder: [0, head) and [head + 4*nv, L)
+    const long rem = L - 4 * nv;
+    for (long r = t; r < rem; r += stride) {
+        const long i = r < head ? r : r + 4 * nv;
         const float v = gp[i] * gelu_grad_f(pp[i]);
         op[i] = v;
         s += v;
     }
-    const double t = block_sum((double)s, sh);
-    if (threadIdx.x == 0) atomicAdd(gbias + (p % C), alpha * (float)t);
+    const double tot = block_sum((double)s, sh);
+    if (threadIdx.x == 0) atomicAdd(gbias + (p % C), alpha * (float)tot);
 }
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -806,11 +831,12 @@ struct TcImage {
     int n_tiles = 0, N_t = 0, K_pad = 0;
 };
 struct TcKey {
-    const void* p; int K, N; long ldb;
+    const void* p; int K, N; long ldb; int variant = 0;
     bool operator<(const TcKey& o) const {
         if (p != o.p) return p < o.p;
         if (K != o.K) return K < o.K;
         if (N != o.N) return N < o.N;
+        if (variant != o.variant) return variant < o.variant;
         return ldb < o.ldb;
     }
 };
@@ -824,9 +850,11 @@ bool tc_enabled() {   // read every call so tests can flip UNO_B200_DISABLE_TC a
 
 // B [K x N] (device, row-major, ldb) -> per n-tile [hi | lo] images in the UMMA K-major interleave layout
 // of the transposed operand (N_t rows x K_pad): element (n, k) at float offset (k/4)*N_t*4 + n*4 + k%4.
-int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, TcImage* out) {
+// With `shifts` == 2 a second set of tiles follows in which tile column n holds B column t*N_t + n - 1 (the images
+// the odd-row CTAs of the parity mode load, tc_rowgemm.cuh).
+int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, int shifts, TcImage* out) {
     std::lock_guard<std::mutex> lk(g_tc_mu);
-    TcKey key{B, K, N, ldb};
+    TcKey key{B, K, N, ldb, shifts};
     auto it = g_tc_images.find(key);
     if (it != g_tc_images.end()) { *out = it->second; return 0; }
     TcImage img;
@@ -838,20 +866,22 @@ int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, TcImage* out) {
     cudaError_t e = cudaMemcpy2D(hB.data(), (size_t)N * 4, B, (size_t)ldb * 4, (size_t)N * 4, K, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return (int)e;
     const size_t half = (size_t)img.K_pad * img.N_t;
-    std::vector<float> h((size_t)img.n_tiles * 2 * half, 0.0f);
-    for (int t = 0; t < img.n_tiles; ++t)
-        for (int n = 0; n < img.N_t; ++n) {
-            const int gn = t * img.N_t + n;
-            if (gn >= N) continue;
-            for (int k = 0; k < K; ++k) {
-                const float b = hB[(size_t)k * N + gn];
-                const float hi = tf32_rn(b);
-                const float lo = tf32_rn(b - hi);
-                const size_t o = (size_t)(k / 4) * img.N_t * 4 + (size_t)n * 4 + (k % 4);
-                h[(size_t)t * 2 * half + o] = hi;
-                h[(size_t)t * 2 * half + half + o] = lo;
+    std::vector<float> h((size_t)shifts * img.n_tiles * 2 * half, 0.0f);
+    for (int sh = 0; sh < shifts; ++sh)
+        for (int t = 0; t < img.n_tiles; ++t)
+            for (int n = 0; n < img.N_t; ++n) {
+                const int gn = t * img.N_t + n - sh;
+                if (gn < 0 || gn >= N) continue;
+                const size_t base = (size_t)(sh * img.n_tiles + t) * 2 * half;
+                for (int k = 0; k < K; ++k) {
+                    const float b = hB[(size_t)k * N + gn];
+                    const float hi = tf32_rn(b);
+                    const float lo = tf32_rn(b - hi);
+                    const size_t o = (size_t)(k / 4) * img.N_t * 4 + (size_t)n * 4 + (k % 4);
+                    h[base + o] = hi;
+                    h[base + half + o] = lo;
+                }
             }
-        }
     e = cudaMalloc(&img.dev, h.size() * 4);
     if (e != cudaSuccess) return (int)e;
     e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
@@ -894,7 +924,8 @@ int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
         configured = true;
     }
     int gx = num_sms() / p.n_tiles;
-    if (gx < 1) gx = 1;
+    if (p.parity) gx &= ~1;                 // a CTA must only ever see tiles of one row parity (m_tiles is even too)
+    if (gx < 1 + p.parity) gx = 1 + p.parity;
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     tc::rowgemm_smallk_kernel<EPI><<<dim3(gx, p.n_tiles), tc::kRowGemmThreads, smem, st>>>(p);
     CU_LAUNCH_CHECK();
@@ -1057,14 +1088,19 @@ int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     const int N_t = ((((a.N + n_tiles - 1) / n_tiles) + 15) / 16) * 16;
     const size_t smem = tc::rowgemm_smem_bytes(K_pad, N_t);
     if (smem > 220 * 1024) return -1;
-    int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, &img);
+    // odd row pitch: split the rows by parity so that both halves store aligned float2 (tc_rowgemm.cuh)
+    static const bool no_parity = [] { const char* e = getenv("UNO_B200_ROWGEMM_NO_PARITY"); return e && e[0] && e[0] != '0'; }();
+    const bool c2_ok = a.epi != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(a.C2) & 7) == 0;
+    const int parity = (!no_parity && (a.ldc & 1) && (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && c2_ok && n_tiles * N_t > a.N) ? 1 : 0;
+    int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, 1 + parity, &img);
     if (rc) return rc;
     tc::RowGemmParams p;
     p.A = a.A; p.lda = a.a_rs; p.R = a.M;
     p.Bimg = img.dev;
     p.C = a.C; p.C2 = a.C2; p.ldc = a.ldc;
     p.N = a.N; p.K = a.K; p.K_pad = img.K_pad; p.n_tiles = img.n_tiles; p.N_t = img.N_t;
-    p.m_tiles = ((long)a.M + 127) / 128;
+    p.parity = parity;
+    p.m_tiles = parity ? 2 * (((long)a.M + 255) / 256) : ((long)a.M + 127) / 128;
     p.epi = a.epi;
     int cols = 32;
     while (cols < 2 * img.N_t) cols *= 2;
@@ -1425,8 +1461,9 @@ int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, i
     if (planes <= 0 || L <= 0) return 0;
     ProfScope ps("gelu_bwd", 12.0 * planes * L, 0, S(s));
     // enough CTAs per plane to fill the machine, few enough that the atomics stay negligible
-    unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 8191) / 8192, (148L * 8 + planes - 1) / planes));
-    gelu_bwd_bias_kernel<<<dim3((unsigned)planes, gy_), 256, 0, S(s)>>>(gy, pre, g, C, L, gbias, alpha);
+    unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 2047) / 2048, (148L * 32 + planes - 1) / planes));
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    gelu_bwd_bias_kernel<<<dim3((unsigned)planes, gy_), 256, 0, S(s)>>>(gy, pre, g, C, L, gbias, alpha, vec_ok);
     CU_LAUNCH_CHECK();
     return 0;
 }

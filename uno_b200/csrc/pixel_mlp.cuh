@@ -415,7 +415,7 @@ __device__ __forceinline__ float proj_hidden_row(const float* sW1_row, float bia
     return (acc0 + acc1) + (acc2 + acc3);
 }
 
-inline size_t proj_table_bytes(int CT) { return (size_t)CT * (2 * sizeof(void*) + sizeof(long)); }
+__host__ __device__ inline size_t proj_table_bytes(int CT) { return (size_t)CT * (2 * sizeof(void*) + sizeof(long)); }
 
 // Forward of the projection: a CTA walks 256-pixel tiles of the cropped grid; the tile's inputs are staged with LDGSTS
 // (thread t copies pixel t, all channels) and the hidden layer is a register-tiled product out of shared memory,

@@ -231,22 +231,21 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
         // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
         const int q = warp - kKpLoadWarps;
         RowGemmParams ep;
-        ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R;
+        ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R; ep.parity = 0;
         const bool vec2 = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
         int it = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait_relaxed(&d_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            const long row0 = tile * 128 + q * 32;
             const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
             // both column "halves" handled by this warp
             if (vec2) {
-                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, row0, 0, 0, lane);
-                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, row0, 0, 1, lane);
+                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, tile, q, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, tile, q, 0, 1, lane);
             } else {
-                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, row0, 0, 0, lane);
-                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, row0, 0, 1, lane);
+                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, tile, q, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, tile, q, 0, 1, lane);
             }
             tc_fence_before();
             mbar_arrive(&d_empty[buf]);

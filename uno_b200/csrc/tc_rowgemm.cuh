@@ -30,7 +30,18 @@ struct RowGemmParams {
     int epi;
     int tmem_cols;                // power of two >= 2*N_t
     int a_vec_ok;                 // A rows are 16-byte aligned and K % 4 == 0
+    int parity;                   // odd ldc: tiles hold rows of ONE parity and the odd ones use a B image shifted by a column (see below)
 };
+
+// Odd leading dimension (the 481-wide Darcy grid): every other row of C starts 4 bytes off an 8-byte boundary, so
+// the accumulator layout (a thread owns columns 2j, 2j+1) cannot be stored as float2 and the epilogue falls to
+// half-filled 32-byte sectors.  In parity mode a tile is 128 rows of the SAME parity out of a block of 256
+// (row = 256*(tile/2) + 2*i + tile%2), a CTA only ever sees one parity (even grid), and the CTAs of the odd rows
+// load a twiddle image whose columns are shifted by one (accumulator column c = output column c-1): the pair a
+// thread owns is then 8-byte aligned in every row and both parities take the float2 path.
+__device__ __forceinline__ long rowgemm_row(const RowGemmParams& p, long tile, int i) {
+    return p.parity ? (tile >> 1) * 256 + 2 * i + (tile & 1) : tile * 128 + i;
+}
 
 constexpr int kRowGemmEpiWarps = 8;                      // two per TMEM lane quarter, splitting the columns
 constexpr int kRowGemmLoadWarps = 2;
@@ -49,18 +60,20 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // All loads of a 32-column group are issued before any store so that they are in flight together; the four
 // row pointers of a thread are formed once per tile (no 64-bit multiplies in the column loop).
 template <int EPI, bool VEC2>
-__device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long row0, int n_base, int half, int lane) {
+__device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half, int lane) {
     constexpr bool kAccum = (EPI != EPI_STORE);
     const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
     float* rowp[4];          // index hh*2 + rr
     bool rok[4];
+    n_base -= p.parity ? (int)(tile & 1) : 0;            // accumulator column c of this tile = output column n_base + c
 #pragma unroll
     for (int hr = 0; hr < 4; ++hr) {
-        const long grow = row0 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2);
+        const long grow = rowgemm_row(p, tile, q * 32 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2));
         rok[hr] = grow < p.R;
         rowp[hr] = p.C + (rok[hr] ? grow : 0) * p.ldc + n_base + 2 * (lane & 3);
     }
-    const int ncol = p.N - n_base - 2 * (lane & 3);     // column c (relative) valid iff c < ncol
+    const int ncol = p.N - n_base - 2 * (lane & 3);     // column c (relative) valid iff cmin <= c < ncol
+    const int cmin = -(n_base + 2 * (lane & 3));        // 1 for the first thread of a shifted first tile, else <= 0
     for (int ci = half; ci * 16 < p.N_t; ci += 4) {
         const int c0a = ci * 16, c0b = (ci + 2) * 16;
         const bool has_b = c0b < p.N_t && n_base + c0b < p.N;
@@ -82,12 +95,11 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
                 const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
                 const float* q = rowp[hh * 2 + rr] + c;
                 cz[e] = make_float2(0.f, 0.f);
-                if (VEC2) {
-                    if (live && c + 1 < ncol) cz[e] = *reinterpret_cast<const float2*>(q);
-                    else if (live && c < ncol) cz[e].x = q[0];
-                } else {
-                    if (live && c < ncol) cz[e].x = q[0];
-                    if (live && c + 1 < ncol) cz[e].y = q[1];
+                const bool in0 = live && c >= cmin && c < ncol, in1 = live && c + 1 < ncol;
+                if (VEC2 && in0 && in1) cz[e] = *reinterpret_cast<const float2*>(q);
+                else {
+                    if (in0) cz[e].x = q[0];
+                    if (in1) cz[e].y = q[1];
                 }
             }
         }
@@ -97,14 +109,14 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
             const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
             const int c = (j ? c0b : c0a) + rep * 8;
             const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
-            const bool ok0 = live && c < ncol, ok1 = live && c + 1 < ncol;
+            const bool ok0 = live && c >= cmin && c < ncol, ok1 = live && c + 1 < ncol;
             float* q = rowp[hh * 2 + rr] + c;
             float2 acc = make_float2(__uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 0]), __uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 1]));
             if (kAccum) { acc.x += cz[e].x; acc.y += cz[e].y; }
             float2 act = acc;
             if (EPI == EPI_ACCUM_GELU || EPI == EPI_ACCUM_GELU_INPLACE) { act.x = gelu_erf(acc.x); act.y = gelu_erf(acc.y); }
             const float2 out1 = (EPI == EPI_ACCUM_GELU_INPLACE) ? act : acc;
-            if (VEC2 && ok1) {
+            if (VEC2 && ok0 && ok1) {
                 *reinterpret_cast<float2*>(q) = out1;
                 if (EPI == EPI_ACCUM_GELU) *reinterpret_cast<float2*>(q + c2_delta) = act;
             } else {
@@ -155,7 +167,8 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             mbar_arrive_expect_tx(b_full, 2 * b_half);
-            bulk_g2s(sB, p.Bimg + (size_t)nt * (2 * b_half / 4), 2 * b_half, b_full);
+            const int shifted = p.parity ? (int)(blockIdx.x & 1) : 0;       // gridDim.x is even in parity mode
+            bulk_g2s(sB, p.Bimg + (size_t)(shifted * p.n_tiles + nt) * (2 * b_half / 4), 2 * b_half, b_full);
             mbar_wait(b_full, 0);
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
             const uint32_t lbo_b = (uint32_t)p.N_t * 16;
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
 #pragma unroll
             for (int rr = 0; rr < 128 / NL; ++rr) {
                 const int row = ltid + rr * NL;
-                const long grow = tile * 128 + row;
+                const long grow = rowgemm_row(p, tile, row);
                 const bool rvalid = grow < p.R;
                 const float* src = p.A + (rvalid ? grow : 0) * p.lda;
                 const uint32_t ro = (uint32_t)row * 16;
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
         }
     } else {
         // ------------------------------------------------------------------ epilogue: warp e -> TMEM lane quarter e%4, column half e/4
-        const bool vec2 = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) &&
+        const bool vec2 = (p.ldc % 2 == 0 || p.parity) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) &&
                           (EPI != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(p.C2) & 7) == 0);
         const int q = warp & 3, half = warp >> 2;
         const int n_base = nt * p.N_t;
@@ -250,10 +263,9 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
             mbar_wait_relaxed(&d_full[s], ph);
             tc_fence_after();
-            const long row0 = tile * 128 + q * 32;
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);
-            if (vec2) rowgemm_epilogue_tile<EPI, true>(p, t_base, row0, n_base, half, lane);
-            else rowgemm_epilogue_tile<EPI, false>(p, t_base, row0, n_base, half, lane);
+            if (vec2) rowgemm_epilogue_tile<EPI, true>(p, t_base, tile, q, n_base, half, lane);
+            else rowgemm_epilogue_tile<EPI, false>(p, t_base, tile, q, n_base, half, lane);
             tc_fence_before();
             mbar_arrive(&d_empty[s]);
         }

@@ -987,6 +987,7 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     while (cols < 2 * img.N_t) cols *= 2;
     p.tmem_cols = cols;
     p.a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    { const char* e = getenv("UNO_B200_KPIPE_DEBUG"); p.debug = e ? atoi(e) : 0; }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1376,12 +1377,15 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     k.tiles_w = (a.n_out1 + rs_tile_w(G1) - 1) / rs_tile_w(G1);
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
-    int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1>, smem);
+    static const int minb = [] { const char* e = getenv("UNO_B200_RS_MINB"); return e && e[0] == '3' ? 3 : 2; }();
+    int rc = minb == 3 ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 3>, smem) : ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem);
     if (rc) return rc;
     if (a.planes > 65535) return -1;          // planes ride on grid.z
     ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
                  2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
-    resample2d_kernel<G0, W0, G1, W1><<<dim3((unsigned)k.tiles_w, (unsigned)k.tiles_h, (unsigned)a.planes), 256, smem, st>>>(k);
+    const dim3 grid((unsigned)k.tiles_w, (unsigned)k.tiles_h, (unsigned)a.planes);
+    if (minb == 3) resample2d_kernel<G0, W0, G1, W1, 3><<<grid, 256, smem, st>>>(k);
+    else resample2d_kernel<G0, W0, G1, W1, 2><<<grid, 256, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;
 }

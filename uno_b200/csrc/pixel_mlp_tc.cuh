@@ -494,8 +494,9 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
     } else {
         // ------------------------------------------------------------------ group B: activation backward + MMA issue
         const uint32_t idesc_din = tc::make_idesc_tf32(128, 64, 0, 0), idesc_dw = tc::make_idesc_tf32(128, kProjHC, 0, 0);
-        const uint32_t img_a = tc::smem_u32(IMG), a1hi_a = tc::smem_u32(A1hi), a1lo_a = tc::smem_u32(A1lo), dhi_a = tc::smem_u32(Dhi),
-                       dlo_a = tc::smem_u32(Dlo), w_a = tc::smem_u32(Wimg);
+        const uint64_t d_img = tc::make_smem_desc(tc::smem_u32(IMG), kPtLboA, 128), d_a1hi = tc::make_smem_desc(tc::smem_u32(A1hi), kPtLboA, 128),
+                       d_dhi = tc::make_smem_desc(tc::smem_u32(Dhi), kPtLboD, 128), d_w = tc::make_smem_desc(tc::smem_u32(Wimg), kPtLboW, 128);
+        const uint32_t a1lo_off = (tc::smem_u32(A1lo) - tc::smem_u32(A1hi)) >> 4, dlo_off = (tc::smem_u32(Dlo) - tc::smem_u32(Dhi)) >> 4;
         // (single output channel: every shipped model projects to one field; other widths run the fp32 kernel)
         constexpr int NH = kProjHC / 2;                       // hidden units per thread
         const int n0 = NH * half;
@@ -543,29 +544,30 @@ __global__ void __launch_bounds__(kTcpThreads, 1) proj_bwd_tcp_kernel(const Proj
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bar_full);
-            if (tid == 256) {
-                tc::mbar_wait(bar_full, (uint32_t)it & 1u);
-                tc::tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < kProjHC / 8; ++ks) {
-                    const uint64_t da_hi = tc::make_smem_desc(a1hi_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t da_lo = tc::make_smem_desc(a1lo_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t db_hi = tc::make_smem_desc(w_a + ks * 2 * kPtLboW, kPtLboW, 128);
-                    const uint64_t db_lo = tc::make_smem_desc(w_a + kPtWBytes + ks * 2 * kPtLboW, kPtLboW, 128);
+            if (warp == 8) {                             // warp-uniform; one elected lane issues, descriptors are only advanced
+                if (tc::elect_one()) {
+                    tc::mbar_wait(bar_full, (uint32_t)it & 1u);
+                    tc::tc_fence_after();
                     const uint32_t din = tmem_base + (uint32_t)(it & 1) * 64u;
-                    tc::mma_tf32(din, da_hi, db_hi, idesc_din, ks ? 1u : 0u);
-                    tc::mma_tf32(din, da_hi, db_lo, idesc_din, 1u);
-                    tc::mma_tf32(din, da_lo, db_hi, idesc_din, 1u);
-                }
+                    uint64_t da = d_a1hi, db = d_w;
+#pragma unroll
+                    for (int ks = 0; ks < kProjHC / 8; ++ks) {
+                        tc::mma_tf32(din, da, db, idesc_din, ks ? 1u : 0u);
+                        tc::mma_tf32(din, da, db + (kPtWBytes >> 4), idesc_din, 1u);
+                        tc::mma_tf32(din, da + a1lo_off, db, idesc_din, 1u);
+                        da += (2 * kPtLboA) >> 4;
+                        db += (2 * kPtLboW) >> 4;
+                    }
+                    uint64_t di = d_img, dd = d_dhi;
 #pragma unroll 4
-                for (int ks = 0; ks < kPtPix / 8; ++ks) {
-                    const uint64_t da = tc::make_smem_desc(img_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t db_hi = tc::make_smem_desc(dhi_a + ks * 2 * kPtLboD, kPtLboD, 128);
-                    const uint64_t db_lo = tc::make_smem_desc(dlo_a + ks * 2 * kPtLboD, kPtLboD, 128);
-                    tc::mma_tf32(tmem_base + 128u, da, db_hi, idesc_dw, (it | ks) ? 1u : 0u);
-                    tc::mma_tf32(tmem_base + 128u, da, db_lo, idesc_dw, 1u);
+                    for (int ks = 0; ks < kPtPix / 8; ++ks) {
+                        tc::mma_tf32(tmem_base + 128u, di, dd, idesc_dw, (it | ks) ? 1u : 0u);
+                        tc::mma_tf32(tmem_base + 128u, di, dd + dlo_off, idesc_dw, 1u);
+                        di += (2 * kPtLboA) >> 4;
+                        dd += (2 * kPtLboD) >> 4;
+                    }
+                    tc::tc_commit(bar_mma);
                 }
-                tc::tc_commit(bar_mma);
             }
             __syncwarp();
         }

@@ -28,8 +28,8 @@ struct Resample2K {
 // per-tile overheads, 64 for the others
 __host__ __device__ constexpr int rs_tile_w(int G1) { return G1 == 8 ? 128 : 64; }
 
-template <int G0, int W0, int G1, int W1>
-__global__ void __launch_bounds__(256, 3) resample2d_kernel(const Resample2K k) {
+template <int G0, int W0, int G1, int W1, int MINB>
+__global__ void __launch_bounds__(256, MINB) resample2d_kernel(const Resample2K k) {
     extern __shared__ __align__(16) float rsm[];
     constexpr int kRsTW = rs_tile_w(G1), kRsMidLd = kRsTW + 1;
     constexpr int NG1 = kRsTW / G1;                      // column groups per tile

@@ -111,6 +111,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// The issuing thread is the critical path of the pipelined kernels (measured: with loads, stores and MMAs of the
+// analysis kernel switched off, the descriptor arithmetic and per-instruction election of the issuer alone kept
+// 40-55 % of its run time), so descriptors are formed once and then only ADVANCED: the start address is the low
+// 14 bits of the low word in 16-byte units, a byte offset adds (bytes >> 4) there (no carry: shared memory < 256 KB).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+// one lane of a converged warp (elect.sync); tcgen05.mma / commit issued under it need no per-instruction election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // TMEM -> registers.  16x256b: a warp reads 16 lanes x 8 columns per repeat; thread t holds
 //   (row t/4, cols 2(t%4), 2(t%4)+1) in regs 4r+0,4r+1 and (row t/4 + 8, same cols) in regs 4r+2,4r+3.
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {

@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
     const int NKC = p.n_chunks;
 
     if (warp == kMmaWarp) {
-        // ------------------------------------------------------------------ MMA issuer
+        // ------------------------------------------------------------------ MMA issuer (whole warp loops, one elected lane
+        // issues; descriptors are advanced, never rebuilt: tc_common.cuh)
         if (lane == 0) {
             // resident weight image, in pieces of <= 64 KB
             mbar_arrive_expect_tx(b_full, 2 * b_half);
@@ -114,37 +115,53 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
                 bulk_g2s(sB + off, reinterpret_cast<const uint8_t*>(p.Bimg) + off, n, b_full);
             }
             mbar_wait(b_full, 0);
+        }
+        __syncwarp();
+        {
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, /*a MN-major*/ 1, /*b K-major*/ 0);
             const uint32_t lbo_b = (uint32_t)p.N_t * 16;
-            const uint32_t sB_addr = smem_u32(sB);
+            const uint64_t a_hi0 = make_smem_desc(smem_u32(sA), kCvLbo, kCvSbo, kCvLayout);
+            const uint64_t b_hi0 = make_smem_desc(smem_u32(sB), lbo_b, 128);
+            const uint32_t a_lo_off = kCvAHalf >> 4, b_lo_off = b_half >> 4;
+            const uint32_t a_step = (2 * kCvSbo) >> 4, b_step = (2 * lbo_b) >> 4, stage_step = (uint32_t)stage_bytes >> 4;
+            const int last_nks = (p.K - (NKC - 1) * kKC + 7) / 8;
             int s = 0;
             uint32_t ph = 0;
+            uint64_t a_st = a_hi0;
             int it = 0;
             for (long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
+                uint64_t db = b_hi0;                     // the weight image is walked once per tile
+                uint32_t acc = 0;
                 for (int kc = 0; kc < NKC; ++kc) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(sA + (size_t)s * stage_bytes), a_lo = a_hi + kCvAHalf;
+                    const int nks = (kc == NKC - 1) ? last_nks : kKC / 8;
+                    if (elect_one()) {
+                        uint64_t da = a_st, dbk = db;
 #pragma unroll
-                    for (int ks = 0; ks < kKC / 8; ++ks) {
-                        const int kglob = kc * (kKC / 8) + ks;      // global 8-channel step
-                        if (kglob * 8 >= p.K) break;
-                        const uint64_t da_hi = make_smem_desc(a_hi + ks * 2 * kCvSbo, kCvLbo, kCvSbo, kCvLayout);
-                        const uint64_t da_lo = make_smem_desc(a_lo + ks * 2 * kCvSbo, kCvLbo, kCvSbo, kCvLayout);
-                        const uint64_t db_hi = make_smem_desc(sB_addr + kglob * 2 * lbo_b, lbo_b, 128);
-                        const uint64_t db_lo = make_smem_desc(sB_addr + b_half + kglob * 2 * lbo_b, lbo_b, 128);
-                        mma_tf32(d_tmem, da_hi, db_hi, idesc, kglob ? 1u : 0u);
-                        mma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-                        mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+                        for (int ks = 0; ks < kKC / 8; ++ks) {
+                            if (ks < nks) {
+                                mma_tf32(d_tmem, da, dbk, idesc, ks ? 1u : acc);
+                                mma_tf32(d_tmem, da, dbk + b_lo_off, idesc, 1u);
+                                mma_tf32(d_tmem, da + a_lo_off, dbk, idesc, 1u);
+                            }
+                            da += a_step;
+                            dbk += b_step;
+                        }
+                        tc_commit(&empty[s]);
                     }
-                    tc_commit(&empty[s]);
-                    if (++s == S) { s = 0; ph ^= 1u; }
+                    __syncwarp();
+                    acc = 1u;
+                    db += (uint64_t)(kKC / 8) * b_step;
+                    a_st += stage_step;
+                    if (++s == S) { s = 0; ph ^= 1u; a_st = a_hi0; }
                 }
-                tc_commit(&d_full[buf]);
+                if (elect_one()) tc_commit(&d_full[buf]);
+                __syncwarp();
             }
         }
     } else if (warp < kCvLoadWarps) {

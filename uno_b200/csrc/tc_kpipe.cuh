@@ -29,6 +29,8 @@ struct KPipeParams {
     long m_tiles;
     int tmem_cols;
     int a_vec_ok;          // rows 16-byte aligned (lda % 4 == 0, base aligned)
+    int debug;             // timing probes (UNO_B200_KPIPE_DEBUG, results are garbage): 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads,
+                           // 16 no proxy fence
 };
 
 constexpr int kKC = 32;                       // K elements per stage
@@ -76,39 +78,53 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
 
     if (warp == kMmaWarp) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // One elected lane; every descriptor is the stage-0 descriptor advanced by constants (no per-MMA descriptor
+        // construction, no multiplies): this thread's instruction stream bounds the kernel when K is long.
+        {
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
             const uint32_t lbo_b = (uint32_t)p.N_t * 16;
             const uint32_t smem_base = smem_u32(smem);
+            const uint64_t a_hi0 = make_smem_desc(smem_base, kLboA, 128);
+            const uint64_t b_hi0 = make_smem_desc(smem_base + 2 * kKpAHalf, lbo_b, 128);
+            const uint32_t a_lo_off = kKpAHalf >> 4, b_lo_off = b_half >> 4;     // descriptor units (16 bytes)
+            const uint32_t a_step = (2 * kLboA) >> 4, b_step = (2 * lbo_b) >> 4, stage_step = stage_bytes >> 4;
+            const int last_nks = (p.K - (NKC - 1) * kKC + 7) / 8;               // k-steps of the ragged last chunk
             int s = 0;
             uint32_t ph = 0;
+            uint64_t a_st = a_hi0, b_st = b_hi0;                                 // descriptors of the current stage
             int it = 0;
             for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&d_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * buf_cols;
+                uint32_t acc = 0;
                 for (int kc = 0; kc < NKC; ++kc) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t base = smem_base + (uint32_t)s * stage_bytes;
-                    const uint32_t a_hi = base, a_lo = base + kKpAHalf;
-                    const uint32_t bh = base + 2 * kKpAHalf, bl = bh + b_half;
+                    const int nks = (kc == NKC - 1) ? last_nks : kKC / 8;
+                    uint64_t da = a_st, db = b_st;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < kKC / 8; ++ks) {
-                        if (kc * kKC + ks * 8 >= p.K) break;
-                        const uint64_t da_hi = make_smem_desc(a_hi + ks * 2 * kLboA, kLboA, 128);
-                        const uint64_t da_lo = make_smem_desc(a_lo + ks * 2 * kLboA, kLboA, 128);
-                        const uint64_t db_hi = make_smem_desc(bh + ks * 2 * lbo_b, lbo_b, 128);
-                        const uint64_t db_lo = make_smem_desc(bl + ks * 2 * lbo_b, lbo_b, 128);
-                        mma_tf32(d_tmem, da_hi, db_hi, idesc, (kc | ks) ? 1u : 0u);
-                        mma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-                        mma_tf32(d_tmem, da_lo, db_hi, idesc, 1u);
+                        for (int ks = 0; ks < kKC / 8; ++ks) {
+                            if (ks < nks && !(p.debug & 1)) {
+                                mma_tf32(d_tmem, da, db, idesc, ks ? 1u : acc);
+                                mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1u);
+                                mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1u);
+                            }
+                            da += a_step;
+                            db += b_step;
+                        }
+                        tc_commit(&empty[s]);
                     }
-                    tc_commit(&empty[s]);
-                    if (++s == S) { s = 0; ph ^= 1u; }
+                    acc = 1u;
+                    __syncwarp();
+                    a_st += stage_step;
+                    b_st += stage_step;
+                    if (++s == S) { s = 0; ph ^= 1u; a_st = a_hi0; b_st = b_hi0; }
                 }
-                tc_commit(&d_full[buf]);
+                if (elect_one()) tc_commit(&d_full[buf]);
+                __syncwarp();
             }
         }
     } else if (warp < kKpLoadWarps) {
@@ -129,13 +145,16 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
             if (ltid == 0) {
-                mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
-                bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
+                if (p.debug & 4) mbar_arrive(&full[p_s]);
+                else {
+                    mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
+                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
+                }
             }
             return st;
         };
         auto stage_epilogue = [&]() {
-            fence_proxy_async();
+            if (!(p.debug & 16)) fence_proxy_async();
             mbar_arrive(&full[p_s]);
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
             if (++p_kc == NKC) p_kc = 0;
@@ -151,14 +170,19 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 const int k0 = i_kc * kKC + kq * 4;
                 const float* src = p.A + row0 * p.lda + k0;
                 const long rows_left = p.R - row0;            // row (32*i) valid iff 32*i < rows_left
-                const bool full4 = k0 + 4 <= p.K;
+                if (k0 + 4 <= p.K) {
+                    // every chunk but a ragged last one: straight-line predicated 16-byte loads (the loader warps' serial
+                    // instruction stream per chunk is what bounds this kernel, tools/kpipe_probe.py)
+                    const long lim = (p.debug & 8) ? 0 : rows_left;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (32 * i < rows_left) {
-                        const float* q = src + i * stride32;
-                        if (full4) v[i] = __ldg(reinterpret_cast<const float4*>(q));
-                        else {
+                    for (int i = 0; i < 4; ++i)
+                        v[i] = (32 * i < lim) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (32 * i < rows_left && !(p.debug & 8)) {
+                            const float* q = src + i * stride32;
                             if (k0 + 0 < p.K) v[i].x = __ldg(q + 0);
                             if (k0 + 1 < p.K) v[i].y = __ldg(q + 1);
                             if (k0 + 2 < p.K) v[i].z = __ldg(q + 2);
@@ -171,6 +195,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    if (p.debug & 2) break;
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);
                     split_tf32(v[i].y, hi.y, lo.y);
@@ -202,13 +227,14 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 const float* src = p.A + row0 * p.lda + k;
                 const long rows_left = (k < p.K) ? (p.R - row0) : 0;   // row (8*i) valid iff 8*i < rows_left
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (8 * i < rows_left) ? __ldg(src + i * stride8) : 0.f;
+                for (int i = 0; i < 16; ++i) v[i] = (8 * i < rows_left && !(p.debug & 8)) ? __ldg(src + i * stride8) : 0.f;
                 if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
             auto process = [&](const float (&v)[16]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
+                    if (p.debug & 2) break;
                     float hi, lo;
                     split_tf32(v[i], hi, lo);
                     *reinterpret_cast<float*>(st + i * 128) = hi;

@@ -69,30 +69,36 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == kMmaWarp) {
-        if (lane == 0 && total > 0) {
+        // whole warp loops, one elected lane issues; descriptors are advanced, never rebuilt (tc_common.cuh)
+        if (total > 0) {
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
-            const uint32_t smem_base = smem_u32(smem);
+            const uint64_t a_hi0 = make_smem_desc(smem_u32(smem), kLboA, 128);
+            constexpr uint32_t half = kKpAHalf >> 4, step = (2 * kLboA) >> 4, stage_step = kWgStage >> 4;
             int s = 0;
             uint32_t ph = 0;
+            uint64_t a_st = a_hi0;
+            uint32_t acc = 0;
             for (long g = 0; g < total; ++g) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t base = smem_base + (uint32_t)s * kWgStage;
-                const uint32_t a_hi = base, a_lo = base + kKpAHalf, b_hi = base + 2 * kKpAHalf, b_lo = base + 3 * kKpAHalf;
+                if (elect_one()) {
+                    uint64_t da = a_st;                  // stage layout: [A hi | A lo | B hi | B lo], each kKpAHalf bytes
 #pragma unroll
-                for (int ks = 0; ks < kKC / 8; ++ks) {
-                    const uint64_t da_hi = make_smem_desc(a_hi + ks * 2 * kLboA, kLboA, 128);
-                    const uint64_t da_lo = make_smem_desc(a_lo + ks * 2 * kLboA, kLboA, 128);
-                    const uint64_t db_hi = make_smem_desc(b_hi + ks * 2 * kLboA, kLboA, 128);
-                    const uint64_t db_lo = make_smem_desc(b_lo + ks * 2 * kLboA, kLboA, 128);
-                    mma_tf32(tmem_base, da_hi, db_hi, idesc, (g | ks) ? 1u : 0u);
-                    mma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
-                    mma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+                    for (int ks = 0; ks < kKC / 8; ++ks) {
+                        mma_tf32(tmem_base, da, da + 2 * half, idesc, ks ? 1u : acc);
+                        mma_tf32(tmem_base, da, da + 3 * half, idesc, 1u);
+                        mma_tf32(tmem_base, da + half, da + 2 * half, idesc, 1u);
+                        da += step;
+                    }
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);
-                if (++s == S) { s = 0; ph ^= 1u; }
+                __syncwarp();
+                acc = 1u;
+                a_st += stage_step;
+                if (++s == S) { s = 0; ph ^= 1u; a_st = a_hi0; }
             }
-            tc_commit(done);
+            if (elect_one()) tc_commit(done);
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ loaders

@@ -33,19 +33,6 @@ constexpr int kProjHC = 32;        // hidden units per round of the projection b
 // so Phi(x) = h for x < 0 and 1 - h for x >= 0 with h = E*poly/2 (no cancellation in the negative tail), and the
 // derivative Phi(x) + x*E/sqrt(2 pi) reuses E.  Measured in fp32 against fp64: |gelu error| <= 4.3e-7,
 // |gelu' error| <= 3.2e-7 over [-12, 12] -- two orders below the parity tolerance; ~16 instructions instead of ~60.
-__device__ __forceinline__ void gelu_both(float x, float& act, float& grad) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    const float E = __expf(-0.5f * x * x);
-    float poly = fmaf(t, 1.061405429f, -1.453152027f);
-    poly = fmaf(t, poly, 1.421413741f);
-    poly = fmaf(t, poly, -0.284496736f);
-    poly = fmaf(t, poly, 0.254829592f);
-    const float h = 0.5f * poly * t * E;
-    const float cdf = x < 0.f ? h : 1.0f - h;
-    act = x * cdf;
-    grad = fmaf(x * 0.39894228040143267794f, E, cdf);
-}
 __device__ __forceinline__ float gelu_act(float x) {
     float a, g;
     gelu_both(x, a, g);

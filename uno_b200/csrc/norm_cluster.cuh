@@ -37,23 +37,41 @@ __global__ void __launch_bounds__(kNormThreads) norm_fwd_cluster_kernel(const fl
     const long lo = (long)rank * slice;
     const int n = (int)max(0L, min((long)slice, L - lo));
     const float* xp = x + p * L + lo;
+    float* yp = y + p * L + lo;
+    // 16-byte body when every slice starts on a 16-byte boundary (L % 4 == 0; slices are multiples of 4), scalar tail
+    const bool vec = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const int nv = vec ? n >> 2 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(xp);
+    float4* s4 = reinterpret_cast<float4*>(nsm);
     float s = 0.f;
     double sd = 0.0;
     int cnt = 0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
+    for (int i = threadIdx.x; i < nv; i += kNormThreads) {
+        const float4 v = __ldcs(x4 + i);
+        s4[i] = v;
+        s += (v.x + v.y) + (v.z + v.w);
+        if (++cnt == 16) { sd += s; s = 0.f; cnt = 0; }
+    }
+    for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) {
         const float v = xp[i];
         nsm[i] = v;
         s += v;
-        if (++cnt == 64) { sd += s; s = 0.f; cnt = 0; }
+        if (++cnt == 16) { sd += s; s = 0.f; cnt = 0; }
     }
     sd += s;
     const double mu = cluster_total(cluster, &mail[0], block_sum(sd, sh)) / (double)L;
     const float muf = (float)mu;
     s = 0.f; sd = 0.0; cnt = 0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
+    for (int i = threadIdx.x; i < nv; i += kNormThreads) {
+        const float4 v = s4[i];
+        const float a = v.x - muf, b = v.y - muf, c2 = v.z - muf, d = v.w - muf;
+        s = fmaf(a, a, s); s = fmaf(b, b, s); s = fmaf(c2, c2, s); s = fmaf(d, d, s);
+        if (++cnt == 16) { sd += s; s = 0.f; cnt = 0; }
+    }
+    for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) {
         const float d = nsm[i] - muf;
         s = fmaf(d, d, s);
-        if (++cnt == 64) { sd += s; s = 0.f; cnt = 0; }
+        if (++cnt == 16) { sd += s; s = 0.f; cnt = 0; }
     }
     sd += s;
     const double var = cluster_total(cluster, &mail[1], block_sum(sd, sh)) / (double)L;
@@ -64,8 +82,14 @@ __global__ void __launch_bounds__(kNormThreads) norm_fwd_cluster_kernel(const fl
     }
     const int c = (int)(p % C);
     const float g = gamma[c] * rstd, b = beta[c] - muf * rstd * gamma[c];
-    float* yp = y + p * L + lo;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
+    float4* y4 = reinterpret_cast<float4*>(yp);
+    for (int i = threadIdx.x; i < nv; i += kNormThreads) {
+        float4 v = s4[i];
+        v.x = fmaf(v.x, g, b); v.y = fmaf(v.y, g, b); v.z = fmaf(v.z, g, b); v.w = fmaf(v.w, g, b);
+        if (non_lin) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+        y4[i] = v;
+    }
+    for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) {
         const float v = fmaf(nsm[i], g, b);
         yp[i] = non_lin ? gelu_f(v) : v;
     }
@@ -92,17 +116,41 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const fl
     const float ga = gamma[c], be = beta[c];
     const float* xp = x + p * L + lo;
     const float* gp = gy + p * L + lo;
+    const bool vec = (L & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    const int nv = vec ? n >> 2 : 0;
     float s1 = 0.f, s2 = 0.f;
     double d1 = 0.0, d2 = 0.0;
     int cnt = 0;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) {
+    {
+        const float4* x4 = reinterpret_cast<const float4*>(xp);
+        const float4* g4 = reinterpret_cast<const float4*>(gp);
+        float4* gn4 = reinterpret_cast<float4*>(gn_s);
+        float4* xh4 = reinterpret_cast<float4*>(xh_s);
+        for (int i = threadIdx.x; i < nv; i += kNormThreads) {
+            const float4 xv = __ldcs(x4 + i), gv = __ldcs(g4 + i);
+            float4 xh, gn;
+            xh.x = (xv.x - mu) * rstd; xh.y = (xv.y - mu) * rstd; xh.z = (xv.z - mu) * rstd; xh.w = (xv.w - mu) * rstd;
+            gn = gv;
+            if (non_lin) {
+                gn.x *= gelu_grad_f(fmaf(xh.x, ga, be)); gn.y *= gelu_grad_f(fmaf(xh.y, ga, be));
+                gn.z *= gelu_grad_f(fmaf(xh.z, ga, be)); gn.w *= gelu_grad_f(fmaf(xh.w, ga, be));
+            }
+            gn4[i] = gn;
+            xh4[i] = xh;
+            s1 += (gn.x + gn.y) + (gn.z + gn.w);
+            s2 = fmaf(gn.x, xh.x, s2); s2 = fmaf(gn.y, xh.y, s2); s2 = fmaf(gn.z, xh.z, s2); s2 = fmaf(gn.w, xh.w, s2);
+            if (++cnt == 16) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+        }
+    }
+    for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) {
         const float xh = (xp[i] - mu) * rstd;
         const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
         gn_s[i] = gn;
         xh_s[i] = xh;
         s1 += gn;
         s2 = fmaf(gn, xh, s2);
-        if (++cnt == 64) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
+        if (++cnt == 16) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
     }
     d1 += s1; d2 += s2;
     const double b1 = block_sum(d1, sh);
@@ -122,7 +170,16 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const fl
     const float m1 = (float)(t1 / (double)L), m2 = (float)(t2 / (double)L);
     const float k = ga * rstd;
     float* op = g + p * L + lo;
-    for (int i = threadIdx.x; i < n; i += kNormThreads) op[i] = k * (gn_s[i] - m1 - xh_s[i] * m2);
+    {
+        const float4* gn4 = reinterpret_cast<const float4*>(gn_s);
+        const float4* xh4 = reinterpret_cast<const float4*>(xh_s);
+        float4* o4 = reinterpret_cast<float4*>(op);
+        for (int i = threadIdx.x; i < nv; i += kNormThreads) {
+            const float4 a = gn4[i], b = xh4[i];
+            o4[i] = make_float4(k * (a.x - m1 - b.x * m2), k * (a.y - m1 - b.y * m2), k * (a.z - m1 - b.z * m2), k * (a.w - m1 - b.w * m2));
+        }
+    }
+    for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) op[i] = k * (gn_s[i] - m1 - xh_s[i] * m2);
     cluster.sync();
 }
 

@@ -321,25 +321,39 @@ __global__ void __launch_bounds__(256) mid2_kernel(const Mid2K k) {
     // arithmetic of chunk c (out-of-range elements are zero-filled through src-size 0)
     const size_t ms_elems = (size_t)k.HK * JTP + (((size_t)k.HK * JTP) & 1);
     const size_t buf_elems = ms_elems + (size_t)k.ppc * k.HK * IT;
+    // Staging cursors without divisions: element idx = tid + 256*n of a chunk maps to (j, h) resp. (plane g, h, i); the
+    // mapping is the same for every chunk, so the first one is divided out once and the others follow by carry
+    // propagation (the index arithmetic used to cost a quarter of the kernel's instructions).
+    const int m_h0 = tid % k.HK, m_j0 = tid / k.HK, m_dh = 256 % k.HK, m_dj = 256 / k.HK;
+    const int x_i0 = tid % IT, x_r0 = tid / IT, x_di = 256 % IT, x_dr = 256 / IT;
     auto stage = [&](int h0, int buf) {
         float2* Mb = msm + (size_t)buf * buf_elems;
         float2* Xb = Mb + ms_elems;
         const int hk = min(k.HK, k.H - h0);
-        for (int idx = tid; idx < JT * k.HK; idx += 256) {
-            const int h = idx % k.HK, j = idx / k.HK;
-            const bool on = j0 + j < k.J && h < hk;
-            const float2* src = on ? k.Mat + (long)(j0 + j) * k.H + h0 + h : k.Mat;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Mb + h * JTP + j);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+        {
+            int h = m_h0, j = m_j0;
+            for (int idx = tid; idx < JT * k.HK; idx += 256) {
+                const bool on = j0 + j < k.J && h < hk;
+                const float2* src = on ? k.Mat + (long)(j0 + j) * k.H + h0 + h : k.Mat;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Mb + h * JTP + j);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+                h += m_dh; j += m_dj;
+                if (h >= k.HK) { h -= k.HK; ++j; }
+            }
         }
-        for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
-            const int i = idx % IT;
-            const int r = idx / IT;
-            const int h = r % k.HK, g = r / k.HK;
-            const bool on = o0 + g < k.O && h < hk && i0 + i < k.I;
-            const float2* src = on ? k.X + ((o0 + g) * k.H + h0 + h) * (long)k.I + i0 + i : k.X;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xb + idx);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+        {
+            int i = x_i0, r = x_r0;                      // r = g * HK + h
+            int h = r % k.HK, g = r / k.HK;
+            const int x_dh = x_dr % k.HK, x_dg = x_dr / k.HK;
+            for (int idx = tid; idx < k.ppc * k.HK * IT; idx += 256) {
+                const bool on = o0 + g < k.O && h < hk && i0 + i < k.I;
+                const float2* src = on ? k.X + ((o0 + g) * k.H + h0 + h) * (long)k.I + i0 + i : k.X;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Xb + idx);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(on ? 8 : 0) : "memory");
+                i += x_di; h += x_dh; g += x_dg;
+                if (i >= IT) { i -= IT; ++h; }
+                if (h >= k.HK) { h -= k.HK; ++g; }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };

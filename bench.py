@@ -217,7 +217,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: while the communicator is created, file descriptor 1 points at stderr so that
+        # NCCL's own banner ("NCCL version ...", written straight to stdout under NCCL_DEBUG=VERSION/WARN) lands there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     from uno_b200 import _lib, build as _build
     from uno_b200.losses import LpLoss
     from uno_b200.parallel import GradReducer

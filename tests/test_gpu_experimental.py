@@ -1,0 +1,144 @@
+"""GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
+(tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction).  They are off by default in the library
+(UNO_B200_MID_TC / UNO_B200_CMM_TC) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+`pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
+
+    UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import BWD_TOL, FWD_TOL, rel_err
+from oracle import uno_oracle as orc
+
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("UNO_B200_EXPERIMENTAL", "0") in ("", "0"), reason="opt-in: UNO_B200_EXPERIMENTAL=1"),
+]
+
+
+def _with_env(fn, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        out = fn()
+        torch.cuda.synchronize()
+        return out
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+# (B, Ci, Co, in, out, modes): leading-axis sizes with one / two / four column tiles of the transform matrix, ragged row
+# tiles (B*C*modes2 not a multiple of 128), ragged last k chunk (2*H % 32 != 0), odd trailing extents; channel counts that
+# give the contraction partial row tiles (2*Co % 128 != 0), several column tiles (B > 128) and a ragged k chunk (Ci % 16 != 0)
+SHAPES_2D = [
+    (8, 8, 8, (64, 64), (64, 64), (20, 20)),
+    (4, 16, 24, (48, 40), (130, 36), (12, 9)),
+    (2, 32, 64, (481, 64), (240, 32), (18, 18)),
+    (3, 5, 7, (33, 31), (45, 29), (7, 5)),
+    (32, 32, 32, (32, 32), (32, 32), (6, 6)),
+    (4, 192, 192, (16, 16), (16, 16), (6, 6)),
+    (130, 9, 70, (24, 24), (20, 20), (5, 4)),
+]
+
+
+@pytest.mark.parametrize("which", ["mid", "cmm", "both"])
+@pytest.mark.parametrize("shape", SHAPES_2D)
+def test_spectral2d_experimental_tc(shape, which, cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    B, Ci, Co, idim, odim, modes = shape
+    torch.manual_seed(0)
+    m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
+    x = torch.randn(B, Ci, *idim, device="cuda")
+    gy = torch.randn(B, Co, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        y.backward(gy)
+        return (y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy(),
+                torch.view_as_real(m.weights2.grad).cpu().numpy())
+
+    env = {"UNO_B200_MID_TC": int(which in ("mid", "both")), "UNO_B200_CMM_TC": int(which in ("cmm", "both"))}
+    y_tc, gx_tc, gw1_tc, gw2_tc = _with_env(run, **env)
+    ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
+    y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)
+    gx_or, gw_or = orc.spectral_conv_bwd(x.cpu().numpy(), ws, odim, modes, gy.cpu().numpy())
+    assert rel_err(y_tc, y_or) < FWD_TOL, rel_err(y_tc, y_or)
+    assert rel_err(gx_tc, gx_or) < BWD_TOL, rel_err(gx_tc, gx_or)
+    assert rel_err(gw1_tc[..., 0] + 1j * gw1_tc[..., 1], gw_or[0]) < BWD_TOL
+    assert rel_err(gw2_tc[..., 0] + 1j * gw2_tc[..., 1], gw_or[1]) < BWD_TOL
+
+
+SHAPES_3D = [
+    (2, 4, 6, (16, 16, 13), (12, 12, 13), (5, 5, 4)),
+    (1, 8, 16, (24, 20, 21), (24, 20, 21), (8, 6, 5)),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES_3D)
+def test_spectral3d_experimental_tc(shape, cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    B, Ci, Co, idim, odim, modes = shape
+    torch.manual_seed(0)
+    m = ops.SpectralConv3d_Uno(Ci, Co, *odim, *modes).cuda()
+    x = torch.randn(B, Ci, *idim, device="cuda")
+    gy = torch.randn(B, Co, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        y.backward(gy)
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), [torch.view_as_real(w.grad).cpu().numpy() for w in (m.weights1, m.weights2, m.weights3, m.weights4)]
+
+    y_tc, gx_tc, gw_tc = _with_env(run, UNO_B200_MID_TC=1, UNO_B200_CMM_TC=1)
+    y_si, gx_si, gw_si = _with_env(run, UNO_B200_MID_TC=0, UNO_B200_CMM_TC=0)
+    # the default kernels are pinned to the oracle by tests/test_gpu_parity.py; here the two device paths are compared
+    assert rel_err(y_tc, y_si) < FWD_TOL, rel_err(y_tc, y_si)
+    assert rel_err(gx_tc, gx_si) < BWD_TOL, rel_err(gx_tc, gx_si)
+    for a, b in zip(gw_tc, gw_si):
+        assert rel_err(a, b) < BWD_TOL, rel_err(a, b)
+
+
+def test_experimental_tc_timing(cuda_lib, capsys):
+    """Not an assertion: prints per-launch times of the default and the tcgen05 paths at the NS-2D inner level and the Darcy top level."""
+    from uno_b200 import integral_operators as ops
+
+    for (B, Ci, Co, idim, odim, modes) in [(64, 192, 192, (16, 16), (16, 16), (6, 6)), (32, 32, 64, (481, 481), (240, 240), (18, 18))]:
+        torch.manual_seed(0)
+        m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
+        x = torch.randn(B, Ci, *idim, device="cuda", requires_grad=True)
+        gy = torch.randn(B, Co, *odim, device="cuda")
+
+        def step():
+            m.zero_grad(set_to_none=True)
+            x.grad = None
+            m(x).backward(gy)
+
+        for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
+                    {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1}):
+            def timed():
+                for _ in range(3):
+                    step()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 10
+
+            ms = _with_env(timed, **env)
+            with capsys.disabled():
+                print(f"\n[experimental] B={B} C={Ci}->{Co} {idim}->{odim} modes={modes} {env}: {ms:.3f} ms fwd+bwd")

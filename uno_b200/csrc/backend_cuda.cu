@@ -27,6 +27,8 @@
 #include "backend.h"
 #include "tc_rowgemm.cuh"
 #include "tc_kpipe.cuh"
+#include "tc_mid.cuh"
+#include "tc_cmm.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
 
@@ -938,6 +940,9 @@ int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, int shifts, TcI
 struct TcKpImage { float* dev = nullptr; int N_t = 0, n_chunks = 0; };
 std::map<TcKey, TcKpImage> g_tc_kp_images;
 
+struct TcMidImage { float* dev = nullptr; int N_t = 0, n_tiles = 0, n_chunks = 0; };
+std::map<TcKey, TcMidImage> g_tc_mid_images;
+
 void tc_forget(const void* p) {
     std::lock_guard<std::mutex> lk(g_tc_mu);
     for (auto it = g_tc_images.begin(); it != g_tc_images.end();) {
@@ -945,6 +950,9 @@ void tc_forget(const void* p) {
     }
     for (auto it = g_tc_kp_images.begin(); it != g_tc_kp_images.end();) {
         if (it->first.p == p) { cudaFree(it->second.dev); it = g_tc_kp_images.erase(it); } else ++it;
+    }
+    for (auto it = g_tc_mid_images.begin(); it != g_tc_mid_images.end();) {
+        if (it->first.p == p) { cudaFree(it->second.dev); it = g_tc_mid_images.erase(it); } else ++it;
     }
 }
 
@@ -1041,6 +1049,141 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     int gx = num_sms();
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     tc::kpipe_kernel<<<gx, tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- leading-axis complex transform on tcgen05 (tc_mid.cuh), opt-in: UNO_B200_MID_TC=1 -------------------------------
+// Image of the real expansion of the complex matrix Mat[J, H] (device, interleaved):
+//   B[(h,re), (j,re)] = Re   B[(h,im), (j,re)] = -Im   B[(h,re), (j,im)] = Im   B[(h,im), (j,im)] = Re
+// per column tile: [chunk][hi | lo], half = (KC/4) x N_t x 16 bytes, element (n, k) at ((k%32)/4)*N_t*4 + n*4 + k%4.
+int tc_get_mid_image(const float* Mat, int J, int H, TcMidImage* out) {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    TcKey key{Mat, H, J, 0};
+    auto it = g_tc_mid_images.find(key);
+    if (it != g_tc_mid_images.end()) { *out = it->second; return 0; }
+    TcMidImage img;
+    const int N = 2 * J, K = 2 * H;
+    img.n_tiles = (N + 255) / 256;
+    const int per = (N + img.n_tiles - 1) / img.n_tiles;
+    img.N_t = ((per + 15) / 16) * 16;
+    img.n_chunks = (K + tc::kKC - 1) / tc::kKC;
+    std::vector<float> hM((size_t)J * H * 2);
+    cudaError_t e = cudaMemcpy(hM.data(), Mat, hM.size() * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    const size_t half = (size_t)img.N_t * tc::kKC;
+    std::vector<float> h((size_t)img.n_tiles * img.n_chunks * 2 * half, 0.0f);
+    for (int j = 0; j < J; ++j)
+        for (int hh = 0; hh < H; ++hh) {
+            const float re = hM[((size_t)j * H + hh) * 2], im = hM[((size_t)j * H + hh) * 2 + 1];
+            for (int ci = 0; ci < 2; ++ci)
+                for (int co = 0; co < 2; ++co) {
+                    const float b = (ci == co) ? re : (ci == 1 ? -im : im);
+                    const int k = 2 * hh + ci, n = 2 * j + co;
+                    const int t = n / img.N_t, nl = n % img.N_t;
+                    const int c = k / tc::kKC, kk = k % tc::kKC;
+                    const float hi = tf32_rn(b);
+                    const float lo = tf32_rn(b - hi);
+                    const size_t base = ((size_t)t * img.n_chunks + c) * 2 * half;
+                    const size_t o = (size_t)(kk / 4) * img.N_t * 4 + (size_t)nl * 4 + (kk % 4);
+                    h[base + o] = hi;
+                    h[base + half + o] = lo;
+                }
+        }
+    e = cudaMalloc(&img.dev, h.size() * 4);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return (int)e;
+    g_tc_mid_images[key] = img;
+    *out = img;
+    return 0;
+}
+
+bool mid_tc_enabled() {
+    const char* e = getenv("UNO_B200_MID_TC");
+    return e && e[0] && e[0] != '0';
+}
+
+// returns -1 when the shape is not taken (the caller runs the SIMT kernel)
+int try_tc_mid(const MidArgs& a, cudaStream_t st) {
+    if (!mid_tc_enabled() || !tc_enabled()) return -1;
+    const long R = (long)a.O * a.I;
+    if (a.H < 4 || a.J < 4 || R < 128) return -1;
+    if ((reinterpret_cast<uintptr_t>(a.X) & 7) || (reinterpret_cast<uintptr_t>(a.Y) & 7)) return -1;
+    bool capturing = false;
+    {   // the first call for a matrix builds its image with synchronous copies: not inside a stream capture
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) capturing = true;
+    }
+    if (capturing) {
+        std::lock_guard<std::mutex> lk(g_tc_mu);
+        if (g_tc_mid_images.find(TcKey{a.Mat, a.H, a.J, 0}) == g_tc_mid_images.end()) return -1;
+    }
+    TcMidImage img;
+    int rc = tc_get_mid_image(a.Mat, a.J, a.H, &img);
+    if (rc) return rc;
+    int stages = (int)((200 * 1024) / tc::kpipe_stage_bytes(img.N_t));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return -1;
+    tc::MidTcParams p;
+    p.X = a.X; p.Y = a.Y; p.Bimg = img.dev;
+    p.O = a.O; p.H = a.H; p.J = a.J; p.I = a.I;
+    p.R = R; p.K = 2 * a.H;
+    p.N_t = img.N_t; p.n_tiles = img.n_tiles; p.n_chunks = img.n_chunks; p.stages = stages;
+    p.m_tiles = (R + 127) / 128;
+    int cols = 32;
+    while (cols < 2 * img.N_t) cols *= 2;
+    p.tmem_cols = cols;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::mid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    int gx = std::max(1, num_sms() / img.n_tiles);
+    if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
+    tc::mid_tc_kernel<<<dim3(gx, img.n_tiles), tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- per-mode complex contraction on tcgen05 (tc_cmm.cuh), opt-in: UNO_B200_CMM_TC=1 ---------------------------------
+bool cmm_tc_enabled() {
+    const char* e = getenv("UNO_B200_CMM_TC");
+    return e && e[0] && e[0] != '0';
+}
+
+// returns -1 when the shape is not taken (the caller runs the SIMT kernels)
+int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
+    if (!cmm_tc_enabled() || !tc_enabled()) return -1;
+    if (a.K < 4 || a.M < 4 || a.N < 8) return -1;
+    for (int c = 0; c < a.ncorner; ++c)
+        if ((reinterpret_cast<uintptr_t>(a.A[c]) & 7) || (reinterpret_cast<uintptr_t>(a.B[c]) & 7) || (reinterpret_cast<uintptr_t>(a.C[c]) & 7))
+            return -1;
+    tc::CmmTcParams p;
+    p.a = a;
+    p.ns_tiles = (a.M + 127) / 128;
+    const int per = (a.M + p.ns_tiles - 1) / p.ns_tiles;
+    p.N_t = ((per + 15) / 16) * 16;
+    p.ms_tiles = (2 * a.N + 127) / 128;
+    p.n_chunks = (a.K + tc::kCmKC - 1) / tc::kCmKC;
+    int stages = (int)((200 * 1024) / tc::kpipe_stage_bytes(p.N_t));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return -1;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * p.N_t) cols *= 2;
+    p.tmem_cols = cols;
+    p.items = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * a.q_inner;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::cmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    long gx = num_sms();
+    if (gx > p.items) gx = p.items;
+    tc::cmm_tc_kernel<<<(unsigned)gx, tc::kKpThreads, tc::kpipe_smem_bytes(p.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1364,6 +1507,10 @@ int be_mid(const MidArgs& a, stream_t s) {
     const size_t smem = 2 * (ms + (size_t)k.ppc * k.HK * IT) * sizeof(float2);   // double buffered
     const long blocks = (long)((a.O + k.ppc - 1) / k.ppc) * k.tilesJ * k.tilesI;
     ProfScope ps("dft_mid", 8.0 * ((double)a.O * a.I * (a.H + a.J) + (double)a.J * a.H), 8.0 * a.O * (double)a.J * a.H * a.I, S(s));
+    {
+        const int rc = try_tc_mid(a, S(s));   // opt-in tcgen05 path (UNO_B200_MID_TC=1)
+        if (rc >= 0) return rc;
+    }
     switch (TJ * 10 + TI) {
         case 42: return launch_mid2<4, 2>(k, smem, blocks, threads, S(s));
         case 32: return launch_mid2<3, 2>(k, smem, blocks, threads, S(s));
@@ -1379,6 +1526,10 @@ int be_cmm(const CmmArgs& a, stream_t s) {
     const int chunks = (a.q_inner + 31) / 32;
     const double q = (double)a.q_inner * a.q_outer * a.ncorner;
     ProfScope ps("mode_contraction", 8.0 * q * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N), 8.0 * q * a.M * a.N * a.K, S(s));
+    {
+        const int rc = try_tc_cmm(a, S(s));   // opt-in tcgen05 path (UNO_B200_CMM_TC=1)
+        if (rc >= 0) return rc;
+    }
     if (a.M >= 16 && a.N >= 16) {
         // enough rows and columns to fill 32 x 32 tiles: the shared-memory tiled kernel (4 modes per CTA)
         const int qchunks = (a.q_inner + kC2Q - 1) / kC2Q;

@@ -1,6 +1,7 @@
 """GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
-(tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction).  They are off by default in the library
-(UNO_B200_MID_TC / UNO_B200_CMM_TC) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+(tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
+rows that are not 16-byte aligned).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
+UNO_B200_KPIPE_ALIGN) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
 `pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
 
     UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
@@ -79,6 +80,59 @@ def test_spectral2d_experimental_tc(shape, which, cuda_lib):
     assert rel_err(gw2_tc[..., 0] + 1j * gw2_tc[..., 1], gw_or[1]) < BWD_TOL
 
 
+# last-axis analysis with rows that are not 16-byte aligned and >= 512 rows: pitches = 1, 2, 3 mod 4, ragged 512-row blocks,
+# a ragged last chunk, inputs narrower and wider than one chunk ring
+SHAPES_ALIGN = [
+    (4, 8, 2, (40, 481), (20, 240), (5, 18)),
+    (3, 6, 4, (30, 83), (30, 83), (6, 5)),
+    (3, 9, 3, (33, 130), (16, 64), (4, 9)),
+    (5, 7, 2, (17, 223), (17, 111), (3, 33)),
+    (3, 4, 4, (129, 67), (64, 67), (8, 12)),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES_ALIGN)
+def test_analysis_row_classes(shape, cuda_lib):
+    from uno_b200 import integral_operators as ops
+
+    B, Ci, Co, idim, odim, modes = shape
+    torch.manual_seed(0)
+    m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
+    x = torch.randn(B, Ci, *idim, device="cuda")
+    # non-finite values in the first and the last sample must not leak into the samples between them (the aligned loads of a
+    # row start in the tail of the previous row and end in the head of the next one; both ends are masked)
+    x[0] = float("inf")
+    x[-1] = float("inf")
+    gy = torch.randn(B, Co, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        return y.detach()[1:-1].cpu().numpy()
+
+    y_al = _with_env(run, UNO_B200_KPIPE_ALIGN=1)
+    y_df = _with_env(run, UNO_B200_KPIPE_ALIGN=0)
+    assert np.isfinite(y_al).all()
+    assert rel_err(y_al, y_df) < FWD_TOL, rel_err(y_al, y_df)
+    x[0] = torch.randn_like(x[0])
+    x[-1] = torch.randn_like(x[-1])
+
+    def run2():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        y.backward(gy)
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy()
+
+    a = _with_env(run2, UNO_B200_KPIPE_ALIGN=1)
+    b = _with_env(run2, UNO_B200_KPIPE_ALIGN=0)
+    ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
+    y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)
+    assert rel_err(a[0], y_or) < FWD_TOL, rel_err(a[0], y_or)
+    assert rel_err(a[1], b[1]) < BWD_TOL and rel_err(a[2], b[2]) < BWD_TOL
+
+
 SHAPES_3D = [
     (2, 4, 6, (16, 16, 13), (12, 12, 13), (5, 5, 4)),
     (1, 8, 16, (24, 20, 21), (24, 20, 21), (8, 6, 5)),
@@ -127,7 +181,8 @@ def test_experimental_tc_timing(cuda_lib, capsys):
             m(x).backward(gy)
 
         for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
-                    {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1}):
+                    {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1},
+                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1}):
             def timed():
                 for _ in range(3):
                     step()

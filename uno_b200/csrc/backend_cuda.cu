@@ -987,28 +987,35 @@ int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
 // chunk-major image for the K-pipelined kernel: [chunk][hi | lo], half = (KC/4) x N_t x 16 bytes,
 // element (n, k) of chunk c at float offset ((k%32)/4)*N_t*4 + n*4 + k%4
 
-int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out) {
+// `lda_mod4` < 0: one image.  Otherwise the four row-class images of tc_kpipe.cuh follow each other ([class][chunk][hi | lo]),
+// all with ceil((K + 3) / 32) chunks: class c holds B shifted down by sh = (c * lda) % 4 rows (rows k' < sh are zero).
+int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, int lda_mod4 = -1) {
     std::lock_guard<std::mutex> lk(g_tc_mu);
-    TcKey key{B, K, N, ldb};
+    TcKey key{B, K, N, ldb, lda_mod4 < 0 ? 0 : 4 + lda_mod4};
     auto it = g_tc_kp_images.find(key);
     if (it != g_tc_kp_images.end()) { *out = it->second; return 0; }
     TcKpImage img;
+    const int classes = lda_mod4 < 0 ? 1 : 4;
     img.N_t = ((N + 15) / 16) * 16;
-    img.n_chunks = (K + tc::kKC - 1) / tc::kKC;
+    img.n_chunks = ((lda_mod4 < 0 ? K : K + 3) + tc::kKC - 1) / tc::kKC;
     std::vector<float> hB((size_t)K * N);
     cudaError_t e = cudaMemcpy2D(hB.data(), (size_t)N * 4, B, (size_t)ldb * 4, (size_t)N * 4, K, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return (int)e;
     const size_t half = (size_t)img.N_t * tc::kKC;
-    std::vector<float> h((size_t)img.n_chunks * 2 * half, 0.0f);
-    for (int k = 0; k < K; ++k) {
-        const int c = k / tc::kKC, kk = k % tc::kKC;
-        for (int n = 0; n < N; ++n) {
-            const float b = hB[(size_t)k * N + n];
-            const float hi = tf32_rn(b);
-            const float lo = tf32_rn(b - hi);
-            const size_t o = (size_t)(kk / 4) * img.N_t * 4 + (size_t)n * 4 + (kk % 4);
-            h[(size_t)c * 2 * half + o] = hi;
-            h[(size_t)c * 2 * half + half + o] = lo;
+    std::vector<float> h((size_t)classes * img.n_chunks * 2 * half, 0.0f);
+    for (int cls = 0; cls < classes; ++cls) {
+        const int sh = lda_mod4 < 0 ? 0 : (cls * lda_mod4) % 4;
+        const size_t cbase = (size_t)cls * img.n_chunks * 2 * half;
+        for (int k = 0; k < K; ++k) {
+            const int c = (k + sh) / tc::kKC, kk = (k + sh) % tc::kKC;
+            for (int n = 0; n < N; ++n) {
+                const float b = hB[(size_t)k * N + n];
+                const float hi = tf32_rn(b);
+                const float lo = tf32_rn(b - hi);
+                const size_t o = (size_t)(kk / 4) * img.N_t * 4 + (size_t)n * 4 + (kk % 4);
+                h[cbase + (size_t)c * 2 * half + o] = hi;
+                h[cbase + (size_t)c * 2 * half + half + o] = lo;
+            }
         }
     }
     e = cudaMalloc(&img.dev, h.size() * 4);
@@ -1027,18 +1034,27 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     int stages = (int)((200 * 1024) / tc::kpipe_stage_bytes(N_t));
     if (stages > 4) stages = 4;
     if (stages < 2) return -1;
+    const bool a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    // opt-in row-class mode (tc_kpipe.cuh) for rows that are not 16-byte aligned: UNO_B200_KPIPE_ALIGN=1
+    bool rclass = false;
+    if (!a_vec_ok && a.a_rs % 4 != 0 && a.a_rs >= 8 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && a.N % 2 == 0 && a.ldc % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && a.M >= 512) {
+        const char* e = getenv("UNO_B200_KPIPE_ALIGN");
+        rclass = e && e[0] && e[0] != '0';
+    }
     TcKpImage img;
-    int rc = tc_get_kpipe_image(a.B, a.ldb, a.K, a.N, &img);
+    int rc = tc_get_kpipe_image(a.B, a.ldb, a.K, a.N, &img, rclass ? (int)(a.a_rs % 4) : -1);
     if (rc) return rc;
     tc::KPipeParams p;
     p.A = a.A; p.lda = a.a_rs; p.R = a.M;
     p.Bimg = img.dev; p.C = a.C; p.ldc = a.ldc;
-    p.N = a.N; p.K = a.K; p.N_t = img.N_t; p.n_chunks = img.n_chunks; p.stages = stages;
-    p.m_tiles = ((long)a.M + 127) / 128;
+    p.N = a.N; p.K = rclass ? a.K + 3 : a.K; p.N_t = img.N_t; p.n_chunks = img.n_chunks; p.stages = stages;
+    p.rclass = rclass ? 1 : 0; p.k_valid = a.K;
+    p.m_tiles = rclass ? 4 * (((long)a.M + 511) / 512) : ((long)a.M + 127) / 128;
     int cols = 32;
     while (cols < 2 * img.N_t) cols *= 2;
     p.tmem_cols = cols;
-    p.a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
+    p.a_vec_ok = a_vec_ok;
     { const char* e = getenv("UNO_B200_KPIPE_DEBUG"); p.debug = e ? atoi(e) : 0; }
     static bool configured = false;
     if (!configured) {
@@ -1047,6 +1063,7 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
         configured = true;
     }
     int gx = num_sms();
+    if (rclass) gx &= ~3;                   // a CTA must only ever see tiles of one row class (m_tiles is a multiple of 4 too)
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     tc::kpipe_kernel<<<gx, tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();

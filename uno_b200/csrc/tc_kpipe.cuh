@@ -29,10 +29,20 @@ struct KPipeParams {
     long m_tiles;
     int tmem_cols;
     int a_vec_ok;          // rows 16-byte aligned (lda % 4 == 0, base aligned)
+    int rclass;            // opt-in (UNO_B200_KPIPE_ALIGN=1) for rows that are NOT 16-byte aligned: see "row classes" below
+    int k_valid;           // row-class mode: the real contraction length (K is then k_valid + 3, the longest shifted row)
     int debug;             // timing probes (UNO_B200_KPIPE_DEBUG, results are garbage): 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads,
                            // 16 no proxy fence
 };
 
+// Row classes (rclass = 1).  With an odd row pitch (the 481-wide Darcy grid, the 83-long NS-3D time axis) only every fourth
+// row starts on a 16-byte boundary and the loaders fall to 4-byte loads, whose instruction count is what bounds this kernel
+// (tools/kpipe_probe.py: 0.69 us per chunk against 0.39 us with 16-byte loads).  In this mode a tile holds 128 rows of ONE
+// residue class mod 4 out of a block of 512 (row = 512*(tile/4) + 4*i + tile%4) and a CTA only ever sees one class (the grid
+// is a multiple of 4).  All rows of a class start the same number of floats sh = (class*lda) % 4 past a 16-byte boundary, so
+// the loaders read each row from that boundary with 16-byte loads -- the contraction index is then shifted by sh -- and the
+// CTA streams a B image whose rows are shifted by the same sh (rows k' < sh are zero; the loaders also zero those elements,
+// which belong to the previous row).  The same idea as the column-shifted twiddle image of tc_rowgemm.cuh's parity mode.
 constexpr int kKC = 32;                       // K elements per stage
 constexpr int kKpLoadWarps = 8;
 constexpr int kKpDepth = 4;                   // chunks of global loads kept in flight per loader thread
@@ -141,6 +151,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
         int p_kc = 0, p_s = 0;
         uint32_t p_ph = 0;
         const uint32_t img_chunk_floats = 2 * b_half / 4;
+        const float* bimg = p.Bimg + (p.rclass ? (size_t)(blockIdx.x & 3) * NKC * img_chunk_floats : (size_t)0);
         auto stage_prologue = [&]() -> uint8_t* {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
@@ -148,7 +159,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 if (p.debug & 4) mbar_arrive(&full[p_s]);
                 else {
                     mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
-                    bulk_g2s(st + 2 * kKpAHalf, p.Bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
+                    bulk_g2s(st + 2 * kKpAHalf, bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
                 }
             }
             return st;
@@ -159,7 +170,64 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
             if (++p_kc == NKC) p_kc = 0;
         };
-        if (p.a_vec_ok) {
+        if (p.rclass) {
+            // row-class path: 16-byte loads from the 16-byte boundary at or before the row start (see "row classes" above)
+            const int cls = (int)(blockIdx.x & 3);
+            const int sh = (int)(((long)cls * p.lda) & 3);
+            const int kq = ltid & 7, rbase = ltid >> 3;
+            const long stride32 = 128 * p.lda;                // rows 32 apart in the tile are 128 apart in the tensor
+            const int k_end = p.k_valid + sh;                 // shifted index k' is real iff sh <= k' < k_end
+            const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
+            float4 ring[kKpDepth][4];
+            auto issue = [&](float4 (&v)[4]) {
+                const long row0 = (i_tile >> 2) * 512 + 4 * rbase + cls;
+                const int k0 = i_kc * kKC + kq * 4;
+                const float* src = p.A + row0 * p.lda - sh + k0;
+                const long rows_left = p.R - row0;            // row (128*i) valid iff 128*i < rows_left
+                if (k0 >= sh && k0 + 4 <= k_end) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        v[i] = (128 * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (128 * i < rows_left) {
+                            const float* q = src + i * stride32;
+                            if (k0 + 0 >= sh && k0 + 0 < k_end) v[i].x = __ldg(q + 0);
+                            if (k0 + 1 >= sh && k0 + 1 < k_end) v[i].y = __ldg(q + 1);
+                            if (k0 + 2 >= sh && k0 + 2 < k_end) v[i].z = __ldg(q + 2);
+                            if (k0 + 3 >= sh && k0 + 3 < k_end) v[i].w = __ldg(q + 3);
+                        }
+                    }
+                }
+                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
+            };
+            auto process = [&](const float4 (&v)[4]) {
+                uint8_t* st = stage_prologue() + so;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 hi, lo;
+                    split_tf32(v[i].x, hi.x, lo.x);
+                    split_tf32(v[i].y, hi.y, lo.y);
+                    split_tf32(v[i].z, hi.z, lo.z);
+                    split_tf32(v[i].w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(st + i * 512) = hi;
+                    *reinterpret_cast<float4*>(st + kKpAHalf + i * 512) = lo;
+                }
+                stage_epilogue();
+            };
+#pragma unroll
+            for (int d = 0; d < kKpDepth - 1; ++d)
+                if (d < total) issue(ring[d]);
+            for (long g = 0; g < total; g += kKpDepth) {
+#pragma unroll
+                for (int d = 0; d < kKpDepth; ++d) {
+                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                    if (g + d < total) process(ring[d]);
+                }
+            }
+        } else if (p.a_vec_ok) {
             // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
             const int kq = ltid & 7, rbase = ltid >> 3;
             const long stride32 = 32 * p.lda;
@@ -265,6 +333,25 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
             mbar_wait_relaxed(&d_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
+            if (p.rclass) {
+                // row-class mode: thread = one row of the class, float2 stores (N even, ldc even, C 8-byte aligned: host-checked)
+                const long grow = (tile >> 2) * 512 + 4 * (q * 32 + lane) + (tile & 3);
+                float* crow = p.C + (grow < p.R ? grow : 0) * p.ldc;
+                for (int c0 = 0; c0 < p.N; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(t_base + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (grow < p.R) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (c0 + 2 * u < p.N)
+                                *reinterpret_cast<float2*>(crow + c0 + 2 * u) = make_float2(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&d_empty[buf]);
+                continue;
+            }
             // both column "halves" handled by this warp
             if (vec2) {
                 rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, tile, q, 0, 0, lane);

@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU call for the opt-in kernels (tc_mid.cuh, tc_cmm.cuh, tc_kpipe.cuh row classes): parity against the oracle / the
+# default kernels, then the Darcy, NS-2D and NS-3D benches with and without them.  Everything lands in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/run_experimental_gpu.sh'
+# Each stage has its own timeout so that a hung kernel cannot hold the box until gpurun's limit.
+set -u
+mkdir -p gpurun_out
+OUT=gpurun_out/experimental
+: > $OUT.log
+run() { echo "=== $*" >> $OUT.log; "$@" >> $OUT.log 2>&1; echo "=== exit $?" >> $OUT.log; }
+export UNO_B200_EXPERIMENTAL=1
+for t in test_analysis_row_classes test_spectral2d_experimental_tc test_spectral3d_experimental_tc test_experimental_tc_timing; do
+    run timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q -s -k $t
+done
+unset UNO_B200_EXPERIMENTAL
+for wl in darcy ns2d ns3d; do
+    for flags in "" "UNO_B200_MID_TC=1" "UNO_B200_CMM_TC=1" "UNO_B200_KPIPE_ALIGN=1" "UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1"; do
+        echo "=== bench $wl [$flags]" >> $OUT.log
+        env $flags timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline >> $OUT.log 2>&1
+    done
+done
+tail -5 $OUT.log

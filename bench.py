@@ -56,6 +56,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def measured_traffic(role, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `role`, from the committed ncu --set full capture of
     one step of this workload (profiles/r01_traffic.json, made by tools/ncu_traffic.py); None when there is none."""
@@ -172,6 +180,32 @@ def cpu_reference_run(workload, steps, warmup, batch=None):
     return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"batch {B} of the same workload, {steps} steps after {warmup} warm-up, fp32 torch CPU (oracle/uno_torch_port.py)",
             "ms_per_step": dt * 1e3, "batch": B}
+
+
+def spectral_levels(lib, nprof, hbm_gbs):
+    """Per U-level roofline of the fused spectral convolution (north_star: 'achieved fraction of HBM and tensor-core roofline
+    reported per U-level'): for every distinct call shape and direction, the summed CUDA-event time of the kernels that call
+    launched against its ALGORITHMIC bytes and contraction flops.  The tensor-core peak is taken as half the
+    measured dense bf16 rate (tf32 operands), MEASURED_PEAKS.json.  None if the library cannot report it."""
+    try:
+        n = lib.uno_profile_report_levels(None, 0)
+        buf = C.create_string_buffer(n + 16)
+        lib.uno_profile_report_levels(buf, n + 16)
+        rep = json.loads(buf.value.decode())
+        tf32_peak = 0.5 * measured_peaks().get("bf16_tflops", 1665.0)
+        out = []
+        for label, v in rep.items():
+            if v["ms"] <= 0 or v["calls"] <= 0:
+                continue
+            sec = v["ms"] * 1e-3
+            gbs = v["bytes"] / sec / 1e9
+            tfl = v["flops"] / sec / 1e12
+            out.append({"level": label, "calls_per_step": v["calls"] / nprof, "launches_per_call": v["launches"] / v["calls"],
+                        "ms_per_call": v["ms"] / v["calls"], "algorithmic_bytes_per_call": v["bytes"] / v["calls"],
+                        "GBps": gbs, "hbm_frac": gbs / hbm_gbs, "contraction_TFLOPs": tfl, "tensor_frac": tfl / tf32_peak})
+        return out or None
+    except Exception as e:   # the headline line must survive a reporting problem
+        return {"error": repr(e)}
 
 
 def main():
@@ -300,7 +334,7 @@ def main():
 
     # --- per-kernel roofline, CUDA events around every launch of OUR kernels (separate steps so the
     #     event records do not perturb `value`)
-    roofline, breakdown = None, None
+    roofline, breakdown, levels = None, None, None
     if not args.no_profile:
         # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
         hbm, how = peaks()
@@ -315,6 +349,7 @@ def main():
             n = lib.uno_profile_report(None, 0)
             buf = C.create_string_buffer(n + 16)
             lib.uno_profile_report(buf, n + 16)
+            levels = spectral_levels(lib, nprof, hbm)
             lib.uno_profile_enable(0)
             prof = json.loads(buf.value.decode())
             tot = sum(v["ms"] for v in prof.values()) or 1.0
@@ -344,7 +379,7 @@ def main():
                        "parallelism": f"dp{world} (batch shard, flat-buffer gradient all-reduce)" if world > 1 else "single GPU",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "spectral_levels": levels,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

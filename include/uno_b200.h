@@ -194,10 +194,15 @@ int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const fl
  * uno_profile_enable(1) brackets every kernel launch with a CUDA-event pair on the launching stream;
  * uno_profile_report synchronises the device and writes a JSON object
  *   {"<kernel role>": {"launches": n, "ms": total, "bytes": algorithmic, "flops": algorithmic}, ...}
- * into buf (truncated to cap) and returns the untruncated length.  Off by default.                   */
+ * into buf (truncated to cap) and returns the untruncated length.  Off by default.
+ * uno_profile_report_levels does the same per fused spectral-convolution call shape (one entry per U-level and
+ * direction, "spectral fwd|bwd B=.. Ci->Co [in]->[out] modes=[..]"): its launches' summed time against the call's
+ * ALGORITHMIC bytes (x, y, the spectral weights, + the block epilogue's tensors) and contraction flops
+ *   {"<label>": {"calls": c, "launches": n, "ms": total, "bytes": total, "flops": total}, ...}                */
 long uno_launch_count(void);
 void uno_profile_enable(int on);
 size_t uno_profile_report(char* buf, size_t cap);
+size_t uno_profile_report_levels(char* buf, size_t cap);
 
 /* ---- host-only planning helpers (no GPU touched; exercised by the CPU test-suite) ----------------
  * Each writes the dense fp32 matrix the kernels multiply by.  Sizes: see uno_b200/csrc/plan.h.      */

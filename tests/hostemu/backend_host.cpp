@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../uno_b200/csrc/backend.h"
@@ -26,9 +28,40 @@ const char* be_error_string(int) { return "host emulation error"; }
 stream_t be_side_stream() { return nullptr; }
 int be_fork(stream_t, stream_t) { return 0; }
 int be_join(stream_t, stream_t) { return 0; }
-void be_profile_enable(int) {}
 size_t be_profile_report(char* buf, size_t cap) { if (buf && cap > 2) { buf[0] = '{'; buf[1] = '}'; buf[2] = 0; } return 2; }
 long be_launch_count() { return 0; }
+// scopes are recorded (no timing here: ms = 0) so that the labels and the algorithmic-byte accounting of uno_api.cpp can be
+// checked on the CPU
+namespace {
+struct HostScope { std::string label; long calls; double bytes, flops; };
+std::vector<HostScope> g_scopes;
+bool g_prof = false;
+}
+void be_profile_enable(int on) { if (on && !g_prof) g_scopes.clear(); g_prof = on != 0; }
+int be_profile_enabled() { return g_prof ? 1 : 0; }
+void be_profile_scope_begin(const char* label, double bytes, double flops) {
+    if (!g_prof) return;
+    for (auto& s : g_scopes)
+        if (s.label == label) { s.calls += 1; s.bytes += bytes; s.flops += flops; return; }
+    g_scopes.push_back(HostScope{label, 1, bytes, flops});
+}
+void be_profile_scope_end() {}
+size_t be_profile_report_scopes(char* buf, size_t cap) {
+    std::string out = "{";
+    for (size_t i = 0; i < g_scopes.size(); ++i) {
+        char line[384];
+        snprintf(line, sizeof line, "%s\"%s\": {\"calls\": %ld, \"launches\": 0, \"ms\": 0.0, \"bytes\": %.0f, \"flops\": %.0f}",
+                 i ? ", " : "", g_scopes[i].label.c_str(), g_scopes[i].calls, g_scopes[i].bytes, g_scopes[i].flops);
+        out += line;
+    }
+    out += "}";
+    if (buf && cap) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
+}
 
 static inline float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 static inline float gelu_grad_f(float x) {

@@ -80,3 +80,42 @@ def test_error_codes():
         emu.spectral_fwd(x, [np.zeros((2, 2, 5, 3), np.complex64)] * 2, (4, 8), (5, 3))
     with pytest.raises(RuntimeError, match="pointwise_op_1D"):
         emu.pointwise_fwd(np.zeros((1, 2, 8), np.float32), np.zeros((2, 2), np.float32), np.zeros(2, np.float32), (4,))
+
+
+def test_profile_levels_report_labels_and_algorithmic_bytes():
+    """bench.py's per-U-level roofline: one scope per fused spectral-conv call shape and direction, charged with the
+    algorithmic bytes / contraction flops of SURVEY.md 8(d)."""
+    import ctypes as C
+    import json
+
+    import emu
+
+    L = emu.lib()
+    rng = np.random.default_rng(0)
+    B, Ci, Co, idim, odim, modes = 2, 3, 5, (12, 10), (8, 14), (3, 4)
+    x = rng.standard_normal((B, Ci) + idim).astype(np.float32)
+    ws = [(rng.standard_normal((Ci, Co) + modes) + 1j * rng.standard_normal((Ci, Co) + modes)).astype(np.complex64) for _ in range(2)]
+    L.uno_profile_enable(1)
+    try:
+        for _ in range(2):
+            y, xhat = emu.spectral_fwd(x, ws, odim, modes)
+        emu.spectral_bwd(x.shape, ws, odim, modes, np.ones_like(y), xhat)
+        n = L.uno_profile_report_levels(None, 0)
+        buf = C.create_string_buffer(n + 16)
+        L.uno_profile_report_levels(buf, n + 16)
+    finally:
+        L.uno_profile_enable(0)
+    rep = json.loads(buf.value.decode())
+    fwd = rep["spectral fwd B=2 3->5 [12,10]->[8,14] modes=[3,4]"]
+    bwd = rep["spectral bwd B=2 3->5 [12,10]->[8,14] modes=[3,4]"]
+    n_in, n_out, M, nW = 12 * 10, 8 * 14, 3 * 4, 2
+    fwd_bytes = 4 * B * (Ci * n_in + Co * n_out) + 8 * nW * Ci * Co * M
+    bwd_bytes = 4 * B * (Co * n_out + Ci * n_in) + 8 * B * Ci * nW * M + 16 * nW * Ci * Co * M
+    assert fwd["calls"] == 2 and fwd["bytes"] == 2 * fwd_bytes and fwd["flops"] == 2 * 8 * B * Ci * Co * nW * M
+    assert bwd["calls"] == 1 and bwd["bytes"] == bwd_bytes and bwd["flops"] == 2 * 8 * B * Ci * Co * nW * M
+    # profiling off: nothing is recorded
+    emu.spectral_fwd(x, ws, odim, modes)
+    L.uno_profile_enable(1)
+    n = L.uno_profile_report_levels(None, 0)
+    L.uno_profile_enable(0)
+    assert n == 2

@@ -90,6 +90,7 @@ SYMBOLS = {
     "uno_launch_count": (C.c_long, []),
     "uno_profile_enable": (None, [C.c_int]),
     "uno_profile_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "uno_profile_report_levels": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "uno_plan_dft_last_analysis": (C.c_int, [C.c_int, C.c_int, C.c_double, _P]),
     "uno_plan_dft_last_synthesis": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, _P]),
     "uno_plan_dft_mid_analysis": (C.c_int, [C.c_int, C.c_int, _P]),

@@ -33,6 +33,15 @@ int be_join(stream_t main_stream, stream_t side);
 //   {"tag": {"launches": n, "ms": total, "bytes": total, "flops": total}, ...}
 void be_profile_enable(int on);
 size_t be_profile_report(char* buf, size_t cap);
+// Scopes group the launches of one operator call (a fused spectral convolution at one U-level): between
+// be_profile_scope_begin and be_profile_scope_end every launch of the calling thread is also charged to `label`, together
+// with the call's algorithmic bytes / flops (tensors in and out of the operator, not its intermediates).
+// be_profile_report_scopes writes {"label": {"calls": c, "launches": n, "ms": total, "bytes": total, "flops": total}, ...}.
+// No-ops while profiling is off.
+int be_profile_enabled();
+void be_profile_scope_begin(const char* label, double bytes, double flops);
+void be_profile_scope_end();
+size_t be_profile_report_scopes(char* buf, size_t cap);
 long be_launch_count();                  // kernels launched by this library since load
 
 // ---- C[M,N] = A[M,K] * B[K,N]  (fp32, row-major B and C, strided A), optionally batched -----------

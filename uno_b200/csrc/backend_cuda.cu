@@ -39,10 +39,13 @@ namespace {
 inline cudaStream_t S(stream_t s) { return (cudaStream_t)s; }
 
 // ---- per-launch profiling (off by default) -----------------------------------------------------------
-struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; };
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; int scope; };
+struct ProfScopeInfo { std::string label; long calls = 0; double bytes = 0, flops = 0; };
 bool g_prof_on = false;
 long g_launches = 0;
 std::vector<ProfRec> g_prof;
+std::vector<ProfScopeInfo> g_prof_scopes;
+thread_local int t_prof_scope = -1;
 std::mutex g_prof_mu;
 
 struct ProfScope {
@@ -52,7 +55,7 @@ struct ProfScope {
     ProfScope(const char* tag, double bytes, double flops, cudaStream_t s) : on(g_prof_on), st(s) {
         ++g_launches;
         if (!on) return;
-        ProfRec r{tag, nullptr, nullptr, bytes, flops};
+        ProfRec r{tag, nullptr, nullptr, bytes, flops, t_prof_scope};
         cudaEventCreate(&r.e0);
         cudaEventCreate(&r.e1);
         cudaEventRecord(r.e0, st);
@@ -1333,8 +1336,58 @@ void be_profile_enable(int on) {
     if (on && !g_prof_on) {
         for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
         g_prof.clear();
+        g_prof_scopes.clear();
     }
     g_prof_on = on != 0;
+}
+
+int be_profile_enabled() { return g_prof_on ? 1 : 0; }
+
+void be_profile_scope_begin(const char* label, double bytes, double flops) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int idx = -1;
+    for (size_t i = 0; i < g_prof_scopes.size(); ++i)
+        if (g_prof_scopes[i].label == label) { idx = (int)i; break; }
+    if (idx < 0) {
+        idx = (int)g_prof_scopes.size();
+        g_prof_scopes.push_back(ProfScopeInfo{label});
+    }
+    g_prof_scopes[idx].calls += 1;
+    g_prof_scopes[idx].bytes += bytes;
+    g_prof_scopes[idx].flops += flops;
+    t_prof_scope = idx;
+}
+
+void be_profile_scope_end() { t_prof_scope = -1; }
+
+size_t be_profile_report_scopes(char* buf, size_t cap) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::vector<double> ms(g_prof_scopes.size(), 0.0);
+    std::vector<long> n(g_prof_scopes.size(), 0);
+    for (auto& r : g_prof) {
+        if (r.scope < 0 || r.scope >= (int)g_prof_scopes.size()) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) continue;
+        ms[r.scope] += t;
+        n[r.scope] += 1;
+    }
+    std::string out = "{";
+    for (size_t i = 0; i < g_prof_scopes.size(); ++i) {
+        char line[384];
+        snprintf(line, sizeof line, "%s\"%s\": {\"calls\": %ld, \"launches\": %ld, \"ms\": %.6f, \"bytes\": %.0f, \"flops\": %.0f}",
+                 i ? ", " : "", g_prof_scopes[i].label.c_str(), g_prof_scopes[i].calls, n[i], ms[i], g_prof_scopes[i].bytes,
+                 g_prof_scopes[i].flops);
+        out += line;
+    }
+    out += "}";
+    if (buf && cap) {
+        size_t len = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), len);
+        buf[len] = 0;
+    }
+    return out.size();
 }
 
 size_t be_profile_report(char* buf, size_t cap) {

@@ -371,6 +371,37 @@ void corner_geometry(const SpectralPlan* p, int c, long* off, int* q_outer, int*
     }
 }
 
+// Profiling scope of one fused spectral-convolution call (bench.py's per-U-level roofline): algorithmic bytes and
+// contraction flops as SURVEY.md 8(d) defines them.  `extra_out_tensors`: output-sized tensors the fused block epilogue
+// reads / writes on top of the plain layer (forward: the pointwise sum it accumulates onto and, with GELU to a second
+// tensor, that tensor; backward: none -- the gradient it accumulates onto is counted as the read-modify-write it is).
+struct SpectralProfScope {
+    bool on = false;
+    SpectralProfScope(const uno_conv_desc* d, bool backward, int extra_out_tensors) {
+        if (!be_profile_enabled()) return;
+        const int nd = d->ndim;
+        double n_in = 1, n_out = 1, M = 1;
+        for (int a = 0; a < nd; ++a) { n_in *= d->in_dim[a]; n_out *= d->out_dim[a]; M *= d->modes[a]; }
+        const double nW = (double)(1 << (nd - 1)), B = d->batch, Ci = d->in_ch, Co = d->out_ch;
+        double bytes = 4.0 * B * (Ci * n_in + Co * n_out);
+        if (!backward) bytes += 8.0 * nW * Ci * Co * M;
+        else bytes += 8.0 * B * Ci * nW * M + 16.0 * nW * Ci * Co * M;
+        bytes += 4.0 * B * (backward ? Ci * n_in : Co * n_out) * extra_out_tensors;
+        const double flops = 8.0 * B * Ci * Co * nW * M * (backward ? 2.0 : 1.0);
+        char label[256];
+        int o = snprintf(label, sizeof label, "spectral %s B=%d %d->%d [", backward ? "bwd" : "fwd", d->batch, d->in_ch, d->out_ch);
+        for (int a = 0; a < nd; ++a) o += snprintf(label + o, sizeof label - o, "%s%d", a ? "," : "", d->in_dim[a]);
+        o += snprintf(label + o, sizeof label - o, "]->[");
+        for (int a = 0; a < nd; ++a) o += snprintf(label + o, sizeof label - o, "%s%d", a ? "," : "", d->out_dim[a]);
+        o += snprintf(label + o, sizeof label - o, "] modes=[");
+        for (int a = 0; a < nd; ++a) o += snprintf(label + o, sizeof label - o, "%s%d", a ? "," : "", d->modes[a]);
+        snprintf(label + o, sizeof label - o, "]");
+        be_profile_scope_begin(label, bytes, flops);
+        on = true;
+    }
+    ~SpectralProfScope() { if (on) be_profile_scope_end(); }
+};
+
 int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, const float* const* w,
                       float* y, int epi, float* y2, float* xhat, Arena& ar, stream_t st, stream_t join_side = nullptr) {
     const int nd = d->ndim, nmid = nd - 1, ml = d->modes[nd - 1];
@@ -381,6 +412,7 @@ int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, c
     float* yhat = ar.take(sz.yh);
     if (!xhat) xhat = ar.take(sz.xh);
     if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for spectral conv forward");
+    SpectralProfScope prof_scope(d, false, epi == EPI_STORE ? 0 : (epi == EPI_ACCUM_GELU ? 2 : 1));
     UNO_TRY(analyse(x, Pin, nmid, p->fa, d->in_dim[nd - 1], p->a_last.d, ml, xhat, ws0, ws1, st));
     const long Q = p->Q;
     const int ncorner = 1 << nmid;
@@ -417,6 +449,7 @@ int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, 
     float* ghat = ar.take(sz.yh);
     float* dxhat = gx ? ar.take(sz.xh) : nullptr;
     if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for spectral conv backward");
+    SpectralProfScope prof_scope(d, true, (gx && accumulate_gx) ? 1 : 0);
     UNO_TRY(analyse(gy, Pout, nmid, p->ba, d->out_dim[nd - 1], p->ga_last.d, ml, ghat, ws0, ws1, st));
     const long Q = p->Q;
     long Qw = 1;
@@ -1087,6 +1120,7 @@ int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const fl
 
 void uno_profile_enable(int on) { be_profile_enable(on); }
 size_t uno_profile_report(char* buf, size_t cap) { return be_profile_report(buf, cap); }
+size_t uno_profile_report_levels(char* buf, size_t cap) { return be_profile_report_scopes(buf, cap); }
 long uno_launch_count(void) { return be_launch_count(); }
 
 // ---- host-only planning helpers -------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
 (tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
-rows that are not 16-byte aligned).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
-UNO_B200_KPIPE_ALIGN) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+rows that are not 16-byte aligned, tc_rowgemm.cuh with 16 epilogue warps).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
+UNO_B200_KPIPE_ALIGN / UNO_B200_ROWGEMM_EPI16) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
 `pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
 
     UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
@@ -133,6 +133,38 @@ def test_analysis_row_classes(shape, cuda_lib):
     assert rel_err(a[1], b[1]) < BWD_TOL and rel_err(a[2], b[2]) < BWD_TOL
 
 
+@pytest.mark.parametrize("odim", [(24, 240), (24, 120), (10, 481), (12, 63), (45, 301), (70, 33), (300, 64), (130, 446)])
+@pytest.mark.parametrize("norm,nl", [(False, True), (True, True), (False, False)])
+def test_synthesis_16_warp_epilogue(odim, norm, nl, cuda_lib):
+    """UNO_B200_ROWGEMM_EPI16=1: the synthesis kernel with 16 epilogue warps (store, accumulate, accumulate+GELU to a second
+    tensor, in place; one and two column tiles, parity mode, ragged tiles) against the default 8-warp configuration, which
+    tests/test_gpu_tc.py pins to the oracle."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(1)
+    blk = ops.OperatorBlock_2D(3, 4, *odim, 5, 9, Normalize=norm, Non_Lin=nl).cuda()
+    conv = ops.SpectralConv2d_Uno(3, 4, *odim, 5, 9).cuda()
+    x = torch.randn(2, 3, 30, 100, device="cuda")
+    gy = torch.randn(2, 4, *odim, device="cuda")
+
+    def run():
+        out = []
+        for m in (blk, conv):
+            xx = x.clone().requires_grad_(True)
+            m.zero_grad(set_to_none=True)
+            y = m(xx, *odim)
+            y.backward(gy)
+            with torch.no_grad():
+                y_inf = m(x, *odim)
+            out += [y.detach().cpu().numpy(), y_inf.cpu().numpy(), xx.grad.cpu().numpy()]
+        return out
+
+    a = _with_env(run, UNO_B200_ROWGEMM_EPI16=1)
+    b = _with_env(run, UNO_B200_ROWGEMM_EPI16=0)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v), rel_err(u, v)     # same arithmetic in the same order: bit-identical
+
+
 SHAPES_3D = [
     (2, 4, 6, (16, 16, 13), (12, 12, 13), (5, 5, 4)),
     (1, 8, 16, (24, 20, 21), (24, 20, 21), (8, 6, 5)),
@@ -182,7 +214,9 @@ def test_experimental_tc_timing(cuda_lib, capsys):
 
         for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
                     {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1},
-                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1}):
+                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1},
+                    {"UNO_B200_ROWGEMM_EPI16": 1},
+                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1, "UNO_B200_ROWGEMM_EPI16": 1}):
             def timed():
                 for _ in range(3):
                     step()

@@ -970,11 +970,16 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int EPI>
-int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
+bool rowgemm_epi16_enabled() {   // opt-in 16-warp epilogue (tc_rowgemm.cuh), read every call so tests can flip it
+    const char* e = getenv("UNO_B200_ROWGEMM_EPI16");
+    return e && e[0] && e[0] != '0';
+}
+
+template <int EPI, int G, int J>
+int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI, G, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -982,9 +987,15 @@ int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
     if (p.parity) gx &= ~1;                 // a CTA must only ever see tiles of one row parity (m_tiles is even too)
     if (gx < 1 + p.parity) gx = 1 + p.parity;
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
-    tc::rowgemm_smallk_kernel<EPI><<<dim3(gx, p.n_tiles), tc::kRowGemmThreads, smem, st>>>(p);
+    tc::rowgemm_smallk_kernel<EPI, G, J><<<dim3(gx, p.n_tiles), tc::rowgemm_threads(G), smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
+}
+
+template <int EPI>
+int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
+    if (rowgemm_epi16_enabled()) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
+    return launch_rowgemm_variant<EPI, 2, 2>(p, smem, st);
 }
 
 // chunk-major image for the K-pipelined kernel: [chunk][hi | lo], half = (KC/4) x N_t x 16 bytes,

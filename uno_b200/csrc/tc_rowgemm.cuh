@@ -43,9 +43,17 @@ __device__ __forceinline__ long rowgemm_row(const RowGemmParams& p, long tile, i
     return p.parity ? (tile >> 1) * 256 + 2 * i + (tile & 1) : tile * 128 + i;
 }
 
-constexpr int kRowGemmEpiWarps = 8;                      // two per TMEM lane quarter, splitting the columns
+// Epilogue warps come in groups of four (one warp per TMEM lane quarter); the G groups split the 16-column chunks of a tile
+// between them and a warp handles J chunks per round.  Default G = 2, J = 2 (8 warps, 32 x 32 elements per warp and round).
+// Opt-in (UNO_B200_ROWGEMM_EPI16=1): G = 4, J = 1 -- 16 warps of 32 x 16 elements per round, i.e. the same bytes in flight
+// spread over twice the warps, so that four warps per scheduler instead of two cover each other's load latency (the
+// accumulate launches of this kernel sit at 17 % warp occupancy with 4-6 long-scoreboard stalls per issue, profiles/
+// r01_ncu_full_v43_synthesis_resample.txt) within the 107 registers per thread that 608 threads leave.
 constexpr int kRowGemmLoadWarps = 2;
-constexpr int kRowGemmThreads = (kRowGemmEpiWarps + kRowGemmLoadWarps + 1) * 32;
+__host__ __device__ constexpr int rowgemm_epi_warps(int G) { return 4 * G; }
+__host__ __device__ constexpr int rowgemm_threads(int G) { return (4 * G + kRowGemmLoadWarps + 1) * 32; }
+constexpr int kRowGemmEpiWarps = rowgemm_epi_warps(2);
+constexpr int kRowGemmThreads = rowgemm_threads(2);
 constexpr uint32_t kLboA = 128 * 16 + 16;   // +16 B: the loaders' 16-byte stores of one warp fall in distinct bank groups
 
 __host__ __device__ inline size_t rowgemm_smem_bytes(int K_pad, int N_t) {
@@ -62,8 +70,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // Epilogue of one 128-row tile for one warp: TMEM lane quarter `q`, 16-column chunks c0 = 16*(2*i + half).
 // All loads of a 32-column group are issued before any store so that they are in flight together; the four
 // row pointers of a thread are formed once per tile (no 64-bit multiplies in the column loop).
-template <int EPI, bool VEC2>
+template <int EPI, bool VEC2, int G = 2, int J = 2>
 __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half, int lane) {
+    static_assert(J == 1 || J == 2, "one or two 16-column chunks per round");
     constexpr bool kAccum = (EPI != EPI_STORE);
     const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
     float* rowp[4];          // index hh*2 + rr
@@ -77,22 +86,22 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
     }
     const int ncol = p.N - n_base - 2 * (lane & 3);     // column c (relative) valid iff cmin <= c < ncol
     const int cmin = -(n_base + 2 * (lane & 3));        // 1 for the first thread of a shifted first tile, else <= 0
-    for (int ci = half; ci * 16 < p.N_t; ci += 4) {
-        const int c0a = ci * 16, c0b = (ci + 2) * 16;
-        const bool has_b = c0b < p.N_t && n_base + c0b < p.N;
+    for (int ci = half; ci * 16 < p.N_t; ci += J * G) {
+        const int c0a = ci * 16, c0b = (ci + G) * 16;
+        const bool has_b = J == 2 && c0b < p.N_t && n_base + c0b < p.N;
         if (n_base + c0a >= p.N) break;
-        uint32_t r[4][8];
+        uint32_t r[2 * J][8];
         tmem_ld_16x256b_x2(t_base + (uint32_t)c0a, r[0]);
         tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0a, r[1]);
-        if (has_b) {
-            tmem_ld_16x256b_x2(t_base + (uint32_t)c0b, r[2]);
-            tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0b, r[3]);
+        if (J == 2 && has_b) {
+            tmem_ld_16x256b_x2(t_base + (uint32_t)c0b, r[2 * J - 2]);
+            tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0b, r[2 * J - 1]);
         }
         // element pair e = (chunk j, half hh, repeat rep, row-pair rr)
-        float2 cz[16];
+        float2 cz[8 * J];
         if (kAccum) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
+            for (int e = 0; e < 8 * J; ++e) {
                 const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
                 const int c = (j ? c0b : c0a) + rep * 8;
                 const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
@@ -108,7 +117,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < 8 * J; ++e) {
             const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
             const int c = (j ? c0b : c0a) + rep * 8;
             const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
@@ -130,8 +139,9 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
     }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(const RowGemmParams p) {
+template <int EPI, int G = 2, int J = 2>
+__global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(const RowGemmParams p) {
+    constexpr int kRowGemmEpiWarps = rowgemm_epi_warps(G);   // shadows the default-configuration constant
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nt = blockIdx.y;
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
         // ------------------------------------------------------------------ epilogue: warp e -> TMEM lane quarter e%4, column half e/4
         const bool vec2 = (p.ldc % 2 == 0 || p.parity) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) &&
                           (EPI != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(p.C2) & 7) == 0);
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, half = warp >> 2;      // half = column group 0 .. G-1
         const int n_base = nt * p.N_t;
         int it = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
@@ -267,8 +277,8 @@ __global__ void __launch_bounds__(kRowGemmThreads, 1) rowgemm_smallk_kernel(cons
             mbar_wait_relaxed(&d_full[s], ph);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);
-            if (vec2) rowgemm_epilogue_tile<EPI, true>(p, t_base, tile, q, n_base, half, lane);
-            else rowgemm_epilogue_tile<EPI, false>(p, t_base, tile, q, n_base, half, lane);
+            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane);
+            else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane);
             tc_fence_before();
             mbar_arrive(&d_empty[s]);
         }

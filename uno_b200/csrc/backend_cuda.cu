@@ -14,6 +14,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -41,8 +42,8 @@ inline cudaStream_t S(stream_t s) { return (cudaStream_t)s; }
 // ---- per-launch profiling (off by default) -----------------------------------------------------------
 struct ProfRec { const char* tag; cudaEvent_t e0, e1; double bytes, flops; int scope; };
 struct ProfScopeInfo { std::string label; long calls = 0; double bytes = 0, flops = 0; };
-bool g_prof_on = false;
-long g_launches = 0;
+std::atomic<bool> g_prof_on{false};
+std::atomic<long> g_launches{0};   // forward and autograd's backward thread both launch
 std::vector<ProfRec> g_prof;
 std::vector<ProfScopeInfo> g_prof_scopes;
 thread_local int t_prof_scope = -1;
@@ -1430,7 +1431,7 @@ size_t be_profile_report(char* buf, size_t cap) {
     return out.size();
 }
 
-long be_launch_count() { return g_launches; }
+long be_launch_count() { return g_launches.load(); }
 
 // ---- side stream + event ring for fork / join -----------------------------------------------------------
 namespace {

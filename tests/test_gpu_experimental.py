@@ -1,7 +1,7 @@
 """GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
 (tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
 rows that are not 16-byte aligned, tc_rowgemm.cuh with 16 epilogue warps).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
-UNO_B200_KPIPE_ALIGN / UNO_B200_ROWGEMM_EPI16) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+UNO_B200_KPIPE_ALIGN / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
 `pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
 
     UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
@@ -163,6 +163,33 @@ def test_synthesis_16_warp_epilogue(odim, norm, nl, cuda_lib):
     b = _with_env(run, UNO_B200_ROWGEMM_EPI16=0)
     for u, v in zip(a, b):
         assert np.array_equal(u, v), rel_err(u, v)     # same arithmetic in the same order: bit-identical
+
+
+@pytest.mark.parametrize("odim", [(400, 400), (481, 481), (300, 350)])
+def test_instance_norm_big_cluster(odim, cuda_lib):
+    """UNO_B200_NORM_BIG_CLUSTER=1: planes too large for 8 x 72 KB take the cluster kernels with 200 KB per CTA (forward 4 bytes,
+    backward 8 bytes per element: the sizes cover 'both fit', 'forward only' and 'backward at the limit') -- against the
+    two-kernel path."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(2)
+    blk = ops.OperatorBlock_2D(2, 3, *odim, 4, 4, Normalize=True).cuda()
+    x = torch.randn(2, 2, 64, 64, device="cuda")
+    gy = torch.randn(2, 3, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        blk.zero_grad(set_to_none=True)
+        y = blk(xx, *odim)
+        y.backward(gy)
+        return [y.detach().cpu().numpy(), xx.grad.cpu().numpy(), blk.normalize_layer.weight.grad.cpu().numpy(),
+                blk.normalize_layer.bias.grad.cpu().numpy()]
+
+    a = _with_env(run, UNO_B200_NORM_BIG_CLUSTER=1)
+    b = _with_env(run, UNO_B200_NORM_BIG_CLUSTER=0)
+    assert rel_err(a[0], b[0]) < FWD_TOL, rel_err(a[0], b[0])
+    for u, v in zip(a[1:], b[1:]):
+        assert rel_err(u, v) < BWD_TOL, rel_err(u, v)
 
 
 SHAPES_3D = [

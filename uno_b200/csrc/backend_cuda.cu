@@ -1755,11 +1755,23 @@ int be_plane_stats(const float* x, float* stats, long planes, long L, float eps,
     CU_LAUNCH_CHECK();
     return 0;
 }
+// Shared-memory budget per CTA of the InstanceNorm cluster kernels: 72 KB (three CTAs per SM) is what the Darcy levels were
+// tuned with.  Opt-in (UNO_B200_NORM_BIG_CLUSTER=1, not yet measured): planes that do not fit 8 x 72 KB -- the NS-3D levels, where
+// plane_stats + norm_act_fwd + norm_act_bwd are 1.45 of 15.8 ms -- get a second try with 200 KB per CTA (one CTA per SM) before
+// the two-kernel path.
+inline int norm_cluster_pick(long L, int bytes_per_elem, int* slice) {
+    int cs = norm_cluster_size(L, bytes_per_elem, 72 * 1024, slice);
+    if (cs > 0) return cs;
+    const char* e = getenv("UNO_B200_NORM_BIG_CLUSTER");
+    if (e && e[0] && e[0] != '0') return norm_cluster_size(L, bytes_per_elem, 200 * 1024, slice);
+    return 0;
+}
+
 int be_norm_fused_fwd(const float* x, float* stats, const float* gamma, const float* beta, float* y, long planes, int C,
                       long L, float eps, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
     int slice = 0;
-    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_size(L, 4, 72 * 1024, &slice) : 0;
+    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_pick(L, 4, &slice) : 0;
     if (cs > 0) {
         // one sweep: the plane stays in the shared memory of a cluster of `cs` CTAs between statistics and normalisation
         ProfScope ps("instnorm_gelu_fwd", 8.0 * planes * L, 0, S(s));
@@ -1786,7 +1798,7 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
     if (planes <= 0) return 0;
     ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
     int slice = 0;
-    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_size(L, 8, 72 * 1024, &slice) : 0;
+    const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_pick(L, 8, &slice) : 0;
     if (cs > 0) {
         const int rc = launch_cluster(norm_bwd_cluster_kernel, planes, cs, (size_t)slice * 8, S(s), gy, x, stats, gamma, beta, g, ggamma,
                                       gbeta, C, L, slice, non_lin);

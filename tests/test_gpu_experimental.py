@@ -42,7 +42,7 @@ def _with_env(fn, **env):
 SHAPES_2D = [
     (8, 8, 8, (64, 64), (64, 64), (20, 20)),
     (4, 16, 24, (48, 40), (130, 36), (12, 9)),
-    (2, 32, 64, (481, 64), (240, 32), (18, 18)),
+    (2, 32, 64, (481, 64), (240, 40), (18, 18)),
     (3, 5, 7, (33, 31), (45, 29), (7, 5)),
     (32, 32, 32, (32, 32), (32, 32), (6, 6)),
     (4, 192, 192, (16, 16), (16, 16), (6, 6)),

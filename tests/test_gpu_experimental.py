@@ -135,8 +135,9 @@ def test_analysis_row_classes(shape, cuda_lib):
 
 @pytest.mark.parametrize("odim", [(24, 240), (24, 120), (10, 481), (12, 63), (45, 301), (70, 33), (300, 64), (130, 446)])
 @pytest.mark.parametrize("norm,nl", [(False, True), (True, True), (False, False)])
-def test_synthesis_16_warp_epilogue(odim, norm, nl, cuda_lib):
-    """UNO_B200_ROWGEMM_EPI16=1: the synthesis kernel with 16 epilogue warps (store, accumulate, accumulate+GELU to a second
+@pytest.mark.parametrize("mode", [1, 2])
+def test_synthesis_16_warp_epilogue(odim, norm, nl, mode, cuda_lib):
+    """UNO_B200_ROWGEMM_EPI16=1 (2: with the next round's addend prefetched): the synthesis kernel with 16 epilogue warps (store, accumulate, accumulate+GELU to a second
     tensor, in place; one and two column tiles, parity mode, ragged tiles) against the default 8-warp configuration, which
     tests/test_gpu_tc.py pins to the oracle."""
     from uno_b200 import integral_operators as ops
@@ -159,7 +160,7 @@ def test_synthesis_16_warp_epilogue(odim, norm, nl, cuda_lib):
             out += [y.detach().cpu().numpy(), y_inf.cpu().numpy(), xx.grad.cpu().numpy()]
         return out
 
-    a = _with_env(run, UNO_B200_ROWGEMM_EPI16=1)
+    a = _with_env(run, UNO_B200_ROWGEMM_EPI16=mode)
     b = _with_env(run, UNO_B200_ROWGEMM_EPI16=0)
     for u, v in zip(a, b):
         assert np.array_equal(u, v), rel_err(u, v)     # same arithmetic in the same order: bit-identical
@@ -242,7 +243,7 @@ def test_experimental_tc_timing(cuda_lib, capsys):
         for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
                     {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1},
                     {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1},
-                    {"UNO_B200_ROWGEMM_EPI16": 1},
+                    {"UNO_B200_ROWGEMM_EPI16": 1}, {"UNO_B200_ROWGEMM_EPI16": 2},
                     {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1, "UNO_B200_ROWGEMM_EPI16": 1}):
             def timed():
                 for _ in range(3):

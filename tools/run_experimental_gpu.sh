@@ -14,7 +14,7 @@ for t in test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_ana
 done
 unset UNO_B200_EXPERIMENTAL
 for wl in darcy ns2d ns3d; do
-    for flags in "" "UNO_B200_MID_TC=1" "UNO_B200_CMM_TC=1" "UNO_B200_KPIPE_ALIGN=1" "UNO_B200_ROWGEMM_EPI16=1" "UNO_B200_NORM_BIG_CLUSTER=1" "UNO_B200_NORM_BIG_CLUSTER=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_ROWGEMM_EPI16=1"; do
+    for flags in "" "UNO_B200_MID_TC=1" "UNO_B200_CMM_TC=1" "UNO_B200_KPIPE_ALIGN=1" "UNO_B200_ROWGEMM_EPI16=1" "UNO_B200_ROWGEMM_EPI16=2" "UNO_B200_NORM_BIG_CLUSTER=1" "UNO_B200_NORM_BIG_CLUSTER=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_ROWGEMM_EPI16=1"; do
         echo "=== bench $wl [$flags]" >> $OUT.log
         env $flags timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline >> $OUT.log 2>&1
     done

@@ -971,9 +971,10 @@ int num_sms() {
     return g_num_sms;
 }
 
-bool rowgemm_epi16_enabled() {   // opt-in 16-warp epilogue (tc_rowgemm.cuh), read every call so tests can flip it
+int rowgemm_epi16_mode() {   // opt-in 16-warp epilogue (tc_rowgemm.cuh): 1 = plain, 2 = with next-round prefetch; read every call
     const char* e = getenv("UNO_B200_ROWGEMM_EPI16");
-    return e && e[0] && e[0] != '0';
+    if (!e || !e[0] || e[0] == '0') return 0;
+    return e[0] == '2' ? 2 : 1;
 }
 
 template <int EPI, int G, int J>
@@ -995,7 +996,9 @@ int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t
 
 template <int EPI>
 int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
-    if (rowgemm_epi16_enabled()) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
+    const int mode = rowgemm_epi16_mode();
+    if (mode == 2) return launch_rowgemm_variant<EPI, 4, 0>(p, smem, st);
+    if (mode == 1) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
     return launch_rowgemm_variant<EPI, 2, 2>(p, smem, st);
 }
 

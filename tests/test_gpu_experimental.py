@@ -1,7 +1,7 @@
 """GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
 (tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
 rows that are not 16-byte aligned, tc_rowgemm.cuh with 16 epilogue warps).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
-UNO_B200_KPIPE_ALIGN / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+UNO_B200_KPIPE_ALIGN / UNO_B200_KPIPE_LW16 / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
 `pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
 
     UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
@@ -89,6 +89,41 @@ SHAPES_ALIGN = [
     (5, 7, 2, (17, 223), (17, 111), (3, 33)),
     (3, 4, 4, (129, 67), (64, 67), (8, 12)),
 ]
+
+
+# long contraction (input width > 64): 16-byte aligned rows, 4-byte rows, ragged last chunk, several row tiles per CTA
+SHAPES_LW16 = SHAPES_ALIGN + [
+    (1, 2, 2, (20, 481), (10, 240), (5, 18)),
+    (2, 2, 3, (12, 240), (12, 120), (4, 8)),
+    (1, 3, 2, (8, 130), (8, 64), (3, 5)),
+    (4, 8, 2, (1200, 100), (16, 16), (4, 6)),
+    (8, 16, 2, (240, 240), (120, 120), (6, 18)),
+]
+
+
+@pytest.mark.parametrize("align", [0, 1])
+@pytest.mark.parametrize("shape", SHAPES_LW16)
+def test_analysis_16_loader_warps(shape, align, cuda_lib):
+    """UNO_B200_KPIPE_LW16=1: the analysis kernel with 16 loader warps (all three loader paths) against the default 8."""
+    from uno_b200 import integral_operators as ops
+
+    B, Ci, Co, idim, odim, modes = shape
+    torch.manual_seed(0)
+    m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
+    x = torch.randn(B, Ci, *idim, device="cuda")
+    gy = torch.randn(B, Co, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx)
+        y.backward(gy)
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy()
+
+    a = _with_env(run, UNO_B200_KPIPE_LW16=1, UNO_B200_KPIPE_ALIGN=align)
+    b = _with_env(run, UNO_B200_KPIPE_LW16=0, UNO_B200_KPIPE_ALIGN=0)
+    assert rel_err(a[0], b[0]) < FWD_TOL, rel_err(a[0], b[0])
+    assert rel_err(a[1], b[1]) < BWD_TOL and rel_err(a[2], b[2]) < BWD_TOL
 
 
 @pytest.mark.parametrize("shape", SHAPES_ALIGN)
@@ -243,7 +278,8 @@ def test_experimental_tc_timing(cuda_lib, capsys):
         for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
                     {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1},
                     {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1},
-                    {"UNO_B200_ROWGEMM_EPI16": 1}, {"UNO_B200_ROWGEMM_EPI16": 2},
+                    {"UNO_B200_ROWGEMM_EPI16": 1}, {"UNO_B200_ROWGEMM_EPI16": 2}, {"UNO_B200_KPIPE_LW16": 1},
+                    {"UNO_B200_KPIPE_LW16": 1, "UNO_B200_KPIPE_ALIGN": 1},
                     {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1, "UNO_B200_ROWGEMM_EPI16": 1}):
             def timed():
                 for _ in range(3):

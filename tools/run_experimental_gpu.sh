@@ -9,12 +9,12 @@ OUT=gpurun_out/experimental
 : > $OUT.log
 run() { echo "=== $*" >> $OUT.log; "$@" >> $OUT.log 2>&1; echo "=== exit $?" >> $OUT.log; }
 export UNO_B200_EXPERIMENTAL=1
-for t in test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_spectral2d_experimental_tc test_spectral3d_experimental_tc test_experimental_tc_timing; do
+for t in test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_analysis_16_loader_warps test_spectral2d_experimental_tc test_spectral3d_experimental_tc test_experimental_tc_timing; do
     run timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q -s -k $t
 done
 unset UNO_B200_EXPERIMENTAL
 for wl in darcy ns2d ns3d; do
-    for flags in "" "UNO_B200_MID_TC=1" "UNO_B200_CMM_TC=1" "UNO_B200_KPIPE_ALIGN=1" "UNO_B200_ROWGEMM_EPI16=1" "UNO_B200_ROWGEMM_EPI16=2" "UNO_B200_NORM_BIG_CLUSTER=1" "UNO_B200_NORM_BIG_CLUSTER=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_ROWGEMM_EPI16=1"; do
+    for flags in "" "UNO_B200_MID_TC=1" "UNO_B200_CMM_TC=1" "UNO_B200_KPIPE_ALIGN=1" "UNO_B200_KPIPE_LW16=1" "UNO_B200_KPIPE_LW16=1 UNO_B200_KPIPE_ALIGN=1" "UNO_B200_ROWGEMM_EPI16=1" "UNO_B200_ROWGEMM_EPI16=2" "UNO_B200_NORM_BIG_CLUSTER=1" "UNO_B200_NORM_BIG_CLUSTER=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_ROWGEMM_EPI16=1"; do
         echo "=== bench $wl [$flags]" >> $OUT.log
         env $flags timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline >> $OUT.log 2>&1
     done

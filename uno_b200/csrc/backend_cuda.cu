@@ -1045,6 +1045,19 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     return 0;
 }
 
+template <int LW>
+int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    tc::kpipe_kernel<LW><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if (!tc_enabled() || !a.b_const || a.batch != 1 || a.a_cs != 1 || a.bias || a.epi != EPI_STORE || a.K <= 64 || a.N < 8 || a.N > 256 || a.M < 1)
         return -1;
@@ -1074,18 +1087,12 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     p.tmem_cols = cols;
     p.a_vec_ok = a_vec_ok;
     { const char* e = getenv("UNO_B200_KPIPE_DEBUG"); p.debug = e ? atoi(e) : 0; }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
     int gx = num_sms();
     if (rclass) gx &= ~3;                   // a CTA must only ever see tiles of one row class (m_tiles is a multiple of 4 too)
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
-    tc::kpipe_kernel<<<gx, tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
-    CU_LAUNCH_CHECK();
-    return 0;
+    const char* lw = getenv("UNO_B200_KPIPE_LW16");   // opt-in: 16 loader warps (tc_kpipe.cuh)
+    if (lw && lw[0] && lw[0] != '0') return launch_kpipe<16>(p, gx, tc::kpipe_smem_bytes(img.N_t, stages), st);
+    return launch_kpipe<tc::kKpLoadWarps>(p, gx, tc::kpipe_smem_bytes(img.N_t, stages), st);
 }
 
 // ---- leading-axis complex transform on tcgen05 (tc_mid.cuh), opt-in: UNO_B200_MID_TC=1 -------------------------------

@@ -47,13 +47,24 @@ constexpr int kKC = 32;                       // K elements per stage
 constexpr int kKpLoadWarps = 8;
 constexpr int kKpDepth = 4;                   // chunks of global loads kept in flight per loader thread
 constexpr int kKpEpiWarps = 4;
+#ifndef KPIPE_LW16_DEPTH
+#define KPIPE_LW16_DEPTH 4
+#endif
 constexpr int kKpThreads = (kKpLoadWarps + kKpEpiWarps + 1) * 32;
 constexpr uint32_t kKpAHalf = (kKC / 4) * kLboA;   // bytes of one A image (hi or lo) per stage
 
 __host__ __device__ inline size_t kpipe_stage_bytes(int N_t) { return (size_t)2 * kKpAHalf + (size_t)2 * N_t * kKC * 4; }
 __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return stages * kpipe_stage_bytes(N_t) + 32 * 8 + 16; }
 
-__global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams p) {
+// LW = loader warps: 8 (default) or 16 (opt-in UNO_B200_KPIPE_LW16=1: the loader warps' serial instruction stream per chunk is
+// what bounds this kernel, tools/kpipe_probe.py -- twice the warps, half the rows per thread).
+template <int LW = kKpLoadWarps>
+__global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
+    static_assert(LW == 8 || LW == 16, "loader warps");
+    constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
+    constexpr int RP = 128 / RB;          // 16-byte paths: rows per thread
+    constexpr int RP4 = 128 / LW;         // 4-byte path: rows per thread (warp w -> rows w + LW*i)
+    constexpr int DEPTH = LW == 8 ? kKpDepth : KPIPE_LW16_DEPTH;   // chunks of global loads in flight per loader thread
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -65,11 +76,11 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
     uint64_t* d_full = bars + 16;     // [2]
     uint64_t* d_empty = bars + 18;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    constexpr int kMmaWarp = kKpLoadWarps + kKpEpiWarps;
+    constexpr int kMmaWarp = LW + kKpEpiWarps;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], kKpLoadWarps * 32 + 1);   // +1: the arrive.expect_tx of the B copy
+            mbar_init(&full[s], LW * 32 + 1);   // +1: the arrive.expect_tx of the B copy
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 __syncwarp();
             }
         }
-    } else if (warp < kKpLoadWarps) {
+    } else if (warp < LW) {
         // ------------------------------------------------------------------ loaders: 256 threads, chunk = 128 rows x 32 k
         // All indexing is incremental (no divisions, one 64-bit multiply per chunk): the loaders are the
         // instruction-issue critical path of this kernel.
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
         long n_my_tiles = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) ++n_my_tiles;
         const long total = n_my_tiles * NKC;   // chunks this CTA processes, in order
-        // issue-side cursor (runs kKpDepth-1 chunks ahead) and process-side cursor
+        // issue-side cursor (runs DEPTH-1 chunks ahead) and process-side cursor
         long i_tile = blockIdx.x;
         int i_kc = 0;
         int p_kc = 0, p_s = 0;
@@ -175,24 +186,24 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
             const int cls = (int)(blockIdx.x & 3);
             const int sh = (int)(((long)cls * p.lda) & 3);
             const int kq = ltid & 7, rbase = ltid >> 3;
-            const long stride32 = 128 * p.lda;                // rows 32 apart in the tile are 128 apart in the tensor
+            const long stride32 = 4 * RB * p.lda;                // rows RB apart in the tile are 4*RB apart in the tensor
             const int k_end = p.k_valid + sh;                 // shifted index k' is real iff sh <= k' < k_end
             const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
-            float4 ring[kKpDepth][4];
-            auto issue = [&](float4 (&v)[4]) {
+            float4 ring[DEPTH][RP];
+            auto issue = [&](float4 (&v)[RP]) {
                 const long row0 = (i_tile >> 2) * 512 + 4 * rbase + cls;
                 const int k0 = i_kc * kKC + kq * 4;
                 const float* src = p.A + row0 * p.lda - sh + k0;
-                const long rows_left = p.R - row0;            // row (128*i) valid iff 128*i < rows_left
+                const long rows_left = p.R - row0;            // row (4*RB*i) valid iff 4*RB*i < rows_left
                 if (k0 >= sh && k0 + 4 <= k_end) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        v[i] = (128 * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < RP; ++i)
+                        v[i] = (4 * RB * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < RP; ++i) {
                         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (128 * i < rows_left) {
+                        if (4 * RB * i < rows_left) {
                             const float* q = src + i * stride32;
                             if (k0 + 0 >= sh && k0 + 0 < k_end) v[i].x = __ldg(q + 0);
                             if (k0 + 1 >= sh && k0 + 1 < k_end) v[i].y = __ldg(q + 1);
@@ -203,53 +214,53 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 }
                 if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
-            auto process = [&](const float4 (&v)[4]) {
+            auto process = [&](const float4 (&v)[RP]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RP; ++i) {
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);
                     split_tf32(v[i].y, hi.y, lo.y);
                     split_tf32(v[i].z, hi.z, lo.z);
                     split_tf32(v[i].w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(st + i * 512) = hi;
-                    *reinterpret_cast<float4*>(st + kKpAHalf + i * 512) = lo;
+                    *reinterpret_cast<float4*>(st + i * (RB * 16)) = hi;
+                    *reinterpret_cast<float4*>(st + kKpAHalf + i * (RB * 16)) = lo;
                 }
                 stage_epilogue();
             };
 #pragma unroll
-            for (int d = 0; d < kKpDepth - 1; ++d)
+            for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += kKpDepth) {
+            for (long g = 0; g < total; g += DEPTH) {
 #pragma unroll
-                for (int d = 0; d < kKpDepth; ++d) {
-                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                for (int d = 0; d < DEPTH; ++d) {
+                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
             }
         } else if (p.a_vec_ok) {
             // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
             const int kq = ltid & 7, rbase = ltid >> 3;
-            const long stride32 = 32 * p.lda;
+            const long stride32 = RB * p.lda;
             const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
-            float4 ring[kKpDepth][4];
-            auto issue = [&](float4 (&v)[4]) {
+            float4 ring[DEPTH][RP];
+            auto issue = [&](float4 (&v)[RP]) {
                 const long row0 = i_tile * 128 + rbase;
                 const int k0 = i_kc * kKC + kq * 4;
                 const float* src = p.A + row0 * p.lda + k0;
-                const long rows_left = p.R - row0;            // row (32*i) valid iff 32*i < rows_left
+                const long rows_left = p.R - row0;            // row (RB*i) valid iff RB*i < rows_left
                 if (k0 + 4 <= p.K) {
                     // every chunk but a ragged last one: straight-line predicated 16-byte loads (the loader warps' serial
                     // instruction stream per chunk is what bounds this kernel, tools/kpipe_probe.py)
                     const long lim = (p.debug & 8) ? 0 : rows_left;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        v[i] = (32 * i < lim) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = 0; i < RP; ++i)
+                        v[i] = (RB * i < lim) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < RP; ++i) {
                         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (32 * i < rows_left && !(p.debug & 8)) {
+                        if (RB * i < rows_left && !(p.debug & 8)) {
                             const float* q = src + i * stride32;
                             if (k0 + 0 < p.K) v[i].x = __ldg(q + 0);
                             if (k0 + 1 < p.K) v[i].y = __ldg(q + 1);
@@ -259,71 +270,71 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 }
                 if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
-            auto process = [&](const float4 (&v)[4]) {
+            auto process = [&](const float4 (&v)[RP]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < RP; ++i) {
                     if (p.debug & 2) break;
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);
                     split_tf32(v[i].y, hi.y, lo.y);
                     split_tf32(v[i].z, hi.z, lo.z);
                     split_tf32(v[i].w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(st + i * 512) = hi;
-                    *reinterpret_cast<float4*>(st + kKpAHalf + i * 512) = lo;
+                    *reinterpret_cast<float4*>(st + i * (RB * 16)) = hi;
+                    *reinterpret_cast<float4*>(st + kKpAHalf + i * (RB * 16)) = lo;
                 }
                 stage_epilogue();
             };
 #pragma unroll
-            for (int d = 0; d < kKpDepth - 1; ++d)
+            for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += kKpDepth) {
+            for (long g = 0; g < total; g += DEPTH) {
 #pragma unroll
-                for (int d = 0; d < kKpDepth; ++d) {
-                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                for (int d = 0; d < DEPTH; ++d) {
+                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
             }
         } else {
             // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
-            const long stride8 = 8 * p.lda;
+            const long stride8 = LW * p.lda;
             const uint32_t so = (uint32_t)(lane >> 2) * kLboA + (uint32_t)(lane & 3) * 4 + (uint32_t)warp * 16;
-            float ring[kKpDepth][16];
-            auto issue = [&](float (&v)[16]) {
+            float ring[DEPTH][RP4];
+            auto issue = [&](float (&v)[RP4]) {
                 const long row0 = i_tile * 128 + warp;
                 const int k = i_kc * kKC + lane;
                 const float* src = p.A + row0 * p.lda + k;
-                const long rows_left = (k < p.K) ? (p.R - row0) : 0;   // row (8*i) valid iff 8*i < rows_left
+                const long rows_left = (k < p.K) ? (p.R - row0) : 0;   // row (LW*i) valid iff LW*i < rows_left
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (8 * i < rows_left && !(p.debug & 8)) ? __ldg(src + i * stride8) : 0.f;
+                for (int i = 0; i < RP4; ++i) v[i] = (LW * i < rows_left && !(p.debug & 8)) ? __ldg(src + i * stride8) : 0.f;
                 if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
-            auto process = [&](const float (&v)[16]) {
+            auto process = [&](const float (&v)[RP4]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < RP4; ++i) {
                     if (p.debug & 2) break;
                     float hi, lo;
                     split_tf32(v[i], hi, lo);
-                    *reinterpret_cast<float*>(st + i * 128) = hi;
-                    *reinterpret_cast<float*>(st + kKpAHalf + i * 128) = lo;
+                    *reinterpret_cast<float*>(st + i * (LW * 16)) = hi;
+                    *reinterpret_cast<float*>(st + kKpAHalf + i * (LW * 16)) = lo;
                 }
                 stage_epilogue();
             };
 #pragma unroll
-            for (int d = 0; d < kKpDepth - 1; ++d)
+            for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += kKpDepth) {
+            for (long g = 0; g < total; g += DEPTH) {
 #pragma unroll
-                for (int d = 0; d < kKpDepth; ++d) {
-                    if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
+                for (int d = 0; d < DEPTH; ++d) {
+                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
             }
         }
     } else {
         // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
-        const int q = warp - kKpLoadWarps;
+        const int q = warp - LW;
         RowGemmParams ep;
         ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R; ep.parity = 0;
         const bool vec2 = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
@@ -353,12 +364,13 @@ __global__ void __launch_bounds__(kKpThreads, 1) kpipe_kernel(const KPipeParams 
                 continue;
             }
             // both column "halves" handled by this warp
+            constexpr int EJ = LW == 8 ? 2 : 1;      // 16 loader warps leave 80 registers per thread: one chunk per round
             if (vec2) {
-                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, tile, q, 0, 0, lane);
-                rowgemm_epilogue_tile<EPI_STORE, true>(ep, t_base, tile, q, 0, 1, lane);
+                rowgemm_epilogue_tile<EPI_STORE, true, 2, EJ>(ep, t_base, tile, q, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, true, 2, EJ>(ep, t_base, tile, q, 0, 1, lane);
             } else {
-                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, tile, q, 0, 0, lane);
-                rowgemm_epilogue_tile<EPI_STORE, false>(ep, t_base, tile, q, 0, 1, lane);
+                rowgemm_epilogue_tile<EPI_STORE, false, 2, EJ>(ep, t_base, tile, q, 0, 0, lane);
+                rowgemm_epilogue_tile<EPI_STORE, false, 2, EJ>(ep, t_base, tile, q, 0, 1, lane);
             }
             tc_fence_before();
             mbar_arrive(&d_empty[buf]);

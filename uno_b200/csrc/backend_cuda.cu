@@ -1045,15 +1045,15 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     return 0;
 }
 
-template <int LW>
+template <int LW, bool RC>
 int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    tc::kpipe_kernel<LW><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    tc::kpipe_kernel<LW, RC><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1091,8 +1091,9 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if (rclass) gx &= ~3;                   // a CTA must only ever see tiles of one row class (m_tiles is a multiple of 4 too)
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     const char* lw = getenv("UNO_B200_KPIPE_LW16");   // opt-in: 16 loader warps (tc_kpipe.cuh)
-    if (lw && lw[0] && lw[0] != '0') return launch_kpipe<16>(p, gx, tc::kpipe_smem_bytes(img.N_t, stages), st);
-    return launch_kpipe<tc::kKpLoadWarps>(p, gx, tc::kpipe_smem_bytes(img.N_t, stages), st);
+    const size_t smem = tc::kpipe_smem_bytes(img.N_t, stages);
+    if (lw && lw[0] && lw[0] != '0') return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
+    return rclass ? launch_kpipe<tc::kKpLoadWarps, true>(p, gx, smem, st) : launch_kpipe<tc::kKpLoadWarps, false>(p, gx, smem, st);
 }
 
 // ---- leading-axis complex transform on tcgen05 (tc_mid.cuh), opt-in: UNO_B200_MID_TC=1 -------------------------------

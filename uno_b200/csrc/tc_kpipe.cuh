@@ -56,9 +56,10 @@ constexpr uint32_t kKpAHalf = (kKC / 4) * kLboA;   // bytes of one A image (hi o
 __host__ __device__ inline size_t kpipe_stage_bytes(int N_t) { return (size_t)2 * kKpAHalf + (size_t)2 * N_t * kKC * 4; }
 __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return stages * kpipe_stage_bytes(N_t) + 32 * 8 + 16; }
 
+// RC = row-class mode (see above), compiled separately so that the default instantiation carries none of it.
 // LW = loader warps: 8 (default) or 16 (opt-in UNO_B200_KPIPE_LW16=1: the loader warps' serial instruction stream per chunk is
 // what bounds this kernel, tools/kpipe_probe.py -- twice the warps, half the rows per thread).
-template <int LW = kKpLoadWarps>
+template <int LW = kKpLoadWarps, bool RC = false>
 __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
     static_assert(LW == 8 || LW == 16, "loader warps");
     constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
         int p_kc = 0, p_s = 0;
         uint32_t p_ph = 0;
         const uint32_t img_chunk_floats = 2 * b_half / 4;
-        const float* bimg = p.Bimg + (p.rclass ? (size_t)(blockIdx.x & 3) * NKC * img_chunk_floats : (size_t)0);
+        const float* bimg = p.Bimg + (RC ? (size_t)(blockIdx.x & 3) * NKC * img_chunk_floats : (size_t)0);
         auto stage_prologue = [&]() -> uint8_t* {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
             if (++p_kc == NKC) p_kc = 0;
         };
-        if (p.rclass) {
+        if constexpr (RC) {
             // row-class path: 16-byte loads from the 16-byte boundary at or before the row start (see "row classes" above)
             const int cls = (int)(blockIdx.x & 3);
             const int sh = (int)(((long)cls * p.lda) & 3);
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             mbar_wait_relaxed(&d_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)buf * buf_cols + ((uint32_t)(q * 32) << 16);
-            if (p.rclass) {
+            if constexpr (RC) {
                 // row-class mode: thread = one row of the class, float2 stores (N even, ldc even, C 8-byte aligned: host-checked)
                 const long grow = (tile >> 2) * 512 + 4 * (q * 32 + lane) + (tile & 3);
                 float* crow = p.C + (grow < p.R ? grow : 0) * p.ldc;

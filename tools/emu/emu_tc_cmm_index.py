@@ -4,7 +4,7 @@ kLboA=128*16+16; kKC=32; kKpAHalf=(kKC//4)*kLboA
 def run(M,N,K,conjA,conjB):
     A=rng.standard_normal((M,K))+1j*rng.standard_normal((M,K))
     B=rng.standard_normal((K,N))+1j*rng.standard_normal((K,N))
-    ns_tiles=(M+127)//128; per=(M+ns_tiles-1)//ns_tiles; N_t=((per+15)//16)*16
+    ns_tiles=(M+63)//64; per=(M+ns_tiles-1)//ns_tiles; N_t=((per+15)//16)*16
     ms_tiles=(2*N+127)//128; NKC=(K+15)//16
     b_half=N_t*kKC*4; stage_bytes=2*kKpAHalf+2*b_half
     sa=-1. if conjA else 1.; sb=-1. if conjB else 1.
@@ -26,7 +26,7 @@ def run(M,N,K,conjA,conjB):
                     d=(w_so+(4*j)*kLboA)//4
                     st[d:d+4]=(e[0],-sb*e[1],e[2],-sb*e[3])
                     st[d+4:d+8]=(sb*e[1],e[0],sb*e[3],e[2])
-                for j in range(4):
+                for j in range(2):
                     idx=ltid+256*j
                     if idx>=8*N_t: continue
                     kp=idx//N_t; xm=idx-kp*N_t

@@ -1205,7 +1205,7 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
             return -1;
     tc::CmmTcParams p;
     p.a = a;
-    p.ns_tiles = (a.M + 127) / 128;
+    p.ns_tiles = (a.M + 63) / 64;
     const int per = (a.M + p.ns_tiles - 1) / p.ns_tiles;
     p.N_t = ((per + 15) / 16) * 16;
     p.ms_tiles = (2 * a.N + 127) / 128;

@@ -7,7 +7,7 @@
 //     Ximg[m, (k,re)] = Re A      Ximg[m, (k,im)] = sa Im A                      (sa, sb = -1 when conjugated)
 //     Wimg[(n,re), (k,re)] = Re B   Wimg[(n,re), (k,im)] = -sb Im B   Wimg[(n,im), (k,re)] = sb Im B   Wimg[(n,im), (k,im)] = Re B
 // The operand with the many rows -- the (n, re|im) rows of the weights, 128 - 384 of them -- sits on the UMMA M side
-// (128 rows per tile, no padding waste) and the sample index on the N side (16 - 128 columns).  Both images are K-major
+// (128 rows per tile, no padding waste) and the sample index on the N side (16 - 64 columns).  Both images are K-major
 // "interleave" layouts written by the loader warps from 8-byte global loads (tf32 hi/lo split on the way, as in
 // tc_kpipe.cuh); MMA issue, stage ring and TMEM double buffering are tc_kpipe.cuh's.
 //
@@ -27,7 +27,7 @@ namespace tc {
 
 struct CmmTcParams {
     CmmArgs a;
-    int N_t;          // columns of a tile (samples m), multiple of 16, <= 128
+    int N_t;          // columns of a tile (samples m), multiple of 16, <= 64 (two sample-side tasks per loader thread)
     int ns_tiles;     // column tiles
     int ms_tiles;     // 128-row tiles over the 2*N rows (n, re|im)
     int n_chunks;     // ceil(K / 16): a chunk is 16 complex k = 32 real k'
@@ -36,7 +36,8 @@ struct CmmTcParams {
 };
 
 constexpr int kCmKC = kKC / 2;        // complex k per chunk
-constexpr int kCmDepth = 2;           // chunks of global loads in flight per loader thread
+constexpr int kCmDepth = 4;           // chunks of global loads in flight per loader thread
+constexpr int kCmXT = 2;              // sample-side tasks per loader thread: 8 * N_t <= 256 * kCmXT
 
 struct CmmItem {
     int ms, ns, corner, qo, qi;
@@ -144,11 +145,11 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc_kernel(const CmmTcParams
         const int wn = ltid & 63;                       // weight row pair within the tile
         const int wkp0 = ltid >> 6;                     // k pairs wkp0, wkp0 + 4
         const uint32_t w_so = (uint32_t)wkp0 * kLboA + (uint32_t)(2 * wn) * 16;
-        int xm[4], xkp[4];
-        uint32_t x_so[4];
+        int xm[kCmXT], xkp[kCmXT];
+        uint32_t x_so[kCmXT];
         const int n_xtasks = 8 * p.N_t;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kCmXT; ++j) {
             const int idx = ltid + 256 * j;
             xkp[j] = idx / p.N_t;
             xm[j] = idx - xkp[j] * p.N_t;
@@ -159,18 +160,18 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc_kernel(const CmmTcParams
         long i_w = blockIdx.x;
         int i_kc = 0;
         const float2* gB = nullptr;       // &B[k = 0, n of this thread, q]   (null: row beyond N)
-        const float2* gA[4];              // &A[m of task j, k = 0, q]        (null: row beyond M or no task)
+        const float2* gA[kCmXT];              // &A[m of task j, k = 0, q]        (null: row beyond M or no task)
         auto seek = [&]() {
             gB = nullptr;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) gA[j] = nullptr;
+            for (int j = 0; j < kCmXT; ++j) gA[j] = nullptr;
             if (i_w >= p.items) return;
             const CmmItem it = cmm_item(p, i_w);
             const int n = it.ms * 64 + wn;
             if (n < p.a.N)
                 gB = reinterpret_cast<const float2*>(p.a.B[it.corner]) + (long)it.qo * p.a.b_sqo + it.qi + (long)n * p.a.b_sn;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kCmXT; ++j) {
                 const int m = it.ns * p.N_t + xm[j];
                 if (xkp[j] >= 0 && m < p.a.M)
                     gA[j] = reinterpret_cast<const float2*>(p.a.A[it.corner]) + (long)it.qo * p.a.a_sqo + it.qi + (long)m * p.a.a_sm;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc_kernel(const CmmTcParams
         seek();
         int p_s = 0;
         uint32_t p_ph = 0;
-        struct Slot { float4 w[2]; float4 x[4]; };
+        struct Slot { float4 w[2]; float4 x[kCmXT]; };
         Slot ring[kCmDepth];
         auto issue = [&](Slot& v) {
             const int k0 = i_kc * kCmKC;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc_kernel(const CmmTcParams
                 v.w[j] = make_float4(e0.x, e0.y, e1.x, e1.y);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kCmXT; ++j) {
                 float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
                 if (gA[j]) {
                     const int k = k0 + 2 * xkp[j];
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc_kernel(const CmmTcParams
                 put(d + 16, kKpAHalf, make_float4(sb * e.y, e.x, sb * e.w, e.z));     // row (n, im)
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kCmXT; ++j) {
                 if (xkp[j] < 0) continue;
                 const float4 e = v.x[j];
                 put(st + x_so[j], b_half, make_float4(e.x, sa * e.y, e.z, sa * e.w));

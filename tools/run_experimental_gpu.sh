@@ -19,11 +19,14 @@ for wl in darcy ns2d ns3d; do
         env $flags timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline >> $OUT.log 2>&1
     done
 done
-tail -5 $OUT.log
+
 # the regime where the default leading-axis transform and mode contraction lose to cuFFT (S = 64, most of the spectrum kept)
 for flags in "" "UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1"; do
     echo "=== sweep S=64 [$flags]" >> $OUT.log
     env $flags timeout 600 python tools/sweep_spectral.py --sizes 64,128 --modes 20,32 --channels 32,128 --iters 5 \
         --out "gpurun_out/sweep_s64_$(echo $flags | tr -c 'A-Z0-9_\n' '_').json" >> $OUT.log 2>&1
 done
+
+echo "=== wgrad probe" >> $OUT.log
+timeout 300 python tools/wgrad_probe.py >> $OUT.log 2>&1
 tail -5 $OUT.log

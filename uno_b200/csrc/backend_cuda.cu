@@ -1283,6 +1283,19 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     return 0;
 }
 
+template <bool DBG>
+int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    tc::wgrad_tc_kernel<DBG><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     if (!tc_enabled() || a.M < 1 || a.N < 1 || a.M > 128 || a.N > 128 || a.K % 4 != 0 || a.K < 256) return -1;
     if (a.lda != a.K || a.ldb != a.K || a.sA != (long)a.M * a.K || a.sB != (long)a.N * a.K) return -1;
@@ -1296,18 +1309,12 @@ int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < p.N_t) cols *= 2;
     p.tmem_cols = cols;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
     long gx = num_sms();
     if (gx > (p.total_chunks + 3) / 4) gx = (p.total_chunks + 3) / 4;
     if (gx < 1) gx = 1;
-    tc::wgrad_tc_kernel<<<(unsigned)gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
-    CU_LAUNCH_CHECK();
-    return 0;
+    { const char* e = getenv("UNO_B200_WGRAD_DEBUG"); p.debug = e ? atoi(e) : 0; }   // timing probes (tools/wgrad_probe.py)
+    if (p.debug) return launch_wgrad<true>(p, (unsigned)gx, st);
+    return launch_wgrad<false>(p, (unsigned)gx, st);
 }
 
 // returns -1 when the shape does not qualify (caller falls back to the SIMT kernel)

@@ -25,6 +25,8 @@ struct WgradParams {
     int chunks_per_b;             // ceil(npix / 32)
     long total_chunks;
     int tmem_cols;
+    int debug;                    // only read by the <true> instantiation (UNO_B200_WGRAD_DEBUG, results are garbage): 1 no MMA,
+                                  // 2 no operand stores, 8 no global loads, 16 no proxy fence, 32 no final flush
 };
 
 constexpr int kWgLoadWarps = 8;
@@ -33,7 +35,10 @@ constexpr uint32_t kWgStage = 4 * kKpAHalf;   // A_hi, A_lo, B_hi, B_lo (each 12
 
 __host__ __device__ inline size_t wgrad_smem_bytes(int stages) { return (size_t)stages * kWgStage + 32 * 8 + 16; }
 
+// DBG = timing-probe instantiation (tools/wgrad_probe.py); the default <false> carries none of the probe branches
+template <bool DBG = false>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradParams p) {
+    const int dbg = DBG ? p.debug : 0;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -85,9 +90,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
                     uint64_t da = a_st;                  // stage layout: [A hi | A lo | B hi | B lo], each kKpAHalf bytes
 #pragma unroll
                     for (int ks = 0; ks < kKC / 8; ++ks) {
-                        mma_tf32(tmem_base, da, da + 2 * half, idesc, ks ? 1u : acc);
-                        mma_tf32(tmem_base, da, da + 3 * half, idesc, 1u);
-                        mma_tf32(tmem_base, da + half, da + 2 * half, idesc, 1u);
+                        if (!(DBG && (dbg & 1))) {
+                            mma_tf32(tmem_base, da, da + 2 * half, idesc, ks ? 1u : acc);
+                            mma_tf32(tmem_base, da, da + 3 * half, idesc, 1u);
+                            mma_tf32(tmem_base, da + half, da + 2 * half, idesc, 1u);
+                        }
                         da += step;
                     }
                     tc_commit(&empty[s]);
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
             for (int i = 0; i < RPT; ++i) {
                 const int r = rbase + 32 * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pxok && r < rows) {
+                if (pxok && r < rows && !(DBG && (dbg & 8))) {
                     const float* q = (r < p.M) ? gsrc + (long)r * p.npix : xsrc + (long)(r - p.M) * p.npix;
                     v[i] = __ldg(reinterpret_cast<const float4*>(q));
                 }
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
                 const int r = rbase + 32 * i;
-                if (r < rows) {
+                if (r < rows && !(DBG && (dbg & 2))) {
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);
                     split_tf32(v[i].y, hi.y, lo.y);
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
                     *reinterpret_cast<float4*>(d + kKpAHalf) = lo;
                 }
             }
-            fence_proxy_async();
+            if (!(DBG && (dbg & 16))) fence_proxy_async();
             mbar_arrive(&full[p_s]);
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
         };
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
                 tmem_ld_wait();
-                if (m < p.M) {
+                if (m < p.M && !(DBG && (dbg & 32))) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c0 + j < p.N) atomicAdd(p.dW + (long)m * p.ldw + c0 + j, __uint_as_float(r[j]));

@@ -374,7 +374,7 @@ void corner_geometry(const SpectralPlan* p, int c, long* off, int* q_outer, int*
 // Profiling scope of one fused spectral-convolution call (bench.py's per-U-level roofline): algorithmic bytes and
 // contraction flops as SURVEY.md 8(d) defines them.  `extra_out_tensors`: output-sized tensors the fused block epilogue
 // reads / writes on top of the plain layer (forward: the pointwise sum it accumulates onto and, with GELU to a second
-// tensor, that tensor; backward: none -- the gradient it accumulates onto is counted as the read-modify-write it is).
+// tensor, that tensor; backward: the input gradient it accumulates onto, when it does).
 struct SpectralProfScope {
     bool on = false;
     SpectralProfScope(const uno_conv_desc* d, bool backward, int extra_out_tensors) {

@@ -119,3 +119,40 @@ def test_profile_levels_report_labels_and_algorithmic_bytes():
     n = L.uno_profile_report_levels(None, 0)
     L.uno_profile_enable(0)
     assert n == 2
+
+
+def test_bench_spectral_levels_from_report():
+    """bench.py turns uno_profile_report_levels' JSON into the per-U-level roofline entries of its output line."""
+    import ctypes as C
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rep = {
+        "spectral fwd B=32 32->64 [481,481]->[240,240] modes=[18,18]": {"calls": 2, "launches": 10, "ms": 2.0, "bytes": 2.0e9, "flops": 4.0e9},
+        "spectral bwd B=32 32->64 [481,481]->[240,240] modes=[18,18]": {"calls": 2, "launches": 12, "ms": 0.0, "bytes": 1.0, "flops": 1.0},
+    }
+    payload = json.dumps(rep).encode()
+
+    class FakeLib:
+        @staticmethod
+        def uno_profile_report_levels(buf, cap):
+            if buf is not None:
+                C.memmove(buf, payload, min(len(payload), cap - 1))
+            return len(payload)
+
+    out = bench.spectral_levels(FakeLib, 2, 6500.0)
+    assert len(out) == 1                                   # the entry without a time is dropped
+    e = out[0]
+    assert e["level"].startswith("spectral fwd") and e["calls_per_step"] == 1 and e["launches_per_call"] == 5
+    assert abs(e["ms_per_call"] - 1.0) < 1e-12 and abs(e["GBps"] - 1000.0) < 1e-6 and abs(e["hbm_frac"] - 1000.0 / 6500.0) < 1e-9
+    assert abs(e["contraction_TFLOPs"] - 2.0) < 1e-9 and 0 < e["tensor_frac"] < 1
+
+    class Broken:
+        @staticmethod
+        def uno_profile_report_levels(buf, cap):
+            raise OSError("no such symbol")
+
+    assert "error" in bench.spectral_levels(Broken, 2, 6500.0)

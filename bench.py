@@ -377,10 +377,14 @@ def main():
         if not ok:
             raise RuntimeError(why or "another rank could not run the overlapped-copy step")
         ov_ms = timed(e2e_step_overlap, args.steps) / args.steps
-        e2e = {"value": B * world / (ov_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
-               "d2h_bytes_per_step": 4, "ms_per_step": ov_ms,
-               "copies": "input copied on the compute stream, target on a copy stream behind it (waited for at the loss)",
-               "serial_copy_value": e2e["value"], "serial_copy_ms_per_step": e2e_ms}
+        if ov_ms < e2e_ms:
+            e2e = {"value": B * world / (ov_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": 4, "ms_per_step": ov_ms,
+                   "copies": "input copied on the compute stream, target on a copy stream behind it (waited for at the loss)",
+                   "serial_copy_value": e2e["value"], "serial_copy_ms_per_step": e2e_ms}
+        else:   # no gain on this box: the serial-copy figure stays the headline
+            e2e["overlapped_copy_value"] = B * world / (ov_ms * 1e-3)
+            e2e["overlapped_copy_ms_per_step"] = ov_ms
     except Exception as exc:   # the serial-copy measurement above stands
         e2e["overlap_error"] = repr(exc)
 

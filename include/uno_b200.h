@@ -212,6 +212,9 @@ int uno_plan_dft_mid_analysis(int n, int m, float* out /* [2m, n] complex */);
 int uno_plan_dft_mid_synthesis(int n, int m, float* out /* [n, 2m] complex */);
 int uno_plan_sr_mid(int n_in, int n_out, float* out /* [n_out, n_in] complex */);
 int uno_plan_sr_last_modes(int n_in, int n_out);
+/* opt-in band-limited variant of the 3-D pointwise resample (UNO_B200_POINTWISE3D_FIXED=1; not the reference's behaviour) */
+int uno_plan_sr_mid_fixed(int n_in, int n_out, float* out /* [n_out, n_in] complex */);
+int uno_plan_sr_last_modes_fixed(int n_in, int n_out);
 int uno_plan_bicubic_aa(int n_in, int n_out, int transpose, float* out /* dense [n_out,n_in] or its transpose */);
 /* the register-blocked image of the same band that the fused 2-D resample kernel consumes, expanded to dense;
  * gw[0], gw[1] receive the chosen (outputs per group, window) or (0,0) when the band does not fit (generic kernel) */

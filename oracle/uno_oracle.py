@@ -289,6 +289,26 @@ def pointwise_op_3d_fwd(x, conv_w, conv_b, out_dims):
     return np.fft.irfftn(ft_u, s=(d1, d2, d3), axes=(-3, -2, -1))
 
 
+def fourier_resample_matrix(n_in: int, n_out: int) -> np.ndarray:
+    """NOT the reference: the band-limited Fourier resample that the library offers as an opt-in replacement for
+    pointwise_op_3D's quirky spectral resample (UNO_B200_POINTWISE3D_FIXED=1).  Real [n_out, n_in]:
+    R[j, h] = (1/n_in) * sum_{|k| <= K} exp(2 pi i k (j/n_out - h/n_in)),  K = (min(n_in, n_out) - 1) // 2."""
+    K = (min(n_in, n_out) - 1) // 2
+    j = np.arange(n_out, dtype=np.float64)[:, None] / n_out
+    h = np.arange(n_in, dtype=np.float64)[None, :] / n_in
+    R = np.ones((n_out, n_in))
+    for k in range(1, K + 1):
+        R += 2.0 * np.cos(2.0 * np.pi * k * (j - h))
+    return R / n_in
+
+
+def pointwise_op_3d_fixed_fwd(x, conv_w, conv_b, out_dims):
+    """Conv3d(k=1) followed by the separable band-limited Fourier resample above (the opt-in mode; not the reference)."""
+    z = conv1x1(x, conv_w, conv_b)
+    R = [fourier_resample_matrix(z.shape[2 + a], out_dims[a]) for a in range(3)]
+    return np.einsum("pd,qe,rf,bcdef->bcpqr", R[0], R[1], R[2], z)
+
+
 # ---------------------------------------------------------------------------------------------
 # InstanceNorm / GELU / OperatorBlock
 # ---------------------------------------------------------------------------------------------

@@ -228,6 +228,31 @@ def test_instance_norm_big_cluster(odim, cuda_lib):
         assert rel_err(u, v) < BWD_TOL, rel_err(u, v)
 
 
+@pytest.mark.parametrize("idim,odim", [((16, 12, 13), (12, 12, 9)), ((12, 10, 9), (16, 14, 13)), ((24, 24, 21), (24, 24, 21))])
+def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
+    """UNO_B200_POINTWISE3D_FIXED=1 on the CUDA kernels (the CPU suite checks the same orchestration on the host emulation)."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(0)
+    m = ops.pointwise_op_3D(4, 6, *odim).cuda()
+    x = torch.randn(2, 4, *idim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        y = m(xx, *odim)
+        y.sum().backward()
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy()
+
+    y, gx = _with_env(run, UNO_B200_POINTWISE3D_FIXED=1)
+    cw = m.conv.weight.detach().cpu().numpy().reshape(6, 4)
+    y_or = orc.pointwise_op_3d_fixed_fwd(x.cpu().numpy(), cw, m.conv.bias.detach().cpu().numpy(), odim)
+    assert rel_err(y, y_or) < FWD_TOL, rel_err(y, y_or)
+    R = [orc.fourier_resample_matrix(idim[a], odim[a]) for a in range(3)]
+    gt = np.einsum("pd,qe,rf,bcpqr->bcdef", R[0], R[1], R[2], np.ones(y.shape))
+    gx_or = np.einsum("oc,bodef->bcdef", cw.astype(np.float64), gt)
+    assert rel_err(gx, gx_or) < BWD_TOL, rel_err(gx, gx_or)
+
+
 SHAPES_3D = [
     (2, 4, 6, (16, 16, 13), (12, 12, 13), (5, 5, 4)),
     (1, 8, 16, (24, 20, 21), (24, 20, 21), (8, 6, 5)),

@@ -140,3 +140,13 @@ def test_band_groups_reproduce_the_band(pair, transpose, lib):
         return
     assert (gw[0], gw[1]) in ((8, 8), (4, 8), (4, 16))
     assert np.array_equal(grouped, dense)
+
+
+@pytest.mark.parametrize("n_in,n_out", [(8, 6), (6, 9), (7, 7), (13, 8), (5, 16)])
+def test_sr_mid_fixed_is_the_dirichlet_kernel(lib, n_in, n_out):
+    from oracle import uno_oracle as orc
+
+    L = _call(lib.uno_plan_sr_mid_fixed, (n_out, n_in, 2), n_in, n_out)
+    R = orc.fourier_resample_matrix(n_in, n_out) * n_in       # the plan keeps the 1/N of the whole operator in the last-axis matrix
+    assert np.abs(L[..., 0] - R).max() < 1e-5 and np.abs(L[..., 1]).max() < 1e-5
+    assert lib.uno_plan_sr_last_modes_fixed(n_in, n_out) == (min(n_in, n_out) - 1) // 2 + 1

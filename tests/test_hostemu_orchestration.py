@@ -156,3 +156,46 @@ def test_bench_spectral_levels_from_report():
             raise OSError("no such symbol")
 
     assert "error" in bench.spectral_levels(Broken, 2, 6500.0)
+
+
+@pytest.mark.parametrize("idim,odim", [((8, 6, 9), (6, 6, 7)), ((6, 5, 7), (9, 8, 10)), ((7, 7, 7), (7, 7, 7)), ((8, 8, 8), (4, 12, 8))])
+def test_pointwise3d_fixed_mode(idim, odim, monkeypatch):
+    """UNO_B200_POINTWISE3D_FIXED=1 (opt-in, not the reference): pointwise_op_3D with the band-limited Fourier resample --
+    against the separable Dirichlet-kernel oracle, with the properties the quirky operator lacks (a constant stays the same
+    constant; a trigonometric polynomial inside the kept band is reproduced exactly on the new grid) and the adjoint backward."""
+    rng = np.random.default_rng(3)
+    B, Ci, Co = 2, 3, 2
+    x = rng.standard_normal((B, Ci) + idim).astype(np.float32)
+    cw = rng.standard_normal((Co, Ci)).astype(np.float32)
+    cb = rng.standard_normal(Co).astype(np.float32)
+    monkeypatch.setenv("UNO_B200_POINTWISE3D_FIXED", "1")
+    z, saved = emu.pointwise_fwd(x, cw, cb, odim, True)
+    z_or = orc.pointwise_op_3d_fixed_fwd(x, cw, cb, odim)
+    assert rel_err(z, z_or) < FWD_TOL, rel_err(z, z_or)
+    # constants: conv of a constant field is a constant per channel, and the resample keeps it (gain 1)
+    xc = np.ones_like(x)
+    zc, _ = emu.pointwise_fwd(xc, cw, cb, odim, True)
+    want = (cw.sum(axis=1) + cb).reshape(1, Co, 1, 1, 1)
+    assert np.abs(zc - want).max() < 2e-5 * np.abs(want).max()
+    # a band-limited plane wave is reproduced on the new grid
+    K = [(min(a, b) - 1) // 2 for a, b in zip(idim, odim)]
+    k = [min(1, K[0]), -min(1, K[1]), min(2, K[2])]
+    def wave(dims):
+        g = np.meshgrid(*[np.arange(n) / n for n in dims], indexing="ij")
+        return np.cos(2 * np.pi * (k[0] * g[0] + k[1] * g[1] + k[2] * g[2]) + 0.3)
+    xw = np.broadcast_to(wave(idim), (1, 1) + idim).astype(np.float32)
+    zw, _ = emu.pointwise_fwd(xw, np.ones((1, 1), np.float32), np.zeros(1, np.float32), odim, True)
+    assert np.abs(zw[0, 0] - wave(odim)).max() < 2e-5
+    # backward = adjoint: <R(Wx + b), g> differentiated by hand
+    gz = rng.standard_normal(z.shape).astype(np.float32)
+    gx, gcw, gcb = emu.pointwise_bwd(x, cw, odim, gz, saved)
+    R = [orc.fourier_resample_matrix(idim[a], odim[a]) for a in range(3)]
+    gt = np.einsum("pd,qe,rf,bcpqr->bcdef", R[0], R[1], R[2], gz.astype(np.float64))      # R^T g on the conv output grid
+    gx_or = np.einsum("oc,bodef->bcdef", cw.astype(np.float64), gt)
+    gcw_or = np.einsum("bodef,bcdef->oc", gt, x.astype(np.float64))
+    gcb_or = gt.sum(axis=(0, 2, 3, 4))
+    assert rel_err(gx, gx_or) < BWD_TOL and rel_err(gcw.reshape(Co, Ci), gcw_or) < BWD_TOL and rel_err(gcb, gcb_or) < BWD_TOL
+    # the default (reference) behaviour is untouched once the switch is off
+    monkeypatch.delenv("UNO_B200_POINTWISE3D_FIXED")
+    z_ref, _ = emu.pointwise_fwd(x, cw, cb, odim, True)
+    assert rel_err(z_ref, orc.pointwise_op_3d_fwd(x, cw, cb, odim)) < FWD_TOL

@@ -97,6 +97,8 @@ SYMBOLS = {
     "uno_plan_dft_mid_synthesis": (C.c_int, [C.c_int, C.c_int, _P]),
     "uno_plan_sr_mid": (C.c_int, [C.c_int, C.c_int, _P]),
     "uno_plan_sr_last_modes": (C.c_int, [C.c_int, C.c_int]),
+    "uno_plan_sr_mid_fixed": (C.c_int, [C.c_int, C.c_int, _P]),
+    "uno_plan_sr_last_modes_fixed": (C.c_int, [C.c_int, C.c_int]),
     "uno_plan_bicubic_aa": (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
     "uno_plan_band_groups": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
 }

@@ -129,6 +129,28 @@ std::vector<float> sr_mid(int n_in, int n_out) {
 
 int sr_last_modes(int n_in, int n_out) { return std::max(0, std::min(n_out / 2, n_in / 2 + 1)); }
 
+std::vector<float> sr_mid_fixed(int n_in, int n_out) {
+    const int K = (std::min(n_in, n_out) - 1) / 2;
+    std::vector<float> a((size_t)n_out * n_in * 2, 0.0f);
+    for (int j = 0; j < n_out; ++j)
+        for (int hh = 0; hh < n_in; ++hh) {
+            long double re = 0, im = 0;
+            for (int k = -K; k <= K; ++k) {
+                // frequency k on the input grid is bin (k mod n_in), on the output grid bin (k mod n_out)
+                long double c1, s1, c2, s2;
+                cis(((k % n_out) + n_out) % n_out, j, n_out, c1, s1);   // e^{+i a1}
+                cis(((k % n_in) + n_in) % n_in, hh, n_in, c2, s2);      // e^{-i a2} (as in sr_mid)
+                re += c1 * c2 + s1 * s2;
+                im += s1 * c2 - c1 * s2;
+            }
+            a[((size_t)j * n_in + hh) * 2] = (float)re;
+            a[((size_t)j * n_in + hh) * 2 + 1] = (float)im;
+        }
+    return a;
+}
+
+int sr_last_modes_fixed(int n_in, int n_out) { return (std::min(n_in, n_out) - 1) / 2 + 1; }
+
 // ---------------------------------------------------------------------------------------------
 // ATen upsample_bicubic2d_aa weights, fp32 arithmetic in ATen's order of operations
 // ---------------------------------------------------------------------------------------------

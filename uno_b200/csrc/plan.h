@@ -43,6 +43,13 @@ std::vector<float> conj_transpose(const std::vector<float>& a, int r, int c);
 std::vector<float> sr_mid(int n_in, int n_out);
 // last axis: number of kept half-spectrum bins
 int sr_last_modes(int n_in, int n_out);
+// Opt-in "fixed" variant (NOT the reference's behaviour): the band-limited Fourier resample the reference's
+// operator approximates -- the symmetric band |k| <= K = (min(n_in, n_out) - 1) / 2 is kept on every axis, negative frequencies
+// map to negative frequencies, nothing is aliased and a constant stays the same constant (gain 1 instead of N_in / N_out).
+//   leading axes: L[j,h] = sum_{k=-K..K} e^{2 pi i k j/n_out} e^{-2 pi i k h/n_in}   (real: a Dirichlet kernel; stored complex)
+std::vector<float> sr_mid_fixed(int n_in, int n_out);
+// last axis: bins 0..K of the half spectrum
+int sr_last_modes_fixed(int n_in, int n_out);
 
 // ---- anti-aliased bicubic (align_corners=True) as a banded matrix ---------------------------------
 struct Banded {

@@ -503,8 +503,17 @@ int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, 
 // R is linear and acts per channel, so it commutes with the channel mix; it is applied on whichever
 // side has fewer channels.  R(1) = gain (1 for bicubic; N_in/N_out for the 3-D operator).
 // ---------------------------------------------------------------------------------------------------
+// Opt-in, NOT the reference's behaviour: UNO_B200_POINTWISE3D_FIXED=1 replaces pointwise_op_3D's quirky
+// "spectral resample" by the band-limited Fourier resample it approximates (plan.h sr_mid_fixed).  Read when a call looks its
+// plan up, so set it before the first forward and keep it for the matching backward.
+inline bool pointwise3d_fixed() {
+    const char* e = getenv("UNO_B200_POINTWISE3D_FIXED");
+    return e && e[0] && e[0] != '0';
+}
+
 struct ResamplePlan {
     int d = 0;
+    bool fixed3d = false;
     int in[3], out[3];
     bool identity = false;
     double gain = 1.0;
@@ -532,17 +541,17 @@ struct ResamplePlan {
         }
         // 3-D spectral resample (never the identity: even same-size drops the top half-axis bins)
         identity = false;
-        m3 = sr_last_modes(in[2], out[2]);
-        gain = m3 >= 1 ? (double)n_in / (double)n_out : 0.0;
+        m3 = fixed3d ? sr_last_modes_fixed(in[2], out[2]) : sr_last_modes(in[2], out[2]);
+        gain = fixed3d ? 1.0 : (m3 >= 1 ? (double)n_in / (double)n_out : 0.0);
         if (m3 == 0) return 0;
         auto al = dft_last_analysis(in[2], m3, 1.0);
-        auto sl = dft_last_synthesis(out[2], m3, 1.0 / (double)n_out, true);
+        auto sl = dft_last_synthesis(out[2], m3, 1.0 / (double)(fixed3d ? n_in : n_out), true);
         BE_TRY(sa_last.upload(al));
         BE_TRY(ss_last.upload(sl));
         BE_TRY(sga_last.upload(transpose_real(sl, 2 * m3, out[2])));
         BE_TRY(sgs_last.upload(transpose_real(al, in[2], 2 * m3)));
         for (int a = 0; a < 2; ++a) {
-            auto L = sr_mid(in[a], out[a]);
+            auto L = fixed3d ? sr_mid_fixed(in[a], out[a]) : sr_mid(in[a], out[a]);
             BE_TRY(l_mid[a].upload(L));
             BE_TRY(lh_mid[a].upload(conj_transpose(L, out[a], in[a])));
         }
@@ -608,11 +617,14 @@ int get_resample_plan(const uno_conv_desc* d, ResamplePlan** out) {
     memset(&k, 0, sizeof k);
     k.v[0] = d->ndim;
     for (int a = 0; a < d->ndim; ++a) { k.v[1 + a] = d->in_dim[a]; k.v[4 + a] = d->out_dim[a]; }
+    const bool fixed3d = d->ndim == 3 && pointwise3d_fixed();
+    k.v[7] = fixed3d ? 1 : 0;
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_resample.find(k);
     if (it == g_resample.end()) {
         std::unique_ptr<ResamplePlan> p(new ResamplePlan());
         p->d = d->ndim;
+        p->fixed3d = fixed3d;
         for (int a = 0; a < 3; ++a) { p->in[a] = d->in_dim[a]; p->out[a] = d->out_dim[a]; }
         int rc = p->build();
         if (rc) return fail(UNO_ECUDA, "failed to upload resample plan (%s)", g_err.c_str());
@@ -639,7 +651,8 @@ size_t pw_resample_ws(const uno_conv_desc* d, long P) {
     tmp.d = d->ndim;
     for (int a = 0; a < 3; ++a) { tmp.in[a] = d->in_dim[a]; tmp.out[a] = d->out_dim[a]; }
     tmp.identity = pw_geom(d).identity;
-    tmp.m3 = d->ndim == 3 ? sr_last_modes(d->in_dim[2], d->out_dim[2]) : 0;
+    // the larger of the two modes' kept-bin counts: the workspace query must not depend on an environment switch
+    tmp.m3 = d->ndim == 3 ? std::max(sr_last_modes(d->in_dim[2], d->out_dim[2]), sr_last_modes_fixed(d->in_dim[2], d->out_dim[2])) : 0;
     return tmp.ws_floats(P);
 }
 
@@ -1155,6 +1168,13 @@ int uno_plan_sr_mid(int n_in, int n_out, float* out) {
     return 0;
 }
 int uno_plan_sr_last_modes(int n_in, int n_out) { return sr_last_modes(n_in, n_out); }
+int uno_plan_sr_mid_fixed(int n_in, int n_out, float* out) {
+    if (n_in < 1 || n_out < 1 || !out) return fail(UNO_EINVAL, "bad arguments");
+    auto v = sr_mid_fixed(n_in, n_out);
+    memcpy(out, v.data(), v.size() * sizeof(float));
+    return 0;
+}
+int uno_plan_sr_last_modes_fixed(int n_in, int n_out) { return sr_last_modes_fixed(n_in, n_out); }
 int uno_plan_bicubic_aa(int n_in, int n_out, int transpose, float* out) {
     if (n_in < 1 || n_out < 1 || !out) return fail(UNO_EINVAL, "bad arguments");
     Banded b = bicubic_aa(n_in, n_out);

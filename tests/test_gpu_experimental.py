@@ -253,6 +253,32 @@ def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
     assert rel_err(gx, gx_or) < BWD_TOL, rel_err(gx, gx_or)
 
 
+def test_empty_batch_like_the_reference(cuda_lib):
+    """B = 0: the reference's torch ops return empty tensors and zero parameter gradients; so do the modules and the model."""
+    from uno_b200 import integral_operators as ops
+    from uno_b200 import models
+
+    torch.manual_seed(0)
+    for m, x, args in [
+        (ops.SpectralConv2d_Uno(3, 5, 12, 10, 4, 4).cuda(), torch.zeros(0, 3, 16, 16, device="cuda"), (12, 10)),
+        (ops.pointwise_op_2D(3, 5, 12, 10).cuda(), torch.zeros(0, 3, 16, 16, device="cuda"), (12, 10)),
+        (ops.OperatorBlock_2D(3, 5, 12, 10, 4, 4, Normalize=True).cuda(), torch.zeros(0, 3, 16, 16, device="cuda"), (12, 10)),
+        (ops.OperatorBlock_3D(2, 4, 8, 8, 9, 3, 3, 3).cuda(), torch.zeros(0, 2, 8, 8, 9, device="cuda"), (8, 8, 9)),
+    ]:
+        x.requires_grad_(True)
+        y = m(x, *args)
+        assert y.shape == (0, y.shape[1]) + tuple(args) and y.is_cuda
+        y.sum().backward()
+        assert x.grad.shape == x.shape
+        for p in m.parameters():
+            assert p.grad is not None and float(p.grad.abs().max() if p.grad.numel() else 0) == 0.0
+    net = models.UNO_9(3, 8, pad=5).cuda()
+    out = net(torch.zeros(0, 85, 85, 1, device="cuda"))
+    assert out.shape == (0, 85, 85, 1)
+    out.sum().backward()
+    assert all(p.grad is not None for p in net.parameters())
+
+
 SHAPES_3D = [
     (2, 4, 6, (16, 16, 13), (12, 12, 13), (5, 5, 4)),
     (1, 8, 16, (24, 20, 21), (24, 20, 21), (8, 6, 5)),

@@ -26,7 +26,7 @@ ALL="UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_KPIPE_L
 
 if [[ $STAGES == *tests* ]]; then
     export UNO_B200_EXPERIMENTAL=1
-    for t in test_pointwise3d_fixed_mode_gpu test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_analysis_16_loader_warps \
+    for t in test_empty_batch_like_the_reference test_pointwise3d_fixed_mode_gpu test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_analysis_16_loader_warps \
              test_spectral2d_experimental_tc test_spectral3d_experimental_tc test_experimental_tc_timing; do
         run timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q -s -k $t
     done

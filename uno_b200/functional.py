@@ -317,26 +317,63 @@ def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+def _empty_batch(x, shape, *params):
+    """Empty batch: the reference's torch ops (fft, einsum, conv, interpolate, linear) accept one and return an empty tensor whose
+    graph still reaches the parameters, so their gradients come out as zeros.  No kernel is launched (the C ABI takes B >= 1)."""
+    y = x.new_zeros(tuple(int(v) for v in shape))
+    if torch.is_grad_enabled():
+        tie = None
+        for p in (x,) + params:
+            if p is not None and p.requires_grad:
+                t = (torch.view_as_real(p) if p.is_complex() else p).sum() * 0
+                tie = t if tie is None else tie + t
+        if tie is not None:
+            y = y + tie      # a 0-dim tensor broadcast onto [0, ...] keeps the empty shape
+    return y
+
+
 def spectral_conv(x, weights, out_dims, modes):
+    if x.shape[0] == 0:
+        _check_input(x)
+        return _empty_batch(x, (0, weights[0].shape[1]) + tuple(out_dims), *weights)
     return SpectralConvFn.apply(x, tuple(out_dims), tuple(modes), _needs_grad(x, *weights), *weights)
 
 
 def pointwise_op(x, conv_w, conv_b, out_dims):
+    if x.shape[0] == 0:
+        _check_input(x)
+        return _empty_batch(x, (0, conv_w.shape[0]) + tuple(out_dims), conv_w, conv_b)
     return PointwiseFn.apply(x, tuple(out_dims), _needs_grad(x, conv_w, conv_b), conv_w, conv_b)
 
 
 def operator_block(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None, non_lin=True, eps=1e-5):
     normalize = gamma is not None
+    if x.shape[0] == 0:
+        _check_input(x)
+        return _empty_batch(x, (0, weights[0].shape[1]) + tuple(out_dims), conv_w, conv_b, gamma, beta, *weights)
     need = _needs_grad(x, conv_w, conv_b, gamma, beta, *weights)
     return OperatorBlockFn.apply(x, tuple(out_dims), tuple(modes), normalize, bool(non_lin), float(eps), need, conv_w, conv_b, gamma, beta, *weights)
 
 
 def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
     """h[B, C, *padded] = pad(gelu(fc_b(gelu(fc_a(cat(a, grid))))))  -- a [B, *dims, raw_ch] channels-last, grid [*dims, G]."""
+    if a.shape[0] == 0:
+        _check_input(a)
+        dims = tuple(n + int(lo) + int(hi) for n, lo, hi in zip(a.shape[1:-1], pad_lo, pad_hi))
+        return _empty_batch(a, (0, w_b.shape[0]) + dims, w_a, b_a, w_b, b_b)
     return LiftFn.apply(a, grid, w_a, b_a, w_b, b_b, tuple(int(v) for v in pad_lo), tuple(int(v) for v in pad_hi))
 
 
 def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):
     """out[B, *cropped, out_ch] = fc2(gelu(fc1(crop(cat(srcs, dim=1)) channels-last)))."""
+    if srcs[0].shape[0] == 0:
+        for t in srcs:
+            _check_input(t)
+        dims = tuple(n - int(lo) - int(hi) for n, lo, hi in zip(srcs[0].shape[2:], crop_lo, crop_hi))
+        out = _empty_batch(srcs[0], (0,) + dims + (w2.shape[0],), w1, b1, w2, b2)
+        for t in srcs[1:]:
+            if torch.is_grad_enabled() and t.requires_grad:
+                out = out + t.sum() * 0
+        return out
     need = _needs_grad(w1, b1, w2, b2, *srcs)
     return ProjectFn.apply(w1, b1, w2, b2, tuple(int(v) for v in crop_lo), tuple(int(v) for v in crop_hi), need, *srcs)

@@ -94,7 +94,7 @@ class UNO_9(nn.Module):
     def forward(self, x):
         # lift + permute + pad (darcy_flow_uno2d.py:96-107) and cat + crop + permute + projection (:121-131) are one
         # kernel each; the padding grows the grid to the right / bottom only
-        grid = self.get_grid(x.shape, x.device)[0]
+        grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         grow = math.ceil(x.shape[2] / 85) * self.padding
         h = self._glue.lift(x, grid, self.fc_n1.weight, self.fc_n1.bias, self.fc0.weight, self.fc0.bias, (0, 0), (grow, grow))
         D1, D2 = h.shape[-2], h.shape[-1]
@@ -119,7 +119,7 @@ class _NS2DBase(nn.Module):
 
     def _lift(self, x):
         # navier_stokes_uno2d.py:191-201 -- F.pad on all four sides
-        grid = self.get_grid(x.shape, x.device)[0]
+        grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         p = self.padding
         return self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (p, p), (p, p))
 
@@ -252,7 +252,7 @@ class Uno3D_T10(nn.Module):
 
     def forward(self, x):
         # navier_stokes_uno3d.py:497-511: lift, channels-first, pad the time axis (trailing edge, or both)
-        grid = self.get_grid(x.shape, x.device)[0]
+        grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         self.padding = int(self.pad * 0.1 * x.shape[3])
         lo = self.padding if self.pad_both else 0
         h = self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (0, 0, lo), (0, 0, self.padding))

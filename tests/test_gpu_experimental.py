@@ -1,7 +1,7 @@
 """GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
 (tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
 rows that are not 16-byte aligned, tc_rowgemm.cuh with 16 epilogue warps).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
-UNO_B200_KPIPE_ALIGN / UNO_B200_KPIPE_LW16 / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
+UNO_B200_KPIPE_ALIGN / UNO_B200_KPIPE_LW16 / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER / UNO_B200_RS_SPLIT) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
 `pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
 
     UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
@@ -251,6 +251,30 @@ def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
     gt = np.einsum("pd,qe,rf,bcpqr->bcdef", R[0], R[1], R[2], np.ones(y.shape))
     gx_or = np.einsum("oc,bodef->bcdef", cw.astype(np.float64), gt)
     assert rel_err(gx, gx_or) < BWD_TOL, rel_err(gx, gx_or)
+
+
+@pytest.mark.parametrize("idim,odim", [((481, 481), (240, 240)), ((240, 240), (481, 481)), ((120, 120), (240, 240)), ((240, 240), (120, 120)),
+                                       ((64, 64), (48, 48)), ((33, 47), (70, 20)), ((446, 446), (223, 223))])
+def test_resample_split_staging(idim, odim, cuda_lib):
+    """UNO_B200_RS_SPLIT=1: the fused resample with its window staged as two cp.async groups -- same arithmetic in the same order
+    as the default kernel, so forward and backward must be bit-identical."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(0)
+    m = ops.pointwise_op_2D(3, 5, *odim).cuda()
+    x = torch.randn(2, 3, *idim, device="cuda")
+    gy = torch.randn(2, 5, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = m(xx, *odim)
+        y.backward(gy)
+        return y.detach().cpu().numpy(), xx.grad.cpu().numpy()
+
+    a = _with_env(run, UNO_B200_RS_SPLIT=1)
+    b = _with_env(run, UNO_B200_RS_SPLIT=0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (rel_err(a[0], b[0]), rel_err(a[1], b[1]))
 
 
 def test_empty_batch_like_the_reference(cuda_lib):

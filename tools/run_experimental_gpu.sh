@@ -22,11 +22,11 @@ for l in sys.stdin:
     print(json.dumps({'ms_per_step':d['ms_per_step'],'value':d['value'],'e2e':d['e2e']['value'],'top':{k:round(v['ms_per_step'],3) for k,v in list(kb.items())[:8]}}))
     print(json.dumps({'spectral_levels':d.get('spectral_levels')}))" >> $OUT.log 2>&1
 }
-ALL="UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_KPIPE_LW16=1 UNO_B200_ROWGEMM_EPI16=2 UNO_B200_NORM_BIG_CLUSTER=1"
+ALL="UNO_B200_RS_SPLIT=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_KPIPE_LW16=1 UNO_B200_ROWGEMM_EPI16=2 UNO_B200_NORM_BIG_CLUSTER=1"
 
 if [[ $STAGES == *tests* ]]; then
     export UNO_B200_EXPERIMENTAL=1
-    for t in test_empty_batch_like_the_reference test_pointwise3d_fixed_mode_gpu test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_analysis_16_loader_warps \
+    for t in test_resample_split_staging test_empty_batch_like_the_reference test_pointwise3d_fixed_mode_gpu test_instance_norm_big_cluster test_synthesis_16_warp_epilogue test_analysis_row_classes test_analysis_16_loader_warps \
              test_spectral2d_experimental_tc test_spectral3d_experimental_tc test_experimental_tc_timing; do
         run timeout 300 python -m pytest tests/test_gpu_experimental.py -x -q -s -k $t
     done
@@ -35,7 +35,7 @@ fi
 if [[ $STAGES == *bench* ]]; then
     for wl in darcy ns2d; do
         bench $wl UNO_NOFLAG=1
-        for f in UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_KPIPE_LW16=1 UNO_B200_ROWGEMM_EPI16=1 UNO_B200_ROWGEMM_EPI16=2; do
+        for f in UNO_B200_RS_SPLIT=1 UNO_B200_MID_TC=1 UNO_B200_CMM_TC=1 UNO_B200_KPIPE_ALIGN=1 UNO_B200_KPIPE_LW16=1 UNO_B200_ROWGEMM_EPI16=1 UNO_B200_ROWGEMM_EPI16=2; do
             bench $wl $f
         done
         bench $wl $ALL

@@ -1673,13 +1673,16 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
     static const int minb = [] { const char* e = getenv("UNO_B200_RS_MINB"); return e && e[0] == '3' ? 3 : 2; }();
-    int rc = minb == 3 ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 3>, smem) : ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem);
+    const bool split = [] { const char* e = getenv("UNO_B200_RS_SPLIT"); return e && e[0] && e[0] != '0'; }();   // opt-in, resample2d.cuh
+    int rc = minb == 3 ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 3>, smem)
+                       : (split ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2, true>, smem) : ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem));
     if (rc) return rc;
     if (a.planes > 65535) return -1;          // planes ride on grid.z
     ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
                  2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
     const dim3 grid((unsigned)k.tiles_w, (unsigned)k.tiles_h, (unsigned)a.planes);
     if (minb == 3) resample2d_kernel<G0, W0, G1, W1, 3><<<grid, 256, smem, st>>>(k);
+    else if (split) resample2d_kernel<G0, W0, G1, W1, 2, true><<<grid, 256, smem, st>>>(k);
     else resample2d_kernel<G0, W0, G1, W1, 2><<<grid, 256, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;

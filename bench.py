@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the U-NO hot path on B200 (contract: see the task prompt / DESIGN.md section "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload darcy|ns2d|ns3d]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload darcy|ns2d|ns3d|ns2d_ar]
 
-Default workload = BASELINE.json configs[1]: UNO_9(3, 32, pad=12) (darcy_flow_main.py:95) on synthetic
+Headline workload = BASELINE.json configs[1]: UNO_9(3, 32, pad=12) (darcy_flow_main.py:95) on synthetic
 421x421 Darcy inputs, batch 32 per GPU, forward + rel-L2 loss + backward (train_darcy.py:50-54), no
 optimizer step.  One JSON line is printed by rank 0.
 
-  value      samples/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e        same step driven from pinned HOST buffers (H2D of x,y and D2H of the loss inside the timed region)
-  roofline   dominant kernel family of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline / --impl reference: the oracle torch port (same MKL/ATen calls as the reference's CPU path)
-             timed on the host cores on a bounded sample of the same workload
+  value        samples/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same step driven from pinned HOST buffers (H2D of x,y and D2H of the loss inside the timed region)
+  roofline     dominant kernel family of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
+  secondary    the other half of BASELINE's metric in the same invocation, at every --gpus N: configs[3] (Uno3D_T10 64^3,
+               batch 8) and configs[2] (UNO 10-step autoregressive rollout + BPTT, batch 64) -- value, e2e, roofline each;
+               at N > 1 both the weak (per-GPU batch fixed) and the strong (global batch fixed) split
+  strong       (N > 1) the headline workload with the GLOBAL batch fixed at the BASELINE batch
+  reference_gpu (N = 1) the reference's OWN model files (oracle/_ref, staged byte for byte by build()) run through
+               torch-CUDA (cuFFT / cuBLAS / cuDNN, TF32 off) on the same B200 at the same batch -- the real bar
+  sweep        (N = 1) BASELINE configs[4]: SpectralConv2d S x m x C grid, GB/s and fraction of HBM, vs stock cuFFT path
+  cpu_baseline / --impl reference: the reference's own model (kind "reference") on the host cores, bounded sample
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -46,6 +52,7 @@ WORKLOAD_DESC = {
     "ns3d": "Uno3D_T10(6,8,pad=3) Navier-Stokes 64x64x64 fwd+loss+bwd",
     "ns2d_ar": "UNO(14,32) Navier-Stokes 64x64, 10-step autoregressive rollout + BPTT (ns_train_2d.py:46-67)",
 }
+SECONDARY = ("ns3d", "ns2d_ar")
 
 
 def peaks():
@@ -64,14 +71,27 @@ def measured_peaks():
         return {}
 
 
+def source_sha16():
+    """Identity of the device code a traffic capture belongs to: sha256 over the kernel sources."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "uno_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic(role, workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `role`, from the committed ncu --set full capture of
-    one step of this workload (profiles/r01_traffic.json, made by tools/ncu_traffic.py); None when there is none."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if workload != "darcy" or not os.path.exists(path):
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `role` from the committed ncu capture of one step of this
+    workload (profiles/r02_traffic_<workload>.json, tools/ncu_traffic.py) -- only when that capture was taken on the device
+    code that is running now (its `src_sha16` matches); otherwise None: a stale capture says nothing about this build."""
+    path = os.path.join(ROOT, "profiles", f"r02_traffic_{workload}.json")
     try:
-        return float(json.load(open(path))["roles"][role]["dram_bytes_per_launch"])
+        doc = json.load(open(path))
+        if doc.get("src_sha16") != source_sha16():
+            return None
+        return float(doc["roles"][role]["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -133,12 +153,17 @@ def build_model(workload, ops=None, device="cuda"):
     return getattr(models, cls)(*args, **kw).to(device)
 
 
-def make_step(model, loss_fn, B, tshape, reducer=None, ar_steps=0):
+def make_step(model, loss_fn, B, tshape, reducer=None, ar_steps=0, zero_grad=None):
+    """One training step without the optimizer: zero_grad -> forward -> loss -> backward, exactly the reference's loops
+    (train_darcy.py:50-54, ns_train_3d.py:51-65; ns_train_2d.py:52-67 for the autoregressive rollout)."""
+
     def step(x, y, before_loss=None):
         """`before_loss`: called once after the first forward, before the target is first read (the end-to-end arm waits there
         for the target's host-to-device copy, which it lets overlap the forward)."""
         if reducer is not None:
             reducer.zero_grad()
+        elif zero_grad is not None:
+            zero_grad()
         else:
             model.zero_grad(set_to_none=True)
         if ar_steps:
@@ -163,31 +188,98 @@ def make_step(model, loss_fn, B, tshape, reducer=None, ar_steps=0):
     return step
 
 
-def cpu_reference_run(workload, steps, warmup, batch=None):
-    """The oracle torch port (kind "port") on the host cores: fwd + loss + bwd, bounded batch."""
-    from oracle import uno_torch_port as port
+# ----------------------------------------------------------------------------------------------------------------------
+# the reference itself (oracle/_ref: its own model files, unmodified) -- CPU arm and torch-CUDA leg
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_model(workload, device):
+    """(model, loss class, kind): the reference's own nn.Module when oracle/_ref (or /root/reference) is there, else the
+    functional port of its operators under the same model table (kind "port")."""
+    cls, args, kw, *_ = WORKLOADS[workload]
+    try:
+        from oracle import ref_loader
 
-    LpLoss = port.LpLoss          # the CPU arm runs no code of the product
-    _, _, _, xshape, tshape, _, cpu_b = WORKLOADS[workload]
-    B = batch or cpu_b
+        torch.manual_seed(0)
+        model = ref_loader.model_class(workload)(*args, **kw).to(device)
+        return model, ref_loader.lp_loss(), "reference"
+    except ImportError:
+        from oracle import uno_torch_port as port
+
+        return build_model(workload, ops=port, device=device), port.LpLoss, "port"
+
+
+def cpu_reference_run(workload, steps, warmup, batch=None, budget_s=60.0):
+    """The reference's own model on the host cores: fwd + loss + bwd on a bounded sample of the workload (the per-GPU batch
+    when one step of it fits the time budget, else the largest power-of-two fraction that does)."""
+    _, _, _, xshape, tshape, full_b, cpu_b = WORKLOADS[workload]
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    model = build_model(workload, ops=port, device="cpu")
-    torch.manual_seed(1)
-    x = torch.randn(B, *xshape)
-    y = torch.randn(B, *tshape)
-    step = make_step(model, LpLoss(size_average=False), B, tshape, ar_steps=AR_STEPS.get(workload, 0))
-    for _ in range(warmup):
-        step(x, y)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step(x, y)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"batch {B} of the same workload, {steps} steps after {warmup} warm-up, fp32 torch CPU (oracle/uno_torch_port.py)",
+    model, LpLoss, kind = reference_model(workload, "cpu")
+    ar = AR_STEPS.get(workload, 0)
+
+    def run(B, n):
+        torch.manual_seed(1)
+        x, y = torch.randn(B, *xshape), torch.randn(B, *tshape)
+        step = make_step(model, LpLoss(size_average=False), B, tshape, ar_steps=ar)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step(x, y)
+        return (time.perf_counter() - t0) / n
+
+    B = batch or cpu_b
+    t_small = run(B, 1)                        # also the warm-up (MKL plans, allocator)
+    if batch is None:
+        want = full_b
+        try:
+            import psutil
+
+            mem_cap = psutil.virtual_memory().available * 0.25
+        except Exception:
+            mem_cap = 16e9
+        per_sample = 1.0e9      # autograd-saved activations per sample: upper bound (measured 0.5 GB Darcy, < 1 GB NS-3D)
+        while want > B and (t_small * want / B * (steps + max(warmup - 1, 0)) > budget_s or want * per_sample > mem_cap):
+            want //= 2
+        B = max(B, want)
+    for _ in range(max(warmup - 1, 0)):
+        run(B, 1)
+    dt = run(B, steps)
+    src = "oracle/_ref: the reference's own model files" if kind == "reference" else "oracle/uno_torch_port.py"
+    return {"value": B / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"batch {B} of the same workload (full per-GPU batch {full_b}), {steps} steps after {max(warmup, 1)} warm-up, "
+                      f"fp32 torch CPU ({src})",
             "ms_per_step": dt * 1e3, "batch": B}
 
 
+def reference_gpu_run(workload, B, steps, warmup, dev):
+    """The reference's own model through torch-CUDA on this GPU (cuFFT + cuBLAS cgemm + cuDNN / ATen kernels; TF32 off so
+    that it computes what its CPU path computes), same batch, same step, CUDA-event timed."""
+    _, _, _, xshape, tshape, _, _ = WORKLOADS[workload]
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model, LpLoss, kind = reference_model(workload, dev)
+        step = make_step(model, LpLoss(size_average=False), B, tshape, ar_steps=AR_STEPS.get(workload, 0))
+        torch.manual_seed(1)
+        x = torch.randn(B, *xshape, device=dev)
+        y = torch.randn(B, *tshape, device=dev)
+        for _ in range(warmup):
+            step(x, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "batch": B, "kind": kind, "steps": steps,
+                "path": "torch-CUDA eager (cuFFT, cuBLAS, cuDNN/ATen), allow_tf32=False, same B200"}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 def spectral_levels(lib, nprof, hbm_gbs):
     """Per U-level roofline of the fused spectral convolution (north_star: 'achieved fraction of HBM and tensor-core roofline
     reported per U-level'): for every distinct call shape and direction, the summed CUDA-event time of the kernels that call
@@ -214,6 +306,200 @@ def spectral_levels(lib, nprof, hbm_gbs):
         return {"error": repr(e)}
 
 
+class Ctx:
+    def __init__(self, rank, world, local, dev, lib):
+        self.rank, self.world, self.local, self.dev, self.lib = rank, world, local, dev, lib
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(self, fn, n):
+        """n calls of fn between barrier + synchronize on both sides, CUDA events, max over ranks (ms total)."""
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        self.sync_all()
+        return ms
+
+
+def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=None):
+    """Measure one workload on this job's GPUs: device-resident value, end-to-end from pinned host buffers, per-kernel roofline."""
+    from uno_b200.losses import LpLoss
+    from uno_b200.parallel import GradReducer
+
+    lib, dev, world, rank = ctx.lib, ctx.dev, ctx.world, ctx.rank
+    _, _, _, xshape, tshape, _, _ = WORKLOADS[workload]
+    model = build_model(workload, device=dev)
+    reducer = GradReducer(model) if world > 1 else None
+    ar = AR_STEPS.get(workload, 0)
+    step = make_step(model, LpLoss(size_average=False), B, tshape, reducer, ar_steps=ar)
+    rollout = "eager"
+    if ar:
+        try:   # the captured rollout (uno_b200/rollout.py): window shift fused into the lift, whole rollout + BPTT in one graph
+            from uno_b200.rollout import GraphedRollout
+
+            step = GraphedRollout(model, LpLoss(size_average=False), B, ar, reducer=reducer)
+            rollout = step.mode
+        except ImportError:
+            pass
+
+    torch.manual_seed(1 + rank)
+    x_host = torch.randn(B, *xshape).pin_memory()
+    y_host = torch.randn(B, *tshape).pin_memory()
+    x = x_host.to(dev)
+    y = y_host.to(dev)
+
+    for _ in range(warmup):
+        step(x, y)
+    # --- device-resident timing
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    l0 = lib.uno_launch_count()
+    total_ms = ctx.timed(lambda: step(x, y), steps)
+    launches = lib.uno_launch_count() - l0
+    clocks = sampler.finish()
+    ms_per_step = total_ms / steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    # --- end to end from pinned host memory
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        return float(step(xd, yd).item())
+
+    e2e_step()
+    e2e_ms = ctx.timed(e2e_step, steps) / steps
+    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s",
+           "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms, "copies": "input and target copied on the compute stream before the step"}
+
+    # Same step, same bytes, same loss read-back, but the target's copy is issued on a copy stream right behind the input's and
+    # the compute stream only waits for it where the loss first reads it: half of the host-to-device time hides behind the
+    # forward.  Reported as `e2e` when it ran and was faster; the serial-copy figure stays next to it.
+    if rollout == "eager":
+        try:
+            copy_stream = None
+
+            def e2e_step_overlap():
+                cur = torch.cuda.current_stream(dev)
+                xd = x_host.to(dev, non_blocking=True)
+                x_done = torch.cuda.Event()
+                x_done.record(cur)
+                copy_stream.wait_event(x_done)
+                with torch.cuda.stream(copy_stream):
+                    yd = y_host.to(dev, non_blocking=True)
+                    y_done = torch.cuda.Event()
+                    y_done.record(copy_stream)
+
+                def before_loss():
+                    cur.wait_event(y_done)
+                    yd.record_stream(cur)
+
+                return float(step(xd, yd, before_loss).item())
+
+            ok, why = 1, ""
+            try:
+                copy_stream = torch.cuda.Stream(device=dev)
+                ref_loss = e2e_step()
+                got_loss = e2e_step_overlap()
+                if abs(got_loss - ref_loss) > 1e-4 * max(1.0, abs(ref_loss)):
+                    ok, why = 0, f"overlapped-copy step changed the loss: {got_loss} vs {ref_loss}"
+            except Exception as exc:
+                ok, why = 0, repr(exc)
+            if world > 1:   # every rank takes the same branch (the timed loop below contains collectives)
+                flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                ok = int(flag.item())
+            if not ok:
+                raise RuntimeError(why or "another rank could not run the overlapped-copy step")
+            ov_ms = ctx.timed(e2e_step_overlap, steps) / steps
+            if ov_ms < e2e_ms:
+                e2e = {"value": B * world / (ov_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
+                       "d2h_bytes_per_step": 4, "ms_per_step": ov_ms,
+                       "copies": "input copied on the compute stream, target on a copy stream behind it (waited for at the loss)",
+                       "serial_copy_value": e2e["value"], "serial_copy_ms_per_step": e2e_ms}
+            else:   # no gain on this box: the serial-copy figure stays the headline
+                e2e["overlapped_copy_value"] = B * world / (ov_ms * 1e-3)
+                e2e["overlapped_copy_ms_per_step"] = ov_ms
+        except Exception as exc:   # the serial-copy measurement above stands
+            e2e["overlap_error"] = repr(exc)
+
+    # --- per-kernel roofline, CUDA events around every launch of OUR kernels (separate steps so the
+    #     event records do not perturb `value`; a captured rollout is re-run eagerly for it: events cannot be captured)
+    roofline, breakdown, levels = None, None, None
+    if profile:
+        hbm, how = peaks()
+        prof_step = step.eager_step if hasattr(step, "eager_step") else step
+        ctx.sync_all()
+        if rank == 0:
+            lib.uno_profile_enable(1)
+        nprof = 2
+        for _ in range(nprof):
+            prof_step(x, y)
+        ctx.sync_all()
+        if rank == 0:
+            n = lib.uno_profile_report(None, 0)
+            buf = C.create_string_buffer(n + 16)
+            lib.uno_profile_report(buf, n + 16)
+            levels = spectral_levels(lib, nprof, hbm)
+            lib.uno_profile_enable(0)
+            prof = json.loads(buf.value.decode())
+            tot = sum(v["ms"] for v in prof.values()) or 1.0
+            breakdown = {k: {"launches_per_step": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
+                             "share_of_uno_kernels": v["ms"] / tot,
+                             "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
+                             "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm if v["ms"] > 0 else None,
+                             "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
+                         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+            top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
+            achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                        "traffic": measured_traffic(top, workload), "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
+                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
+                        "uno_kernel_ms_per_step": tot / nprof}
+            if breakdown_top:
+                breakdown = dict(list(breakdown.items())[:breakdown_top])
+        elif rank != 0:
+            pass
+    del model, step, reducer, x, y
+    torch.cuda.empty_cache()
+    return {"workload": WORKLOAD_DESC[workload], "per_gpu_batch": B, "global_batch": B * world, "value": value, "unit": "samples/s",
+            "ms_per_step": ms_per_step, "steps": steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "rollout": rollout if ar else None, "roofline": roofline, "kernel_breakdown": breakdown, "spectral_levels": levels}
+
+
+def spectral_sweep(iters=3):
+    """BASELINE configs[4]: SpectralConv2d_Uno(C,C,S,S,m,m), 512 MiB inputs, fwd and bwd separately,
+    against 8(d)'s algorithmic bytes and against the stock torch-CUDA layer (cuFFT rfft2 / complex einsum / irfft2)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep_spectral as sw
+
+    hbm, _ = peaks()
+    timer = sw.Timer(flush=False)
+    rows = []
+    for S in (64, 128, 256, 512):
+        for m in (12, 20, 32):
+            for Cc in (32, 64, 128):
+                r = sw.measure(timer, (1 << 27) // (Cc * S * S), Cc, Cc, S, S, S, S, m, m, iters, hbm)
+                rows.append({k: r[k] for k in ("B", "Ci", "in", "modes", "fwd_ms", "bwd_ms", "fwd_gbs", "bwd_gbs", "fwd_frac", "bwd_frac",
+                                               "speedup_fwd", "speedup_bwd")})
+    return {"what": "SpectralConv2d_Uno(C,C,S,S,m,m), 512 MiB input (> L2), median of %d, CUDA events; *_frac = SURVEY 8(d) algorithmic "
+                    "bytes / time / measured HBM peak; speedup_* = stock torch-CUDA layer (cuFFT + complex einsum) time / ours" % iters,
+            "rows": rows}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -222,10 +508,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="darcy", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the BASELINE config's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="headline split at N > 1: per-GPU batch fixed (weak) or global batch fixed (strong); the other one is reported beside it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="headline workload only (no secondary / reference / sweep legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.lean:
+        args.no_secondary = args.no_reference_gpu = args.no_sweep = args.no_cpu_baseline = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,15 +527,15 @@ def main():
     cls, cargs, ckw, xshape, tshape, def_b, _ = WORKLOADS[args.workload]
     B = args.batch or def_b
 
-    # ------------------------------------------------------------------ reference arm (CPU port)
+    # ------------------------------------------------------------------ reference arm (the reference on the host cores)
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = min(args.steps, 5)
-        r = cpu_reference_run(args.workload, steps, min(args.warmup, 1))
+        steps, warm = min(args.steps, 3), min(args.warmup, 1)
+        r = cpu_reference_run(args.workload, steps, warm)
         line = {
             "impl": "reference", "metric": "UNO samples/sec (fwd+bwd)", "value": r["value"], "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[args.workload], "per_gpu_batch": B, "cpu_sample_batch": r["batch"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -272,170 +566,88 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     from uno_b200 import _lib, build as _build
-    from uno_b200.losses import LpLoss
-    from uno_b200.parallel import GradReducer
 
     if rank == 0:
         _build.build()
     if world > 1:
         dist.barrier()
-    lib = _lib.get()
+    ctx = Ctx(rank, world, local, dev, _lib.get())
 
-    model = build_model(args.workload, device=dev)
-    reducer = GradReducer(model) if world > 1 else None
-    loss_fn = LpLoss(size_average=False)
-    step = make_step(model, loss_fn, B, tshape, reducer, ar_steps=AR_STEPS.get(args.workload, 0))
+    def split(full, mode):
+        """per-GPU batch of a workload whose BASELINE batch is `full`"""
+        if mode == "weak" or world == 1:
+            return full
+        return max(full // world, 1)
 
-    torch.manual_seed(1 + rank)
-    x_host = torch.randn(B, *xshape).pin_memory()
-    y_host = torch.randn(B, *tshape).pin_memory()
-    x = x_host.to(dev)
-    y = y_host.to(dev)
+    main_mode = args.scaling
+    head = run_workload(ctx, args.workload, args.batch or split(def_b, main_mode), args.steps, args.warmup, profile=not args.no_profile)
+    other = None
+    if world > 1 and args.batch is None:
+        om = "strong" if main_mode == "weak" else "weak"
+        o = run_workload(ctx, args.workload, split(def_b, om), args.steps, args.warmup, profile=False)
+        other = {k: o[k] for k in ("per_gpu_batch", "global_batch", "value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+        other["scaling"] = om
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    secondary = None
+    if not args.no_secondary and args.workload == "darcy":
+        secondary = {}
+        for wl in SECONDARY:
+            full = WORKLOADS[wl][5]
+            try:
+                modes = ["weak"] if world == 1 else ["weak", "strong"]
+                ent = {}
+                for mode in modes:
+                    r = run_workload(ctx, wl, split(full, mode), min(args.steps, 10), args.warmup, profile=(mode == "weak"), breakdown_top=10)
+                    r["scaling"] = mode
+                    ent[mode] = r
+                secondary[wl] = ent["weak"] if world == 1 else ent
+            except Exception as exc:   # the headline must survive a problem in a secondary workload
+                if world > 1:
+                    raise
+                secondary[wl] = {"error": repr(exc)}
 
-    def timed(fn, n):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        sync_all()
-        return ms
-
-    for _ in range(args.warmup):
-        step(x, y)
-    # --- device-resident timing
-    sampler = ClockSampler(local)
-    sampler.start()
-    l0 = lib.uno_launch_count()
-    total_ms = timed(lambda: step(x, y), args.steps)
-    launches = lib.uno_launch_count() - l0
-    clocks = sampler.finish()
-    ms_per_step = total_ms / args.steps
-    value = B * world / (ms_per_step * 1e-3)
-
-    # --- end to end from pinned host memory
-    def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        yd = y_host.to(dev, non_blocking=True)
-        return float(step(xd, yd).item())
-
-    e2e_step()
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
-    e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s",
-           "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
-           "ms_per_step": e2e_ms, "copies": "input and target copied on the compute stream before the step"}
-
-    # Same step, same bytes, same loss read-back, but the target's copy is issued on a copy stream right behind the input's and
-    # the compute stream only waits for it where the loss first reads it: half of the host-to-device time hides behind the
-    # forward.  Reported as `e2e` when it ran; the serial-copy figure stays next to it.
-    try:
-        copy_stream = None
-
-        def e2e_step_overlap():
-            cur = torch.cuda.current_stream(dev)
-            xd = x_host.to(dev, non_blocking=True)
-            x_done = torch.cuda.Event()
-            x_done.record(cur)
-            copy_stream.wait_event(x_done)
-            with torch.cuda.stream(copy_stream):
-                yd = y_host.to(dev, non_blocking=True)
-                y_done = torch.cuda.Event()
-                y_done.record(copy_stream)
-
-            def before_loss():
-                cur.wait_event(y_done)
-                yd.record_stream(cur)
-
-            return float(step(xd, yd, before_loss).item())
-
-        ok, why = 1, ""
-        try:
-            copy_stream = torch.cuda.Stream(device=dev)
-            ref_loss = e2e_step()
-            got_loss = e2e_step_overlap()
-            if abs(got_loss - ref_loss) > 1e-4 * max(1.0, abs(ref_loss)):
-                ok, why = 0, f"overlapped-copy step changed the loss: {got_loss} vs {ref_loss}"
-        except Exception as exc:
-            ok, why = 0, repr(exc)
-        if world > 1:   # every rank takes the same branch (the timed loop below contains collectives)
-            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            ok = int(flag.item())
-        if not ok:
-            raise RuntimeError(why or "another rank could not run the overlapped-copy step")
-        ov_ms = timed(e2e_step_overlap, args.steps) / args.steps
-        if ov_ms < e2e_ms:
-            e2e = {"value": B * world / (ov_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": e2e["h2d_bytes_per_step"],
-                   "d2h_bytes_per_step": 4, "ms_per_step": ov_ms,
-                   "copies": "input copied on the compute stream, target on a copy stream behind it (waited for at the loss)",
-                   "serial_copy_value": e2e["value"], "serial_copy_ms_per_step": e2e_ms}
-        else:   # no gain on this box: the serial-copy figure stays the headline
-            e2e["overlapped_copy_value"] = B * world / (ov_ms * 1e-3)
-            e2e["overlapped_copy_ms_per_step"] = ov_ms
-    except Exception as exc:   # the serial-copy measurement above stands
-        e2e["overlap_error"] = repr(exc)
-
-    # --- per-kernel roofline, CUDA events around every launch of OUR kernels (separate steps so the
-    #     event records do not perturb `value`)
-    roofline, breakdown, levels = None, None, None
-    if not args.no_profile:
-        # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records events
-        hbm, how = peaks()
-        sync_all()
-        if rank == 0:
-            lib.uno_profile_enable(1)
-        nprof = 2
-        for _ in range(nprof):
-            step(x, y)
-        sync_all()
-        if rank == 0:
-            n = lib.uno_profile_report(None, 0)
-            buf = C.create_string_buffer(n + 16)
-            lib.uno_profile_report(buf, n + 16)
-            levels = spectral_levels(lib, nprof, hbm)
-            lib.uno_profile_enable(0)
-            prof = json.loads(buf.value.decode())
-            tot = sum(v["ms"] for v in prof.values()) or 1.0
-            breakdown = {k: {"launches_per_step": v["launches"] // nprof, "ms_per_step": v["ms"] / nprof,
-                             "share_of_uno_kernels": v["ms"] / tot,
-                             "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None,
-                             "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None}
-                         for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-            top, tv = max(prof.items(), key=lambda kv: kv[1]["ms"])
-            achieved = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                        "traffic": measured_traffic(top, args.workload), "peak_source": how, "avg_launch_ms": tv["ms"] / tv["launches"],
-                        "algorithmic_bytes_per_launch": tv["bytes"] / tv["launches"],
-                        "uno_kernel_ms_per_step": tot / nprof}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(args.workload, 3, 1)
-        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    cpu_baseline = reference_gpu = sweep = None
+    if rank == 0 and world == 1:
+        if not args.no_reference_gpu:
+            reference_gpu = {}
+            mine = {args.workload: head}
+            mine.update({k: v for k, v in (secondary or {}).items() if "value" in v})
+            for wl, r in mine.items():
+                try:
+                    g = reference_gpu_run(wl, r["per_gpu_batch"], 5, 2, dev)
+                    g["speedup"] = r["value"] / g["value"]
+                    reference_gpu[wl] = g
+                except Exception as exc:
+                    reference_gpu[wl] = {"error": repr(exc)}
+        if not args.no_sweep and args.workload == "darcy":
+            try:
+                sweep = spectral_sweep()
+            except Exception as exc:
+                sweep = {"error": repr(exc)}
+        if not args.no_cpu_baseline:
+            r = cpu_reference_run(args.workload, 3, 1, batch=WORKLOADS[args.workload][6])
+            cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            for wl, ent in (secondary or {}).items():
+                if "value" in ent:
+                    try:
+                        rr = cpu_reference_run(wl, 2, 1, batch=WORKLOADS[wl][6])
+                        ent["cpu_baseline"] = {k: rr[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    except Exception as exc:
+                        ent["cpu_baseline"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {
-            "metric": "UNO samples/sec (fwd+bwd)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "UNO samples/sec (fwd+bwd)", "value": head["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": main_mode, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC[args.workload], "per_gpu_batch": B, "global_batch": B * world,
+            "config": {"workload": WORKLOAD_DESC[args.workload], "per_gpu_batch": head["per_gpu_batch"], "global_batch": head["global_batch"],
                        "parallelism": f"dp{world} (batch shard, flat-buffer gradient all-reduce)" if world > 1 else "single GPU",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "kernel_breakdown": breakdown, "spectral_levels": levels,
+            "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
+            ("strong" if main_mode == "weak" else "weak"): other, "secondary": secondary,
+            "kernel_breakdown": head["kernel_breakdown"], "spectral_levels": head["spectral_levels"], "sweep": sweep,
+            "src_sha16": source_sha16(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

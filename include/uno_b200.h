@@ -189,6 +189,17 @@ int uno_lp_loss_fwd(const float* x, const float* y, int batch, long n, int reduc
 int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const float* gloss, int batch, long n,
                     int reduction, float* gx, void* stream);
 
+/* ---- run-time switches -------------------------------------------------------------------------------
+ * Kernel-selection switches (uno_b200/csrc/config.h: "tc", "mid_tc", "cmm_tc", "kpipe_align", "kpipe_lw16",
+ * "rowgemm_epi16", "rowgemm_parity", "norm_big_cluster", "overlap", "pointwise3d_fixed", "proj_simt", "fused_core", ...).
+ * Their initial values come from the environment ONCE, at first use (UNO_B200_<NAME>); afterwards only these calls change
+ * them -- no call path reads the environment.  Every setting computes the same function (parity-tested on B200) except
+ * "pointwise3d_fixed", which is documented as deviating from the reference.  uno_config_name(i) enumerates the names
+ * (NULL past the end).  Unknown name -> UNO_EINVAL.                                                             */
+int uno_config_set(const char* name, int value);
+int uno_config_get(const char* name, int* value);
+const char* uno_config_name(int index);
+
 /* ---- measurement hooks (bench.py) -----------------------------------------------------------------
  * uno_launch_count: kernels this library has launched since it was loaded.
  * uno_profile_enable(1) brackets every kernel launch with a CUDA-event pair on the launching stream;

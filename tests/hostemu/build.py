@@ -10,8 +10,8 @@ OUT = os.path.join(HERE, "libuno_hostemu.so")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, "uno_api.cpp"), os.path.join(CSRC, "plan.cpp"), os.path.join(HERE, "backend_host.cpp")]
-    deps = srcs + [os.path.join(CSRC, "backend.h"), os.path.join(CSRC, "plan.h"), os.path.join(ROOT, "include", "uno_b200.h")]
+    srcs = [os.path.join(CSRC, "uno_api.cpp"), os.path.join(CSRC, "plan.cpp"), os.path.join(CSRC, "config.cpp"), os.path.join(HERE, "backend_host.cpp")]
+    deps = srcs + [os.path.join(CSRC, "backend.h"), os.path.join(CSRC, "plan.h"), os.path.join(CSRC, "config.h"), os.path.join(ROOT, "include", "uno_b200.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", OUT] + srcs

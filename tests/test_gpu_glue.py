@@ -110,14 +110,11 @@ def test_glue_matches_torch_at_darcy_size(cuda_lib):
     assert float(g0[0][..., S:, :].abs().max()) == 0.0 and float(g0[1][..., :, S:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("env", ["UNO_B200_PROJ_SIMT", "UNO_B200_PROJ_TC", "UNO_B200_PROJ_MMA"])
 @pytest.mark.parametrize("name", ["darcy", "tc_two_chunks", "tc_wide", "tc_one_chunk"])
-def test_project_backward_tensor_core_variants(env, name, cuda_lib):
-    """The selectable variants of the projection backward against the fp64 oracle, same tolerance for all: the fp32 kernel
-    (forced with UNO_B200_PROJ_SIMT; the default is the warp-specialised tcgen05 kernel where the shape allows it, which
-    test_project covers), the first barrier-synchronised tcgen05 kernel, and the warp-level mma.sync kernel (both 3xTF32)."""
-    import os
-
+def test_project_backward_fp32_kernel(name, cuda_lib):
+    """The fp32 projection backward (switch proj_simt) against the fp64 oracle on the shapes whose default is the
+    warp-specialised tcgen05 kernel (which test_project covers), same tolerance."""
+    from uno_b200 import config
     from uno_b200 import functional as Fn
 
     case = PROJECT_CASES[name]
@@ -126,13 +123,10 @@ def test_project_backward_tensor_core_variants(env, name, cuda_lib):
     ref = project_oracle(case, t)
     srcs = [_cu(s, True) for s in t["srcs"]]
     w1, b1, w2, b2 = (_cu(t[k], True) for k in ("w1", "b1", "w2", "b2"))
-    os.environ[env] = "1"
-    try:
+    with config.switches(proj_simt=1):
         out = Fn.project(srcs, w1, b1, w2, b2, lo, hi)
         out.backward(_cu(t["gout"]))
         torch.cuda.synchronize()
-    finally:
-        del os.environ[env]
     for s, r in zip(srcs, ref["gsrcs"]):
         assert rel_err(s.grad.cpu().numpy(), r) < BWD_TOL
     for got, key in ((w1, "gw1"), (b1, "gb1"), (w2, "gw2"), (b2, "gb2")):

@@ -1,6 +1,4 @@
 """GPU: the tcgen05 (3xTF32) kernels against the SIMT fp32 kernels and the oracle, shape by shape."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -12,17 +10,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(fn, disable_tc):
-    old = os.environ.get("UNO_B200_DISABLE_TC")
-    os.environ["UNO_B200_DISABLE_TC"] = "1" if disable_tc else "0"
-    try:
+    from uno_b200 import config
+
+    with config.switches(tc=0 if disable_tc else 1):
         out = fn()
         torch.cuda.synchronize()
         return out
-    finally:
-        if old is None:
-            os.environ.pop("UNO_B200_DISABLE_TC", None)
-        else:
-            os.environ["UNO_B200_DISABLE_TC"] = old
 
 
 # (B, Ci, Co, in, out, modes): output widths cover one/two N tiles, padded tiles, odd leading dims,

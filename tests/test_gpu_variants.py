@@ -1,13 +1,9 @@
-"""GPU, opt-in: tcgen05 kernels that have been compiled and index-checked but NOT yet run on a B200
-(tc_mid.cuh: leading-axis transform, tc_cmm.cuh: per-mode channel contraction, tc_kpipe.cuh row-class mode: 16-byte loads for
-rows that are not 16-byte aligned, tc_rowgemm.cuh with 16 epilogue warps).  They are off by default in the library (UNO_B200_MID_TC / UNO_B200_CMM_TC /
-UNO_B200_KPIPE_ALIGN / UNO_B200_KPIPE_LW16 / UNO_B200_ROWGEMM_EPI16 / UNO_B200_NORM_BIG_CLUSTER / UNO_B200_RS_SPLIT) and these tests are skipped unless UNO_B200_EXPERIMENTAL=1, so that the default
-`pytest -m gpu` run only exercises kernels that have been measured.  First thing to run on a GPU box:
-
-    UNO_B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -x -q
+"""GPU: every kernel-selection switch of the library (uno_b200/csrc/config.h) against the oracle and against the
+alternative kernel it replaces -- tcgen05 leading-axis transform (tc_mid.cuh) and per-mode channel contraction (tc_cmm.cuh),
+row-class and 16-loader-warp analysis (tc_kpipe.cuh), 16-warp synthesis epilogue (tc_rowgemm.cuh), big-cluster InstanceNorm,
+the band-limited 3-D pointwise mode, empty batches.  All of these ran green on a B200 (profiles/r02_experimental_v44.log)
+before they became defaults; both settings of each switch stay covered here so that the driver's `pytest -m gpu` runs them.
 """
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -15,25 +11,17 @@ import torch
 from conftest import BWD_TOL, FWD_TOL, rel_err
 from oracle import uno_oracle as orc
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("UNO_B200_EXPERIMENTAL", "0") in ("", "0"), reason="opt-in: UNO_B200_EXPERIMENTAL=1"),
-]
+pytestmark = [pytest.mark.gpu]
 
 
-def _with_env(fn, **env):
-    old = {k: os.environ.get(k) for k in env}
-    os.environ.update({k: str(v) for k, v in env.items()})
-    try:
+def _with(fn, **switches):
+    """run fn() with the library switches set (uno_config_set), restore them afterwards"""
+    from uno_b200 import config
+
+    with config.switches(**switches):
         out = fn()
         torch.cuda.synchronize()
         return out
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
 
 
 # (B, Ci, Co, in, out, modes): leading-axis sizes with one / two / four column tiles of the transform matrix, ragged row
@@ -50,9 +38,9 @@ SHAPES_2D = [
 ]
 
 
-@pytest.mark.parametrize("which", ["mid", "cmm", "both"])
+@pytest.mark.parametrize("which", ["mid", "cmm", "both", "simt"])
 @pytest.mark.parametrize("shape", SHAPES_2D)
-def test_spectral2d_experimental_tc(shape, which, cuda_lib):
+def test_spectral2d_tc_core(shape, which, cuda_lib):
     from uno_b200 import integral_operators as ops
 
     B, Ci, Co, idim, odim, modes = shape
@@ -69,8 +57,8 @@ def test_spectral2d_experimental_tc(shape, which, cuda_lib):
         return (y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy(),
                 torch.view_as_real(m.weights2.grad).cpu().numpy())
 
-    env = {"UNO_B200_MID_TC": int(which in ("mid", "both")), "UNO_B200_CMM_TC": int(which in ("cmm", "both"))}
-    y_tc, gx_tc, gw1_tc, gw2_tc = _with_env(run, **env)
+    sw = {"mid_tc": int(which in ("mid", "both")), "cmm_tc": 2 * int(which in ("cmm", "both"))}   # 2 = every shape, not only tile-filling ones
+    y_tc, gx_tc, gw1_tc, gw2_tc = _with(run, **sw)
     ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
     y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)
     gx_or, gw_or = orc.spectral_conv_bwd(x.cpu().numpy(), ws, odim, modes, gy.cpu().numpy())
@@ -104,7 +92,7 @@ SHAPES_LW16 = SHAPES_ALIGN + [
 @pytest.mark.parametrize("align", [0, 1])
 @pytest.mark.parametrize("shape", SHAPES_LW16)
 def test_analysis_16_loader_warps(shape, align, cuda_lib):
-    """UNO_B200_KPIPE_LW16=1: the analysis kernel with 16 loader warps (all three loader paths) against the default 8."""
+    """kpipe_lw16: the analysis kernel with 16 loader warps (all three loader paths) against 8."""
     from uno_b200 import integral_operators as ops
 
     B, Ci, Co, idim, odim, modes = shape
@@ -120,8 +108,8 @@ def test_analysis_16_loader_warps(shape, align, cuda_lib):
         y.backward(gy)
         return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy()
 
-    a = _with_env(run, UNO_B200_KPIPE_LW16=1, UNO_B200_KPIPE_ALIGN=align)
-    b = _with_env(run, UNO_B200_KPIPE_LW16=0, UNO_B200_KPIPE_ALIGN=0)
+    a = _with(run, kpipe_lw16=1, kpipe_align=align)
+    b = _with(run, kpipe_lw16=0, kpipe_align=0)
     assert rel_err(a[0], b[0]) < FWD_TOL, rel_err(a[0], b[0])
     assert rel_err(a[1], b[1]) < BWD_TOL and rel_err(a[2], b[2]) < BWD_TOL
 
@@ -146,8 +134,8 @@ def test_analysis_row_classes(shape, cuda_lib):
         y = m(xx)
         return y.detach()[1:-1].cpu().numpy()
 
-    y_al = _with_env(run, UNO_B200_KPIPE_ALIGN=1)
-    y_df = _with_env(run, UNO_B200_KPIPE_ALIGN=0)
+    y_al = _with(run, kpipe_align=1)
+    y_df = _with(run, kpipe_align=0)
     assert np.isfinite(y_al).all()
     assert rel_err(y_al, y_df) < FWD_TOL, rel_err(y_al, y_df)
     x[0] = torch.randn_like(x[0])
@@ -160,8 +148,8 @@ def test_analysis_row_classes(shape, cuda_lib):
         y.backward(gy)
         return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy()
 
-    a = _with_env(run2, UNO_B200_KPIPE_ALIGN=1)
-    b = _with_env(run2, UNO_B200_KPIPE_ALIGN=0)
+    a = _with(run2, kpipe_align=1)
+    b = _with(run2, kpipe_align=0)
     ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
     y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)
     assert rel_err(a[0], y_or) < FWD_TOL, rel_err(a[0], y_or)
@@ -170,11 +158,10 @@ def test_analysis_row_classes(shape, cuda_lib):
 
 @pytest.mark.parametrize("odim", [(24, 240), (24, 120), (10, 481), (12, 63), (45, 301), (70, 33), (300, 64), (130, 446)])
 @pytest.mark.parametrize("norm,nl", [(False, True), (True, True), (False, False)])
-@pytest.mark.parametrize("mode", [1, 2])
-def test_synthesis_16_warp_epilogue(odim, norm, nl, mode, cuda_lib):
-    """UNO_B200_ROWGEMM_EPI16=1 (2: with the next round's addend prefetched): the synthesis kernel with 16 epilogue warps (store, accumulate, accumulate+GELU to a second
-    tensor, in place; one and two column tiles, parity mode, ragged tiles) against the default 8-warp configuration, which
-    tests/test_gpu_tc.py pins to the oracle."""
+def test_synthesis_16_warp_epilogue(odim, norm, nl, cuda_lib):
+    """rowgemm_epi16: the synthesis kernel with 16 epilogue warps (store, accumulate, accumulate+GELU to a second
+    tensor, in place; one and two column tiles, parity mode, ragged tiles) against the 8-warp configuration
+    (both are pinned to the oracle by tests/test_gpu_tc.py)."""
     from uno_b200 import integral_operators as ops
 
     torch.manual_seed(1)
@@ -195,15 +182,15 @@ def test_synthesis_16_warp_epilogue(odim, norm, nl, mode, cuda_lib):
             out += [y.detach().cpu().numpy(), y_inf.cpu().numpy(), xx.grad.cpu().numpy()]
         return out
 
-    a = _with_env(run, UNO_B200_ROWGEMM_EPI16=mode)
-    b = _with_env(run, UNO_B200_ROWGEMM_EPI16=0)
+    a = _with(run, rowgemm_epi16=1)
+    b = _with(run, rowgemm_epi16=0)
     for u, v in zip(a, b):
         assert np.array_equal(u, v), rel_err(u, v)     # same arithmetic in the same order: bit-identical
 
 
 @pytest.mark.parametrize("odim", [(400, 400), (481, 481), (300, 350)])
 def test_instance_norm_big_cluster(odim, cuda_lib):
-    """UNO_B200_NORM_BIG_CLUSTER=1: planes too large for 8 x 72 KB take the cluster kernels with 200 KB per CTA (forward 4 bytes,
+    """norm_big_cluster: planes too large for 8 x 72 KB take the cluster kernels with 200 KB per CTA (forward 4 bytes,
     backward 8 bytes per element: the sizes cover 'both fit', 'forward only' and 'backward at the limit') -- against the
     two-kernel path."""
     from uno_b200 import integral_operators as ops
@@ -221,8 +208,8 @@ def test_instance_norm_big_cluster(odim, cuda_lib):
         return [y.detach().cpu().numpy(), xx.grad.cpu().numpy(), blk.normalize_layer.weight.grad.cpu().numpy(),
                 blk.normalize_layer.bias.grad.cpu().numpy()]
 
-    a = _with_env(run, UNO_B200_NORM_BIG_CLUSTER=1)
-    b = _with_env(run, UNO_B200_NORM_BIG_CLUSTER=0)
+    a = _with(run, norm_big_cluster=1)
+    b = _with(run, norm_big_cluster=0)
     assert rel_err(a[0], b[0]) < FWD_TOL, rel_err(a[0], b[0])
     for u, v in zip(a[1:], b[1:]):
         assert rel_err(u, v) < BWD_TOL, rel_err(u, v)
@@ -230,7 +217,7 @@ def test_instance_norm_big_cluster(odim, cuda_lib):
 
 @pytest.mark.parametrize("idim,odim", [((16, 12, 13), (12, 12, 9)), ((12, 10, 9), (16, 14, 13)), ((24, 24, 21), (24, 24, 21))])
 def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
-    """UNO_B200_POINTWISE3D_FIXED=1 on the CUDA kernels (the CPU suite checks the same orchestration on the host emulation)."""
+    """pointwise3d_fixed=1 (opt-in, not the reference) on the CUDA kernels (the CPU suite checks the same orchestration on the host emulation)."""
     from uno_b200 import integral_operators as ops
 
     torch.manual_seed(0)
@@ -243,7 +230,7 @@ def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
         y.sum().backward()
         return y.detach().cpu().numpy(), xx.grad.cpu().numpy()
 
-    y, gx = _with_env(run, UNO_B200_POINTWISE3D_FIXED=1)
+    y, gx = _with(run, pointwise3d_fixed=1)
     cw = m.conv.weight.detach().cpu().numpy().reshape(6, 4)
     y_or = orc.pointwise_op_3d_fixed_fwd(x.cpu().numpy(), cw, m.conv.bias.detach().cpu().numpy(), odim)
     assert rel_err(y, y_or) < FWD_TOL, rel_err(y, y_or)
@@ -251,30 +238,6 @@ def test_pointwise3d_fixed_mode_gpu(idim, odim, cuda_lib):
     gt = np.einsum("pd,qe,rf,bcpqr->bcdef", R[0], R[1], R[2], np.ones(y.shape))
     gx_or = np.einsum("oc,bodef->bcdef", cw.astype(np.float64), gt)
     assert rel_err(gx, gx_or) < BWD_TOL, rel_err(gx, gx_or)
-
-
-@pytest.mark.parametrize("idim,odim", [((481, 481), (240, 240)), ((240, 240), (481, 481)), ((120, 120), (240, 240)), ((240, 240), (120, 120)),
-                                       ((64, 64), (48, 48)), ((33, 47), (70, 20)), ((446, 446), (223, 223))])
-def test_resample_split_staging(idim, odim, cuda_lib):
-    """UNO_B200_RS_SPLIT=1: the fused resample with its window staged as two cp.async groups -- same arithmetic in the same order
-    as the default kernel, so forward and backward must be bit-identical."""
-    from uno_b200 import integral_operators as ops
-
-    torch.manual_seed(0)
-    m = ops.pointwise_op_2D(3, 5, *odim).cuda()
-    x = torch.randn(2, 3, *idim, device="cuda")
-    gy = torch.randn(2, 5, *odim, device="cuda")
-
-    def run():
-        xx = x.clone().requires_grad_(True)
-        m.zero_grad(set_to_none=True)
-        y = m(xx, *odim)
-        y.backward(gy)
-        return y.detach().cpu().numpy(), xx.grad.cpu().numpy()
-
-    a = _with_env(run, UNO_B200_RS_SPLIT=1)
-    b = _with_env(run, UNO_B200_RS_SPLIT=0)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (rel_err(a[0], b[0]), rel_err(a[1], b[1]))
 
 
 def test_empty_batch_like_the_reference(cuda_lib):
@@ -310,7 +273,7 @@ SHAPES_3D = [
 
 
 @pytest.mark.parametrize("shape", SHAPES_3D)
-def test_spectral3d_experimental_tc(shape, cuda_lib):
+def test_spectral3d_tc_core(shape, cuda_lib):
     from uno_b200 import integral_operators as ops
 
     B, Ci, Co, idim, odim, modes = shape
@@ -326,47 +289,10 @@ def test_spectral3d_experimental_tc(shape, cuda_lib):
         y.backward(gy)
         return y.detach().cpu().numpy(), xx.grad.cpu().numpy(), [torch.view_as_real(w.grad).cpu().numpy() for w in (m.weights1, m.weights2, m.weights3, m.weights4)]
 
-    y_tc, gx_tc, gw_tc = _with_env(run, UNO_B200_MID_TC=1, UNO_B200_CMM_TC=1)
-    y_si, gx_si, gw_si = _with_env(run, UNO_B200_MID_TC=0, UNO_B200_CMM_TC=0)
+    y_tc, gx_tc, gw_tc = _with(run, mid_tc=1, cmm_tc=2)
+    y_si, gx_si, gw_si = _with(run, mid_tc=0, cmm_tc=0)
     # the default kernels are pinned to the oracle by tests/test_gpu_parity.py; here the two device paths are compared
     assert rel_err(y_tc, y_si) < FWD_TOL, rel_err(y_tc, y_si)
     assert rel_err(gx_tc, gx_si) < BWD_TOL, rel_err(gx_tc, gx_si)
     for a, b in zip(gw_tc, gw_si):
         assert rel_err(a, b) < BWD_TOL, rel_err(a, b)
-
-
-def test_experimental_tc_timing(cuda_lib, capsys):
-    """Not an assertion: prints per-launch times of the default and the tcgen05 paths at the NS-2D inner level and the Darcy top level."""
-    from uno_b200 import integral_operators as ops
-
-    for (B, Ci, Co, idim, odim, modes) in [(64, 192, 192, (16, 16), (16, 16), (6, 6)), (32, 32, 64, (481, 481), (240, 240), (18, 18))]:
-        torch.manual_seed(0)
-        m = ops.SpectralConv2d_Uno(Ci, Co, *odim, *modes).cuda()
-        x = torch.randn(B, Ci, *idim, device="cuda", requires_grad=True)
-        gy = torch.randn(B, Co, *odim, device="cuda")
-
-        def step():
-            m.zero_grad(set_to_none=True)
-            x.grad = None
-            m(x).backward(gy)
-
-        for env in ({"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 0}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 0},
-                    {"UNO_B200_MID_TC": 0, "UNO_B200_CMM_TC": 1}, {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1},
-                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1},
-                    {"UNO_B200_ROWGEMM_EPI16": 1}, {"UNO_B200_ROWGEMM_EPI16": 2}, {"UNO_B200_KPIPE_LW16": 1},
-                    {"UNO_B200_KPIPE_LW16": 1, "UNO_B200_KPIPE_ALIGN": 1},
-                    {"UNO_B200_MID_TC": 1, "UNO_B200_CMM_TC": 1, "UNO_B200_KPIPE_ALIGN": 1, "UNO_B200_ROWGEMM_EPI16": 1}):
-            def timed():
-                for _ in range(3):
-                    step()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(10):
-                    step()
-                e1.record()
-                torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / 10
-
-            ms = _with_env(timed, **env)
-            with capsys.disabled():
-                print(f"\n[experimental] B={B} C={Ci}->{Co} {idim}->{odim} modes={modes} {env}: {ms:.3f} ms fwd+bwd")

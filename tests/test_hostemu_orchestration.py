@@ -159,8 +159,8 @@ def test_bench_spectral_levels_from_report():
 
 
 @pytest.mark.parametrize("idim,odim", [((8, 6, 9), (6, 6, 7)), ((6, 5, 7), (9, 8, 10)), ((7, 7, 7), (7, 7, 7)), ((8, 8, 8), (4, 12, 8))])
-def test_pointwise3d_fixed_mode(idim, odim, monkeypatch):
-    """UNO_B200_POINTWISE3D_FIXED=1 (opt-in, not the reference): pointwise_op_3D with the band-limited Fourier resample --
+def test_pointwise3d_fixed_mode(idim, odim):
+    """switch pointwise3d_fixed=1 (opt-in, not the reference): pointwise_op_3D with the band-limited Fourier resample --
     against the separable Dirichlet-kernel oracle, with the properties the quirky operator lacks (a constant stays the same
     constant; a trigonometric polynomial inside the kept band is reproduced exactly on the new grid) and the adjoint backward."""
     rng = np.random.default_rng(3)
@@ -168,7 +168,17 @@ def test_pointwise3d_fixed_mode(idim, odim, monkeypatch):
     x = rng.standard_normal((B, Ci) + idim).astype(np.float32)
     cw = rng.standard_normal((Co, Ci)).astype(np.float32)
     cb = rng.standard_normal(Co).astype(np.float32)
-    monkeypatch.setenv("UNO_B200_POINTWISE3D_FIXED", "1")
+    assert emu.lib().uno_config_set(b"pointwise3d_fixed", 1) == 0
+    try:
+        _pointwise3d_fixed_checks(rng, x, cw, cb, idim, odim, B, Ci, Co)
+    finally:
+        assert emu.lib().uno_config_set(b"pointwise3d_fixed", 0) == 0
+    # the default (reference) behaviour is untouched once the switch is off
+    z_ref, _ = emu.pointwise_fwd(x, cw, cb, odim, True)
+    assert rel_err(z_ref, orc.pointwise_op_3d_fwd(x, cw, cb, odim)) < FWD_TOL
+
+
+def _pointwise3d_fixed_checks(rng, x, cw, cb, idim, odim, B, Ci, Co):
     z, saved = emu.pointwise_fwd(x, cw, cb, odim, True)
     z_or = orc.pointwise_op_3d_fixed_fwd(x, cw, cb, odim)
     assert rel_err(z, z_or) < FWD_TOL, rel_err(z, z_or)
@@ -195,7 +205,3 @@ def test_pointwise3d_fixed_mode(idim, odim, monkeypatch):
     gcw_or = np.einsum("bodef,bcdef->oc", gt, x.astype(np.float64))
     gcb_or = gt.sum(axis=(0, 2, 3, 4))
     assert rel_err(gx, gx_or) < BWD_TOL and rel_err(gcw.reshape(Co, Ci), gcw_or) < BWD_TOL and rel_err(gcb, gcb_or) < BWD_TOL
-    # the default (reference) behaviour is untouched once the switch is off
-    monkeypatch.delenv("UNO_B200_POINTWISE3D_FIXED")
-    z_ref, _ = emu.pointwise_fwd(x, cw, cb, odim, True)
-    assert rel_err(z_ref, orc.pointwise_op_3d_fwd(x, cw, cb, odim)) < FWD_TOL

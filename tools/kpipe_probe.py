@@ -1,5 +1,5 @@
 """Timing probes of the last-axis analysis kernel (tc_kpipe.cuh): the forward of one spectral convolution with parts of the
-kernel switched off through UNO_B200_KPIPE_DEBUG (bit 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads, 16 no
+kernel switched off through the switch kpipe_debug (bit 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads, 16 no
 proxy fence; results are garbage, only the time means something).  The kernel's own
 time comes from the library's per-launch CUDA events (uno_profile_*); what a part costs on the critical path is the
 difference to mode 0."""
@@ -11,6 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
+
+from uno_b200 import config  # noqa: E402
 
 from uno_b200 import _lib  # noqa: E402
 from uno_b200 import integral_operators as IO  # noqa: E402
@@ -44,8 +46,8 @@ for name, (B, Ci, Co, S, D, m) in {"481 (4-byte rows)": (32, 32, 64, 481, 240, 1
     x = torch.randn(B, Ci, S, S, device="cuda")
     out = []
     for mode in MODES:
-        os.environ["UNO_B200_KPIPE_DEBUG"] = str(mode)
+        config.set("kpipe_debug", mode)
         a, tot = analysis_ms(layer, x, (D, D))
         out.append(f"{mode}:{a:.3f}")
-    os.environ["UNO_B200_KPIPE_DEBUG"] = "0"
+    config.set("kpipe_debug", 0)
     print(f"{name}: x {x.numel() * 4 / 1e6:.0f} MB, all kernels of the forward {tot:.3f} ms | analysis kernel ms by debug mode |", "  ".join(out), flush=True)

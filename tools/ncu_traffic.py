@@ -65,7 +65,10 @@ def main(src, dst):
         e["us"] += m["gpu__time_duration.sum"]
     res = {k: {"launches": v["launches"], "dram_bytes_per_launch": v["bytes"] / v["launches"], "ncu_time_us_per_launch": v["us"] / v["launches"]}
            for k, v in sorted(out.items())}
-    json.dump({"source": os.path.basename(src), "note": "ncu --clock-control none, one step of tools/profile_step.py (cold-cache, serialised launches)", "roles": res},
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench   # the capture is tied to the device code it was taken on (bench.py drops it when the sources changed)
+
+    json.dump({"source": os.path.basename(src), "src_sha16": bench.source_sha16(), "note": "ncu --clock-control none, one step of tools/profile_step.py (cold-cache, serialised launches)", "roles": res},
               open(dst, "w"), indent=1)
     for k, v in res.items():
         print(f"{k:22s} n={v['launches']:3d}  {v['dram_bytes_per_launch'] / 1e6:10.1f} MB/launch  {v['ncu_time_us_per_launch']:9.1f} us")

@@ -1,5 +1,5 @@
 """Timing probes of the tcgen05 weight-gradient kernel (tc_wgrad.cuh): the backward of one 1x1 channel mix with parts of the
-kernel switched off through UNO_B200_WGRAD_DEBUG (bit 1 no MMA, 2 no operand stores, 8 no global loads, 16 no proxy fence,
+kernel switched off through the switch wgrad_debug (bit 1 no MMA, 2 no operand stores, 8 no global loads, 16 no proxy fence,
 32 no final flush; results are garbage, only the time means something).  Any non-zero value selects the probe instantiation
 wgrad_tc_kernel<true>; 0 is the shipped kernel.  Times come from the library's per-launch CUDA events (uno_profile_*); what a
 part costs on the critical path is the difference to mode 0.  Written for the open question in DESIGN.md section 8: 1.8 us per
@@ -15,6 +15,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
+
+from uno_b200 import config  # noqa: E402
 
 from uno_b200 import _lib  # noqa: E402
 from uno_b200 import integral_operators as IO  # noqa: E402
@@ -55,9 +57,9 @@ for name, (B, Ci, Co, S) in SHAPES.items():
     out = []
     nbytes = 0
     for mode in MODES:
-        os.environ["UNO_B200_WGRAD_DEBUG"] = str(mode)
+        config.set("wgrad_debug", mode)
         ms, nbytes = wgrad_ms(layer, x, gy, (S, S))
         out.append(f"{mode}:{ms:.3f}")
-    os.environ["UNO_B200_WGRAD_DEBUG"] = "0"
+    config.set("wgrad_debug", 0)
     chunks_per_cta = B * ((S * S + 31) // 32) / 148
     print(f"{name}: {nbytes / 1e6:.0f} MB per launch, {chunks_per_cta:.0f} chunks per CTA | weight-gradient kernel ms by debug mode |", "  ".join(out), flush=True)

@@ -87,6 +87,9 @@ SYMBOLS = {
     "uno_adam_step": (C.c_int, [C.POINTER(AdamTensor), C.c_int, C.POINTER(AdamHyper), _P]),
     "uno_lp_loss_fwd": (C.c_int, [_P, _P, C.c_int, C.c_long, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "uno_lp_loss_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_long, C.c_int, _P, _P]),
+    "uno_config_set": (C.c_int, [C.c_char_p, C.c_int]),
+    "uno_config_get": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
+    "uno_config_name": (C.c_char_p, [C.c_int]),
     "uno_launch_count": (C.c_long, []),
     "uno_profile_enable": (None, [C.c_int]),
     "uno_profile_report": (C.c_size_t, [C.c_char_p, C.c_size_t]),

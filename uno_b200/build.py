@@ -14,8 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(CSRC, "libuno_b200.so")
 
-SOURCES = ["backend_cuda.cu", "uno_api.cpp", "plan.cpp"]
-HEADERS = ["backend.h", "plan.h", os.path.join(ROOT, "include", "uno_b200.h")]
+SOURCES = ["backend_cuda.cu", "uno_api.cpp", "plan.cpp", "config.cpp"]
+HEADERS = ["backend.h", "plan.h", "config.h", os.path.join(ROOT, "include", "uno_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

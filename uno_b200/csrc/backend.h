@@ -7,6 +7,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "config.h"
+
 namespace uno {
 
 typedef void* stream_t;

@@ -856,7 +856,6 @@ int ensure_smem(K kernel, size_t bytes) {
 }
 
 #include "pixel_mlp.cuh"
-#include "pixel_mlp_mma.cuh"
 #include "pixel_mlp_tc.cuh"
 #include "resample2d.cuh"
 #include "norm_cluster.cuh"
@@ -893,10 +892,7 @@ struct TcKey {
 std::map<TcKey, TcImage> g_tc_images;
 std::mutex g_tc_mu;
 
-bool tc_enabled() {   // read every call so tests can flip UNO_B200_DISABLE_TC at run time
-    const char* e = getenv("UNO_B200_DISABLE_TC");
-    return !(e && e[0] && e[0] != '0');
-}
+bool tc_enabled() { return cfg(CFG_TC) != 0; }
 
 // B [K x N] (device, row-major, ldb) -> per n-tile [hi | lo] images in the UMMA K-major interleave layout
 // of the transposed operand (N_t rows x K_pad): element (n, k) at float offset (k/4)*N_t*4 + n*4 + k%4.
@@ -971,11 +967,6 @@ int num_sms() {
     return g_num_sms;
 }
 
-int rowgemm_epi16_mode() {   // opt-in 16-warp epilogue (tc_rowgemm.cuh): 1 = plain, 2 = with next-round prefetch; read every call
-    const char* e = getenv("UNO_B200_ROWGEMM_EPI16");
-    if (!e || !e[0] || e[0] == '0') return 0;
-    return e[0] == '2' ? 2 : 1;
-}
 
 template <int EPI, int G, int J>
 int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
@@ -996,9 +987,9 @@ int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t
 
 template <int EPI>
 int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
-    const int mode = rowgemm_epi16_mode();
-    if (mode == 2) return launch_rowgemm_variant<EPI, 4, 0>(p, smem, st);
-    if (mode == 1) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
+    // 16 epilogue warps of 32x16 elements per round (default: measured 3.66 -> 3.62 ms per Darcy step, 0.57 -> 0.51 ms per
+    // NS-2D call) or 8 warps of 32x32; same arithmetic in the same order, bit-identical results
+    if (cfg(CFG_ROWGEMM_EPI16)) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
     return launch_rowgemm_variant<EPI, 2, 2>(p, smem, st);
 }
 
@@ -1066,13 +1057,9 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if (stages > 4) stages = 4;
     if (stages < 2) return -1;
     const bool a_vec_ok = (a.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
-    // opt-in row-class mode (tc_kpipe.cuh) for rows that are not 16-byte aligned: UNO_B200_KPIPE_ALIGN=1
-    bool rclass = false;
-    if (!a_vec_ok && a.a_rs % 4 != 0 && a.a_rs >= 8 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && a.N % 2 == 0 && a.ldc % 2 == 0 &&
-        (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && a.M >= 512) {
-        const char* e = getenv("UNO_B200_KPIPE_ALIGN");
-        rclass = e && e[0] && e[0] != '0';
-    }
+    // row-class mode (tc_kpipe.cuh) for rows that are not 16-byte aligned (the 481-wide Darcy grid, the 83-long NS-3D axis)
+    const bool rclass = !a_vec_ok && a.a_rs % 4 != 0 && a.a_rs >= 8 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && a.N % 2 == 0 &&
+                        a.ldc % 2 == 0 && (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && a.M >= 512 && cfg(CFG_KPIPE_ALIGN) != 0;
     TcKpImage img;
     int rc = tc_get_kpipe_image(a.B, a.ldb, a.K, a.N, &img, rclass ? (int)(a.a_rs % 4) : -1);
     if (rc) return rc;
@@ -1086,17 +1073,17 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     while (cols < 2 * img.N_t) cols *= 2;
     p.tmem_cols = cols;
     p.a_vec_ok = a_vec_ok;
-    { const char* e = getenv("UNO_B200_KPIPE_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.debug = cfg(CFG_KPIPE_DEBUG);
     int gx = num_sms();
     if (rclass) gx &= ~3;                   // a CTA must only ever see tiles of one row class (m_tiles is a multiple of 4 too)
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
-    const char* lw = getenv("UNO_B200_KPIPE_LW16");   // opt-in: 16 loader warps (tc_kpipe.cuh)
     const size_t smem = tc::kpipe_smem_bytes(img.N_t, stages);
-    if (lw && lw[0] && lw[0] != '0') return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
+    // 16 loader warps (default: analysis 2.49 -> 2.19 ms per Darcy step, 2.13 with the row classes) or 8
+    if (cfg(CFG_KPIPE_LW16)) return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
     return rclass ? launch_kpipe<tc::kKpLoadWarps, true>(p, gx, smem, st) : launch_kpipe<tc::kKpLoadWarps, false>(p, gx, smem, st);
 }
 
-// ---- leading-axis complex transform on tcgen05 (tc_mid.cuh), opt-in: UNO_B200_MID_TC=1 -------------------------------
+// ---- leading-axis complex transform on tcgen05 (tc_mid.cuh); switch mid_tc, default on --------------------------------
 // Image of the real expansion of the complex matrix Mat[J, H] (device, interleaved):
 //   B[(h,re), (j,re)] = Re   B[(h,im), (j,re)] = -Im   B[(h,re), (j,im)] = Im   B[(h,im), (j,im)] = Re
 // per column tile: [chunk][hi | lo], half = (KC/4) x N_t x 16 bytes, element (n, k) at ((k%32)/4)*N_t*4 + n*4 + k%4.
@@ -1142,10 +1129,7 @@ int tc_get_mid_image(const float* Mat, int J, int H, TcMidImage* out) {
     return 0;
 }
 
-bool mid_tc_enabled() {
-    const char* e = getenv("UNO_B200_MID_TC");
-    return e && e[0] && e[0] != '0';
-}
+bool mid_tc_enabled() { return cfg(CFG_MID_TC) != 0; }
 
 // returns -1 when the shape is not taken (the caller runs the SIMT kernel)
 int try_tc_mid(const MidArgs& a, cudaStream_t st) {
@@ -1190,16 +1174,21 @@ int try_tc_mid(const MidArgs& a, cudaStream_t st) {
     return 0;
 }
 
-// ---- per-mode complex contraction on tcgen05 (tc_cmm.cuh), opt-in: UNO_B200_CMM_TC=1 ---------------------------------
-bool cmm_tc_enabled() {
-    const char* e = getenv("UNO_B200_CMM_TC");
-    return e && e[0] && e[0] != '0';
-}
+// ---- per-mode complex contraction on tcgen05 (tc_cmm.cuh); switch cmm_tc, default on for shapes that fill a tile -----
+bool cmm_tc_enabled() { return cfg(CFG_CMM_TC) != 0; }
 
 // returns -1 when the shape is not taken (the caller runs the SIMT kernels)
 int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
     if (!cmm_tc_enabled() || !tc_enabled()) return -1;
     if (a.K < 4 || a.M < 4 || a.N < 8) return -1;
+    if (cfg(CFG_CMM_TC) != 2) {
+        // One UMMA per mode is 128 weight rows (n, re|im) x N_t samples: taken only when the operands fill at least half of
+        // that tile and the reduction is long enough to amortise the operand images.  Measured on B200: NS-2D (batch 64,
+        // 32..192 channels) 1.62 -> 1.28 ms per call; NS-3D (batch 8) got SLOWER (0.78 -> 1.47 ms) and stays on the SIMT kernel.
+        const int ns_t = (a.M + 63) / 64, nt = ((((a.M + ns_t - 1) / ns_t) + 15) / 16) * 16;
+        const double fill = (2.0 * a.N / (128.0 * ((2 * a.N + 127) / 128))) * ((double)a.M / ((double)nt * ns_t));
+        if (fill < 0.5 || a.K < 16) return -1;
+    }
     for (int c = 0; c < a.ncorner; ++c)
         if ((reinterpret_cast<uintptr_t>(a.A[c]) & 7) || (reinterpret_cast<uintptr_t>(a.B[c]) & 7) || (reinterpret_cast<uintptr_t>(a.C[c]) & 7))
             return -1;
@@ -1312,7 +1301,7 @@ int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     long gx = num_sms();
     if (gx > (p.total_chunks + 3) / 4) gx = (p.total_chunks + 3) / 4;
     if (gx < 1) gx = 1;
-    { const char* e = getenv("UNO_B200_WGRAD_DEBUG"); p.debug = e ? atoi(e) : 0; }   // timing probes (tools/wgrad_probe.py)
+    p.debug = cfg(CFG_WGRAD_DEBUG);   // timing probes (tools/wgrad_probe.py)
     if (p.debug) return launch_wgrad<true>(p, (unsigned)gx, st);
     return launch_wgrad<false>(p, (unsigned)gx, st);
 }
@@ -1327,7 +1316,7 @@ int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     const size_t smem = tc::rowgemm_smem_bytes(K_pad, N_t);
     if (smem > 220 * 1024) return -1;
     // odd row pitch: split the rows by parity so that both halves store aligned float2 (tc_rowgemm.cuh)
-    static const bool no_parity = [] { const char* e = getenv("UNO_B200_ROWGEMM_NO_PARITY"); return e && e[0] && e[0] != '0'; }();
+    const bool no_parity = cfg(CFG_ROWGEMM_PARITY) == 0;
     const bool c2_ok = a.epi != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(a.C2) & 7) == 0;
     const int parity = (!no_parity && (a.ldc & 1) && (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && c2_ok && n_tiles * N_t > a.N) ? 1 : 0;
     int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, 1 + parity, &img);
@@ -1477,10 +1466,7 @@ stream_t be_side_stream() {
     // opt-in: measured on B200 the two branches of a Darcy-size block already fill the machine one kernel at a
     // time (29.8 vs 30.1 ms per step with the overlap), and concurrent kernels blur the per-kernel timings the
     // roofline report is built from -- so the fork/join path is off unless UNO_B200_OVERLAP=1
-    {
-        const char* env = getenv("UNO_B200_OVERLAP");
-        if (!env || env[0] != '1') { g_side.disabled = true; return nullptr; }
-    }
+    if (!cfg(CFG_OVERLAP)) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     auto it = g_side.streams.find(dev);
@@ -1672,18 +1658,13 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     k.tiles_w = (a.n_out1 + rs_tile_w(G1) - 1) / rs_tile_w(G1);
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
-    static const int minb = [] { const char* e = getenv("UNO_B200_RS_MINB"); return e && e[0] == '3' ? 3 : 2; }();
-    const bool split = [] { const char* e = getenv("UNO_B200_RS_SPLIT"); return e && e[0] && e[0] != '0'; }();   // opt-in, resample2d.cuh
-    int rc = minb == 3 ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 3>, smem)
-                       : (split ? ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2, true>, smem) : ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem));
+    int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem);
     if (rc) return rc;
     if (a.planes > 65535) return -1;          // planes ride on grid.z
     ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
                  2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
     const dim3 grid((unsigned)k.tiles_w, (unsigned)k.tiles_h, (unsigned)a.planes);
-    if (minb == 3) resample2d_kernel<G0, W0, G1, W1, 3><<<grid, 256, smem, st>>>(k);
-    else if (split) resample2d_kernel<G0, W0, G1, W1, 2, true><<<grid, 256, smem, st>>>(k);
-    else resample2d_kernel<G0, W0, G1, W1, 2><<<grid, 256, smem, st>>>(k);
+    resample2d_kernel<G0, W0, G1, W1, 2><<<grid, 256, smem, st>>>(k);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1777,14 +1758,12 @@ int be_plane_stats(const float* x, float* stats, long planes, long L, float eps,
     return 0;
 }
 // Shared-memory budget per CTA of the InstanceNorm cluster kernels: 72 KB (three CTAs per SM) is what the Darcy levels were
-// tuned with.  Opt-in (UNO_B200_NORM_BIG_CLUSTER=1, not yet measured): planes that do not fit 8 x 72 KB -- the NS-3D levels, where
-// plane_stats + norm_act_fwd + norm_act_bwd are 1.45 of 15.8 ms -- get a second try with 200 KB per CTA (one CTA per SM) before
-// the two-kernel path.
+// tuned with.  Planes that do not fit 8 x 72 KB -- the NS-3D levels -- get a second try with 200 KB per CTA (one CTA per SM)
+// before the two-kernel path (measured: NS-3D step 16.1 -> 14.9 ms, InstanceNorm backward 0.98 -> 0.41 ms).
 inline int norm_cluster_pick(long L, int bytes_per_elem, int* slice) {
     int cs = norm_cluster_size(L, bytes_per_elem, 72 * 1024, slice);
     if (cs > 0) return cs;
-    const char* e = getenv("UNO_B200_NORM_BIG_CLUSTER");
-    if (e && e[0] && e[0] != '0') return norm_cluster_size(L, bytes_per_elem, 200 * 1024, slice);
+    if (cfg(CFG_NORM_BIG_CLUSTER)) return norm_cluster_size(L, bytes_per_elem, 200 * 1024, slice);
     return 0;
 }
 
@@ -1933,37 +1912,15 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
-    } else if (CT == 64 && k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && getenv("UNO_B200_PROJ_SIMT") == nullptr &&
-               getenv("UNO_B200_PROJ_TC") == nullptr && getenv("UNO_B200_PROJ_MMA") == nullptr && getenv("UNO_B200_DISABLE_TC") == nullptr) {
+    } else if (CT == 64 && k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && !cfg(CFG_PROJ_SIMT) && tc_enabled()) {
         // DEFAULT for the shipped shapes (64 channels, hid <= 32, one output, pre-activations kept by forward):
-        // warp-specialised tcgen05 kernel, 2.1 ms at Darcy size against 3.4 ms for the fp32 kernel (UNO_B200_PROJ_SIMT=1)
+        // warp-specialised tcgen05 kernel, 1.6 ms at Darcy size against 3.4 ms for the fp32 kernel (switch proj_simt)
         const size_t smem = proj_bwd_tcp_smem(k.hid, k.out_ch);
         int rc = ensure_smem(proj_bwd_tcp_kernel, smem);
         if (rc) return rc;
         const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
         proj_bwd_tcp_kernel<<<grid, kTcpThreads, smem, st>>>(k, ntiles);
-    } else if (CT == 64 && k.hid <= kPtMaxChunks * kProjHC && k.pre_in != nullptr && getenv("UNO_B200_PROJ_TC") != nullptr &&
-               getenv("UNO_B200_DISABLE_TC") == nullptr) {
-        // first tcgen05 version, opt-in: same products, but its phases (stage -> split -> activation -> MMA -> epilogue) run
-        // back to back behind block-wide barriers: 4.07 ms at Darcy size.  Superseded by the warp-specialised kernel above;
-        // kept because it also covers two hidden chunks (hid <= 64).
-        const size_t smem = proj_bwd_tc_smem(k.hid, k.out_ch);
-        int rc = ensure_smem(proj_bwd_tc_kernel, smem);
-        if (rc) return rc;
-        const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
-        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
-        proj_bwd_tc_kernel<<<grid, 256, smem, st>>>(k, ntiles);
-    } else if (k.pre_in != nullptr && getenv("UNO_B200_PROJ_MMA") != nullptr) {
-        // warp-level mma.sync 3xTF32 variant, opt-in: measured on B200 it is SLOWER than the fp32 kernel (5.1 vs 3.5 ms at
-        // Darcy size) -- legacy mma.sync TF32 issues at ~1 instruction per 22 cycles per SM here, below the fp32 FMA pipe
-        const int nbuf = proj_bwd_mma_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;
-        const size_t smem = proj_bwd_mma_smem(CT, k.hid, k.out_ch, nbuf);
-        int rc = ensure_smem(proj_bwd_mma_kernel<CT>, smem);
-        if (rc) return rc;
-        const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
-        const unsigned grid = (unsigned)std::min<long>(ntiles, 148L);
-        proj_bwd_mma_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles, nbuf);
     } else {
         // double-buffer the staged inputs when both copies fit beside the weights (hid <= 64 at 64 channels)
         const int nbuf = proj_bwd_smem(CT, k.hid, k.out_ch, 2) <= 224 * 1024 ? 2 : 1;

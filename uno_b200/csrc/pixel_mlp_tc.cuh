@@ -15,11 +15,10 @@
 // for dW1).  One thread issues the MMAs; everybody waits on one mbarrier (tcgen05.commit) before the images are reused.
 // Takes: 64-channel template, hid <= 64, saved pre-activations.
 //
-// STATUS (measured on B200, Darcy 421^2, batch 32): this first, barrier-synchronised version (proj_bwd_tc_kernel) is
-// parity-green but takes 4.07 ms per launch against 3.4 ms for the fp32 kernel (pixel_mlp.cuh): the tensor-core work is ~1 k
-// cycles of a ~27 k-cycle tile, the rest is the fp32 phases running back to back with five block-wide barriers per tile.
-// It is opt-in (UNO_B200_PROJ_TC=1) and kept for hid in (32, 64].  The warp-specialised kernel at the end of this file
-// (proj_bwd_tcp_kernel) removes the barriers from the critical path: 2.1 ms, the default for the shipped shapes.
+// History (measured on B200, Darcy 421^2, batch 32): a first version that ran these phases back to back behind block-wide
+// barriers took 4.07 ms per launch against 3.4 ms for the fp32 kernel (pixel_mlp.cuh) -- the tensor-core work is ~1 k cycles
+// of a ~27 k-cycle tile -- and was removed.  The warp-specialised kernel below (proj_bwd_tcp_kernel) keeps the barriers off
+// the critical path: 1.6 ms, the default for the shipped shapes; other shapes run the fp32 kernel.
 #pragma once
 
 constexpr int kPtPix = 128;                          // pixels per tile
@@ -32,292 +31,6 @@ constexpr uint32_t kPtDBytes = (kPtPix / 4) * kPtLboD;         // one D image (h
 constexpr uint32_t kPtWBytes = (kProjHC / 4) * kPtLboW;        // one fc1 chunk image (hi or lo)
 constexpr int kPtMaxChunks = 2;                                // hid <= 64
 constexpr uint32_t kPtTmemCols = 128;                          // 64 (DIN) + 32 per chunk (dW1)
-
-__host__ __device__ inline size_t proj_bwd_tc_smem(int hid, int out_ch) {
-    const int nch = (hid + kProjHC - 1) / kProjHC;
-    return 1024 /* alignment slack */ + kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes + (size_t)2 * nch * kPtWBytes + 64 * kPtPix * 4 /* raw */ +
-           proj_table_bytes(64) + sizeof(float) * (2 * round4(out_ch * hid) + round4(hid) + 4) + 64;
-}
-
-__global__ void __launch_bounds__(256, 1) proj_bwd_tc_kernel(const ProjK k, long ntiles) {
-    extern __shared__ __align__(128) uint8_t tsm[];
-    constexpr int CT = 64;
-    uint8_t* p0 = tsm + ((128u - (tc::smem_u32(tsm) & 127u)) & 127u);
-    uint8_t* IMG = p0;                                   // stacked IN image: rows 0-63 tf32(x), rows 64-127 x - tf32(x)
-    uint8_t* A1hi = IMG + kPtImgBytes;                   // D^T (pixels x hidden)
-    uint8_t* A1lo = A1hi + kPtA1Bytes;
-    uint8_t* Dhi = A1lo + kPtA1Bytes;                    // D (hidden x pixels)
-    uint8_t* Dlo = Dhi + kPtDBytes;
-    const int nchunks = (k.hid + kProjHC - 1) / kProjHC;
-    uint8_t* Wimg = Dlo + kPtDBytes;                     // per chunk: [hi | lo] fc1 images
-    float* RAW = reinterpret_cast<float*>(Wimg + (size_t)2 * nchunks * kPtWBytes);   // [64][128] inputs of the NEXT tile
-    const float** sbase = reinterpret_cast<const float**>(RAW + 64 * kPtPix);
-    float** gbase = reinterpret_cast<float**>(const_cast<float**>(sbase) + CT);
-    long* sstride = reinterpret_cast<long*>(gbase + CT);
-    const int H4 = round4(k.hid), OH4 = round4(k.out_ch * k.hid);
-    float* sW2 = reinterpret_cast<float*>(sstride + CT);
-    float* accb1 = sW2 + OH4;
-    float* accW2 = accb1 + H4;
-    float* accb2 = accW2 + OH4;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(accb2 + 4);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    proj_stage_tables<CT>(k, sbase, gbase, sstride);
-    // zero every operand image once: rows of hidden units past hid, channels past ctot and pixels past the end stay zero
-    for (uint32_t i = tid; i < (kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes) / 16; i += 256)
-        reinterpret_cast<float4*>(IMG)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // fc1 weight images: chunk ch, element (row = channel c, k = hidden j) = W1[32 ch + j][c]
-    for (int i = tid; i < nchunks * kProjHC * CT; i += 256) {
-        const int c = i % CT, j = (i / CT) % kProjHC, ch = i / (CT * kProjHC);
-        const int n = ch * kProjHC + j;
-        float hi = 0.f, lo = 0.f;
-        if (n < k.hid && c < k.ctot) tc::split_tf32(__ldg(k.w1 + n * k.ctot + c), hi, lo);
-        uint8_t* d = Wimg + (size_t)2 * ch * kPtWBytes + (uint32_t)(j >> 2) * kPtLboW + (uint32_t)c * 16 + (uint32_t)(j & 3) * 4;
-        *reinterpret_cast<float*>(d) = hi;
-        *reinterpret_cast<float*>(d + kPtWBytes) = lo;
-    }
-    for (int i = tid; i < k.out_ch * k.hid; i += 256) sW2[i] = __ldg(k.w2 + i);
-    for (int i = tid; i < H4 + OH4 + 4; i += 256) accb1[i] = 0.f;
-    if (tid == 0) {
-        tc::mbar_init(bar, 1);
-        tc::fence_barrier_init();
-    }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kPtTmemCols);
-    tc::fence_proxy_async();
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const PixGeom g = k.g;
-    const long total = (long)k.batch * g.nraw;
-    proj_zero_padding(k, gbase, sstride);
-    // LDGSTS of a tile's inputs into RAW[c][p]: threads 0-127 copy one pixel each, all channels (zero-filled past the end)
-    auto stage_raw = [&](long tile) {
-        if (tid < kPtPix) {
-            const long idx = tile * kPtPix + tid;
-            const bool valid = idx < total;
-            long b = 0, rp = 0, pp = 0;
-            if (valid) raw_to_padded(g, idx, b, rp, pp);
-            uint32_t dst = tc::smem_u32(RAW + tid);
-            const int sz = valid ? 4 : 0;
-            const long step = valid ? g.npad : 0;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                if (s < k.nsrc) {
-                    const int nch = k.src_ch[s];
-                    const float* src = valid ? k.src[s] + b * nch * g.npad + pp : k.w1;
-#pragma unroll 4
-                    for (int cl = 0; cl < nch; ++cl) {
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-                        dst += (uint32_t)(kPtPix * 4);
-                        src += step;
-                    }
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const uint32_t idesc_din = tc::make_idesc_tf32(128, 64, 0, 0), idesc_dw = tc::make_idesc_tf32(128, kProjHC, 0, 0);
-    const uint32_t img_a = tc::smem_u32(IMG), a1hi_a = tc::smem_u32(A1hi), a1lo_a = tc::smem_u32(A1lo), dhi_a = tc::smem_u32(Dhi),
-                   dlo_a = tc::smem_u32(Dlo), w_a = tc::smem_u32(Wimg);
-    const int tn = tid >> 6, tp = tid & 63;              // activation phase: hidden block of 8, pixels tp and tp + 64
-    uint32_t phase = 0;
-    long it = 0;
-    if ((long)blockIdx.x < ntiles) stage_raw(blockIdx.x);
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const long base = tile * kPtPix;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                 // RAW complete; TMEM / images of the previous tile are free
-        // ---- raw inputs -> stacked tf32 image (rows c: hi, rows 64 + c: lo); thread: pixel tid & 127, 32 channels
-        {
-            const int px = tid & (kPtPix - 1), c0 = (tid >> 7) * 32;
-            uint8_t* d = IMG + (uint32_t)(px >> 2) * kPtLboA + (uint32_t)(px & 3) * 4;
-#pragma unroll 8
-            for (int c = c0; c < c0 + 32; ++c) {
-                float hi, lo;
-                tc::split_tf32(RAW[c * kPtPix + px], hi, lo);
-                *reinterpret_cast<float*>(d + (uint32_t)c * 16) = hi;
-                *reinterpret_cast<float*>(d + (uint32_t)(64 + c) * 16) = lo;
-            }
-        }
-        __syncthreads();                                 // RAW consumed
-        if (tile + gridDim.x < ntiles) stage_raw(tile + gridDim.x);     // overlaps this tile's work
-        bool vq[2];
-        float go[2][kProjMaxOut];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const long idx = base + tp + 64 * q;
-            vq[q] = idx < total;
-#pragma unroll
-            for (int o = 0; o < kProjMaxOut; ++o) go[q][o] = (vq[q] && o < k.out_ch) ? __ldg(k.gout + idx * k.out_ch + o) : 0.f;
-        }
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int ch0 = ch * kProjHC;
-            const int nn = min(kProjHC, k.hid - ch0);
-            // ---- activation phase: 8 hidden x 2 pixels per thread; all 16 pre-activations are requested before the first use
-            float dp[8][2];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int nc = min(ch0 + 8 * tn + i, k.hid - 1);
-                const float* src = k.pre_in + (size_t)nc * total + base + tp;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) dp[i][q] = vq[q] ? __ldg(src + 64 * q) : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = 8 * tn + i;
-                const int n = ch0 + j;
-                const bool live = j < nn;
-                const int nc = live ? n : k.hid - 1;
-                float w2v[kProjMaxOut];
-#pragma unroll
-                for (int o = 0; o < kProjMaxOut; ++o) w2v[o] = o < k.out_ch ? sW2[o * k.hid + nc] : 0.f;
-                float sb = 0.f, sw[kProjMaxOut];
-#pragma unroll
-                for (int o = 0; o < kProjMaxOut; ++o) sw[o] = 0.f;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    float a, gp;
-                    gelu_both(dp[i][q], a, gp);
-                    float s = 0.f;
-#pragma unroll
-                    for (int o = 0; o < kProjMaxOut; ++o) {
-                        s = fmaf(go[q][o], w2v[o], s);
-                        sw[o] = fmaf(go[q][o], a, sw[o]);
-                    }
-                    dp[i][q] = live ? s * gp : 0.f;
-                    sb += dp[i][q];
-                }
-                sb = warp_sum(sb);
-#pragma unroll
-                for (int o = 0; o < kProjMaxOut; ++o)
-                    if (o < k.out_ch) sw[o] = warp_sum(sw[o]);
-                if (lane == 0 && live) {
-                    atomicAdd(accb1 + n, sb);
-#pragma unroll
-                    for (int o = 0; o < kProjMaxOut; ++o)
-                        if (o < k.out_ch) atomicAdd(accW2 + o * k.hid + n, sw[o]);
-                }
-            }
-            // D into its two operand images
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int px = tp + 64 * q;
-                float hi[8], lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) tc::split_tf32(dp[i][q], hi[i], lo[i]);
-                // pixel-major (row = pixel, k = hidden 8 tn + i): hidden 4 m .. 4 m + 3 are 16 contiguous bytes
-                const uint32_t oa = (uint32_t)(2 * tn) * kPtLboA + (uint32_t)px * 16;
-                *reinterpret_cast<float4*>(A1hi + oa) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<float4*>(A1hi + oa + kPtLboA) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-                *reinterpret_cast<float4*>(A1lo + oa) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                *reinterpret_cast<float4*>(A1lo + oa + kPtLboA) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-                // hidden-major (row = hidden, k = pixel)
-                const uint32_t od = (uint32_t)(px >> 2) * kPtLboD + (uint32_t)(px & 3) * 4 + (uint32_t)(8 * tn) * 16;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    *reinterpret_cast<float*>(Dhi + od + i * 16) = hi[i];
-                    *reinterpret_cast<float*>(Dlo + od + i * 16) = lo[i];
-                }
-            }
-            tc::fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's reads
-            tc::tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc::tc_fence_after();
-                // DIN[pixel][channel]: accumulator columns 0-63
-                const uint32_t wch = w_a + (uint32_t)(2 * ch) * kPtWBytes;
-#pragma unroll
-                for (int ks = 0; ks < kProjHC / 8; ++ks) {
-                    const uint64_t da_hi = tc::make_smem_desc(a1hi_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t da_lo = tc::make_smem_desc(a1lo_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t db_hi = tc::make_smem_desc(wch + ks * 2 * kPtLboW, kPtLboW, 128);
-                    const uint64_t db_lo = tc::make_smem_desc(wch + kPtWBytes + ks * 2 * kPtLboW, kPtLboW, 128);
-                    tc::mma_tf32(tmem_base, da_hi, db_hi, idesc_din, (ch | ks) ? 1u : 0u);
-                    tc::mma_tf32(tmem_base, da_hi, db_lo, idesc_din, 1u);
-                    tc::mma_tf32(tmem_base, da_lo, db_hi, idesc_din, 1u);
-                }
-                // dW1[stacked channel][hidden of this chunk]: accumulator columns 64 + 32 ch .., never cleared after the first tile
-                const uint32_t dw_tmem = tmem_base + 64u + (uint32_t)ch * kProjHC;
-#pragma unroll 4
-                for (int ks = 0; ks < kPtPix / 8; ++ks) {
-                    const uint64_t da = tc::make_smem_desc(img_a + ks * 2 * kPtLboA, kPtLboA, 128);
-                    const uint64_t db_hi = tc::make_smem_desc(dhi_a + ks * 2 * kPtLboD, kPtLboD, 128);
-                    const uint64_t db_lo = tc::make_smem_desc(dlo_a + ks * 2 * kPtLboD, kPtLboD, 128);
-                    tc::mma_tf32(dw_tmem, da, db_hi, idesc_dw, (it | ks) ? 1u : 0u);
-                    tc::mma_tf32(dw_tmem, da, db_lo, idesc_dw, 1u);
-                }
-                tc::tc_commit(bar);
-            }
-            tc::mbar_wait(bar, phase);                   // the images may be rewritten, the accumulators read
-            phase ^= 1u;
-            tc::tc_fence_after();
-        }
-        // ---- input gradients: warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = the tile's pixels
-        if (warp < 4) {
-            const long idx = base + 32 * warp + lane;
-            long b = 0, rp = 0, pp = 0;
-            const bool valid = idx < total;
-            if (valid) raw_to_padded(g, idx, b, rp, pp);
-            long cur_stride = -1, off = 0;
-#pragma unroll
-            for (int c0 = 0; c0 < CT; c0 += 16) {
-                uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, r);
-                tc::tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = c0 + j;
-                        if (c < k.ctot) {
-                            float* gb = gbase[c];
-                            const long st = sstride[c];
-                            if (st != cur_stride) { cur_stride = st; off = b * st + pp; }
-                            if (gb != nullptr) gb[off] = __uint_as_float(r[j]);
-                        }
-                    }
-                }
-            }
-            tc::tc_fence_before();
-        }
-        if (tn == 0) {
-#pragma unroll
-            for (int o = 0; o < kProjMaxOut; ++o)
-                if (o < k.out_ch) {
-                    const float v = warp_sum(go[0][o] + go[1][o]);
-                    if (lane == 0) atomicAdd(accb2 + o, v);
-                }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    tc::tc_fence_after();
-    // ---- dW1: TMEM lanes 0-63 hold the hi-part rows (channel = lane), 64-127 the lo-part rows: both add into gw1
-    if (warp < 4 && it > 0) {
-        const int c = (32 * warp + lane) & 63;
-        for (int ch = 0; ch < nchunks; ++ch)
-            for (int c0 = 0; c0 < kProjHC; c0 += 16) {
-                uint32_t r[16];
-                tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(32 * warp) << 16) + 64u + (uint32_t)(ch * kProjHC + c0), r);
-                tc::tmem_ld_wait();
-                if (c < k.ctot) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = ch * kProjHC + c0 + j;
-                        if (n < k.hid) atomicAdd(k.gw1 + n * k.ctot + c, __uint_as_float(r[j]));
-                    }
-                }
-            }
-    }
-    for (int i = tid; i < k.hid; i += 256) atomicAdd(k.gb1 + i, accb1[i]);
-    for (int i = tid; i < k.out_ch * k.hid; i += 256) atomicAdd(k.gw2 + i, accW2[i]);
-    for (int i = tid; i < k.out_ch; i += 256) atomicAdd(k.gb2 + i, accb2[i]);
-    tc::tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, kPtTmemCols);
-}
 
 // =====================================================================================================
 // Warp-specialised form (hid <= 32: one hidden chunk).  The same tensor-core products as above, but the fp32 phases of a

@@ -28,10 +28,9 @@ struct Resample2K {
 // per-tile overheads, 64 for the others
 __host__ __device__ constexpr int rs_tile_w(int G1) { return G1 == 8 ? 128 : 64; }
 
-// SPLIT (opt-in, UNO_B200_RS_SPLIT=1, not yet measured): the window is staged as two cp.async groups (upper and lower half of
-// its rows) and pass A starts on the upper half while the lower half is still in flight -- the kernel otherwise waits for the
-// whole window before its first FMA and relies on the second resident CTA alone to cover that latency.
-template <int G0, int W0, int G1, int W1, int MINB, bool SPLIT = false>
+// (A variant that staged the window as two cp.async groups so that pass A could start on the upper half measured SLOWER on
+// B200 -- 3.98 vs 3.43 ms per Darcy step -- and was removed: the second resident CTA already covers the staging latency.)
+template <int G0, int W0, int G1, int W1, int MINB>
 __global__ void __launch_bounds__(256, MINB) resample2d_kernel(const Resample2K k) {
     extern __shared__ __align__(16) float rsm[];
     constexpr int kRsTW = rs_tile_w(G1), kRsMidLd = kRsTW + 1;
@@ -55,21 +54,6 @@ __global__ void __launch_bounds__(256, MINB) resample2d_kernel(const Resample2K 
     {
         const float* xp = k.x + (p * k.n_in0 + r0) * (long)k.n_in1 + c0 + lane;
         const uint32_t in_base = (uint32_t)__cvta_generic_to_shared(in_s) + 4u * lane;
-        if constexpr (SPLIT) {
-            // rows [0, h1) form the first cp.async group, the rest the second (h1 is a multiple of 8 or equals rin); every thread
-            // commits exactly two groups, empty or not, so that wait_group counts mean the same thing in all of them
-            const int h1 = min(rin, ((rin >> 1) + 31) & ~31);
-            auto stage_row = [&](int r) {
-                const float* src = xp + (long)r * k.n_in1;
-                const uint32_t dst = in_base + 4u * (uint32_t)(r * k.ldin);
-                for (int c = lane; c < cin; c += 32)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (c - lane)), "l"(src + (c - lane)) : "memory");
-            };
-            for (int r = warp; r < h1; r += 8) stage_row(r);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            for (int r = h1 + warp; r < rin; r += 8) stage_row(r);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        } else {
         for (int r = warp; r < rin; r += 8) {
             const float* src = xp + (long)r * k.n_in1;
             const uint32_t dst = in_base + 4u * (uint32_t)(r * k.ldin);
@@ -81,53 +65,11 @@ __global__ void __launch_bounds__(256, MINB) resample2d_kernel(const Resample2K 
             for (int c = lane + 32 * CIT; c < cin; c += 32)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (c - lane)), "l"(src + (c - lane)) : "memory");
         }
-        }
     }
     for (int i = tid; i < ngw * W1 * G1; i += 256) d1s[i] = __ldg(k.D1 + (size_t)ga1 * W1 * G1 + i);
     for (int i = tid; i < ngh * W0 * G0; i += 256) d0s[i] = __ldg(k.D0 + (size_t)ga0 * W0 * G0 + i);
     if (tid < ngw) gs1s[tid] = __ldg(k.gs1 + ga1 + tid) - c0;
     if (tid >= 64 && tid < 64 + ngh) gs0s[tid - 64] = __ldg(k.gs0 + ga0 + tid - 64) - r0;
-    if constexpr (SPLIT) {
-        const int h1 = min(rin, ((rin >> 1) + 31) & ~31);
-        auto pass_a = [&](int rb0, int rb1) {
-            for (int cg = warp; cg < ngw; cg += 8) {
-                float w[W1][G1];
-                const float4* wsrc = reinterpret_cast<const float4*>(d1s + cg * W1 * G1);
-#pragma unroll
-                for (int u = 0; u < W1; ++u)
-#pragma unroll
-                    for (int q4 = 0; q4 < G1 / 4; ++q4) {
-                        const float4 v = wsrc[u * (G1 / 4) + q4];
-                        w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
-                    }
-                const int cs = gs1s[cg];
-                for (int rb = rb0; rb < rb1; rb += 32) {
-                    const int r = min(rb + lane, rb1 - 1);
-                    const float* src = in_s + r * k.ldin + cs;
-                    float acc[G1];
-#pragma unroll
-                    for (int q = 0; q < G1; ++q) acc[q] = 0.f;
-#pragma unroll
-                    for (int u = 0; u < W1; ++u) {
-                        const float v = src[u];
-#pragma unroll
-                        for (int q = 0; q < G1; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
-                    }
-                    if (rb + lane < rb1) {
-                        float* dst = mid_s + r * kRsMidLd + cg * G1;
-#pragma unroll
-                        for (int q = 0; q < G1; ++q) dst[q] = acc[q];
-                    }
-                }
-            }
-        };
-        asm volatile("cp.async.wait_group 1;" ::: "memory");       // the first of this thread's two groups has landed
-        __syncthreads();
-        pass_a(0, h1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        pass_a(h1, rin);
-    } else {
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     // ---- pass A: mid[r][j] = sum_u D1[g][u][q] * in[r][gs1[g] + u],  j = g*G1 + q
@@ -162,7 +104,6 @@ __global__ void __launch_bounds__(256, MINB) resample2d_kernel(const Resample2K 
             }
         }
     }
-    }   // !SPLIT
     __syncthreads();
     // ---- pass B: y[i][j] = sum_u D0[g][u][q] * mid[gs0[g] + u][j],  i = g*G0 + q
     const int i0 = ga0 * G0, j0 = tw * kRsTW;

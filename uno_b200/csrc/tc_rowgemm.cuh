@@ -139,83 +139,8 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
     }
 }
 
-// Variant of the epilogue for the 16-warp configuration (one 16-column chunk per round) that issues the loads of the NEXT
-// round's addend before it stores the current round, so a warp always has a round of global loads in flight while it computes
-// and stores (opt-in: UNO_B200_ROWGEMM_EPI16=2).  Same arithmetic in the same order as rowgemm_epilogue_tile.
-template <int EPI, bool VEC2, int G>
-__device__ __forceinline__ void rowgemm_epilogue_tile_pf(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int grp, int lane) {
-    constexpr bool kAccum = (EPI != EPI_STORE);
-    const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
-    float* rowp[4];          // index hh*2 + rr
-    bool rok[4];
-    n_base -= p.parity ? (int)(tile & 1) : 0;
-#pragma unroll
-    for (int hr = 0; hr < 4; ++hr) {
-        const long grow = rowgemm_row(p, tile, q * 32 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2));
-        rok[hr] = grow < p.R;
-        rowp[hr] = p.C + (rok[hr] ? grow : 0) * p.ldc + n_base + 2 * (lane & 3);
-    }
-    const int ncol = p.N - n_base - 2 * (lane & 3);
-    const int cmin = -(n_base + 2 * (lane & 3));
-    auto load_z = [&](int c0, float2 (&cz)[8]) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
-            const int c = c0 + rep * 8;
-            const bool live = rok[hh * 2 + rr];
-            const float* z = rowp[hh * 2 + rr] + c;
-            cz[e] = make_float2(0.f, 0.f);
-            const bool in0 = live && c >= cmin && c < ncol, in1 = live && c + 1 < ncol;
-            if (VEC2 && in0 && in1) cz[e] = *reinterpret_cast<const float2*>(z);
-            else {
-                if (in0) cz[e].x = z[0];
-                if (in1) cz[e].y = z[1];
-            }
-        }
-    };
-    int ci = grp;
-    bool have = ci * 16 < p.N_t && n_base + ci * 16 < p.N;
-    float2 cz[8], czn[8];
-    if (kAccum && have) load_z(ci * 16, cz);
-    while (have) {
-        const int c0 = ci * 16;
-        uint32_t r[2][8];
-        tmem_ld_16x256b_x2(t_base + (uint32_t)c0, r[0]);
-        tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0, r[1]);
-        const int cn = ci + G;
-        const bool have_n = cn * 16 < p.N_t && n_base + cn * 16 < p.N;
-        if (kAccum && have_n) load_z(cn * 16, czn);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
-            const int c = c0 + rep * 8;
-            const bool live = rok[hh * 2 + rr];
-            const bool ok0 = live && c >= cmin && c < ncol, ok1 = live && c + 1 < ncol;
-            float* z = rowp[hh * 2 + rr] + c;
-            float2 acc = make_float2(__uint_as_float(r[hh][rep * 4 + rr * 2 + 0]), __uint_as_float(r[hh][rep * 4 + rr * 2 + 1]));
-            if (kAccum) { acc.x += cz[e].x; acc.y += cz[e].y; }
-            float2 act = acc;
-            if (EPI == EPI_ACCUM_GELU || EPI == EPI_ACCUM_GELU_INPLACE) { act.x = gelu_erf(acc.x); act.y = gelu_erf(acc.y); }
-            const float2 out1 = (EPI == EPI_ACCUM_GELU_INPLACE) ? act : acc;
-            if (VEC2 && ok0 && ok1) {
-                *reinterpret_cast<float2*>(z) = out1;
-                if (EPI == EPI_ACCUM_GELU) *reinterpret_cast<float2*>(z + c2_delta) = act;
-            } else {
-                if (ok0) { z[0] = out1.x; if (EPI == EPI_ACCUM_GELU) z[c2_delta] = act.x; }
-                if (ok1) { z[1] = out1.y; if (EPI == EPI_ACCUM_GELU) z[c2_delta + 1] = act.y; }
-            }
-        }
-        if (kAccum) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cz[e] = czn[e];
-        }
-        ci = cn;
-        have = have_n;
-    }
-}
-
-// J == 0 selects the prefetching epilogue above (one chunk per round)
+// (A software-pipelined form of this epilogue that loaded the next round's addend before storing the current round was measured
+// on B200 and was no faster -- 3.68 vs 3.62 ms per Darcy step -- so it was removed.)
 template <int EPI, int G = 2, int J = 2>
 __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(const RowGemmParams p) {
     constexpr int kRowGemmEpiWarps = rowgemm_epi_warps(G);   // shadows the default-configuration constant
@@ -354,13 +279,8 @@ __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(c
             mbar_wait_relaxed(&d_full[s], ph);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);
-            if constexpr (J == 0) {
-                if (vec2) rowgemm_epilogue_tile_pf<EPI, true, G>(p, t_base, tile, q, n_base, half, lane);
-                else rowgemm_epilogue_tile_pf<EPI, false, G>(p, t_base, tile, q, n_base, half, lane);
-            } else {
-                if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane);
-                else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane);
-            }
+            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane);
+            else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane);
             tc_fence_before();
             mbar_arrive(&d_empty[s]);
         }

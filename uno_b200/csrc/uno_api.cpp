@@ -503,13 +503,10 @@ int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, 
 // R is linear and acts per channel, so it commutes with the channel mix; it is applied on whichever
 // side has fewer channels.  R(1) = gain (1 for bicubic; N_in/N_out for the 3-D operator).
 // ---------------------------------------------------------------------------------------------------
-// Opt-in, NOT the reference's behaviour: UNO_B200_POINTWISE3D_FIXED=1 replaces pointwise_op_3D's quirky
+// Opt-in, NOT the reference's behaviour: the switch pointwise3d_fixed replaces pointwise_op_3D's quirky
 // "spectral resample" by the band-limited Fourier resample it approximates (plan.h sr_mid_fixed).  Read when a call looks its
 // plan up, so set it before the first forward and keep it for the matching backward.
-inline bool pointwise3d_fixed() {
-    const char* e = getenv("UNO_B200_POINTWISE3D_FIXED");
-    return e && e[0] && e[0] != '0';
-}
+inline bool pointwise3d_fixed() { return cfg(CFG_POINTWISE3D_FIXED) != 0; }
 
 struct ResamplePlan {
     int d = 0;
@@ -1130,6 +1127,16 @@ int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const fl
     BE_TRY(be_lp_loss_bwd(x, y, norms, gloss, batch, n, reduction, gx, stream));
     return 0;
 }
+
+int uno_config_set(const char* name, int value) {
+    if (cfg_set(name, value)) return fail(UNO_EINVAL, "unknown switch '%s'", name ? name : "(null)");
+    return 0;
+}
+int uno_config_get(const char* name, int* value) {
+    if (cfg_get(name, value)) return fail(UNO_EINVAL, "unknown switch '%s'", name ? name : "(null)");
+    return 0;
+}
+const char* uno_config_name(int index) { return cfg_name(index); }
 
 void uno_profile_enable(int on) { be_profile_enable(on); }
 size_t uno_profile_report(char* buf, size_t cap) { return be_profile_report(buf, cap); }

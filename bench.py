@@ -334,7 +334,7 @@ class Ctx:
         return ms
 
 
-def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=None):
+def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=None, graph_mode="auto"):
     """Measure one workload on this job's GPUs: device-resident value, end-to-end from pinned host buffers, per-kernel roofline."""
     from uno_b200.losses import LpLoss
     from uno_b200.parallel import GradReducer
@@ -342,24 +342,40 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
     lib, dev, world, rank = ctx.lib, ctx.dev, ctx.world, ctx.rank
     _, _, _, xshape, tshape, _, _ = WORKLOADS[workload]
     model = build_model(workload, device=dev)
-    reducer = GradReducer(model) if world > 1 else None
     ar = AR_STEPS.get(workload, 0)
-    step = make_step(model, LpLoss(size_average=False), B, tshape, reducer, ar_steps=ar)
-    rollout = "eager"
-    if ar:
-        try:   # the captured rollout (uno_b200/rollout.py): window shift fused into the lift, whole rollout + BPTT in one graph
-            from uno_b200.rollout import GraphedRollout
-
-            step = GraphedRollout(model, LpLoss(size_average=False), B, ar, reducer=reducer)
-            rollout = step.mode
-        except ImportError:
-            pass
-
     torch.manual_seed(1 + rank)
     x_host = torch.randn(B, *xshape).pin_memory()
     y_host = torch.randn(B, *tshape).pin_memory()
     x = x_host.to(dev)
     y = y_host.to(dev)
+
+    # Execution mode.  "graph": the whole step (zero_grad, forward / rollout, loss, backward) captured once in a CUDA graph and
+    # replayed (uno_b200/graphed.py); the gradient all-reduce follows the replay.  "eager": autograd drives the C ABI call by
+    # call and the bucketed all-reduce overlaps backward.  Replay wins wherever host work per step rivals the kernel time
+    # (the rollout, strong-scaled shards); a full-batch Darcy step on several GPUs is kernel-bound and keeps the overlap.
+    step, reducer, rollout, graph_error = None, None, "eager", None
+    want_graph = graph_mode == "on" or (graph_mode == "auto" and (world == 1 or workload != "darcy" or B < WORKLOADS[workload][5]))
+    if want_graph:
+        ok = 1
+        try:
+            from uno_b200.graphed import GraphedStep
+
+            reducer = GradReducer(model, overlap=False)
+            step = GraphedStep(model, LpLoss(size_average=False), x, y, ar_steps=ar, reducer=reducer)
+            rollout = "graph"
+        except Exception as exc:
+            ok, graph_error = 0, repr(exc)
+        if world > 1:   # every rank runs the same mode
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            step, reducer, rollout = None, None, "eager"
+            model.zero_grad(set_to_none=True)
+            torch.cuda.empty_cache()
+    if step is None:
+        reducer = GradReducer(model) if world > 1 else None
+        step = make_step(model, LpLoss(size_average=False), B, tshape, reducer, ar_steps=ar)
 
     for _ in range(warmup):
         step(x, y)
@@ -369,12 +385,19 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
     l0 = lib.uno_launch_count()
     total_ms = ctx.timed(lambda: step(x, y), steps)
     launches = lib.uno_launch_count() - l0
+    if rollout == "graph":      # replays do not pass through the library's host code: count one eager step of the same work
+        l0 = lib.uno_launch_count()
+        step.eager_step(x, y)
+        torch.cuda.synchronize()
+        launches = (lib.uno_launch_count() - l0) * steps
     clocks = sampler.finish()
     ms_per_step = total_ms / steps
     value = B * world / (ms_per_step * 1e-3)
 
     # --- end to end from pinned host memory
     def e2e_step():
+        if rollout == "graph":      # pinned host buffers -> the graph's static inputs -> replay -> loss read back
+            return float(step.run_from_host(x_host, y_host).item())
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
         return float(step(xd, yd).item())
@@ -383,7 +406,8 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
     e2e_ms = ctx.timed(e2e_step, steps) / steps
     e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": "samples/s",
            "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4), "d2h_bytes_per_step": 4,
-           "ms_per_step": e2e_ms, "copies": "input and target copied on the compute stream before the step"}
+           "ms_per_step": e2e_ms, "copies": "input and target copied from pinned host memory on the compute stream before the step"
+                                           + (" (into the captured graph's static inputs)" if rollout == "graph" else "")}
 
     # Same step, same bytes, same loss read-back, but the target's copy is issued on a copy stream right behind the input's and
     # the compute stream only waits for it where the loss first reads it: half of the host-to-device time hides behind the
@@ -477,7 +501,7 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
     torch.cuda.empty_cache()
     return {"workload": WORKLOAD_DESC[workload], "per_gpu_batch": B, "global_batch": B * world, "value": value, "unit": "samples/s",
             "ms_per_step": ms_per_step, "steps": steps, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "rollout": rollout if ar else None, "roofline": roofline, "kernel_breakdown": breakdown, "spectral_levels": levels}
+            "execution": rollout, "graph_error": graph_error, "roofline": roofline, "kernel_breakdown": breakdown, "spectral_levels": levels}
 
 
 def spectral_sweep(iters=3):
@@ -515,6 +539,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: everywhere except the full-batch multi-GPU Darcy step)")
     ap.add_argument("--lean", action="store_true", help="headline workload only (no secondary / reference / sweep legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -580,11 +606,11 @@ def main():
         return max(full // world, 1)
 
     main_mode = args.scaling
-    head = run_workload(ctx, args.workload, args.batch or split(def_b, main_mode), args.steps, args.warmup, profile=not args.no_profile)
+    head = run_workload(ctx, args.workload, args.batch or split(def_b, main_mode), args.steps, args.warmup, profile=not args.no_profile, graph_mode=args.graph)
     other = None
     if world > 1 and args.batch is None:
         om = "strong" if main_mode == "weak" else "weak"
-        o = run_workload(ctx, args.workload, split(def_b, om), args.steps, args.warmup, profile=False)
+        o = run_workload(ctx, args.workload, split(def_b, om), args.steps, args.warmup, profile=False, graph_mode=args.graph)
         other = {k: o[k] for k in ("per_gpu_batch", "global_batch", "value", "unit", "ms_per_step", "e2e", "gpu_launches")}
         other["scaling"] = om
 
@@ -597,7 +623,7 @@ def main():
                 modes = ["weak"] if world == 1 else ["weak", "strong"]
                 ent = {}
                 for mode in modes:
-                    r = run_workload(ctx, wl, split(full, mode), min(args.steps, 10), args.warmup, profile=(mode == "weak"), breakdown_top=10)
+                    r = run_workload(ctx, wl, split(full, mode), min(args.steps, 10), args.warmup, profile=(mode == "weak"), breakdown_top=10, graph_mode=args.graph)
                     r["scaling"] = mode
                     ent[mode] = r
                 secondary[wl] = ent["weak"] if world == 1 else ent

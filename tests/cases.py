@@ -59,3 +59,12 @@ PROJECT_CASES = {
     "tc_wide": (3, (31, 17), (2, 0), (0, 3), (64,), 64, 1),           # one 64-channel source, two full chunks
     "tc_one_chunk": (3, (29, 23), (1, 0), (0, 2), (40, 24), 20, 1),   # hid < 32, one output: the warp-specialised tcgen05 kernel
 }
+
+
+def grad_sample_indices(i, numel, n=64):
+    """Fixed pseudo-random element indices (into the flattened real view) at which the golden fixtures keep the gradient of
+    parameter number i -- element-wise model gradients without storing 16 M floats."""
+    import numpy as np
+
+    rng = np.random.default_rng(1234 + i)
+    return np.sort(rng.choice(numel, size=min(n, numel), replace=False))

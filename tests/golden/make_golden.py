@@ -24,6 +24,9 @@ for name in ("matplotlib", "matplotlib.pyplot"):  # the model files import it, u
 
 import integral_operators as ref  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(HERE))
+from cases import grad_sample_indices  # noqa: E402
+
 torch.set_num_threads(4)
 
 
@@ -201,6 +204,17 @@ def make_models():
         out[f"{tag}.state_fp"] = _state_fingerprint(model)
         out[f"{tag}.keys"] = np.array(list(model.state_dict().keys()))
         out[f"{tag}.grad_fp"] = np.array([float(torch.view_as_real(p.grad).double().abs().sum()) if p.grad.is_complex() else float(p.grad.double().abs().sum()) for p in model.parameters()])
+        # element-wise gradients at fixed sample positions of every parameter (tests/cases.py grad_sample_indices) and their scale
+        vals, off, gmax = [], [0], []
+        for i, p in enumerate(model.parameters()):
+            g = (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).reshape(-1)
+            idx = grad_sample_indices(i, g.numel())
+            vals.append(n(g)[idx])
+            off.append(off[-1] + len(idx))
+            gmax.append(float(g.abs().max()))
+        out[f"{tag}.grad_sub"] = np.concatenate(vals).astype(np.float32)
+        out[f"{tag}.grad_sub_off"] = np.array(off, dtype=np.int64)
+        out[f"{tag}.grad_max"] = np.array(gmax, dtype=np.float64)
 
     run("uno9_pad5", lambda: d2.UNO_9(3, 8, pad=5), (1, 85, 85, 1), (1, 85, 85))
     run("uno_ns2d", lambda: n2.UNO(14, 8), (1, 64, 64, 10), (1, 64, 64))

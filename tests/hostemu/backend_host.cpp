@@ -24,6 +24,7 @@ int be_upload(void** dptr, const void* host, size_t bytes) {
 void be_free(void* d) { free(d); }
 int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); return 0; }
 const char* be_name() { return "host-emulation"; }
+int be_current_device() { return 0; }
 const char* be_error_string(int) { return "host emulation error"; }
 stream_t be_side_stream() { return nullptr; }
 int be_fork(stream_t, stream_t) { return 0; }
@@ -500,7 +501,7 @@ int be_lp_loss_bwd(const float* x, const float* y, const float* norms, const flo
     for (int b = 0; b < B; ++b) {
         float scale = reduction == 0 ? gl[b] : gl[0];
         if (reduction == 2) scale /= (float)B;
-        scale /= norms[2 * b] * norms[2 * b + 1];
+        scale = norms[2 * b] > 0.0f ? scale / (norms[2 * b] * norms[2 * b + 1]) : 0.0f;   // torch masks a zero residual norm
         for (long i = 0; i < N; ++i) gx[b * N + i] = (x[b * N + i] - y[b * N + i]) * scale;
     }
     return 0;

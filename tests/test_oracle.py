@@ -163,3 +163,17 @@ def test_models_over_port_match_reference(tag, golden):
     loss.backward()
     gfp = np.array([float(torch.view_as_real(p.grad).double().abs().sum()) if p.grad.is_complex() else float(p.grad.double().abs().sum()) for p in model.parameters()])
     assert np.allclose(gfp, g[f"{tag}.grad_fp"], rtol=2e-3, atol=1e-7)
+    check_golden_gradients(model, g, tag, 1e-5)
+
+
+def check_golden_gradients(model, g, tag, tol):
+    """Element-wise: every parameter's gradient at the fixture's fixed sample positions, relative to that gradient's own
+    largest magnitude in the reference run (tests/golden/make_golden.py, tests/cases.py grad_sample_indices)."""
+    from cases import grad_sample_indices
+
+    off, gmax = g[f"{tag}.grad_sub_off"], g[f"{tag}.grad_max"]
+    for i, (k, p) in enumerate(model.named_parameters()):
+        gr = (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).detach().reshape(-1).cpu().numpy()
+        idx = grad_sample_indices(i, gr.size)
+        want = g[f"{tag}.grad_sub"][off[i]:off[i + 1]]
+        assert float(np.abs(gr[idx] - want).max()) <= tol * max(float(gmax[i]), 1e-12), (k, float(np.abs(gr[idx] - want).max()), float(gmax[i]))

@@ -50,6 +50,25 @@ def _worker(rank, world, port, overlap, q):
         loss = model(shard_batch(x, rank, world)).sum()
         loss.backward()
         red.finish()
+    # the reference's training loops call optimizer.zero_grad(), whose default (set_to_none=True) drops the views into the
+    # flat buffer: the reducer must notice, move the fresh gradients into their slots and still reduce the right values
+    model.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    model(shard_batch(x, rank, world)).sum().backward()
+    red.finish()
+    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())
+    # gradient accumulation: two half micro-batches under no_sync + one reduction == the full local batch
+    full = [torch.view_as_real(p.grad).clone() if p.grad.is_complex() else p.grad.clone() for p in model.parameters()]
+    red.zero_grad()
+    xs = shard_batch(x, rank, world)
+    with red.no_sync():
+        model(xs[: xs.shape[0] // 2]).sum().backward()
+        red.finish()
+    model(xs[xs.shape[0] // 2 :]).sum().backward()
+    red.finish()
+    for p, f in zip(model.parameters(), full):
+        g = torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad
+        assert float((g - f).abs().max()) < 1e-5 * max(float(f.abs().max()), 1e-3)
     grads = [torch.view_as_real(p.grad).clone() if p.grad.is_complex() else p.grad.clone() for p in model.parameters()]
     if rank == 0:
         q.put([g.numpy() for g in grads])

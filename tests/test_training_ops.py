@@ -72,6 +72,24 @@ def test_lp_loss_oracle_and_hostemu_match_reference(mode, golden):
     assert rel_err(gxe.reshape(x.shape), g[f"loss.{mode}.gx"]) < 2e-6
 
 
+def test_lp_loss_exactly_matched_sample_gives_zero_gradient():
+    """x[b] == y[b]: torch's norm backward masks the zero norm and returns a zero gradient for that sample (the reference's
+    LpLoss is torch.norm); a 0 * inf = NaN there would poison every parameter gradient."""
+    import emu
+
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((3, 50)).astype(np.float32)
+    x = rng.standard_normal((3, 50)).astype(np.float32)
+    x[1] = y[1]
+    xt = torch.tensor(x, requires_grad=True)
+    lo = port.LpLoss(size_average=False)(xt, torch.tensor(y))
+    lo.backward()
+    assert torch.isfinite(xt.grad).all() and float(xt.grad[1].abs().max()) == 0.0
+    loss, gx = emu.lp_loss(x, y, 1, np.ones(1, np.float32))
+    assert np.isfinite(gx).all() and np.abs(gx.reshape(3, 50)[1]).max() == 0.0
+    assert rel_err(gx.reshape(3, 50), xt.grad.numpy()) < 2e-6
+
+
 def test_adam_argument_errors():
     import emu
 
@@ -182,3 +200,10 @@ def test_lp_loss_cuda_large_and_cpu_rejected(cuda_lib):
     assert float((x.grad.double() - xr.grad).abs().max() / xr.grad.abs().max()) < 1e-5
     with pytest.raises(RuntimeError, match="CUDA float32"):
         LpLoss()(torch.zeros(2, 3), torch.ones(2, 3))
+    # an exactly matched sample: zero gradient for it, finite everywhere (torch masks the zero norm)
+    x2 = torch.randn(3, 1000, device="cuda")
+    y2 = torch.randn(3, 1000, device="cuda")
+    x2[1] = y2[1]
+    x2.requires_grad_(True)
+    LpLoss(size_average=False)(x2, y2).backward()
+    assert torch.isfinite(x2.grad).all() and float(x2.grad[1].abs().max()) == 0.0

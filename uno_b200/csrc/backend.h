@@ -18,6 +18,7 @@ int be_upload(void** dptr, const void* host, size_t bytes);   // allocate + copy
 void be_free(void* dptr);
 int be_memset(void* d, int v, size_t bytes, stream_t s);
 const char* be_name();
+int be_current_device();   // ordinal of the device the calling thread has current (plan constants are cached per device)
 const char* be_error_string(int code);   // message for a non-zero return of any be_* call
 
 // ---- fork / join of independent kernel sequences (the two branches of an operator block) -----------------

@@ -848,6 +848,18 @@ inline unsigned grid_for(size_t n, int block, size_t cap = 148 * 16) {
     return (unsigned)g;
 }
 
+// Function attributes, SM counts and scratch buffers are PER DEVICE: a process may drive several GPUs (a model on cuda:1).
+inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+struct DeviceOnce {   // "has this one-time setup run on the current device yet?"
+    std::atomic<unsigned long long> mask{0};
+    bool done() const { return (mask.load(std::memory_order_acquire) >> (current_device() & 63)) & 1ull; }
+    void mark() { mask.fetch_or(1ull << (current_device() & 63), std::memory_order_release); }
+};
+
 template <typename K>
 int ensure_smem(K kernel, size_t bytes) {
     // raise the dynamic shared-memory limit of this instantiation (idempotent, cheap)
@@ -956,25 +968,25 @@ void tc_forget(const void* p) {
     }
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};
 int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    const int dev = current_device() & 63;
+    if (!g_num_sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms[dev] = n > 0 ? n : 148;
     }
-    return g_num_sms;
+    return g_num_sms[dev];
 }
 
 
 template <int EPI, int G, int J>
 int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI, G, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     int gx = num_sms() / p.n_tiles;
     if (p.parity) gx &= ~1;                 // a CTA must only ever see tiles of one row parity (m_tiles is even too)
@@ -1038,11 +1050,11 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
 
 template <int LW, bool RC>
 int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     tc::kpipe_kernel<LW, RC><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
@@ -1161,11 +1173,11 @@ int try_tc_mid(const MidArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < 2 * img.N_t) cols *= 2;
     p.tmem_cols = cols;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::mid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     int gx = std::max(1, num_sms() / img.n_tiles);
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
@@ -1207,11 +1219,11 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
     while (cols < 2 * p.N_t) cols *= 2;
     p.tmem_cols = cols;
     p.items = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * a.q_inner;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::cmm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     long gx = num_sms();
     if (gx > p.items) gx = p.items;
@@ -1221,7 +1233,7 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
 }
 
 // per-stream scratch for the weight image of the tensor-core channel mix (stream order makes reuse safe)
-std::map<cudaStream_t, float*> g_conv_scratch;
+std::map<std::pair<int, cudaStream_t>, float*> g_conv_scratch;   // (device, stream): the legacy default stream is shared by all devices
 constexpr size_t kConvScratchBytes = 160 * 1024;
 
 int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
@@ -1240,11 +1252,12 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     float* img = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_tc_mu);
-        auto it = g_conv_scratch.find(st);
+        const std::pair<int, cudaStream_t> skey(current_device(), st);
+        auto it = g_conv_scratch.find(skey);
         if (it == g_conv_scratch.end()) {
             cudaError_t e = cudaMalloc(&img, kConvScratchBytes);
             if (e != cudaSuccess) return (int)e;
-            g_conv_scratch[st] = img;
+            g_conv_scratch[skey] = img;
         } else img = it->second;
     }
     const int K_pad = n_chunks * tc::kKC;
@@ -1259,11 +1272,11 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < 2 * N_t) cols *= 2;
     p.tmem_cols = cols;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     int gx = num_sms();
     if ((long)gx > p.n_tiles) gx = (int)p.n_tiles;
@@ -1274,11 +1287,11 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
 
 template <bool DBG>
 int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     tc::wgrad_tc_kernel<DBG><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
     CU_LAUNCH_CHECK();
@@ -1348,6 +1361,7 @@ int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
 // backend.h implementation
 // =====================================================================================================
 const char* be_name() { return "cuda-sm100a"; }
+int be_current_device() { return current_device(); }
 const char* be_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
 void be_profile_enable(int on) {
@@ -1710,11 +1724,11 @@ int be_banded2d(const Banded2DArgs& a, stream_t s) {
         int rc = be_banded(m, s);
         return rc ? rc : be_banded(l, s);
     }
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(banded2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.mark();
     }
     const int tiles_h = (a.n_out0 + kB2TH - 1) / kB2TH, tiles_w = (a.n_out1 + kB2TW - 1) / kB2TW;
     const long blocks = a.planes * tiles_h * tiles_w;

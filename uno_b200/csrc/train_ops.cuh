@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) lp_bwd_kernel(const float* __restrict__ x
     const float dn = norms[2 * b], yn = norms[2 * b + 1];
     float scale = reduction == 0 ? gl[b] : gl[0];
     if (reduction == 2) scale /= (float)B;
-    scale = scale / (dn * yn);          // d||d||/dd = d / ||d||  (inf / nan for a zero residual, as in torch)
+    // d||d||/dd = d / ||d||; torch's norm backward masks ||d|| == 0 and returns a zero gradient there (a sample whose
+    // prediction matches its target exactly must not put NaN into every parameter gradient)
+    scale = dn > 0.0f ? scale / (dn * yn) : 0.0f;
     const float* xp = x + b * N;
     const float* yp = y + b * N;
     float* gp = gx + b * N;

@@ -304,6 +304,7 @@ int get_spectral_plan(const uno_conv_desc* d, SpectralPlan** out) {
     memset(&k, 0, sizeof k);
     k.v[0] = d->ndim;
     for (int a = 0; a < d->ndim; ++a) { k.v[1 + a] = d->in_dim[a]; k.v[4 + a] = d->out_dim[a]; k.v[7 + a] = d->modes[a]; }
+    k.v[11] = be_current_device();   // the constants live in that device's memory
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_spectral.find(k);
     if (it == g_spectral.end()) {
@@ -616,6 +617,7 @@ int get_resample_plan(const uno_conv_desc* d, ResamplePlan** out) {
     for (int a = 0; a < d->ndim; ++a) { k.v[1 + a] = d->in_dim[a]; k.v[4 + a] = d->out_dim[a]; }
     const bool fixed3d = d->ndim == 3 && pointwise3d_fixed();
     k.v[7] = fixed3d ? 1 : 0;
+    k.v[11] = be_current_device();
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_resample.find(k);
     if (it == g_resample.end()) {

@@ -7,9 +7,11 @@ fp32 tensors; there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import List, Optional, Sequence
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _capi
 from ._lib import get as _get_lib
@@ -28,11 +30,33 @@ def _check_input(x: torch.Tensor, name: str = "input") -> None:
         raise RuntimeError(f"uno_b200: expected float32 {name} but found {x.dtype}")
 
 
-def _check_params(*params: torch.Tensor) -> None:
+def _check_params(x: torch.Tensor, *params: Optional[torch.Tensor], dtype=torch.float32) -> None:
+    """Every parameter must live on the input's device with the expected dtype: a model that was never moved with .cuda() (or
+    sits on another GPU) would otherwise hand a host / foreign pointer to the kernels.  The reference's torch ops raise
+    RuntimeError for mismatched devices / dtypes as well."""
     for p in params:
-        if not p.is_cuda or p.dtype != torch.float32:
-            # F.linear raises RuntimeError for mismatched dtypes / devices in the reference as well
-            raise RuntimeError(f"uno_b200: parameters must be CUDA float32 tensors (got {p.dtype} on {p.device})")
+        if p is None:
+            continue
+        if not p.is_cuda or p.device != x.device:
+            raise RuntimeError(f"uno_b200: parameter on {p.device} but input on {x.device}; move the module with .to(input.device)")
+        if p.dtype != dtype:
+            raise RuntimeError(f"uno_b200: expected {dtype} parameter but found {p.dtype}")
+
+
+def _guard(fn):
+    """Run a Function's forward / backward with the device of its first CUDA tensor argument current: the library caches plan
+    constants, function attributes and scratch per device and launches on the current one (a model on cuda:1 while cuda:0 is
+    current would otherwise launch with constants of the wrong device)."""
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+
+    return wrapped
 
 
 def _stream(x: torch.Tensor) -> C.c_void_p:
@@ -47,11 +71,12 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-def _cweights(weights: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+def _cweights(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     out = []
     for w in weights:
         if w.dtype != torch.complex64:
             raise RuntimeError(f"uno_b200: spectral weights must be complex64 (got {w.dtype})")
+        _check_params(x, w, dtype=torch.complex64)
         out.append(w.detach().contiguous())
     return out
 
@@ -64,11 +89,12 @@ class SpectralConvFn(torch.autograd.Function):
     """SpectralConv{1,2,3}d_Uno.forward and its backward (integral_operators.py:47-72, :181-207, :385-427)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, x, out_dims, modes, need_grad, *weights):
         lib = _get_lib()
         _check_input(x)
         x = x.contiguous()
-        ws = _cweights(weights)
+        ws = _cweights(x, weights)
         Co = ws[0].shape[1]
         d = _desc(x, Co, out_dims, modes)
         _capi.check(lib, lib.uno_spectral_conv_check(C.byref(d)))
@@ -86,6 +112,8 @@ class SpectralConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, gy):
         lib = _get_lib()
         xhat, *ws = ctx.saved_tensors
@@ -107,9 +135,11 @@ class PointwiseFn(torch.autograd.Function):
     """pointwise_op_2D / pointwise_op_3D forward + backward (integral_operators.py:224-243, :438-468)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, x, out_dims, need_grad, conv_w, conv_b):
         lib = _get_lib()
         _check_input(x)
+        _check_params(x, conv_w, conv_b)
         x = x.contiguous()
         Co = conv_w.shape[0]
         cw = conv_w.detach().reshape(Co, -1).contiguous()
@@ -130,6 +160,8 @@ class PointwiseFn(torch.autograd.Function):
         return z
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, gz):
         lib = _get_lib()
         x, saved, cw = ctx.saved_tensors
@@ -148,11 +180,13 @@ class OperatorBlockFn(torch.autograd.Function):
     """OperatorBlock_{2,3}D.forward fused: gelu?(IN?(conv(x) + w(x))) (integral_operators.py:272-284, :501-513)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, x, out_dims, modes, normalize, non_lin, eps, need_grad, conv_w, conv_b, gamma, beta, *weights):
         lib = _get_lib()
         _check_input(x)
+        _check_params(x, conv_w, conv_b, gamma if normalize else None, beta if normalize else None)
         x = x.contiguous()
-        ws = _cweights(weights)
+        ws = _cweights(x, weights)
         Co = ws[0].shape[1]
         cw = conv_w.detach().reshape(conv_w.shape[0], -1).contiguous()
         cb = conv_b.detach().contiguous()
@@ -192,6 +226,8 @@ class OperatorBlockFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, gy):
         lib = _get_lib()
         x, xhat, saved, pre, stats, cw, ga, be, *ws = ctx.saved_tensors
@@ -223,11 +259,12 @@ class LiftFn(torch.autograd.Function):
     (darcy_flow_uno2d.py:96-107, navier_stokes_uno2d.py:191-201, navier_stokes_uno3d.py:497-511)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
         lib = _get_lib()
         _check_input(a)
         _check_input(grid, "grid features")
-        _check_params(w_a, b_a, w_b, b_b)
+        _check_params(a, w_a, b_a, w_b, b_b)
         a = a.contiguous()
         grid = grid.contiguous()
         dims = tuple(a.shape[1:-1])
@@ -247,6 +284,8 @@ class LiftFn(torch.autograd.Function):
         return h
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, gh):
         lib = _get_lib()
         a, grid, wa, ba, wb, bb = ctx.saved_tensors
@@ -267,11 +306,12 @@ class ProjectFn(torch.autograd.Function):
     (darcy_flow_uno2d.py:121-131, navier_stokes_uno2d.py:215-225, navier_stokes_uno3d.py:551-575)."""
 
     @staticmethod
+    @_guard
     def forward(ctx, w1, b1, w2, b2, crop_lo, crop_hi, need_grad, *srcs):
         lib = _get_lib()
         for t in srcs:
             _check_input(t)
-        _check_params(w1, b1, w2, b2)
+        _check_params(srcs[0], w1, b1, w2, b2)
         srcs = [t.contiguous() for t in srcs]
         full = tuple(srcs[0].shape[2:])
         if any(tuple(t.shape[2:]) != full or t.shape[0] != srcs[0].shape[0] for t in srcs):
@@ -295,6 +335,8 @@ class ProjectFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
+    @_guard
     def backward(ctx, gout):
         lib = _get_lib()
         w1c, b1c, w2c, pre, *srcs = ctx.saved_tensors

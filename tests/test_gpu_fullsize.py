@@ -28,9 +28,18 @@ def _grads(model):
 def _compare(ours, ref, y_o, y_r, gtol, capsys, tag):
     ey = rel_err(y_o.detach().cpu().numpy(), y_r.detach().numpy())
     worst = ("", 0.0)
+    # Each gradient is compared relative to its own largest magnitude, floored at 1e-4 of the largest gradient of the model: the
+    # conv bias of a block WITH InstanceNorm has an exactly-zero gradient (the norm removes the per-plane mean); the reference
+    # returns the fp32 residue of that sum (~1e-7 of the gradient scale), this library returns 0.
+    gmax = max(float(b.abs().max()) for _, b in _grads(ref))
+    gfloor = 1e-4 * gmax
     for (k, a), (k2, b) in zip(_grads(ours), _grads(ref)):
         assert k == k2 and a.shape == b.shape
-        e = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-12)
+        if k.endswith(".w.conv.bias") and float(a.abs().max()) == 0.0:
+            # mathematically zero (bias in front of an InstanceNorm): the reference's value is pure rounding residue
+            assert float(b.abs().max()) < 1e-5 * gmax, (k, float(b.abs().max()), gmax)
+            continue
+        e = float((a - b).abs().max()) / max(float(b.abs().max()), gfloor, 1e-12)
         if e > worst[1]:
             worst = (k, e)
         assert e < gtol, (k, e)
@@ -61,7 +70,7 @@ def test_full_width_model_matches_reference(workload, B, cuda_lib, capsys):
     y_o = ours(x.cuda()).reshape(B, *tshape)
     l_o = OurLoss(size_average=False)(y_o.reshape(B, -1), t.cuda().reshape(B, -1))
     l_o.backward()
-    assert abs(float(l_o) - float(l_r)) < 1e-4 * abs(float(l_r))
+    assert abs(float(l_o.detach()) - float(l_r.detach())) < 1e-4 * abs(float(l_r.detach()))
     _compare(ours, ref, y_o, y_r, 4 * BWD_TOL, capsys, f"{workload} B={B} vs {kind}")
 
 
@@ -75,7 +84,7 @@ def test_full_width_rollout_matches_reference(cuda_lib, capsys):
     x, t = torch.randn(B, 64, 64, 10), torch.randn(B, 64, 64, T)
     l_r = bench.make_step(ref, RefLoss(size_average=False), B, (64, 64, T), ar_steps=T)(x, t)
     l_o = bench.make_step(ours, OurLoss(size_average=False), B, (64, 64, T), ar_steps=T)(x.cuda(), t.cuda())
-    assert abs(float(l_o) - float(l_r)) < 1e-4 * abs(float(l_r))
+    assert abs(float(l_o.detach()) - float(l_r.detach())) < 1e-4 * abs(float(l_r.detach()))
     with torch.no_grad():
         y_r, y_o = ref(x), ours(x.cuda())
     _compare(ours, ref, y_o, y_r, 8 * BWD_TOL, capsys, f"ns2d_ar B={B} T={T} vs {kind}")

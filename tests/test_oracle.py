@@ -168,7 +168,9 @@ def test_models_over_port_match_reference(tag, golden):
 
 def check_golden_gradients(model, g, tag, tol):
     """Element-wise: every parameter's gradient at the fixture's fixed sample positions, relative to that gradient's own
-    largest magnitude in the reference run (tests/golden/make_golden.py, tests/cases.py grad_sample_indices)."""
+    largest magnitude in the reference run (tests/golden/make_golden.py, tests/cases.py grad_sample_indices), floored at 1e-4
+    of the model's largest gradient: the conv bias of a block with InstanceNorm has an exactly-zero gradient, of which the
+    reference keeps the fp32 residue (~1e-7 of the gradient scale) and the CUDA library returns 0."""
     from cases import grad_sample_indices
 
     off, gmax = g[f"{tag}.grad_sub_off"], g[f"{tag}.grad_max"]
@@ -176,4 +178,7 @@ def check_golden_gradients(model, g, tag, tol):
         gr = (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).detach().reshape(-1).cpu().numpy()
         idx = grad_sample_indices(i, gr.size)
         want = g[f"{tag}.grad_sub"][off[i]:off[i + 1]]
-        assert float(np.abs(gr[idx] - want).max()) <= tol * max(float(gmax[i]), 1e-12), (k, float(np.abs(gr[idx] - want).max()), float(gmax[i]))
+        scale = max(float(gmax[i]), 1e-4 * float(gmax.max()), 1e-12)
+        if k.endswith(".w.conv.bias") and float(np.abs(gr).max()) == 0.0 and float(gmax[i]) < 1e-5 * float(gmax.max()):
+            continue    # mathematically zero: the reference's value is rounding residue, the CUDA library returns exactly 0
+        assert float(np.abs(gr[idx] - want).max()) <= tol * scale, (k, float(np.abs(gr[idx] - want).max()), float(gmax[i]))

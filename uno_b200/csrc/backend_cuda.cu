@@ -1048,15 +1048,15 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     return 0;
 }
 
-template <int LW, bool RC>
+template <int LW, bool RC, bool PAIR = false, bool HINT = false>
 int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC, PAIR, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::kpipe_kernel<LW, RC><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    tc::kpipe_kernel<LW, RC, PAIR, HINT><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1091,7 +1091,13 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     const size_t smem = tc::kpipe_smem_bytes(img.N_t, stages);
     // 16 loader warps (default: analysis 2.49 -> 2.19 ms per Darcy step, 2.13 with the row classes) or 8
-    if (cfg(CFG_KPIPE_LW16)) return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
+    if (cfg(CFG_KPIPE_LW16)) {
+        const int ex = cfg(CFG_EXP0);   // experiment: bit 0 = paired chunk issue, bit 1 = L2::256B hint
+        if (ex == 1) return rclass ? launch_kpipe<16, true, true, false>(p, gx, smem, st) : launch_kpipe<16, false, true, false>(p, gx, smem, st);
+        if (ex == 2) return rclass ? launch_kpipe<16, true, false, true>(p, gx, smem, st) : launch_kpipe<16, false, false, true>(p, gx, smem, st);
+        if (ex == 3) return rclass ? launch_kpipe<16, true, true, true>(p, gx, smem, st) : launch_kpipe<16, false, true, true>(p, gx, smem, st);
+        return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
+    }
     return rclass ? launch_kpipe<tc::kKpLoadWarps, true>(p, gx, smem, st) : launch_kpipe<tc::kKpLoadWarps, false>(p, gx, smem, st);
 }
 
@@ -1236,6 +1242,19 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
 std::map<std::pair<int, cudaStream_t>, float*> g_conv_scratch;   // (device, stream): the legacy default stream is shared by all devices
 constexpr size_t kConvScratchBytes = 160 * 1024;
 
+template <bool HINT>
+int launch_conv_tc(const tc::ConvTcParams& p, int gx, size_t smem, cudaStream_t st) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
+        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel<HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured.mark();
+    }
+    tc::conv1x1_tc_kernel<HINT><<<gx, tc::kCvThreads, smem, st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     // GemmArgs view: C_b[M, N] = A[M, K] * B_b[K, N]  with M = out channels, N = pixels, K = in channels
     if (!tc_enabled() || !a.channel_mix || a.sA != 0 || a.epi != EPI_STORE || a.N % 4 != 0 || a.N < 128 || a.M < 8 || a.M > 256 || a.K < 8)
@@ -1272,28 +1291,22 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     int cols = 32;
     while (cols < 2 * N_t) cols *= 2;
     p.tmem_cols = cols;
-    static DeviceOnce configured;
-    if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        configured.mark();
-    }
     int gx = num_sms();
     if ((long)gx > p.n_tiles) gx = (int)p.n_tiles;
-    tc::conv1x1_tc_kernel<<<gx, tc::kCvThreads, tc::conv_tc_smem_bytes(N_t, n_chunks, stages), st>>>(p);
-    CU_LAUNCH_CHECK();
-    return 0;
+    const size_t smem = tc::conv_tc_smem_bytes(N_t, n_chunks, stages);
+    if (cfg(CFG_EXP1) & 2) return launch_conv_tc<true>(p, gx, smem, st);   // experiment: L2::256B hint
+    return launch_conv_tc<false>(p, gx, smem, st);
 }
 
-template <bool DBG>
+template <bool DBG, bool HINT = false, bool PAIR = false>
 int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG, HINT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::wgrad_tc_kernel<DBG><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
+    tc::wgrad_tc_kernel<DBG, HINT, PAIR><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1316,6 +1329,11 @@ int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     if (gx < 1) gx = 1;
     p.debug = cfg(CFG_WGRAD_DEBUG);   // timing probes (tools/wgrad_probe.py)
     if (p.debug) return launch_wgrad<true>(p, (unsigned)gx, st);
+    switch (cfg(CFG_EXP1) & 5) {   // experiment: bit 0 = L2::256B hint, bit 2 = paired chunk issue
+        case 1: return launch_wgrad<false, true, false>(p, (unsigned)gx, st);
+        case 4: return launch_wgrad<false, false, true>(p, (unsigned)gx, st);
+        case 5: return launch_wgrad<false, true, true>(p, (unsigned)gx, st);
+    }
     return launch_wgrad<false>(p, (unsigned)gx, st);
 }
 
@@ -1672,6 +1690,22 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     k.tiles_w = (a.n_out1 + rs_tile_w(G1) - 1) / rs_tile_w(G1);
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
+    if (cfg(CFG_EXP2) & 1) {   // experiment: persistent, software-pipelined form (resample2d.cuh)
+        const size_t psmem = resample2d_pipe_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
+        if (psmem <= 113 * 1024) {            // two CTAs per SM
+            int rc = ensure_smem(resample2d_pipe_kernel<G0, W0, G1, W1>, psmem);
+            if (rc) return rc;
+            Resample2P pp;
+            pp.k = k;
+            pp.n_tiles = (long)a.planes * k.tiles_h * k.tiles_w;
+            ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
+                         2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
+            const unsigned gx = (unsigned)std::min<long>(pp.n_tiles, 2L * num_sms());
+            resample2d_pipe_kernel<G0, W0, G1, W1><<<gx, 256, psmem, st>>>(pp);
+            CU_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem);
     if (rc) return rc;
     if (a.planes > 65535) return -1;          // planes ride on grid.z

@@ -146,6 +146,19 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 16-byte read-only load; HINT asks L2 to fetch the surrounding 256 bytes (the loaders of the streaming kernels walk every row
+// 128 bytes at a time, so the neighbouring line is always wanted next: one DRAM access of 256 contiguous bytes instead of two)
+template <bool HINT>
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+    if constexpr (HINT) {
+        float4 v;
+        asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+        return v;
+    } else {
+        return __ldg(p);
+    }
+}
+
 // fp32 -> (hi, lo) split for the 3xTF32 scheme
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);

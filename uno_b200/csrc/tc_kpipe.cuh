@@ -59,7 +59,10 @@ __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return
 // RC = row-class mode (see above), compiled separately so that the default instantiation carries none of it.
 // LW = loader warps: 8 (default) or 16 (opt-in UNO_B200_KPIPE_LW16=1: the loader warps' serial instruction stream per chunk is
 // what bounds this kernel, tools/kpipe_probe.py -- twice the warps, half the rows per thread).
-template <int LW = kKpLoadWarps, bool RC = false>
+// PAIR: the loaders issue their global loads two chunks at a time (256 contiguous bytes of every row requested together) instead of
+// one chunk per iteration; HINT: 16-byte loads carry the L2::256B prefetch hint.  Both aim at DRAM efficiency: a chunk is 128 bytes of
+// each of 128 rows that lie a row pitch apart, i.e. 128 scattered 128-byte requests.
+template <int LW = kKpLoadWarps, bool RC = false, bool PAIR = false, bool HINT = false>
 __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
     static_assert(LW == 8 || LW == 16, "loader warps");
     constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 if (k0 >= sh && k0 + 4 <= k_end) {
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
-                        v[i] = (4 * RB * i < rows_left) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i] = (4 * RB * i < rows_left) ? ldg_f4<HINT>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
                     for (int i = 0; i < RP; ++i) {
@@ -229,6 +232,21 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
+            if constexpr (PAIR && DEPTH == 4) {
+                // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                if (0 < total) issue(ring[0]);
+                if (1 < total) issue(ring[1]);
+                for (long g = 0; g < total; g += 4) {
+                    if (g + 2 < total) issue(ring[2]);
+                    if (g + 3 < total) issue(ring[3]);
+                    if (g + 0 < total) process(ring[0]);
+                    if (g + 1 < total) process(ring[1]);
+                    if (g + 4 < total) issue(ring[0]);
+                    if (g + 5 < total) issue(ring[1]);
+                    if (g + 2 < total) process(ring[2]);
+                    if (g + 3 < total) process(ring[3]);
+                }
+            } else {
 #pragma unroll
             for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
@@ -238,6 +256,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
+            }
             }
         } else if (p.a_vec_ok) {
             // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     const long lim = (p.debug & 8) ? 0 : rows_left;
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
-                        v[i] = (RB * i < lim) ? __ldg(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i] = (RB * i < lim) ? ldg_f4<HINT>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
                     for (int i = 0; i < RP; ++i) {
@@ -286,6 +305,21 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
+            if constexpr (PAIR && DEPTH == 4) {
+                // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                if (0 < total) issue(ring[0]);
+                if (1 < total) issue(ring[1]);
+                for (long g = 0; g < total; g += 4) {
+                    if (g + 2 < total) issue(ring[2]);
+                    if (g + 3 < total) issue(ring[3]);
+                    if (g + 0 < total) process(ring[0]);
+                    if (g + 1 < total) process(ring[1]);
+                    if (g + 4 < total) issue(ring[0]);
+                    if (g + 5 < total) issue(ring[1]);
+                    if (g + 2 < total) process(ring[2]);
+                    if (g + 3 < total) process(ring[3]);
+                }
+            } else {
 #pragma unroll
             for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
@@ -295,6 +329,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
+            }
             }
         } else {
             // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
@@ -322,6 +357,21 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
+            if constexpr (PAIR && DEPTH == 4) {
+                // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                if (0 < total) issue(ring[0]);
+                if (1 < total) issue(ring[1]);
+                for (long g = 0; g < total; g += 4) {
+                    if (g + 2 < total) issue(ring[2]);
+                    if (g + 3 < total) issue(ring[3]);
+                    if (g + 0 < total) process(ring[0]);
+                    if (g + 1 < total) process(ring[1]);
+                    if (g + 4 < total) issue(ring[0]);
+                    if (g + 5 < total) issue(ring[1]);
+                    if (g + 2 < total) process(ring[2]);
+                    if (g + 3 < total) process(ring[3]);
+                }
+            } else {
 #pragma unroll
             for (int d = 0; d < DEPTH - 1; ++d)
                 if (d < total) issue(ring[d]);
@@ -331,6 +381,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
                     if (g + d < total) process(ring[d]);
                 }
+            }
             }
         }
     } else {

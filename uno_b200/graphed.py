@@ -96,6 +96,12 @@ class GraphedStep:
         return self.replay()
 
     def eager_step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        loss = self._body(x, y)
+        """The same step without the graph, on the stream the capture used (autograd's AccumulateGrad nodes remember the stream
+        they were created on; running them from another stream makes the engine insert synchronisation and warn)."""
+        cur = torch.cuda.current_stream(x.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            loss = self._body(x, y)
+        cur.wait_stream(self.stream)
         self.reducer.allreduce_now()
         return loss

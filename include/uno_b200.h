@@ -107,6 +107,16 @@ int uno_operator_block_bwd(const uno_block_desc* d, const float* gy, const float
                            const float* gamma, const float* beta, float* gx, float* const* gw,
                            float* gconv_w, float* gconv_b, float* ggamma, float* gbeta, void* ws,
                            size_t ws_bytes, void* stream);
+/* Same, for an upstream gradient that is NOT one contiguous tensor: the sum of gy and (optional) gy2, each [B, out_ch, out_dim..]
+ * with its own batch stride in floats (0 = contiguous).  This is what autograd hands a block whose output was used twice
+ * (two gradients to add) and / or concatenated with a skip tensor along the channels (a channel slice of the concatenation's
+ * gradient): the first kernel of the backward reads the sources in place, so neither the sum nor the slice copy
+ * (the reference's AddBackward / `.contiguous()`) touches HBM. */
+int uno_operator_block_bwd2(const uno_block_desc* d, const float* gy, long gy_batch_stride, const float* gy2,
+                            long gy2_batch_stride, const float* x, const float* xhat, const float* pw_saved,
+                            const float* pre, const float* stats, const float* const* w, const float* conv_w,
+                            const float* gamma, const float* beta, float* gx, float* const* gw, float* gconv_w,
+                            float* gconv_b, float* ggamma, float* gbeta, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- model glue around the blocks ------------------------------------
  * The reference models wrap the operator blocks in two per-pixel MLPs whose permute / pad / cat / crop
@@ -151,6 +161,11 @@ int uno_lift_fwd(const uno_lift_desc* d, const float* a, const float* grid, cons
 int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a, const float* grid,
                  const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
                  float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream);
+/* lift backward with a second upstream gradient gh2 (same shape, contiguous, may be NULL) added on the fly: the lifted input
+ * feeds both the first block and the projection (darcy_flow_uno2d.py:121). */
+int uno_lift_bwd2(const uno_lift_desc* d, const float* gh, const float* gh2, const float* a, const float* grid,
+                  const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga, float* gw_a, float* gb_a,
+                  float* gw_b, float* gb_b, void* stream);
 int uno_project_check(const uno_project_desc* d);
 /* hidden_pre: optional [hidden, B * prod(dim)] floats -- the fc1 pre-activations.  When fwd writes them and bwd gets
  * them back, the backward skips recomputing fc1 (a third of its arithmetic); NULL on either side = recompute. */

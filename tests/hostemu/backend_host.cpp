@@ -219,15 +219,22 @@ int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t) {
     for (size_t i = 0; i < n; ++i) y[i] = gelu_f(pre[i]);
     return 0;
 }
-int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t) {
-    for (size_t i = 0; i < n; ++i) g[i] = gy[i] * gelu_grad_f(pre[i]);
-    return 0;
+// element i of plane p of the upstream gradient: the sum of its (up to two) strided sources
+static inline float upgrad_at(const UpGrad& gy, long p, int C, long L, long i) {
+    const long b = p / C, c = p % C;
+    float v = gy.p0[b * gy.bs0 + c * L + i];
+    if (gy.p1) v += gy.p1[b * gy.bs1 + c * L + i];
+    return v;
 }
-int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha, stream_t) {
+int be_gelu_bwd_bias(const UpGrad& gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha, stream_t) {
     for (long p = 0; p < planes; ++p) {
         double s = 0;
-        for (long i = 0; i < L; ++i) { g[p * L + i] = gy[p * L + i] * gelu_grad_f(pre[p * L + i]); s += g[p * L + i]; }
-        gbias[p % C] += alpha * (float)s;
+        for (long i = 0; i < L; ++i) {
+            const float u = upgrad_at(gy, p, C, L, i);
+            g[p * L + i] = pre ? u * gelu_grad_f(pre[p * L + i]) : u;
+            s += g[p * L + i];
+        }
+        if (gbias) gbias[p % C] += alpha * (float)s;
     }
     return 0;
 }
@@ -263,7 +270,7 @@ int be_norm_fused_fwd(const float* x, float* stats, const float* gamma, const fl
     return rc ? rc : be_norm_act_fwd(x, stats, gamma, beta, y, planes, C, L, non_lin, s);
 }
 
-int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
+int be_norm_act_bwd(const UpGrad& gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
                     long L, int non_lin, stream_t) {
     for (long p = 0; p < planes; ++p) {
@@ -272,7 +279,8 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
         double s1 = 0, s2 = 0;
         for (long i = 0; i < L; ++i) {
             const float xh = (x[p * L + i] - mu) * rstd;
-            const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
+            const float up = upgrad_at(gy, p, C, L, i);
+            const float gn = non_lin ? up * gelu_grad_f(xh * gamma[c] + beta[c]) : up;
             s1 += gn;
             s2 += (double)gn * xh;
         }
@@ -281,7 +289,8 @@ int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const f
         const float m1 = (float)(s1 / L), m2 = (float)(s2 / L);
         for (long i = 0; i < L; ++i) {
             const float xh = (x[p * L + i] - mu) * rstd;
-            const float gn = non_lin ? gy[p * L + i] * gelu_grad_f(xh * gamma[c] + beta[c]) : gy[p * L + i];
+            const float up = upgrad_at(gy, p, C, L, i);
+            const float gn = non_lin ? up * gelu_grad_f(xh * gamma[c] + beta[c]) : up;
             g[p * L + i] = gamma[c] * rstd * (gn - m1 - xh * m2);
         }
     }
@@ -361,7 +370,8 @@ int be_lift_bwd(const LiftArgs& a, stream_t) {
             for (int o = 0; o < a.out_ch; ++o) {
                 double s = a.b_b[o];
                 for (int k = 0; k < a.hid; ++k) s += (double)a.w_b[o * a.hid + k] * a0[k];
-                const double d1 = (double)a.gh[(b * a.out_ch + o) * g.npad + pp] * gelu_grad_f((float)s);
+                const double d1 = ((double)a.gh[(b * a.out_ch + o) * g.npad + pp] + (a.gh2 ? (double)a.gh2[(b * a.out_ch + o) * g.npad + pp] : 0.0)) *
+                                  gelu_grad_f((float)s);
                 gbb[o] += d1;
                 for (int k = 0; k < a.hid; ++k) { gwb[o * a.hid + k] += d1 * a0[k]; da0[k] += d1 * a.w_b[o * a.hid + k]; }
             }

@@ -137,7 +137,9 @@ def block_fwd(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None
     return y, dict(xhat=xhat, saved=saved, pre=pre, stats=stats)
 
 
-def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=None, non_lin=True):
+def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=None, non_lin=True, gy2=None, gy_bs=0, gy2_bs=0):
+    """gy (+ gy2): upstream gradient(s); gy_bs / gy2_bs: batch strides in floats when gy / gy2 are channel slices of wider
+    arrays (pass the wide array's sliced VIEW: the pointer of its first element is taken), 0 = contiguous."""
     L = lib()
     x = _f32(x)
     ws_ = [_c64(w) for w in weights]
@@ -149,7 +151,10 @@ def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=Non
     bt = _f32(beta) if normalize else None
     cd = _capi.conv_desc(B, Ci, Co, x.shape[2:], out_dims, modes)
     bd = _capi.block_desc(cd, normalize, non_lin)
-    gy = _f32(gy)
+    if gy_bs == 0:
+        gy = _f32(gy)
+    if gy2 is not None and gy2_bs == 0:
+        gy2 = _f32(gy2)
     gx = np.empty_like(x)
     gws = [np.empty_like(w) for w in ws_]
     gcw = np.empty_like(cw)
@@ -161,9 +166,9 @@ def block_bwd(x, weights, conv_w, out_dims, modes, gy, ctx, gamma=None, beta=Non
     gwp = _capi.ptr_array([w.ctypes.data for w in gws])
     _capi.check(
         L,
-        L.uno_operator_block_bwd(
-            C.byref(bd), _p(gy), _p(x), _p(ctx["xhat"]), _p(ctx["saved"]), _p(ctx["pre"]), _p(ctx["stats"]), wp, _p(cw), _p(g), _p(bt),
-            _p(gx), gwp, _p(gcw), _p(gcb), _p(gg), _p(gb), _p(ws), ws.nbytes, None,
+        L.uno_operator_block_bwd2(
+            C.byref(bd), _p(gy), gy_bs, _p(gy2), gy2_bs, _p(x), _p(ctx["xhat"]), _p(ctx["saved"]), _p(ctx["pre"]), _p(ctx["stats"]), wp,
+            _p(cw), _p(g), _p(bt), _p(gx), gwp, _p(gcw), _p(gcb), _p(gg), _p(gb), _p(ws), ws.nbytes, None,
         ),
     )
     return gx, gws, gcw, gcb, gg, gb
@@ -182,13 +187,15 @@ def lift_fwd(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
     return h
 
 
-def lift_bwd(gh, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, want_ga=True):
+def lift_bwd(gh, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, want_ga=True, gh2=None):
     L = lib()
     gh, a, grid, w_a, b_a, w_b, b_b = (_f32(t) for t in (gh, a, grid, w_a, b_a, w_b, b_b))
+    gh2 = _f32(gh2) if gh2 is not None else None
     d = _capi.lift_desc(a.shape[0], a.shape[1:-1], pad_lo, pad_hi, a.shape[-1], grid.shape[-1], w_a.shape[0], w_b.shape[0])
     ga = np.full_like(a, np.nan) if want_ga else None
     outs = [np.full_like(t, np.nan) for t in (w_a, b_a, w_b, b_b)]
-    _capi.check(L, L.uno_lift_bwd(C.byref(d), _p(gh), _p(a), _p(grid), _p(w_a), _p(b_a), _p(w_b), _p(b_b), _p(ga), *[_p(o) for o in outs], None))
+    _capi.check(L, L.uno_lift_bwd2(C.byref(d), _p(gh), _p(gh2), _p(a), _p(grid), _p(w_a), _p(b_a), _p(w_b), _p(b_b), _p(ga),
+                                   *[_p(o) for o in outs], None))
     return (ga, *outs)
 
 

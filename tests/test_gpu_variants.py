@@ -296,3 +296,68 @@ def test_spectral3d_tc_core(shape, cuda_lib):
     assert rel_err(gx_tc, gx_si) < BWD_TOL, rel_err(gx_tc, gx_si)
     for a, b in zip(gw_tc, gw_si):
         assert rel_err(a, b) < BWD_TOL, rel_err(a, b)
+
+
+@pytest.mark.parametrize("norm,nl,odim", [(False, True, (24, 20)), (True, True, (16, 16)), (False, False, (12, 15)), (True, False, (10, 9)),
+                                         (False, True, (9, 7, 5)), (True, True, (8, 8, 6))])
+def test_fanout_matches_autograd_accumulation(norm, nl, odim, cuda_lib):
+    """A block output with two consumers, one of them a skip concatenation: with fanout=2 the block's backward receives the two
+    upstream gradients separately -- one contiguous, one a channel slice of the concatenation's gradient (batch-strided) -- and
+    adds them in its first kernel.  Must equal the plain graph, where autograd slices, copies and adds."""
+    from uno_b200 import integral_operators as ops
+
+    nd = len(odim)
+    torch.manual_seed(3)
+    Blk = ops.OperatorBlock_2D if nd == 2 else ops.OperatorBlock_3D
+    modes = (3,) * nd
+    blk = Blk(3, 4, *odim, *modes, Normalize=norm, Non_Lin=nl).cuda()
+    nxt = Blk(4, 2, *odim, *modes).cuda()
+    idim = tuple(n + 2 for n in odim)
+    x = torch.randn(2, 3, *idim, device="cuda")
+    other = torch.randn(2, 5, *odim, device="cuda")
+    wcat = torch.randn(1, 9, *([1] * nd), device="cuda")
+
+    def run(fan):
+        xx = x.clone().requires_grad_(True)
+        for m in (blk, nxt):
+            m.zero_grad(set_to_none=True)
+        if fan:
+            y, y_skip = blk(xx, *odim, fanout=2)
+            assert y.data_ptr() == y_skip.data_ptr()
+        else:
+            y = y_skip = blk(xx, *odim)
+        z = nxt(y, *odim)
+        c = torch.cat([other, y_skip], dim=1)
+        loss = (z ** 2).sum() + (c * wcat).sum() + (c ** 2).sum() * 0.1
+        loss.backward()
+        return [float(loss.detach()), xx.grad.cpu().numpy()] + [
+            (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).cpu().numpy() for p in blk.parameters()]
+
+    a, b = run(True), run(False)
+    assert abs(a[0] - b[0]) < 1e-6 * abs(b[0])
+    for u, v in zip(a[1:], b[1:]):
+        assert np.abs(u - v).max() <= 2e-5 * max(float(np.abs(v).max()), 1e-6), rel_err(u, v)
+
+
+def test_lift_fanout_matches_autograd_accumulation(cuda_lib):
+    """The lifted input feeds the first block and the projection: lift(fanout=2) adds the two gradients inside lift_bwd."""
+    from uno_b200 import functional as Fn
+
+    torch.manual_seed(0)
+    a = torch.randn(2, 20, 18, 1, device="cuda")
+    grid = torch.randn(20, 18, 2, device="cuda")
+    ps = [torch.randn(*s, device="cuda") * 0.3 for s in ((16, 3), (16,), (32, 16), (32,))]
+    w1 = torch.randn(1, 32, 1, 1, device="cuda")
+    w2 = torch.randn(1, 32, 1, 1, device="cuda")
+
+    def run(fan):
+        qs = [p.clone().requires_grad_(True) for p in ps]
+        if fan:
+            h, h2 = Fn.lift(a, grid, *qs, (0, 1), (3, 2), fanout=2)
+        else:
+            h = h2 = Fn.lift(a, grid, *qs, (0, 1), (3, 2))
+        ((h * w1).sum() + ((h2 * w2) ** 2).sum()).backward()
+        return [q.grad.cpu().numpy() for q in qs]
+
+    for u, v in zip(run(True), run(False)):
+        assert np.abs(u - v).max() <= 2e-5 * max(float(np.abs(v).max()), 1e-6)

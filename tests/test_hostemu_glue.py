@@ -27,6 +27,11 @@ def test_lift(name):
     ga, gwa, gba, gwb, gbb = emu.lift_bwd(t["gh"], t["a"], t["grid"], t["w_a"], t["b_a"], t["w_b"], t["b_b"], lo, hi)
     for got, key in ((ga, "ga"), (gwa, "gw_a"), (gba, "gb_a"), (gwb, "gw_b"), (gbb, "gb_b")):
         assert rel_err(got, ref[key]) < BWD_TOL, key
+    # uno_lift_bwd2: the upstream gradient as the sum of two tensors (h feeds the first block AND the projection)
+    part = np.random.default_rng(9).standard_normal(np.shape(t["gh"])).astype(np.float32)
+    two = emu.lift_bwd(part, t["a"], t["grid"], t["w_a"], t["b_a"], t["w_b"], t["b_b"], lo, hi, gh2=np.asarray(t["gh"], np.float32) - part)
+    for got, key in zip(two, ("ga", "gw_a", "gb_a", "gw_b", "gb_b")):
+        assert rel_err(got, ref[key]) < BWD_TOL, key
 
 
 @pytest.mark.parametrize("name", list(PROJECT_CASES))

@@ -72,6 +72,41 @@ def test_block(name, golden):
         assert rel_err(gb, G("normalize_layer.bias")) < BWD_TOL
 
 
+@pytest.mark.parametrize("name", list(BLOCK_CASES))
+def test_block_backward_with_two_strided_gradient_sources(name, golden):
+    """uno_operator_block_bwd2: the upstream gradient as the SUM of two tensors that are channel slices of wider ones (what
+    autograd hands a block whose output feeds a skip concatenation and another block) must give the gradients of the plain call."""
+    B, Ci, Co, idim, odim, modes, norm, nl = BLOCK_CASES[name]
+    g = golden("blocks")
+    nd = len(idim)
+    P = lambda k: g[f"{name}.param.{k}"]
+    ws = [P(f"conv.weights{i + 1}") for i in range(2 ** (nd - 1))]
+    ga, be = (P("normalize_layer.weight"), P("normalize_layer.bias")) if norm else (None, None)
+    _, ctx = emu.block_fwd(g[f"{name}.x"], ws, P("w.conv.weight"), P("w.conv.bias"), odim, modes, ga, be, nl)
+    gy = g[f"{name}.gy"].astype(np.float32)
+    want = emu.block_bwd(g[f"{name}.x"], ws, P("w.conv.weight"), odim, modes, gy, ctx, ga, be, nl)
+    rng = np.random.default_rng(5)
+    part = rng.standard_normal(gy.shape).astype(np.float32)
+    wide_a = rng.standard_normal((B, Co + 3) + tuple(odim)).astype(np.float32)      # gradient of cat([y, skip(3 ch)], dim=1)
+    wide_b = rng.standard_normal((B, 2 + Co) + tuple(odim)).astype(np.float32)      # gradient of cat([other(2 ch), y], dim=1)
+    wide_a[:, :Co] = part
+    wide_b[:, 2:] = gy - part
+    n_out = int(np.prod(odim))
+    got = emu.block_bwd(g[f"{name}.x"], ws, P("w.conv.weight"), odim, modes, wide_a[:, :Co], ctx, ga, be, nl,
+                        gy2=wide_b[:, 2:], gy_bs=(Co + 3) * n_out, gy2_bs=(2 + Co) * n_out)
+    def flat(t):
+        gx, gws, gcw, gcb, gg, gb = t
+        return [gx, *gws, gcw, gcb] + ([gg, gb] if norm else [])
+    for a, b in zip(flat(got), flat(want)):
+        a, b = np.asarray(a), np.asarray(b)
+        assert np.abs(a - b).max() <= 2e-6 * max(float(np.abs(b).max()), 1e-6) + 1e-7
+    # one strided source alone
+    got1 = emu.block_bwd(g[f"{name}.x"], ws, P("w.conv.weight"), odim, modes, wide_a[:, :Co], ctx, ga, be, nl, gy_bs=(Co + 3) * n_out)
+    want1 = emu.block_bwd(g[f"{name}.x"], ws, P("w.conv.weight"), odim, modes, part, ctx, ga, be, nl)
+    for a, b in zip(flat(got1), flat(want1)):
+        assert np.abs(np.asarray(a) - np.asarray(b)).max() <= 2e-6 * max(float(np.abs(np.asarray(b)).max()), 1e-6) + 1e-7
+
+
 def test_error_codes():
     x = np.zeros((1, 2, 8, 8), np.float32)
     with pytest.raises(RuntimeError, match="exceeds the input spectrum"):

@@ -78,9 +78,14 @@ SYMBOLS = {
         C.c_int,
         [_BDESC, _P, _P, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P, C.c_size_t, _P],
     ),
+    "uno_operator_block_bwd2": (
+        C.c_int,
+        [_BDESC, _P, C.c_long, _P, C.c_long, _P, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P, C.c_size_t, _P],
+    ),
     "uno_lift_check": (C.c_int, [_LDESC]),
     "uno_lift_fwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uno_lift_bwd": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "uno_lift_bwd2": (C.c_int, [_LDESC, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "uno_project_check": (C.c_int, [_PDESC]),
     "uno_project_fwd": (C.c_int, [_PDESC, _PP, _P, _P, _P, _P, _P, _P, _P]),
     "uno_project_bwd": (C.c_int, [_PDESC, _P, _PP, _P, _P, _P, _P, _PP, _P, _P, _P, _P, _P]),

@@ -132,10 +132,18 @@ int be_banded2d(const Banded2DArgs& a, stream_t s);
 
 // ---- elementwise / reductions ----------------------------------------------------------------------
 int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s);
-int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s);
-// same, plane-structured, with the per-channel sum of the result folded in:
-//   g = gy * gelu'(pre) ;  gbias[p % C] += alpha * sum over the plane's L elements of g   (gbias pre-zeroed)
-int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias,
+// Upstream gradient of an operator whose output has C planes of L elements per sample: the SUM of up to two tensors, each
+// [B, C, L] with its own batch stride in floats (C*L when contiguous, larger when the tensor is a channel slice of a wider one:
+// the halves of a skip concatenation's gradient).  The kernel that first reads the upstream gradient adds the two on the fly,
+// so neither the slice copy nor the sum of a twice-used tensor's gradients ever exists in HBM.  p1 == NULL: one source.
+struct UpGrad {
+    const float* p0 = nullptr; long bs0 = 0;
+    const float* p1 = nullptr; long bs1 = 0;
+};
+// plane-structured activation backward with the per-channel sum of the result folded in:
+//   g = (gy.p0 + gy.p1) * gelu'(pre)  (pre == NULL: g = gy.p0 + gy.p1) ;
+//   gbias[p % C] += alpha * sum over the plane's L elements of g   (gbias pre-zeroed; NULL: not wanted)
+int be_gelu_bwd_bias(const UpGrad& gy, const float* pre, float* g, long planes, int C, long L, float* gbias,
                      float alpha, stream_t s);
 // per-plane mean / rstd over L contiguous elements: stats[p] = (mean, rstd)
 int be_plane_stats(const float* x, float* stats, long planes, long L, float eps, stream_t s);
@@ -148,7 +156,7 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
                     float* y, long planes, int C, long L, int non_lin, stream_t s);
 // backward of the above: g = d/dx ; ggamma[c] += ..., gbeta[c] += ... (pre-zeroed by the caller).
 // Every plane of g sums to zero in exact arithmetic (the mean is projected out).
-int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma,
+int be_norm_act_bwd(const UpGrad& gy, const float* x, const float* stats, const float* gamma,
                     const float* beta, float* g, float* ggamma, float* gbeta, long planes, int C,
                     long L, int non_lin, stream_t s);
 // out[c] += alpha * sum over planes p with p % C == c and over the plane's L elements  (out pre-zeroed)
@@ -170,6 +178,7 @@ struct LiftArgs {
     const float* w_a = nullptr; const float* b_a = nullptr; const float* w_b = nullptr; const float* b_b = nullptr;
     float* h = nullptr;                 // fwd output
     const float* gh = nullptr;          // bwd input  [B, out_ch, N..]
+    const float* gh2 = nullptr;         // optional second upstream gradient of the same shape, added on the fly (h used twice)
     float* ga = nullptr;                // bwd output [B, n.., raw_ch] (optional)
     float* gw_a = nullptr; float* gb_a = nullptr; float* gw_b = nullptr; float* gb_b = nullptr;   // bwd outputs, PRE-ZEROED (accumulated with atomics)
 };

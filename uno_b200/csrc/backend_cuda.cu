@@ -668,25 +668,32 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const float* __restrict__
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         y[i] = gelu_f(pre[i]);
 }
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ pre,
-                                                       float* __restrict__ g, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        g[i] = gy[i] * gelu_grad_f(pre[i]);
-}
-
 __device__ __forceinline__ double block_sum(double v, double* sh);
 
-// plane-structured GELU backward with the conv-bias gradient folded in: grid (planes, chunks).
+// The (up to two) strided sources of an upstream gradient as the kernels see them (backend.h UpGrad): plane p = (b, c) of
+// source i starts at p_i + b * bs_i + c * L.
+struct UpGradK {
+    const float* p0; long bs0; const float* p1; long bs1;
+};
+__device__ __forceinline__ const float* upgrad_plane(const float* base, long bs, long p, int C, long L) {
+    const long b = p / C;
+    return base + b * bs + (p - b * C) * L;
+}
+
+// plane-structured activation backward with the conv-bias gradient folded in: grid (planes, chunks).
+//   g = (gy0 + gy1) * gelu'(pre)      ACT = false: g = gy0 + gy1 (a block without activation: only sums / gathers its sources)
 // Planes of an odd grid (481 x 481) start at any 4-byte offset, so each plane is cut into a scalar head (up to the next
-// 16-byte boundary), a float4 body and a scalar tail; the three tensors share the cut when `vec_ok` (same shape, bases
-// 16-byte aligned).
-__global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const float* __restrict__ gy, const float* __restrict__ pre,
+// 16-byte boundary), a float4 body and a scalar tail; all tensors share the cut when `vec_ok` (host-checked: bases 16-byte
+// aligned and either every tensor contiguous -- plane p starts at p*L everywhere -- or L and the batch strides multiples of 4).
+template <bool ACT, bool TWO>
+__global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const UpGradK gy, const float* __restrict__ pre,
                                                             float* __restrict__ g, int C, long L, float* __restrict__ gbias,
                                                             float alpha, int vec_ok) {
     __shared__ double sh[32];
     const long p = blockIdx.x;
-    const float* gp = gy + p * L;
-    const float* pp = pre + p * L;
+    const float* gp = upgrad_plane(gy.p0, gy.bs0, p, C, L);
+    const float* hp = TWO ? upgrad_plane(gy.p1, gy.bs1, p, C, L) : nullptr;
+    const float* pp = ACT ? pre + p * L : nullptr;
     float* op = g + p * L;
     const long t = (long)blockIdx.y * blockDim.x + threadIdx.x, stride = (long)gridDim.y * blockDim.x;
     const long head = vec_ok ? min(L, (4 - ((p * L) & 3)) & 3) : L;
@@ -694,16 +701,24 @@ __global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const float* __restr
     float s = 0.f;
     {
         const float4* g4 = reinterpret_cast<const float4*>(gp + head);
-        const float4* p4 = reinterpret_cast<const float4*>(pp + head);
+        const float4* h4 = reinterpret_cast<const float4*>(TWO ? hp + head : gp);
+        const float4* p4 = reinterpret_cast<const float4*>(ACT ? pp + head : gp);
         float4* o4 = reinterpret_cast<float4*>(op + head);
 #pragma unroll 2
         for (long j = t; j < nv; j += stride) {
-            const float4 a = __ldcs(g4 + j), b = __ldcs(p4 + j);
-            float4 v;
-            v.x = a.x * gelu_grad_f(b.x);
-            v.y = a.y * gelu_grad_f(b.y);
-            v.z = a.z * gelu_grad_f(b.z);
-            v.w = a.w * gelu_grad_f(b.w);
+            float4 a = __ldcs(g4 + j);
+            if (TWO) {
+                const float4 c = __ldcs(h4 + j);
+                a.x += c.x; a.y += c.y; a.z += c.z; a.w += c.w;
+            }
+            float4 v = a;
+            if (ACT) {
+                const float4 b = __ldcs(p4 + j);
+                v.x = a.x * gelu_grad_f(b.x);
+                v.y = a.y * gelu_grad_f(b.y);
+                v.z = a.z * gelu_grad_f(b.z);
+                v.w = a.w * gelu_grad_f(b.w);
+            }
             o4[j] = v;
             s += (v.x + v.y) + (v.z + v.w);
         }
@@ -712,12 +727,16 @@ __global__ void __launch_bounds__(256) gelu_bwd_bias_kernel(const float* __restr
     const long rem = L - 4 * nv;
     for (long r = t; r < rem; r += stride) {
         const long i = r < head ? r : r + 4 * nv;
-        const float v = gp[i] * gelu_grad_f(pp[i]);
+        float u = gp[i];
+        if (TWO) u += hp[i];
+        const float v = ACT ? u * gelu_grad_f(pp[i]) : u;
         op[i] = v;
         s += v;
     }
-    const double tot = block_sum((double)s, sh);
-    if (threadIdx.x == 0) atomicAdd(gbias + (p % C), alpha * (float)tot);
+    if (gbias) {
+        const double tot = block_sum((double)s, sh);
+        if (threadIdx.x == 0) atomicAdd(gbias + (p % C), alpha * (float)tot);
+    }
 }
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
@@ -779,7 +798,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(const float* __restri
     }
 }
 
-__global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+__global__ void __launch_bounds__(512) norm_act_bwd_kernel(const UpGradK gy, const float* __restrict__ x,
                                                            const float* __restrict__ stats, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ g,
                                                            float* __restrict__ ggamma, float* __restrict__ gbeta, int C,
@@ -790,13 +809,15 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
     const float mu = stats[2 * p], rstd = stats[2 * p + 1];
     const float ga = gamma[c], be = beta[c];
     const float* xp = x + p * L;
-    const float* gp = gy + p * L;
+    const float* gp = upgrad_plane(gy.p0, gy.bs0, p, C, L);
+    const float* hp = gy.p1 ? upgrad_plane(gy.p1, gy.bs1, p, C, L) : nullptr;
     float s1 = 0.f, s2 = 0.f;
     double d1 = 0.0, d2 = 0.0;
     int cnt = 0;
     for (long i = threadIdx.x; i < L; i += blockDim.x) {
         const float xh = (xp[i] - mu) * rstd;
-        const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
+        const float up = hp ? gp[i] + hp[i] : gp[i];
+        const float gn = non_lin ? up * gelu_grad_f(fmaf(xh, ga, be)) : up;
         s1 += gn;
         s2 = fmaf(gn, xh, s2);
         if (++cnt == 64) { d1 += s1; d2 += s2; s1 = s2 = 0.f; cnt = 0; }
@@ -813,7 +834,8 @@ __global__ void __launch_bounds__(512) norm_act_bwd_kernel(const float* __restri
     float* op = g + p * L;
     for (long i = threadIdx.x; i < L; i += blockDim.x) {
         const float xh = (xp[i] - mu) * rstd;
-        const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
+        const float up = hp ? gp[i] + hp[i] : gp[i];
+        const float gn = non_lin ? up * gelu_grad_f(fmaf(xh, ga, be)) : up;
         op[i] = k * (gn - m1 - xh * m2);
     }
 }
@@ -1048,15 +1070,15 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     return 0;
 }
 
-template <int LW, bool RC, bool PAIR = false, bool HINT = false>
+template <int LW, bool RC>
 int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC, PAIR, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::kpipe_kernel<LW, RC, PAIR, HINT><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    tc::kpipe_kernel<LW, RC><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1091,13 +1113,7 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     const size_t smem = tc::kpipe_smem_bytes(img.N_t, stages);
     // 16 loader warps (default: analysis 2.49 -> 2.19 ms per Darcy step, 2.13 with the row classes) or 8
-    if (cfg(CFG_KPIPE_LW16)) {
-        const int ex = cfg(CFG_EXP0);   // experiment: bit 0 = paired chunk issue, bit 1 = L2::256B hint
-        if (ex == 1) return rclass ? launch_kpipe<16, true, true, false>(p, gx, smem, st) : launch_kpipe<16, false, true, false>(p, gx, smem, st);
-        if (ex == 2) return rclass ? launch_kpipe<16, true, false, true>(p, gx, smem, st) : launch_kpipe<16, false, false, true>(p, gx, smem, st);
-        if (ex == 3) return rclass ? launch_kpipe<16, true, true, true>(p, gx, smem, st) : launch_kpipe<16, false, true, true>(p, gx, smem, st);
-        return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
-    }
+    if (cfg(CFG_KPIPE_LW16)) return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
     return rclass ? launch_kpipe<tc::kKpLoadWarps, true>(p, gx, smem, st) : launch_kpipe<tc::kKpLoadWarps, false>(p, gx, smem, st);
 }
 
@@ -1154,6 +1170,9 @@ int try_tc_mid(const MidArgs& a, cudaStream_t st) {
     if (!mid_tc_enabled() || !tc_enabled()) return -1;
     const long R = (long)a.O * a.I;
     if (a.H < 4 || a.J < 4 || R < 128) return -1;
+    // 3xTF32 drops the lo*lo products (~2^-22 per term): over a contraction of 2*H real terms the error grows like sqrt(H) and
+    // reached the forward tolerance (2e-5) at H = 1200 on B200; every grid of the reference's models is <= 481 (sweep: 512)
+    if (a.H > 768) return -1;
     if ((reinterpret_cast<uintptr_t>(a.X) & 7) || (reinterpret_cast<uintptr_t>(a.Y) & 7)) return -1;
     bool capturing = false;
     {   // the first call for a matrix builds its image with synchronous copies: not inside a stream capture
@@ -1242,19 +1261,6 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
 std::map<std::pair<int, cudaStream_t>, float*> g_conv_scratch;   // (device, stream): the legacy default stream is shared by all devices
 constexpr size_t kConvScratchBytes = 160 * 1024;
 
-template <bool HINT>
-int launch_conv_tc(const tc::ConvTcParams& p, int gx, size_t smem, cudaStream_t st) {
-    static DeviceOnce configured;
-    if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel<HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        configured.mark();
-    }
-    tc::conv1x1_tc_kernel<HINT><<<gx, tc::kCvThreads, smem, st>>>(p);
-    CU_LAUNCH_CHECK();
-    return 0;
-}
-
 int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     // GemmArgs view: C_b[M, N] = A[M, K] * B_b[K, N]  with M = out channels, N = pixels, K = in channels
     if (!tc_enabled() || !a.channel_mix || a.sA != 0 || a.epi != EPI_STORE || a.N % 4 != 0 || a.N < 128 || a.M < 8 || a.M > 256 || a.K < 8)
@@ -1293,20 +1299,26 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     p.tmem_cols = cols;
     int gx = num_sms();
     if ((long)gx > p.n_tiles) gx = (int)p.n_tiles;
-    const size_t smem = tc::conv_tc_smem_bytes(N_t, n_chunks, stages);
-    if (cfg(CFG_EXP1) & 2) return launch_conv_tc<true>(p, gx, smem, st);   // experiment: L2::256B hint
-    return launch_conv_tc<false>(p, gx, smem, st);
-}
-
-template <bool DBG, bool HINT = false, bool PAIR = false>
-int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG, HINT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::wgrad_tc_kernel<DBG, HINT, PAIR><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
+    tc::conv1x1_tc_kernel<<<gx, tc::kCvThreads, tc::conv_tc_smem_bytes(N_t, n_chunks, stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
+template <bool DBG>
+int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
+    static DeviceOnce configured;
+    if (!configured.done()) {
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured.mark();
+    }
+    tc::wgrad_tc_kernel<DBG><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1329,11 +1341,6 @@ int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     if (gx < 1) gx = 1;
     p.debug = cfg(CFG_WGRAD_DEBUG);   // timing probes (tools/wgrad_probe.py)
     if (p.debug) return launch_wgrad<true>(p, (unsigned)gx, st);
-    switch (cfg(CFG_EXP1) & 5) {   // experiment: bit 0 = L2::256B hint, bit 2 = paired chunk issue
-        case 1: return launch_wgrad<false, true, false>(p, (unsigned)gx, st);
-        case 4: return launch_wgrad<false, false, true>(p, (unsigned)gx, st);
-        case 5: return launch_wgrad<false, true, true>(p, (unsigned)gx, st);
-    }
     return launch_wgrad<false>(p, (unsigned)gx, st);
 }
 
@@ -1690,22 +1697,6 @@ int launch_resample2d(const Banded2DArgs& a, cudaStream_t st) {
     k.tiles_w = (a.n_out1 + rs_tile_w(G1) - 1) / rs_tile_w(G1);
     const size_t smem = resample2d_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
     if (smem > 160 * 1024) return -1;
-    if (cfg(CFG_EXP2) & 1) {   // experiment: persistent, software-pipelined form (resample2d.cuh)
-        const size_t psmem = resample2d_pipe_smem(k.RIN, k.ldin, k.TH, G0, W0, G1, W1);
-        if (psmem <= 113 * 1024) {            // two CTAs per SM
-            int rc = ensure_smem(resample2d_pipe_kernel<G0, W0, G1, W1>, psmem);
-            if (rc) return rc;
-            Resample2P pp;
-            pp.k = k;
-            pp.n_tiles = (long)a.planes * k.tiles_h * k.tiles_w;
-            ProfScope ps("resample_banded", 4.0 * a.planes * ((double)a.n_in0 * a.n_in1 + (double)a.n_out0 * a.n_out1),
-                         2.0 * a.planes * ((double)a.n_in0 * a.n_out1 * W1 + (double)a.n_out0 * a.n_out1 * W0), st);
-            const unsigned gx = (unsigned)std::min<long>(pp.n_tiles, 2L * num_sms());
-            resample2d_pipe_kernel<G0, W0, G1, W1><<<gx, 256, psmem, st>>>(pp);
-            CU_LAUNCH_CHECK();
-            return 0;
-        }
-    }
     int rc = ensure_smem(resample2d_kernel<G0, W0, G1, W1, 2>, smem);
     if (rc) return rc;
     if (a.planes > 65535) return -1;          // planes ride on grid.z
@@ -1780,21 +1771,37 @@ int be_gelu_fwd(const float* pre, float* y, size_t n, stream_t s) {
     CU_LAUNCH_CHECK();
     return 0;
 }
-int be_gelu_bwd(const float* gy, const float* pre, float* g, size_t n, stream_t s) {
-    if (!n) return 0;
-    ProfScope ps("gelu_bwd", 12.0 * n, 0, S(s));
-    gelu_bwd_kernel<<<grid_for(n, 256), 256, 0, S(s)>>>(gy, pre, g, n);
-    CU_LAUNCH_CHECK();
-    return 0;
+namespace {
+// every source either contiguous (plane p starts at p*L, like pre and g) or 16-byte friendly (L and batch strides multiples of 4)
+inline bool upgrad_vec_ok(const UpGrad& gy, int C, long L, const void* a, const void* b) {
+    uintptr_t bits = reinterpret_cast<uintptr_t>(gy.p0) | reinterpret_cast<uintptr_t>(gy.p1) | reinterpret_cast<uintptr_t>(a) |
+                     reinterpret_cast<uintptr_t>(b);
+    if (bits & 15) return false;
+    const long cl = (long)C * L;
+    const bool contiguous = gy.bs0 == cl && (!gy.p1 || gy.bs1 == cl);
+    const bool quad = (L & 3) == 0 && (gy.bs0 & 3) == 0 && (!gy.p1 || (gy.bs1 & 3) == 0);
+    return contiguous || quad;
 }
-int be_gelu_bwd_bias(const float* gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha,
+inline UpGradK upgrad_k(const UpGrad& gy) { return UpGradK{gy.p0, gy.bs0, gy.p1, gy.bs1}; }
+}  // namespace
+
+int be_gelu_bwd_bias(const UpGrad& gy, const float* pre, float* g, long planes, int C, long L, float* gbias, float alpha,
                      stream_t s) {
     if (planes <= 0 || L <= 0) return 0;
-    ProfScope ps("gelu_bwd", 12.0 * planes * L, 0, S(s));
+    const int nsrc = gy.p1 ? 2 : 1;
+    ProfScope ps("gelu_bwd", 4.0 * (nsrc + (pre ? 2 : 1)) * planes * L, 0, S(s));
     // enough CTAs per plane to fill the machine, few enough that the atomics stay negligible
     unsigned gy_ = (unsigned)std::max<long>(1, std::min<long>((L + 2047) / 2048, (148L * 32 + planes - 1) / planes));
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
-    gelu_bwd_bias_kernel<<<dim3((unsigned)planes, gy_), 256, 0, S(s)>>>(gy, pre, g, C, L, gbias, alpha, vec_ok);
+    const int vec_ok = upgrad_vec_ok(gy, C, L, pre, g) ? 1 : 0;
+    const dim3 grid((unsigned)planes, gy_);
+    const UpGradK k = upgrad_k(gy);
+    if (pre) {
+        if (gy.p1) gelu_bwd_bias_kernel<true, true><<<grid, 256, 0, S(s)>>>(k, pre, g, C, L, gbias, alpha, vec_ok);
+        else gelu_bwd_bias_kernel<true, false><<<grid, 256, 0, S(s)>>>(k, pre, g, C, L, gbias, alpha, vec_ok);
+    } else {
+        if (gy.p1) gelu_bwd_bias_kernel<false, true><<<grid, 256, 0, S(s)>>>(k, pre, g, C, L, gbias, alpha, vec_ok);
+        else gelu_bwd_bias_kernel<false, false><<<grid, 256, 0, S(s)>>>(k, pre, g, C, L, gbias, alpha, vec_ok);
+    }
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1841,10 +1848,11 @@ int be_norm_act_fwd(const float* x, const float* stats, const float* gamma, cons
     CU_LAUNCH_CHECK();
     return 0;
 }
-int be_norm_act_bwd(const float* gy, const float* x, const float* stats, const float* gamma, const float* beta,
+int be_norm_act_bwd(const UpGrad& gyu, const float* x, const float* stats, const float* gamma, const float* beta,
                     float* g, float* ggamma, float* gbeta, long planes, int C, long L, int non_lin, stream_t s) {
     if (planes <= 0) return 0;
-    ProfScope ps("instnorm_gelu_bwd", 12.0 * planes * L, 0, S(s));
+    const UpGradK gy = upgrad_k(gyu);
+    ProfScope ps("instnorm_gelu_bwd", 4.0 * (gyu.p1 ? 4 : 3) * planes * L, 0, S(s));
     int slice = 0;
     const int cs = planes * 8 <= 0x7fffffffL ? norm_cluster_pick(L, 8, &slice) : 0;
     if (cs > 0) {
@@ -1894,7 +1902,7 @@ LiftK lift_k(const LiftArgs& a) {
     k.g = pix_geom(a.n, a.N, a.lo);
     k.batch = a.batch; k.raw_ch = a.raw_ch; k.grid_ch = a.grid_ch; k.cin = a.raw_ch + a.grid_ch; k.hid = a.hid; k.out_ch = a.out_ch;
     k.a = a.a; k.grid = a.grid; k.w_a = a.w_a; k.b_a = a.b_a; k.w_b = a.w_b; k.b_b = a.b_b;
-    k.h = a.h; k.gh = a.gh; k.ga = a.ga; k.gw_a = a.gw_a; k.gb_a = a.gb_a; k.gw_b = a.gw_b; k.gb_b = a.gb_b;
+    k.h = a.h; k.gh = a.gh; k.gh2 = a.gh2; k.ga = a.ga; k.gw_a = a.gw_a; k.gb_a = a.gb_a; k.gw_b = a.gw_b; k.gb_b = a.gb_b;
     return k;
 }
 

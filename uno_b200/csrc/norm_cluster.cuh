@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_fwd_cluster_kernel(const fl
     cluster.sync();      // no CTA may exit while a neighbour can still read its mailbox
 }
 
-__global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+__global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const UpGradK gy, const float* __restrict__ x,
                                                                         const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                         const float* __restrict__ beta, float* __restrict__ g,
                                                                         float* __restrict__ ggamma, float* __restrict__ gbeta, int C, long L,
@@ -115,9 +115,12 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const fl
     const float mu = stats[2 * p], rstd = stats[2 * p + 1];
     const float ga = gamma[c], be = beta[c];
     const float* xp = x + p * L + lo;
-    const float* gp = gy + p * L + lo;
-    const bool vec = (L & 3) == 0 &&
-                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    // the upstream gradient is the sum of up to two strided sources (backend.h UpGrad)
+    const float* gp = upgrad_plane(gy.p0, gy.bs0, p, C, L) + lo;
+    const float* hp = gy.p1 ? upgrad_plane(gy.p1, gy.bs1, p, C, L) + lo : nullptr;
+    const bool vec = (L & 3) == 0 && ((gy.bs0 | (gy.p1 ? gy.bs1 : 0)) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy.p0) | reinterpret_cast<uintptr_t>(gy.p1) |
+                       reinterpret_cast<uintptr_t>(g)) & 15) == 0;
     const int nv = vec ? n >> 2 : 0;
     float s1 = 0.f, s2 = 0.f;
     double d1 = 0.0, d2 = 0.0;
@@ -125,10 +128,16 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const fl
     {
         const float4* x4 = reinterpret_cast<const float4*>(xp);
         const float4* g4 = reinterpret_cast<const float4*>(gp);
+        const float4* h4 = reinterpret_cast<const float4*>(hp);
         float4* gn4 = reinterpret_cast<float4*>(gn_s);
         float4* xh4 = reinterpret_cast<float4*>(xh_s);
         for (int i = threadIdx.x; i < nv; i += kNormThreads) {
-            const float4 xv = __ldcs(x4 + i), gv = __ldcs(g4 + i);
+            const float4 xv = __ldcs(x4 + i);
+            float4 gv = __ldcs(g4 + i);
+            if (hp) {
+                const float4 hv = __ldcs(h4 + i);
+                gv.x += hv.x; gv.y += hv.y; gv.z += hv.z; gv.w += hv.w;
+            }
             float4 xh, gn;
             xh.x = (xv.x - mu) * rstd; xh.y = (xv.y - mu) * rstd; xh.z = (xv.z - mu) * rstd; xh.w = (xv.w - mu) * rstd;
             gn = gv;
@@ -145,7 +154,8 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_cluster_kernel(const fl
     }
     for (int i = 4 * nv + threadIdx.x; i < n; i += kNormThreads) {
         const float xh = (xp[i] - mu) * rstd;
-        const float gn = non_lin ? gp[i] * gelu_grad_f(fmaf(xh, ga, be)) : gp[i];
+        const float up = hp ? gp[i] + hp[i] : gp[i];
+        const float gn = non_lin ? up * gelu_grad_f(fmaf(xh, ga, be)) : up;
         gn_s[i] = gn;
         xh_s[i] = xh;
         s1 += gn;

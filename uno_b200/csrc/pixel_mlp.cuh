@@ -100,6 +100,7 @@ struct LiftK {
     const float *a, *grid, *w_a, *b_a, *w_b, *b_b;
     float* h;
     const float* gh;
+    const float* gh2;     // optional second upstream gradient (h feeds two consumers): added on the fly
     float *ga, *gw_a, *gb_a, *gw_b, *gb_b;
 };
 
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
         long b = 0, rp = 0, pp = 0;
         if (valid) raw_to_padded(g, idx, b, rp, pp);
         float in[CIN], a0[HID], gp0[HID], da0[HID];
+        const float* gh2p = (k.gh2 != nullptr && valid) ? k.gh2 + b * k.out_ch * g.npad + pp : nullptr;
         lift_load_in<CIN>(k, b, rp, valid, in);
         lift_first_layer<CIN, HID>(sWa, sba, in, a0);
 #pragma unroll
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
 #pragma unroll 4
         for (int c = 0; c < k.out_ch; ++c) {
             const float pre1 = lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0);
-            const float gv = D1[c * kPixTPP + tid];      // this thread's own asynchronous copy (complete after wait_group)
+            float gv = D1[c * kPixTPP + tid];            // this thread's own asynchronous copy (complete after wait_group)
+            if (gh2p) gv += __ldg(gh2p + (long)c * g.npad);
             const float d1 = gv * gelu_der(pre1);
             D1[c * kPixTPP + tid] = d1;
             const float4* w4 = reinterpret_cast<const float4*>(sWb + c * HID);

@@ -149,176 +149,6 @@ inline size_t resample2d_smem(int RIN, int ldin, int TH, int G0, int W0, int G1,
                             TW / G1 + TH / G0);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Persistent, software-pipelined form of the same kernel: a CTA walks tiles t = blockIdx.x + i * gridDim.x and, while it runs
-// the two passes of tile t, the LDGSTS copies of tile t+1 (its input window, both weight images and group tables) are already
-// in flight into the other staging buffer.  The one-tile-per-CTA kernel above has no loads in flight while it computes and
-// relies on the second resident CTA to cover that (measured: 31 % of the HBM roofline, LSU / issue at ~50 %, 16 resident
-// warps); here every CTA keeps one whole window (~40 KB) outstanding all the time.  Same arithmetic in the same order.
-// ---------------------------------------------------------------------------------------------------------------------
-struct Resample2P {
-    Resample2K k;
-    long n_tiles;          // planes * tiles_h * tiles_w
-};
-
-template <int G0, int W0, int G1, int W1>
-__global__ void __launch_bounds__(256, 2) resample2d_pipe_kernel(const Resample2P pp) {
-    const Resample2K& k = pp.k;
-    extern __shared__ __align__(16) float rsm[];
-    constexpr int kRsTW = rs_tile_w(G1), kRsMidLd = kRsTW + 1;
-    constexpr int NG1 = kRsTW / G1;
-    const int NG0 = k.TH / G0;
-    // per staging buffer: window, weight images, group starts (raw, window-relative offsets are formed at use)
-    const size_t in_floats = (size_t)k.RIN * k.ldin;
-    const size_t buf_floats = ((in_floats + 3) & ~size_t(3)) + NG1 * W1 * G1 + NG0 * W0 * G0 + ((NG1 + NG0 + 3) & ~3);
-    float* mid_s = rsm + 2 * buf_floats;                 // [RIN][kRsMidLd]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long tiles_pp = (long)k.tiles_h * k.tiles_w;
-
-    struct Tile { long p; int ga0, ga1, ngh, ngw, r0, c0, rin, cin, tw; };
-    auto geom = [&](long t) {
-        Tile g;
-        g.p = t / tiles_pp;
-        const int rem = (int)(t - g.p * tiles_pp);
-        const int th = rem / k.tiles_w;
-        g.tw = rem - th * k.tiles_w;
-        g.ga0 = th * NG0; g.ga1 = g.tw * NG1;
-        g.ngh = min(NG0, k.ng0 - g.ga0); g.ngw = min(NG1, k.ng1 - g.ga1);
-        g.r0 = __ldg(k.gs0 + g.ga0); g.c0 = __ldg(k.gs1 + g.ga1);
-        g.rin = __ldg(k.gs0 + g.ga0 + g.ngh - 1) + W0 - g.r0;
-        g.cin = __ldg(k.gs1 + g.ga1 + g.ngw - 1) + W1 - g.c0;
-        return g;
-    };
-    auto stage = [&](const Tile& g, int b) {             // all copies of one tile form one cp.async group
-        float* in_s = rsm + (size_t)b * buf_floats;
-        float* d1s = in_s + ((in_floats + 3) & ~size_t(3));
-        float* d0s = d1s + NG1 * W1 * G1;
-        int* gss = reinterpret_cast<int*>(d0s + NG0 * W0 * G0);   // [NG1] column group starts, then [NG0] row group starts
-        const float* xp = k.x + (g.p * k.n_in0 + g.r0) * (long)k.n_in1 + g.c0 + lane;
-        const uint32_t in_base = (uint32_t)__cvta_generic_to_shared(in_s) + 4u * lane;
-        for (int r = warp; r < g.rin; r += 8) {
-            const float* src = xp + (long)r * k.n_in1;
-            const uint32_t dst = in_base + 4u * (uint32_t)(r * k.ldin);
-            constexpr int CIT = W1 == 16 ? 5 : 3;
-#pragma unroll
-            for (int it = 0; it < CIT; ++it)
-                if (lane + 32 * it < g.cin)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * it), "l"(src + 32 * it) : "memory");
-            for (int c = lane + 32 * CIT; c < g.cin; c += 32)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (c - lane)), "l"(src + (c - lane)) : "memory");
-        }
-        const uint32_t d1a = (uint32_t)__cvta_generic_to_shared(d1s), d0a = (uint32_t)__cvta_generic_to_shared(d0s);
-        const float* D1 = k.D1 + (size_t)g.ga1 * W1 * G1;
-        const float* D0 = k.D0 + (size_t)g.ga0 * W0 * G0;
-        for (int i = tid * 4; i < g.ngw * W1 * G1; i += 1024)    // images are 16-byte aligned: W*G is a multiple of 32 floats
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1a + 4u * i), "l"(D1 + i) : "memory");
-        for (int i = tid * 4; i < g.ngh * W0 * G0; i += 1024)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0a + 4u * i), "l"(D0 + i) : "memory");
-        const uint32_t gsa = (uint32_t)__cvta_generic_to_shared(gss);
-        if (tid < g.ngw) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gsa + 4u * tid), "l"(k.gs1 + g.ga1 + tid) : "memory");
-        if (tid >= 64 && tid < 64 + g.ngh)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(gsa + 4u * (NG1 + tid - 64)), "l"(k.gs0 + g.ga0 + tid - 64) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    long t = blockIdx.x;
-    if (t >= pp.n_tiles) return;
-    Tile cur = geom(t);
-    stage(cur, 0);
-    int b = 0;
-    for (; t < pp.n_tiles; t += gridDim.x, b ^= 1) {
-        const long tn = t + gridDim.x;
-        Tile nxt = cur;
-        if (tn < pp.n_tiles) {
-            nxt = geom(tn);
-            stage(nxt, b ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const float* in_s = rsm + (size_t)b * buf_floats;
-        const float* d1s = in_s + ((in_floats + 3) & ~size_t(3));
-        const float* d0s = d1s + NG1 * W1 * G1;
-        const int* gs1s = reinterpret_cast<const int*>(d0s + NG0 * W0 * G0);
-        const int* gs0s = gs1s + NG1;
-        const int rin = cur.rin, ngw = cur.ngw, ngh = cur.ngh;
-        // ---- pass A: mid[r][j] = sum_u D1[g][u][q] * in[r][gs1[g] + u],  j = g*G1 + q
-        for (int cg = warp; cg < ngw; cg += 8) {
-            float w[W1][G1];
-            const float4* wsrc = reinterpret_cast<const float4*>(d1s + cg * W1 * G1);
-#pragma unroll
-            for (int u = 0; u < W1; ++u)
-#pragma unroll
-                for (int q4 = 0; q4 < G1 / 4; ++q4) {
-                    const float4 v = wsrc[u * (G1 / 4) + q4];
-                    w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
-                }
-            const int cs = gs1s[cg] - cur.c0;
-            for (int rb = 0; rb < rin; rb += 32) {
-                const int r = min(rb + lane, rin - 1);
-                const float* src = in_s + r * k.ldin + cs;
-                float acc[G1];
-#pragma unroll
-                for (int q = 0; q < G1; ++q) acc[q] = 0.f;
-#pragma unroll
-                for (int u = 0; u < W1; ++u) {
-                    const float v = src[u];
-#pragma unroll
-                    for (int q = 0; q < G1; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
-                }
-                if (rb + lane < rin) {
-                    float* dst = mid_s + r * kRsMidLd + cg * G1;
-#pragma unroll
-                    for (int q = 0; q < G1; ++q) dst[q] = acc[q];
-                }
-            }
-        }
-        __syncthreads();
-        // ---- pass B: y[i][j] = sum_u D0[g][u][q] * mid[gs0[g] + u][j],  i = g*G0 + q
-        const int i0 = cur.ga0 * G0, j0 = cur.tw * kRsTW;
-        for (int rg = warp; rg < ngh; rg += 8) {
-            float w[W0][G0];
-            const float4* wsrc = reinterpret_cast<const float4*>(d0s + rg * W0 * G0);
-#pragma unroll
-            for (int u = 0; u < W0; ++u)
-#pragma unroll
-                for (int q4 = 0; q4 < G0 / 4; ++q4) {
-                    const float4 v = wsrc[u * (G0 / 4) + q4];
-                    w[u][4 * q4 + 0] = v.x; w[u][4 * q4 + 1] = v.y; w[u][4 * q4 + 2] = v.z; w[u][4 * q4 + 3] = v.w;
-                }
-            const float* srow = mid_s + (gs0s[rg] - cur.r0) * kRsMidLd + lane;
-            float* yrow = k.y + (cur.p * k.n_out0 + i0 + rg * G0) * (long)k.n_out1 + j0 + lane;
-            const int rows_left = k.n_out0 - (i0 + rg * G0);
-#pragma unroll 1
-            for (int half = 0; half < kRsTW / 32; ++half) {
-                const float* src = srow + 32 * half;
-                float acc[G0];
-#pragma unroll
-                for (int q = 0; q < G0; ++q) acc[q] = 0.f;
-#pragma unroll
-                for (int u = 0; u < W0; ++u) {
-                    const float v = src[u * kRsMidLd];
-#pragma unroll
-                    for (int q = 0; q < G0; ++q) acc[q] = fmaf(w[u][q], v, acc[q]);
-                }
-                const bool col_ok = j0 + 32 * half + lane < k.n_out1;
-                float* yp = yrow + 32 * half;
-#pragma unroll
-                for (int q = 0; q < G0; ++q) {
-                    if (col_ok && q < rows_left) *yp = acc[q];
-                    yp += k.n_out1;
-                }
-            }
-        }
-        __syncthreads();      // mid_s and this staging buffer are free again
-        cur = nxt;
-    }
-}
-
-inline size_t resample2d_pipe_smem(int RIN, int ldin, int TH, int G0, int W0, int G1, int W1) {
-    const int TW = rs_tile_w(G1);
-    const size_t in_floats = ((size_t)RIN * ldin + 3) & ~size_t(3);
-    const size_t buf = in_floats + (size_t)(TW / G1) * W1 * G1 + (size_t)(TH / G0) * W0 * G0 + (size_t)((TW / G1 + TH / G0 + 3) & ~3);
-    return sizeof(float) * (2 * buf + (size_t)RIN * (TW + 1));
-}
+// (A persistent, software-pipelined form of this kernel -- the LDGSTS copies of tile t+1 in flight while tile t runs its two
+// passes -- was measured on B200 at 3.36 against 3.43 ms per Darcy step and removed: the kernel is bound by its shared-memory
+// and FMA instruction stream, not by exposed load latency.)

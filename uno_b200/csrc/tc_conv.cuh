@@ -64,7 +64,6 @@ __global__ void conv_weight_image_kernel(const float* __restrict__ W, long w_rs,
     }
 }
 
-template <bool HINT = false>
 __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,7 +197,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i_pxok && c0 + 8 * i < p.K) v[i] = ldg_f4<HINT>(reinterpret_cast<const float4*>(src + i * stride8));
+                if (i_pxok && c0 + 8 * i < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * stride8));
             }
             if (++i_kc == NKC) {
                 i_kc = 0;

@@ -8,9 +8,9 @@
 //   * a ring of S shared-memory stages; per stage the A chunk (tf32 hi and lo images, UMMA K-major
 //     "interleave" layout) written by 8 loader warps and the matching chunk of the constant B image
 //     (pre-split hi/lo, chunk-major in global memory, L2 resident) fetched by one bulk async copy
-//   * loader warps keep TWO chunks of global loads in flight per thread (registers double buffered), which
-//     is what keeps ~32 KB per SM outstanding even when rows are only 4-byte aligned (odd grid widths
-//     such as 481 rule out TMA tensor maps and 16-byte vector loads)
+//   * loader warps keep up to FOUR chunks of global loads in flight per thread (a register ring), issued two
+//     consecutive chunks at a time (see "DRAM locality" below); rows that are only 4-byte aligned (odd grid
+//     widths such as 481 rule out TMA tensor maps) take the row-class path, which still loads 16 bytes at a time
 //   * one lane issues 3 MMAs (hi*hi, hi*lo, lo*hi) per 8-wide k-step into one of two TMEM accumulators
 //   * 4 epilogue warps drain the other accumulator (tcgen05.ld 16x256b -> float2 stores)
 #pragma once
@@ -59,10 +59,11 @@ __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return
 // RC = row-class mode (see above), compiled separately so that the default instantiation carries none of it.
 // LW = loader warps: 8 (default) or 16 (opt-in UNO_B200_KPIPE_LW16=1: the loader warps' serial instruction stream per chunk is
 // what bounds this kernel, tools/kpipe_probe.py -- twice the warps, half the rows per thread).
-// PAIR: the loaders issue their global loads two chunks at a time (256 contiguous bytes of every row requested together) instead of
-// one chunk per iteration; HINT: 16-byte loads carry the L2::256B prefetch hint.  Both aim at DRAM efficiency: a chunk is 128 bytes of
-// each of 128 rows that lie a row pitch apart, i.e. 128 scattered 128-byte requests.
-template <int LW = kKpLoadWarps, bool RC = false, bool PAIR = false, bool HINT = false>
+// DRAM locality: a chunk is 128 bytes of each of 128 rows that lie a row pitch apart, i.e. 128 scattered 128-byte requests.  The
+// loaders therefore issue their global loads for TWO consecutive chunks at a time (256 contiguous bytes of every row requested
+// together) and the 16-byte loads carry the L2::256B prefetch hint.  Measured on B200 (Darcy step, all analysis launches):
+// 2.14 ms one chunk at a time, 2.05 with the hint, 1.83 paired, 1.79 both.
+template <int LW = kKpLoadWarps, bool RC = false>
 __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
     static_assert(LW == 8 || LW == 16, "loader warps");
     constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 if (k0 >= sh && k0 + 4 <= k_end) {
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
-                        v[i] = (4 * RB * i < rows_left) ? ldg_f4<HINT>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i] = (4 * RB * i < rows_left) ? ldg_f4<true>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
                     for (int i = 0; i < RP; ++i) {
@@ -232,8 +233,9 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
-            if constexpr (PAIR && DEPTH == 4) {
+            {
                 // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                static_assert(DEPTH == 4, "ring of four chunks");
                 if (0 < total) issue(ring[0]);
                 if (1 < total) issue(ring[1]);
                 for (long g = 0; g < total; g += 4) {
@@ -246,17 +248,6 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + 2 < total) process(ring[2]);
                     if (g + 3 < total) process(ring[3]);
                 }
-            } else {
-#pragma unroll
-            for (int d = 0; d < DEPTH - 1; ++d)
-                if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += DEPTH) {
-#pragma unroll
-                for (int d = 0; d < DEPTH; ++d) {
-                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
-                    if (g + d < total) process(ring[d]);
-                }
-            }
             }
         } else if (p.a_vec_ok) {
             // 16-byte path: thread -> (row = ltid/8 + 32*i, 4 k at (ltid%8)*4)
@@ -275,7 +266,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     const long lim = (p.debug & 8) ? 0 : rows_left;
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
-                        v[i] = (RB * i < lim) ? ldg_f4<HINT>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[i] = (RB * i < lim) ? ldg_f4<true>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
 #pragma unroll
                     for (int i = 0; i < RP; ++i) {
@@ -305,8 +296,9 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
-            if constexpr (PAIR && DEPTH == 4) {
+            {
                 // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                static_assert(DEPTH == 4, "ring of four chunks");
                 if (0 < total) issue(ring[0]);
                 if (1 < total) issue(ring[1]);
                 for (long g = 0; g < total; g += 4) {
@@ -319,17 +311,6 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + 2 < total) process(ring[2]);
                     if (g + 3 < total) process(ring[3]);
                 }
-            } else {
-#pragma unroll
-            for (int d = 0; d < DEPTH - 1; ++d)
-                if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += DEPTH) {
-#pragma unroll
-                for (int d = 0; d < DEPTH; ++d) {
-                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
-                    if (g + d < total) process(ring[d]);
-                }
-            }
             }
         } else {
             // 4-byte path: lane = k within the chunk, warp w -> rows w + 8*i
@@ -357,8 +338,9 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 }
                 stage_epilogue();
             };
-            if constexpr (PAIR && DEPTH == 4) {
+            {
                 // chunks go to ring slot (chunk % 4); loads are issued for two consecutive chunks at once
+                static_assert(DEPTH == 4, "ring of four chunks");
                 if (0 < total) issue(ring[0]);
                 if (1 < total) issue(ring[1]);
                 for (long g = 0; g < total; g += 4) {
@@ -371,17 +353,6 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + 2 < total) process(ring[2]);
                     if (g + 3 < total) process(ring[3]);
                 }
-            } else {
-#pragma unroll
-            for (int d = 0; d < DEPTH - 1; ++d)
-                if (d < total) issue(ring[d]);
-            for (long g = 0; g < total; g += DEPTH) {
-#pragma unroll
-                for (int d = 0; d < DEPTH; ++d) {
-                    if (g + d + DEPTH - 1 < total) issue(ring[(d + DEPTH - 1) % DEPTH]);
-                    if (g + d < total) process(ring[d]);
-                }
-            }
             }
         }
     } else {

@@ -956,10 +956,26 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
                            const float* gamma, const float* beta, float* gx, float* const* gw,
                            float* gconv_w, float* gconv_b, float* ggamma, float* gbeta, void* ws,
                            size_t ws_bytes, void* stream) {
+    return uno_operator_block_bwd2(bd, gy, 0, nullptr, 0, x, xhat, pw_saved, pre, stats, w, conv_w, gamma, beta, gx, gw, gconv_w,
+                                   gconv_b, ggamma, gbeta, ws, ws_bytes, stream);
+}
+
+int uno_operator_block_bwd2(const uno_block_desc* bd, const float* gy, long gy_batch_stride, const float* gy2,
+                            long gy2_batch_stride, const float* x, const float* xhat, const float* pw_saved,
+                            const float* pre, const float* stats, const float* const* w, const float* conv_w,
+                            const float* gamma, const float* beta, float* gx, float* const* gw, float* gconv_w,
+                            float* gconv_b, float* ggamma, float* gbeta, void* ws, size_t ws_bytes, void* stream) {
     if (!bd) return fail(UNO_EINVAL, "null descriptor");
     const uno_conv_desc* d = &bd->conv;
     UNO_TRY(check_conv_desc(d, true));
     if (!gy || !x || !xhat || !w || !conv_w) return fail(UNO_EINVAL, "null tensor pointer");
+    long n_out_chk = 1;
+    for (int a = 0; a < d->ndim; ++a) n_out_chk *= d->out_dim[a];
+    const long contiguous_bs = (long)d->out_ch * n_out_chk;
+    if (gy_batch_stride == 0) gy_batch_stride = contiguous_bs;
+    if (gy2 && gy2_batch_stride == 0) gy2_batch_stride = contiguous_bs;
+    if (gy_batch_stride < contiguous_bs || (gy2 && gy2_batch_stride < contiguous_bs))
+        return fail(UNO_EINVAL, "upstream-gradient batch stride smaller than one sample (%ld < %ld)", gy_batch_stride, contiguous_bs);
     if ((bd->normalize || bd->non_lin) && !pre) return fail(UNO_EINVAL, "backward needs the saved pre tensor");
     if (bd->normalize && (!stats || !gamma || !beta || !ggamma || !gbeta))
         return fail(UNO_EINVAL, "normalize backward needs stats, gamma, beta, ggamma, gbeta");
@@ -971,7 +987,12 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
     const long planes = (long)d->batch * d->out_ch;
     const size_t nact = (size_t)planes * g.n_out;
     Arena ar(ws, ws_bytes);
-    const float* gs = gy;   // gradient w.r.t. conv(x)+w(x)
+    // Gradient w.r.t. conv(x)+w(x).  The upstream gradient may be the sum of two tensors, each a channel slice of a wider one
+    // (backend.h UpGrad): the first kernel of the backward -- the activation / normalisation backward -- reads them in place.
+    UpGrad up;
+    up.p0 = gy; up.bs0 = gy_batch_stride; up.p1 = gy2; up.bs1 = gy2_batch_stride;
+    const bool plain = !gy2 && gy_batch_stride == contiguous_bs;
+    const float* gs = gy;
     // the conv-bias gradient (gain * per-channel sum of gs) is folded into the kernel that produces gs
     const float bias_gain = g.identity ? 1.0f : (float)rp->gain;
     bool bias_done = false;
@@ -984,19 +1005,17 @@ int uno_operator_block_bwd(const uno_block_desc* bd, const float* gy, const floa
         // zero in exact arithmetic (every plane of `buf` sums to zero).  The reference's autograd returns the
         // floating-point residue of that sum (~1e-7 of the gradient scale); we return the exact value.
         if (gconv_b) BE_TRY(be_memset(gconv_b, 0, d->out_ch * sizeof(float), stream));
-        BE_TRY(be_norm_act_bwd(gy, pre, stats, gamma, beta, buf, ggamma, gbeta, planes, d->out_ch, g.n_out, bd->non_lin, stream));
+        BE_TRY(be_norm_act_bwd(up, pre, stats, gamma, beta, buf, ggamma, gbeta, planes, d->out_ch, g.n_out, bd->non_lin, stream));
         bias_done = true;
         gs = buf;
-    } else if (bd->non_lin) {
+    } else if (bd->non_lin || !plain) {
+        // GELU backward; for a block without activation whose gradient arrives strided or in two parts, the same kernel in
+        // its identity mode gathers / sums the sources into one contiguous tensor
         float* buf = ar.take(nact);
         if (!ar.ok) return fail(UNO_EWORKSPACE, "workspace too small for operator block backward");
-        if (gconv_b) {
-            BE_TRY(be_memset(gconv_b, 0, d->out_ch * sizeof(float), stream));
-            BE_TRY(be_gelu_bwd_bias(gy, pre, buf, planes, d->out_ch, g.n_out, gconv_b, bias_gain, stream));
-            bias_done = true;
-        } else {
-            BE_TRY(be_gelu_bwd(gy, pre, buf, nact, stream));
-        }
+        if (gconv_b) BE_TRY(be_memset(gconv_b, 0, d->out_ch * sizeof(float), stream));
+        BE_TRY(be_gelu_bwd_bias(up, bd->non_lin ? pre : nullptr, buf, planes, d->out_ch, g.n_out, gconv_b, bias_gain, stream));
+        bias_done = gconv_b != nullptr;
         gs = buf;
     }
     // as in forward: the pointwise backward (which overwrites gx) on the side stream, the spectral backward on the
@@ -1032,12 +1051,18 @@ int uno_lift_fwd(const uno_lift_desc* d, const float* a_, const float* grid, con
 int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a_, const float* grid,
                  const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
                  float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream) {
+    return uno_lift_bwd2(d, gh, nullptr, a_, grid, w_a, b_a, w_b, b_b, ga, gw_a, gb_a, gw_b, gb_b, stream);
+}
+
+int uno_lift_bwd2(const uno_lift_desc* d, const float* gh, const float* gh2, const float* a_, const float* grid,
+                  const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
+                  float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream) {
     LiftArgs a;
     UNO_TRY(make_lift_args(d, &a));
     if (!gh || !a_ || (!grid && d->grid_ch > 0) || !w_a || !b_a || !w_b || !b_b || !gw_a || !gb_a || !gw_b || !gb_b)
         return fail(UNO_EINVAL, "null tensor pointer");
     a.a = a_; a.grid = grid; a.w_a = w_a; a.b_a = b_a; a.w_b = w_b; a.b_b = b_b;
-    a.gh = gh; a.ga = ga; a.gw_a = gw_a; a.gb_a = gb_a; a.gw_b = gw_b; a.gb_b = gb_b;
+    a.gh = gh; a.gh2 = gh2; a.ga = ga; a.gw_a = gw_a; a.gb_a = gb_a; a.gw_b = gw_b; a.gb_b = gb_b;
     const int cin = d->raw_ch + d->grid_ch;
     BE_TRY(be_memset(gw_a, 0, sizeof(float) * d->hidden * cin, stream));
     BE_TRY(be_memset(gb_a, 0, sizeof(float) * d->hidden, stream));

@@ -81,6 +81,33 @@ def _cweights(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> List[torch.Te
     return out
 
 
+def _upstream(grads):
+    """The non-None upstream gradients of a (possibly fanned-out) output as [(tensor, batch stride in floats)]: a gradient that
+    is contiguous within each sample -- a contiguous tensor or a channel slice of a wider one, which is what the backward of
+    ``torch.cat(dim=1)`` hands out -- is passed as it is with its batch stride; anything else is made contiguous first."""
+    out = []
+    for g in grads:
+        if g is None:
+            continue
+        if g.dtype != torch.float32:
+            raise RuntimeError(f"uno_b200: expected float32 gradient but found {g.dtype}")
+        inner = g.shape[1:]
+        want, acc = [], 1
+        for n in reversed(inner):
+            want.append(acc)
+            acc *= int(n)
+        ok = tuple(reversed(want)) == tuple(g.stride()[1:]) and (g.shape[0] == 1 or g.stride(0) >= acc) and g.data_ptr() % 4 == 0
+        if not ok:
+            g = g.contiguous()
+        out.append((g, int(g.stride(0)) if g.shape[0] > 1 else acc))
+    return out
+
+
+def _fan(y: torch.Tensor, fanout: int):
+    """``fanout`` aliases of one output tensor (distinct autograd outputs over the same memory)."""
+    return y if fanout == 1 else (y,) + tuple(y.view_as(y) for _ in range(fanout - 1))
+
+
 def _desc(x: torch.Tensor, out_ch: int, out_dims, modes=()) -> _capi.ConvDesc:
     return _capi.conv_desc(x.shape[0], x.shape[1], out_ch, x.shape[2:], [int(v) for v in out_dims], [int(v) for v in modes])
 
@@ -181,8 +208,9 @@ class OperatorBlockFn(torch.autograd.Function):
 
     @staticmethod
     @_guard
-    def forward(ctx, x, out_dims, modes, normalize, non_lin, eps, need_grad, conv_w, conv_b, gamma, beta, *weights):
+    def forward(ctx, x, out_dims, modes, normalize, non_lin, eps, need_grad, fanout, conv_w, conv_b, gamma, beta, *weights):
         lib = _get_lib()
+        ctx.set_materialize_grads(False)      # an unused alias of a fanned-out output arrives as None, not as a zero tensor
         _check_input(x)
         _check_params(x, conv_w, conv_b, gamma if normalize else None, beta if normalize else None)
         x = x.contiguous()
@@ -223,16 +251,23 @@ class OperatorBlockFn(torch.autograd.Function):
         ctx.nw = len(ws)
         if need_grad:
             ctx.save_for_backward(x, xhat, saved, pre, stats, cw, ga, be, *ws)
-        return y
+        return _fan(y, fanout)
 
     @staticmethod
     @once_differentiable
     @_guard
-    def backward(ctx, gy):
+    def backward(ctx, *gys):
         lib = _get_lib()
         x, xhat, saved, pre, stats, cw, ga, be, *ws = ctx.saved_tensors
         bd = ctx.bd
-        gy = gy.contiguous()
+        ups = _upstream(gys)
+        if not ups:
+            return (None,) * (12 + ctx.nw)
+        while len(ups) > 2:                   # the kernels add two sources on the fly; more than two are pre-summed
+            (a, _), (b, _) = ups.pop(), ups.pop()
+            s_ = a + b
+            ups.append((s_, int(s_.stride(0)) if s_.shape[0] > 1 else s_[0].numel()))
+        (gy, gy_bs), (gy2, gy2_bs) = ups[0], (ups[1] if len(ups) > 1 else (None, 0))
         dev = gy.device
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         gws = [torch.empty_like(w) for w in ws]
@@ -245,13 +280,13 @@ class OperatorBlockFn(torch.autograd.Function):
         gwp = _capi.ptr_array([g.data_ptr() for g in gws])
         _capi.check(
             lib,
-            lib.uno_operator_block_bwd(
-                C.byref(bd), _ptr(gy), _ptr(x), _ptr(xhat), _ptr(saved), _ptr(pre), _ptr(stats), wp, _ptr(cw), _ptr(ga), _ptr(be),
-                _ptr(gx), gwp, _ptr(gcw), _ptr(gcb), _ptr(gg), _ptr(gb), _ptr(wsb), wsb.numel(), _stream(gy),
+            lib.uno_operator_block_bwd2(
+                C.byref(bd), _ptr(gy), gy_bs, _ptr(gy2), gy2_bs, _ptr(x), _ptr(xhat), _ptr(saved), _ptr(pre), _ptr(stats), wp, _ptr(cw),
+                _ptr(ga), _ptr(be), _ptr(gx), gwp, _ptr(gcw), _ptr(gcb), _ptr(gg), _ptr(gb), _ptr(wsb), wsb.numel(), _stream(gy),
             ),
         )
         _launch_counter["calls"] += 1
-        return (gx, None, None, None, None, None, None, gcw.reshape(ctx.w_shape), gcb, gg, gb) + tuple(gws)
+        return (gx, None, None, None, None, None, None, None, gcw.reshape(ctx.w_shape), gcb, gg, gb) + tuple(gws)
 
 
 class LiftFn(torch.autograd.Function):
@@ -260,8 +295,9 @@ class LiftFn(torch.autograd.Function):
 
     @staticmethod
     @_guard
-    def forward(ctx, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
+    def forward(ctx, a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, fanout):
         lib = _get_lib()
+        ctx.set_materialize_grads(False)
         _check_input(a)
         _check_input(grid, "grid features")
         _check_params(a, w_a, b_a, w_b, b_b)
@@ -281,24 +317,29 @@ class LiftFn(torch.autograd.Function):
         _launch_counter["calls"] += 1
         ctx.desc = d
         ctx.save_for_backward(a, grid, wa, ba, wb, bb)
-        return h
+        return _fan(h, fanout)
 
     @staticmethod
     @once_differentiable
     @_guard
-    def backward(ctx, gh):
+    def backward(ctx, *ghs):
         lib = _get_lib()
         a, grid, wa, ba, wb, bb = ctx.saved_tensors
-        gh = gh.contiguous()
+        ghs = [g.contiguous() for g in ghs if g is not None]
+        if not ghs:
+            return (None,) * 9
+        while len(ghs) > 2:
+            ghs.append(ghs.pop() + ghs.pop())
+        gh, gh2 = ghs[0], (ghs[1] if len(ghs) > 1 else None)
         ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         gwa, gba, gwb, gbb = (torch.empty_like(t) for t in (wa, ba, wb, bb))
         _capi.check(
             lib,
-            lib.uno_lift_bwd(C.byref(ctx.desc), _ptr(gh), _ptr(a), _ptr(grid), _ptr(wa), _ptr(ba), _ptr(wb), _ptr(bb),
-                             _ptr(ga), _ptr(gwa), _ptr(gba), _ptr(gwb), _ptr(gbb), _stream(gh)),
+            lib.uno_lift_bwd2(C.byref(ctx.desc), _ptr(gh), _ptr(gh2), _ptr(a), _ptr(grid), _ptr(wa), _ptr(ba), _ptr(wb), _ptr(bb),
+                              _ptr(ga), _ptr(gwa), _ptr(gba), _ptr(gwb), _ptr(gbb), _stream(gh)),
         )
         _launch_counter["calls"] += 1
-        return ga, None, gwa, gba, gwb, gbb, None, None
+        return ga, None, gwa, gba, gwb, gbb, None, None, None
 
 
 class ProjectFn(torch.autograd.Function):
@@ -388,22 +429,26 @@ def pointwise_op(x, conv_w, conv_b, out_dims):
     return PointwiseFn.apply(x, tuple(out_dims), _needs_grad(x, conv_w, conv_b), conv_w, conv_b)
 
 
-def operator_block(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None, non_lin=True, eps=1e-5):
+def operator_block(x, weights, conv_w, conv_b, out_dims, modes, gamma=None, beta=None, non_lin=True, eps=1e-5, fanout=1):
     normalize = gamma is not None
     if x.shape[0] == 0:
         _check_input(x)
-        return _empty_batch(x, (0, weights[0].shape[1]) + tuple(out_dims), conv_w, conv_b, gamma, beta, *weights)
+        y = _empty_batch(x, (0, weights[0].shape[1]) + tuple(out_dims), conv_w, conv_b, gamma, beta, *weights)
+        return y if fanout == 1 else (y,) * fanout
     need = _needs_grad(x, conv_w, conv_b, gamma, beta, *weights)
-    return OperatorBlockFn.apply(x, tuple(out_dims), tuple(modes), normalize, bool(non_lin), float(eps), need, conv_w, conv_b, gamma, beta, *weights)
+    return OperatorBlockFn.apply(x, tuple(out_dims), tuple(modes), normalize, bool(non_lin), float(eps), need, int(fanout), conv_w, conv_b,
+                                 gamma, beta, *weights)
 
 
-def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi):
-    """h[B, C, *padded] = pad(gelu(fc_b(gelu(fc_a(cat(a, grid))))))  -- a [B, *dims, raw_ch] channels-last, grid [*dims, G]."""
+def lift(a, grid, w_a, b_a, w_b, b_b, pad_lo, pad_hi, fanout=1):
+    """h[B, C, *padded] = pad(gelu(fc_b(gelu(fc_a(cat(a, grid))))))  -- a [B, *dims, raw_ch] channels-last, grid [*dims, G].
+    ``fanout=2`` returns two aliases of h for its two consumers (first block and projection); see OperatorBlock_2D.forward."""
     if a.shape[0] == 0:
         _check_input(a)
         dims = tuple(n + int(lo) + int(hi) for n, lo, hi in zip(a.shape[1:-1], pad_lo, pad_hi))
-        return _empty_batch(a, (0, w_b.shape[0]) + dims, w_a, b_a, w_b, b_b)
-    return LiftFn.apply(a, grid, w_a, b_a, w_b, b_b, tuple(int(v) for v in pad_lo), tuple(int(v) for v in pad_hi))
+        h = _empty_batch(a, (0, w_b.shape[0]) + dims, w_a, b_a, w_b, b_b)
+        return h if fanout == 1 else (h,) * fanout
+    return LiftFn.apply(a, grid, w_a, b_a, w_b, b_b, tuple(int(v) for v in pad_lo), tuple(int(v) for v in pad_hi), int(fanout))
 
 
 def project(srcs, w1, b1, w2, b2, crop_lo, crop_hi):

@@ -168,7 +168,7 @@ class OperatorBlock_1D(nn.Module):
 
 
 class _OperatorBlockND(nn.Module):
-    def _run(self, x, dims):
+    def _run(self, x, dims, fanout=1):
         conv = self.conv
         nd = len(dims)
         names = ("dim1", "dim2", "dim3")[:nd]
@@ -192,7 +192,8 @@ class _OperatorBlockND(nn.Module):
         eps = 1e-5
         if self.normalize:
             gamma, beta, eps = self.normalize_layer.weight, self.normalize_layer.bias, self.normalize_layer.eps
-        return _fn.operator_block(x, weights, self.w.conv.weight, self.w.conv.bias, out_dims, modes, gamma, beta, self.non_lin, eps)
+        return _fn.operator_block(x, weights, self.w.conv.weight, self.w.conv.bias, out_dims, modes, gamma, beta, self.non_lin, eps,
+                                  fanout=fanout)
 
 
 class OperatorBlock_2D(_OperatorBlockND):
@@ -207,8 +208,11 @@ class OperatorBlock_2D(_OperatorBlockND):
         if Normalize:
             self.normalize_layer = torch.nn.InstanceNorm2d(int(out_codim), affine=True)
 
-    def forward(self, x, dim1=None, dim2=None):
-        return self._run(x, (dim1, dim2))
+    def forward(self, x, dim1=None, dim2=None, fanout=1):
+        """``fanout=2`` (extension, not in the reference's signature): return the output twice, as two aliases of the same
+        memory, for a tensor that feeds two consumers (a skip connection).  The block's backward then receives the two
+        upstream gradients separately and adds them inside its first kernel instead of autograd's separate add pass."""
+        return self._run(x, (dim1, dim2), fanout)
 
 
 class OperatorBlock_3D(_OperatorBlockND):
@@ -223,5 +227,5 @@ class OperatorBlock_3D(_OperatorBlockND):
         if Normalize:
             self.normalize_layer = torch.nn.InstanceNorm3d(int(out_codim), affine=True)
 
-    def forward(self, x, dim1=None, dim2=None, dim3=None):
-        return self._run(x, (dim1, dim2, dim3))
+    def forward(self, x, dim1=None, dim2=None, dim3=None, fanout=1):
+        return self._run(x, (dim1, dim2, dim3), fanout)

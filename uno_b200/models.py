@@ -40,6 +40,16 @@ def _glue_of(ops):
     return functional
 
 
+def _twice(fused, fn, *args):
+    """A tensor with two consumers (a skip connection).  On the CUDA blocks the producer returns two aliases of its output
+    (``fanout=2``) and its backward adds the two upstream gradients inside its first kernel; any other operator module (the CPU
+    oracle port of the tests) just hands the tensor out twice and autograd adds the gradients."""
+    if fused:
+        return fn(*args, fanout=2)
+    y = fn(*args)
+    return y, y
+
+
 class _GridCache:
     """The reference rebuilds its coordinate features with numpy on the host in every forward
     (darcy_flow_uno2d.py:135-141).  Same values, built once per (shape, device)."""
@@ -80,6 +90,7 @@ class UNO_9(nn.Module):
         self.fc2 = nn.Linear(w, 1)
         self._grids = _GridCache()
         self._glue = _glue_of(ops)
+        self._fused = self._glue is not ops
 
     def get_grid(self, shape, device):
         b, sx, sy = shape[0], shape[1], shape[2]
@@ -96,14 +107,16 @@ class UNO_9(nn.Module):
         # kernel each; the padding grows the grid to the right / bottom only
         grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         grow = math.ceil(x.shape[2] / 85) * self.padding
-        h = self._glue.lift(x, grid, self.fc_n1.weight, self.fc_n1.bias, self.fc0.weight, self.fc0.bias, (0, 0), (grow, grow))
+        # h and c0 each feed two consumers: their producers fan them out (see _twice)
+        h, h_skip = _twice(self._fused, self._glue.lift, x, grid, self.fc_n1.weight, self.fc_n1.bias, self.fc0.weight, self.fc0.bias,
+                           (0, 0), (grow, grow))
         D1, D2 = h.shape[-2], h.shape[-1]
-        c0 = self.conv0(h, D1 // 2, D2 // 2)
+        c0, c0_skip = _twice(self._fused, self.conv0, h, D1 // 2, D2 // 2)
         c1 = self.conv1(c0, D1 // 4, D2 // 4)
         c2 = self.conv2(c1, D1 // 4, D2 // 4)
-        c4 = torch.cat([self.conv4(c2, D1 // 2, D2 // 2), c0], dim=1)
+        c4 = torch.cat([self.conv4(c2, D1 // 2, D2 // 2), c0_skip], dim=1)
         c5 = self.conv5(c4, D1, D2)
-        return self._glue.project([c5, h], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, (0, 0), (grow, grow))
+        return self._glue.project([c5, h_skip], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, (0, 0), (grow, grow))
 
 
 class _NS2DBase(nn.Module):
@@ -121,7 +134,7 @@ class _NS2DBase(nn.Module):
         # navier_stokes_uno2d.py:191-201 -- F.pad on all four sides
         grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         p = self.padding
-        return self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (p, p), (p, p))
+        return _twice(self._fused, self._glue.lift, x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (p, p), (p, p))
 
     def _project(self, srcs):
         # navier_stokes_uno2d.py:215-225 -- the reference crops only the trailing edge ([..., :-p, :-p])
@@ -151,18 +164,19 @@ class UNO(_NS2DBase):
         self.fc2 = nn.Linear(4 * w, 1)
         self._grids = _GridCache()
         self._glue = _glue_of(ops)
+        self._fused = self._glue is not ops
 
     def forward(self, x):
-        h = self._lift(x)
+        h, h_skip = self._lift(x)
         D1, D2 = h.shape[-2], h.shape[-1]
         f = self.factor
-        c0 = self.L0(h, int(D1 * f), int(D2 * f))
-        c1 = self.L1(c0, D1 // 2, D2 // 2)
+        c0, c0_skip = _twice(self._fused, self.L0, h, int(D1 * f), int(D2 * f))
+        c1, c1_skip = _twice(self._fused, self.L1, c0, D1 // 2, D2 // 2)
         c2 = self.L2(c1, D1 // 4, D2 // 4)
         c3 = self.L3(c2, D1 // 4, D2 // 4)
-        c4 = torch.cat([self.L4(c3, D1 // 2, D2 // 2), c1], dim=1)
-        c5 = torch.cat([self.L5(c4, int(D1 * f), int(D2 * f)), c0], dim=1)
-        return self._project([self.L6(c5, D1, D2), h])
+        c4 = torch.cat([self.L4(c3, D1 // 2, D2 // 2), c1_skip], dim=1)
+        c5 = torch.cat([self.L5(c4, int(D1 * f), int(D2 * f)), c0_skip], dim=1)
+        return self._project([self.L6(c5, D1, D2), h_skip])
 
 
 class UNO_P(_NS2DBase):
@@ -230,6 +244,7 @@ class Uno3D_T10(nn.Module):
         self.fc2 = nn.Linear(4 * w, 1)
         self._grids = _GridCache()
         self._glue = _glue_of(ops)
+        self._fused = self._glue is not ops
 
     def get_grid(self, shape, device):
         b, sx, sy, sz = shape[0], shape[1], shape[2], shape[3]
@@ -255,17 +270,18 @@ class Uno3D_T10(nn.Module):
         grid = self.get_grid((1,) + tuple(x.shape[1:]), x.device)[0]
         self.padding = int(self.pad * 0.1 * x.shape[3])
         lo = self.padding if self.pad_both else 0
-        h = self._glue.lift(x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias, (0, 0, lo), (0, 0, self.padding))
+        h, h_skip = _twice(self._fused, self._glue.lift, x, grid, self.fc.weight, self.fc.bias, self.fc0.weight, self.fc0.bias,
+                           (0, 0, lo), (0, 0, self.padding))
         D1, D2, D3 = h.shape[-3], h.shape[-2], h.shape[-1]
-        c0 = self.conv0(h, int(3 * D1 / 4), int(3 * D2 / 4), D3)
-        c1 = self.conv1(c0, D1 // 2, D2 // 2, D3)
+        c0, c0_skip = _twice(self._fused, self.conv0, h, int(3 * D1 / 4), int(3 * D2 / 4), D3)
+        c1, c1_skip = _twice(self._fused, self.conv1, c0, D1 // 2, D2 // 2, D3)
         c2 = self.conv2(c1, D1 // 4, D2 // 4, int(1.0 * D3))
         c3 = self.conv3(c2, D1 // 4, D2 // 4, int(1.0 * D3))
         c6 = self.conv6(c3, D1 // 2, D2 // 2, int(1.0 * D3))
-        c6 = torch.cat([c6, self._skip(c1, c6)], dim=1)
+        c6 = torch.cat([c6, self._skip(c1_skip, c6)], dim=1)
         c7 = self.conv7(c6, int(3 * D1 / 4), int(3 * D2 / 4), D3)
-        c7 = torch.cat([c7, self._skip(c0, c7)], dim=1)
+        c7 = torch.cat([c7, self._skip(c0_skip, c7)], dim=1)
         c8 = self.conv8(c7, D1, D2, D3)
         # :551-575: cat with the lifted input, crop the time padding, project
-        return self._glue.project([c8, self._skip(h, c8)], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+        return self._glue.project([c8, self._skip(h_skip, c8)], self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
                                   (0, 0, lo), (0, 0, self.padding))

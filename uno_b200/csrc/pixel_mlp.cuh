@@ -275,21 +275,37 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
             gelu_both(a0[kk], act, grad);
             a0[kk] = act; gp0[kk] = grad; da0[kk] = 0.f;
         }
-#pragma unroll 4
-        for (int c = 0; c < k.out_ch; ++c) {
-            const float pre1 = lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0);
-            float gv = D1[c * kPixTPP + tid];            // this thread's own asynchronous copy (complete after wait_group)
-            if (gh2p) gv += __ldg(gh2p + (long)c * g.npad);
-            const float d1 = gv * gelu_der(pre1);
-            D1[c * kPixTPP + tid] = d1;
-            const float4* w4 = reinterpret_cast<const float4*>(sWb + c * HID);
+        // the second upstream gradient (when h has two consumers) is not staged: its values for the NEXT eight channels are
+        // loaded into registers while the current eight are processed (coalesced: consecutive threads, consecutive pixels)
+        constexpr int G2 = 8;
+        float g2n[G2];
 #pragma unroll
-            for (int q = 0; q < HID / 4; ++q) {
-                const float4 w = w4[q];
-                da0[4 * q + 0] = fmaf(w.x, d1, da0[4 * q + 0]);
-                da0[4 * q + 1] = fmaf(w.y, d1, da0[4 * q + 1]);
-                da0[4 * q + 2] = fmaf(w.z, d1, da0[4 * q + 2]);
-                da0[4 * q + 3] = fmaf(w.w, d1, da0[4 * q + 3]);
+        for (int j = 0; j < G2; ++j) g2n[j] = (gh2p && j < k.out_ch) ? __ldg(gh2p + (long)j * g.npad) : 0.f;
+        for (int c0 = 0; c0 < k.out_ch; c0 += G2) {
+            float g2c[G2];
+#pragma unroll
+            for (int j = 0; j < G2; ++j) {
+                g2c[j] = g2n[j];
+                g2n[j] = (gh2p && c0 + G2 + j < k.out_ch) ? __ldg(gh2p + (long)(c0 + G2 + j) * g.npad) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < G2; ++j) {
+                const int c = c0 + j;
+                if (c < k.out_ch) {
+                    const float pre1 = lift_second_layer_row<HID>(sWb + c * HID, sbb[c], a0);
+                    const float gv = D1[c * kPixTPP + tid] + g2c[j];   // own asynchronous copy (complete after wait_group) + second source
+                    const float d1 = gv * gelu_der(pre1);
+                    D1[c * kPixTPP + tid] = d1;
+                    const float4* w4 = reinterpret_cast<const float4*>(sWb + c * HID);
+#pragma unroll
+                    for (int q = 0; q < HID / 4; ++q) {
+                        const float4 w = w4[q];
+                        da0[4 * q + 0] = fmaf(w.x, d1, da0[4 * q + 0]);
+                        da0[4 * q + 1] = fmaf(w.y, d1, da0[4 * q + 1]);
+                        da0[4 * q + 2] = fmaf(w.z, d1, da0[4 * q + 2]);
+                        da0[4 * q + 3] = fmaf(w.w, d1, da0[4 * q + 3]);
+                    }
+                }
             }
         }
 #pragma unroll

@@ -1002,11 +1002,11 @@ int num_sms() {
 }
 
 
-template <int EPI, int G, int J, bool HINT = false>
+template <int EPI, int G, int J>
 int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI, G, J, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::rowgemm_smallk_kernel<EPI, G, J>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
@@ -1014,7 +1014,7 @@ int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t
     if (p.parity) gx &= ~1;                 // a CTA must only ever see tiles of one row parity (m_tiles is even too)
     if (gx < 1 + p.parity) gx = 1 + p.parity;
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
-    tc::rowgemm_smallk_kernel<EPI, G, J, HINT><<<dim3(gx, p.n_tiles), tc::rowgemm_threads(G), smem, st>>>(p);
+    tc::rowgemm_smallk_kernel<EPI, G, J><<<dim3(gx, p.n_tiles), tc::rowgemm_threads(G), smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1023,10 +1023,7 @@ template <int EPI>
 int launch_rowgemm(const tc::RowGemmParams& p, size_t smem, cudaStream_t st) {
     // 16 epilogue warps of 32x16 elements per round (default: measured 3.66 -> 3.62 ms per Darcy step, 0.57 -> 0.51 ms per
     // NS-2D call) or 8 warps of 32x32; same arithmetic in the same order, bit-identical results
-    if (cfg(CFG_ROWGEMM_EPI16)) {
-        if (EPI != EPI_STORE && (cfg(CFG_EXP0) & 1)) return launch_rowgemm_variant<EPI, 4, 1, true>(p, smem, st);   // experiment: L2::256B addend loads
-        return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
-    }
+    if (cfg(CFG_ROWGEMM_EPI16)) return launch_rowgemm_variant<EPI, 4, 1>(p, smem, st);
     return launch_rowgemm_variant<EPI, 2, 2>(p, smem, st);
 }
 

@@ -70,7 +70,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // Epilogue of one 128-row tile for one warp: TMEM lane quarter `q`, 16-column chunks c0 = 16*(2*i + half).
 // All loads of a 32-column group are issued before any store so that they are in flight together; the four
 // row pointers of a thread are formed once per tile (no 64-bit multiplies in the column loop).
-template <int EPI, bool VEC2, int G = 2, int J = 2, bool HINT = false>
+template <int EPI, bool VEC2, int G = 2, int J = 2>
 __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half, int lane) {
     static_assert(J == 1 || J == 2, "one or two 16-column chunks per round");
     constexpr bool kAccum = (EPI != EPI_STORE);
@@ -108,13 +108,8 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
                 const float* q = rowp[hh * 2 + rr] + c;
                 cz[e] = make_float2(0.f, 0.f);
                 const bool in0 = live && c >= cmin && c < ncol, in1 = live && c + 1 < ncol;
-                if (VEC2 && in0 && in1) {
-                    if constexpr (HINT) {   // a lane quad reads one 32-byte sector of a row per instruction: ask L2 for the whole 256 bytes
-                        asm volatile("ld.global.L2::256B.v2.f32 {%0, %1}, [%2];" : "=f"(cz[e].x), "=f"(cz[e].y) : "l"(q));
-                    } else {
-                        cz[e] = *reinterpret_cast<const float2*>(q);
-                    }
-                }
+                // (an L2::256B prefetch hint on these addend loads measured 3.66 against 3.70 ms per Darcy step: not kept)
+                if (VEC2 && in0 && in1) cz[e] = *reinterpret_cast<const float2*>(q);
                 else {
                     if (in0) cz[e].x = q[0];
                     if (in1) cz[e].y = q[1];
@@ -147,7 +142,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
 
 // (A software-pipelined form of this epilogue that loaded the next round's addend before storing the current round was measured
 // on B200 and was no faster -- 3.68 vs 3.62 ms per Darcy step -- so it was removed.)
-template <int EPI, int G = 2, int J = 2, bool HINT = false>
+template <int EPI, int G = 2, int J = 2>
 __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(const RowGemmParams p) {
     constexpr int kRowGemmEpiWarps = rowgemm_epi_warps(G);   // shadows the default-configuration constant
     extern __shared__ __align__(128) uint8_t smem[];
@@ -285,8 +280,8 @@ __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(c
             mbar_wait_relaxed(&d_full[s], ph);
             tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);
-            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J, HINT>(p, t_base, tile, q, n_base, half, lane);
-            else rowgemm_epilogue_tile<EPI, false, G, J, HINT>(p, t_base, tile, q, n_base, half, lane);
+            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane);
+            else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane);
             tc_fence_before();
             mbar_arrive(&d_empty[s]);
         }

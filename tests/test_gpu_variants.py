@@ -38,7 +38,7 @@ SHAPES_2D = [
 ]
 
 
-@pytest.mark.parametrize("which", ["mid", "cmm", "both", "simt"])
+@pytest.mark.parametrize("which", ["mid", "cmm", "cmm1", "both", "simt"])
 @pytest.mark.parametrize("shape", SHAPES_2D)
 def test_spectral2d_tc_core(shape, which, cuda_lib):
     from uno_b200 import integral_operators as ops
@@ -57,7 +57,9 @@ def test_spectral2d_tc_core(shape, which, cuda_lib):
         return (y.detach().cpu().numpy(), xx.grad.cpu().numpy(), torch.view_as_real(m.weights1.grad).cpu().numpy(),
                 torch.view_as_real(m.weights2.grad).cpu().numpy())
 
-    sw = {"mid_tc": int(which in ("mid", "both")), "cmm_tc": 2 * int(which in ("cmm", "both"))}   # 2 = every shape, not only tile-filling ones
+    # cmm_tc = 2: every shape, not only tile-filling ones; "cmm1": the one-mode-per-item kernel (tc_cmm.cuh) also where the
+    # four-mode kernel (tc_cmm4.cuh) would take the shape
+    sw = {"mid_tc": int(which in ("mid", "both")), "cmm_tc": 2 * int(which in ("cmm", "cmm1", "both")), "exp0": 4 if which == "cmm1" else 0}
     y_tc, gx_tc, gw1_tc, gw2_tc = _with(run, **sw)
     ws = [m.weights1.detach().cpu().numpy(), m.weights2.detach().cpu().numpy()]
     y_or = orc.spectral_conv_fwd(x.cpu().numpy(), ws, odim, modes)

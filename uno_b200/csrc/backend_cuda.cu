@@ -30,6 +30,7 @@
 #include "tc_kpipe.cuh"
 #include "tc_mid.cuh"
 #include "tc_cmm.cuh"
+#include "tc_cmm4.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
 
@@ -1214,6 +1215,37 @@ int try_tc_mid(const MidArgs& a, cudaStream_t st) {
 // ---- per-mode complex contraction on tcgen05 (tc_cmm.cuh); switch cmm_tc, default on for shapes that fill a tile -----
 bool cmm_tc_enabled() { return cfg(CFG_CMM_TC) != 0; }
 
+int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
+    tc::Cmm4Params p;
+    p.a = a;
+    p.ns_tiles = (a.M + 63) / 64;
+    const int per = (a.M + p.ns_tiles - 1) / p.ns_tiles;
+    p.N_t = ((per + 15) / 16) * 16;
+    p.ms_tiles = (2 * a.N + 127) / 128;
+    p.n_chunks = (a.K + 3) / 4;
+    p.qg = (a.q_inner + 3) / 4;
+    int stages = (int)((200 * 1024) / tc::cmm4_stage_bytes(p.N_t));
+    if (stages > 4) stages = 4;
+    if (stages < 2) return -1;
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * tc::kC4Modes * p.N_t) cols *= 2;
+    if (cols > 512) return -1;
+    p.tmem_cols = cols;
+    p.items = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * p.qg;
+    static DeviceOnce configured;
+    if (!configured.done()) {
+        cudaError_t e = cudaFuncSetAttribute(tc::cmm_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured.mark();
+    }
+    long gx = num_sms();
+    if (gx > p.items) gx = p.items;
+    tc::cmm_tc4_kernel<<<(unsigned)gx, tc::kKpThreads, tc::cmm4_smem_bytes(p.N_t, stages), st>>>(p);
+    CU_LAUNCH_CHECK();
+    return 0;
+}
+
 // returns -1 when the shape is not taken (the caller runs the SIMT kernels)
 int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
     if (!cmm_tc_enabled() || !tc_enabled()) return -1;
@@ -1229,6 +1261,15 @@ int try_tc_cmm(const CmmArgs& a, cudaStream_t st) {
     for (int c = 0; c < a.ncorner; ++c)
         if ((reinterpret_cast<uintptr_t>(a.A[c]) & 7) || (reinterpret_cast<uintptr_t>(a.B[c]) & 7) || (reinterpret_cast<uintptr_t>(a.C[c]) & 7))
             return -1;
+    {   // four modes per item (tc_cmm4.cuh) when every operand is 16-byte friendly: whole-sector loads and stores
+        bool even = ((a.a_sm | a.a_sk | a.a_sqo | a.b_sk | a.b_sn | a.b_sqo | a.c_sm | a.c_sn | a.c_sqo) & 1) == 0;
+        for (int c = 0; c < a.ncorner; ++c)
+            if ((reinterpret_cast<uintptr_t>(a.A[c]) | reinterpret_cast<uintptr_t>(a.B[c]) | reinterpret_cast<uintptr_t>(a.C[c])) & 15) even = false;
+        if (even && cfg(CFG_EXP0) != 4) {
+            const int rc = launch_tc_cmm4(a, st);
+            if (rc >= 0) return rc;
+        }
+    }
     tc::CmmTcParams p;
     p.a = a;
     p.ns_tiles = (a.M + 63) / 64;

@@ -18,6 +18,19 @@ BWD_TOL = 5e-5
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs two CUDA devices (run with `gpurun --gpus 2 -- python -m pytest tests -m multigpu`)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Two-GPU tests run only when asked for by name (-m multigpu): a one-GPU box or the CPU suite neither runs nor skips them."""
+    if "multigpu" in (config.getoption("-m") or ""):
+        return
+    keep, drop = [], []
+    for it in items:
+        (drop if it.get_closest_marker("multigpu") else keep).append(it)
+    if drop:
+        config.hook.pytest_deselected(items=drop)
+        items[:] = keep
 
 
 def rel_err(a, b):

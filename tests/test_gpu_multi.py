@@ -1,4 +1,4 @@
-"""GPU, >= 2 devices (run with `gpurun --gpus 2`; skipped on a one-GPU box): batch-sharded data parallelism over NCCL.
+"""GPU, >= 2 devices (`gpurun --gpus 2 -- python -m pytest tests -m multigpu`): batch-sharded data parallelism over NCCL.
 
 SURVEY.md section 4 / 8(e): a global batch B on one GPU and B/N per rank on N ranks with the SUM all-reduce of
 uno_b200.parallel.GradReducer must give the same loss and the same gradient of every parameter -- eagerly (bucketed all-reduce
@@ -15,7 +15,7 @@ import torch.multiprocessing as mp
 
 from conftest import ROOT
 
-pytestmark = pytest.mark.gpu
+pytestmark = pytest.mark.multigpu
 
 
 def _free_port():

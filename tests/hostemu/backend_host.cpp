@@ -26,7 +26,7 @@ int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); ret
 const char* be_name() { return "host-emulation"; }
 int be_current_device() { return 0; }
 const char* be_error_string(int) { return "host emulation error"; }
-stream_t be_side_stream() { return nullptr; }
+stream_t be_side_stream(int) { return nullptr; }
 int be_fork(stream_t, stream_t) { return 0; }
 int be_join(stream_t, stream_t) { return 0; }
 size_t be_profile_report(char* buf, size_t cap) { if (buf && cap > 2) { buf[0] = '{'; buf[1] = '}'; buf[2] = 0; } return 2; }

@@ -363,3 +363,36 @@ def test_lift_fanout_matches_autograd_accumulation(cuda_lib):
 
     for u, v in zip(run(True), run(False)):
         assert np.abs(u - v).max() <= 2e-5 * max(float(np.abs(v).max()), 1e-6)
+
+
+@pytest.mark.parametrize("case", ["2d_norm", "2d_plain", "3d"])
+def test_branch_overlap_matches_serial(case, cuda_lib):
+    """overlap: the pointwise branch of a block on the library's side stream, the spectral branch on the caller's, joined before
+    the fused epilogue (forward) / before the accumulation onto gx (backward).  Same kernels, same results as one stream."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(7)
+    if case == "3d":
+        blk = ops.OperatorBlock_3D(4, 6, 12, 12, 9, 4, 4, 3, Normalize=True).cuda()
+        x = torch.randn(2, 4, 16, 16, 9, device="cuda")
+        odim = (12, 12, 9)
+    else:
+        blk = ops.OperatorBlock_2D(8, 16, 60, 52, 9, 7, Normalize=(case == "2d_norm")).cuda()
+        x = torch.randn(3, 8, 120, 101, device="cuda")
+        odim = (60, 52)
+    gy = torch.randn(x.shape[0], blk.conv.out_channels, *odim, device="cuda")
+
+    def run():
+        out = []
+        for _ in range(3):          # repeated: a missing join shows up as a race between iterations
+            xx = x.clone().requires_grad_(True)
+            blk.zero_grad(set_to_none=True)
+            y = blk(xx, *odim)
+            y.backward(gy)
+            out = [y.detach().cpu().numpy(), xx.grad.cpu().numpy()] + [
+                (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).cpu().numpy() for p in blk.parameters()]
+        return out
+
+    a, b = _with(run, overlap=1), _with(run, overlap=0)
+    for u, v in zip(a, b):
+        assert np.abs(u - v).max() <= 1e-5 * max(float(np.abs(v).max()), 1e-6), rel_err(u, v)

@@ -26,7 +26,7 @@ const char* be_error_string(int code);   // message for a non-zero return of any
 // for everything enqueued on `main` so far; be_join makes `main` wait for everything enqueued on `side` so far.
 // Both are event record + stream-wait pairs: asynchronous, capturable in a CUDA graph, and invisible to the caller,
 // whose stream still orders the whole call.  Returning NULL from be_side_stream disables the overlap.
-stream_t be_side_stream();
+stream_t be_side_stream(int which = 0);   // which = 0, 1: two independent side streams per device
 int be_fork(stream_t main_stream, stream_t side);
 int be_join(stream_t main_stream, stream_t side);
 

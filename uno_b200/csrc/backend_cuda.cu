@@ -1542,20 +1542,23 @@ cudaEvent_t side_event(int dev) {
 }
 }  // namespace
 
-stream_t be_side_stream() {
+stream_t be_side_stream(int which) {
     std::lock_guard<std::mutex> lk(g_side.mu);
     if (g_side.disabled) return nullptr;
-    // opt-in: measured on B200 the two branches of a Darcy-size block already fill the machine one kernel at a
-    // time (29.8 vs 30.1 ms per step with the overlap), and concurrent kernels blur the per-kernel timings the
-    // roofline report is built from -- so the fork/join path is off unless UNO_B200_OVERLAP=1
+    // Round 1 measured no gain from the overlap (every kernel filled the machine: 29.8 vs 30.1 ms per Darcy step).  The kernels
+    // have since become latency-bound persistent ones with 20-30 % of the warp slots occupied, and two of them side by side hide
+    // each other's stalls: 20.50 -> 20.27 ms (Darcy), 10.82 -> 10.43 (NS-3D), 4.76 -> 4.52 (NS-2D call).  Default on; bench.py
+    // switches it off for its per-kernel profiling steps (concurrent kernels blur the per-kernel event timings).
     if (!cfg(CFG_OVERLAP)) return nullptr;
+    if ((which & 1) && cfg(CFG_OVERLAP) == 2) return nullptr;   // 2: the branch overlap only, no third stream
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    auto it = g_side.streams.find(dev);
+    const int key = dev * 2 + (which & 1);
+    auto it = g_side.streams.find(key);
     if (it == g_side.streams.end()) {
         cudaStream_t st = nullptr;
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { g_side.disabled = true; return nullptr; }
-        it = g_side.streams.emplace(dev, st).first;
+        it = g_side.streams.emplace(key, st).first;
     }
     return (stream_t)it->second;
 }

@@ -19,7 +19,7 @@ const Entry kEntries[CFG_COUNT] = {
     {"rowgemm_epi16", "UNO_B200_ROWGEMM_EPI16", 1, false},
     {"rowgemm_parity", "UNO_B200_ROWGEMM_PARITY", 1, false},
     {"norm_big_cluster", "UNO_B200_NORM_BIG_CLUSTER", 1, false},
-    {"overlap", "UNO_B200_OVERLAP", 0, false},
+    {"overlap", "UNO_B200_OVERLAP", 1, false},
     {"pointwise3d_fixed", "UNO_B200_POINTWISE3D_FIXED", 0, false},
     {"proj_simt", "UNO_B200_PROJ_SIMT", 0, false},
     {"fused_core", "UNO_B200_FUSED_CORE", 1, false},

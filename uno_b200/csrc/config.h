@@ -14,7 +14,7 @@ enum CfgKey {
     CFG_ROWGEMM_EPI16,      // synthesis kernel: 16 epilogue warps
     CFG_ROWGEMM_PARITY,     // synthesis kernel: row-parity tiles for odd row pitch
     CFG_NORM_BIG_CLUSTER,   // InstanceNorm cluster kernels with 200 KB per CTA for planes beyond 8 x 72 KB
-    CFG_OVERLAP,            // fork / join of the two block branches on a side stream
+    CFG_OVERLAP,            // fork / join of the two block branches (pointwise / spectral) on a library-owned side stream; default on
     CFG_POINTWISE3D_FIXED,  // NOT the reference's behaviour: band-limited 3-D pointwise resample
     CFG_PROJ_SIMT,          // projection backward on the fp32 kernel instead of the tcgen05 one
     CFG_FUSED_CORE,         // leading-axis analysis + contraction + leading-axis synthesis in one kernel where it applies

@@ -439,9 +439,10 @@ int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, c
     return 0;
 }
 
+// `wst`: stream for the weight-gradient contraction dW (independent of the dX chain once ghat exists); the caller joins it.
 int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, const float* xhat,
                       const float* const* w, float* gx, float* const* gw, int accumulate_gx, Arena& ar,
-                      stream_t st, stream_t join_side = nullptr) {
+                      stream_t st, stream_t join_side = nullptr, stream_t wst = nullptr) {
     const int nd = d->ndim, nmid = nd - 1, ml = d->modes[nd - 1];
     const long Pin = (long)d->batch * d->in_ch, Pout = (long)d->batch * d->out_ch;
     SpectralSizes sz = spectral_sizes(d);
@@ -473,7 +474,14 @@ int spectral_bwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* gy, 
         ca.b_sk = (long)d->out_ch * Q; ca.b_sn = Q; ca.b_sqo = sqx;
         ca.c_sm = (long)d->out_ch * Qw; ca.c_sn = Qw; ca.c_sqo = sqw;
         ca.M = d->in_ch; ca.N = d->out_ch; ca.K = d->batch; ca.q_outer = qo; ca.q_inner = qi;
-        if (n > 0) BE_TRY(be_cmm(ca, st));
+        if (n > 0) {
+            if (wst && wst != st) {
+                BE_TRY(be_fork(st, wst));
+                BE_TRY(be_cmm(ca, wst));
+            } else {
+                BE_TRY(be_cmm(ca, st));
+            }
+        }
     }
     if (gx) {   // dxhat[b,i,q] = sum_o ghat[b,o,q] conj(w[i,o,q])
         CmmArgs ca;
@@ -704,9 +712,13 @@ int pointwise_fwd_impl(const uno_conv_desc* d, ResamplePlan* rp, const float* x,
 }
 
 // gconv_b == NULL: the caller has already produced the bias gradient (fused into the activation backward)
+// `wst`: stream for the weight-gradient reduction (reads gz and the saved / recomputed resampled input, writes gconv_w); the
+// caller forks it from `st` before this call and joins it afterwards.  NULL: everything on `st`.
 int pointwise_bwd_impl(const uno_conv_desc* d, ResamplePlan* rp, const float* gz, const float* x,
                        const float* saved, const float* conv_w, float* gx, float* gconv_w,
-                       float* gconv_b, Arena& ar, stream_t st) {
+                       float* gconv_b, Arena& ar, stream_t st, stream_t wst = nullptr) {
+    if (!wst || (!saved && resample_first(d) && !pw_geom(d).identity)) wst = st;   // (a recomputed resample feeds the reduction: keep one stream)
+    if (wst != st) BE_TRY(be_fork(st, wst));
     PwGeom g = pw_geom(d);
     const int B = d->batch, Ci = d->in_ch, Co = d->out_ch;
     const float gain = g.identity ? 1.0f : (float)rp->gain;
@@ -714,14 +726,18 @@ int pointwise_bwd_impl(const uno_conv_desc* d, ResamplePlan* rp, const float* gz
         BE_TRY(be_memset(gconv_b, 0, Co * sizeof(float), st));
         BE_TRY(be_channel_sum(gz, gconv_b, (long)B * Co, Co, g.n_out, gain, st));
     }
-    if (gconv_w) BE_TRY(be_memset(gconv_w, 0, (size_t)Co * Ci * sizeof(float), st));
+    if (gconv_w) BE_TRY(be_memset(gconv_w, 0, (size_t)Co * Ci * sizeof(float), wst));
     auto wgrad = [&](const float* gmat, const float* act, long npix) {
         GemmNtArgs a;
         a.A = gmat; a.lda = npix; a.sA = (long)Co * npix;
         a.B = act; a.ldb = npix; a.sB = (long)Ci * npix;
         a.C = gconv_w; a.ldc = Ci;
         a.M = Co; a.N = Ci; a.K = (int)npix; a.batch = B;
-        return be_gemm_nt_atomic(a, st);
+        if (wst != st) {            // the reduction's inputs were produced on `st`
+            const int rc = be_fork(st, wst);
+            if (rc) return rc;
+        }
+        return be_gemm_nt_atomic(a, wst);
     };
     if (g.identity) {
         if (gconv_w) BE_TRY(wgrad(gz, x, g.n_in));
@@ -1022,16 +1038,20 @@ int uno_operator_block_bwd2(const uno_block_desc* bd, const float* gy, long gy_b
     // caller's stream up to its last stage, which accumulates onto gx after the join
     const size_t pw_floats = pw_ws_floats(d);
     if (ar.off + pw_floats > ar.cap) return fail(UNO_EWORKSPACE, "workspace too small for operator block backward");
-    stream_t side = be_side_stream();
+    // A third stream takes the two weight-gradient reductions (the 1x1 conv's and the spectral weights'): they only read
+    // tensors the other two chains read too and write nothing those chains touch.
+    stream_t side = be_side_stream(0);
+    stream_t side2 = side ? be_side_stream(1) : nullptr;
     if (side) BE_TRY(be_fork(stream, side));
     {
         Arena sub(ar.base + ar.off, pw_floats * sizeof(float));
-        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, bias_done ? nullptr : gconv_b, sub, side ? side : stream));
+        UNO_TRY(pointwise_bwd_impl(d, rp, gs, x, pw_saved, conv_w, gx, gconv_w, bias_done ? nullptr : gconv_b, sub, side ? side : stream, side2));
     }
     {
         Arena sub(ar.base + ar.off + pw_floats, (ar.cap - ar.off - pw_floats) * sizeof(float));
-        UNO_TRY(spectral_bwd_impl(d, sp, gs, xhat, w, gx, gw, /*accumulate_gx=*/1, sub, stream, side));
+        UNO_TRY(spectral_bwd_impl(d, sp, gs, xhat, w, gx, gw, /*accumulate_gx=*/1, sub, stream, side, side2));
     }
+    if (side2) BE_TRY(be_join(stream, side2));
     return 0;
 }
 

@@ -494,6 +494,8 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
 
         was_overlap = _cfg.get("overlap")
         _cfg.set("overlap", 0)
+        prof_step(x, y)      # untimed: first use of the single-stream configuration (per-stream scratch is allocated on first use)
+        ctx.sync_all()
         if rank == 0:
             lib.uno_profile_enable(1)
         nprof = 2

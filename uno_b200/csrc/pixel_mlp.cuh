@@ -63,6 +63,57 @@ __device__ __forceinline__ float sum_tile(const float* __restrict__ r) {
     }
     return (s0 + s1) + (s2 + s3);
 }
+// acc[(4 ab + r) * ldo + 4 bb + j] += sum over the tile's 256 pixels of A[4 ab + r][px] * Bm[4 bb + j][px]   (rows kPixTPP apart)
+// for ab < nab, bb < nbb, skipping rows >= a_valid and columns >= b_valid.  Register-tiled: a warp takes a block of four A rows,
+// its lanes split into four B blocks x eight pixel phases (lane = 8 * bq + pr, pixels 4 (pr + 8 step) .. +3), so every 16-byte
+// shared-memory load feeds sixteen products -- the one-dot-product-per-thread form it replaces read two floats per product and
+// was bound by shared-memory bandwidth (256 16-byte loads per thread and tile against 64 here).  Partial sums of the eight
+// pixel phases meet in three shuffles.  Every lane of the CTA must call it (uniform control flow).
+__device__ __forceinline__ void tile_outer_4x4(const float* __restrict__ A, int nab, int a_valid, const float* __restrict__ Bm, int nbb,
+                                               int b_valid, float* __restrict__ acc, int ldo) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pr = lane & 7, bq = lane >> 3;
+    for (int ab = warp; ab < nab; ab += kPixTP / 32) {
+        for (int bb0 = 0; bb0 < nbb; bb0 += 4) {
+            const int bb = bb0 + bq;
+            const bool active = bb < nbb;
+            const float* ap = A + (size_t)(4 * ab) * kPixTPP + 4 * pr;
+            const float* bp = Bm + (size_t)(4 * (active ? bb : 0)) * kPixTPP + 4 * pr;
+            float s[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[r][j] = 0.f;
+#pragma unroll 2
+            for (int step = 0; step < kPixTP / 32; ++step) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(ap + r * kPixTPP + 32 * step);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(bp + j * kPixTPP + 32 * step);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s[r][j] = fmaf(a[r].x, b[j].x, s[r][j]);
+                        s[r][j] = fmaf(a[r].y, b[j].y, s[r][j]);
+                        s[r][j] = fmaf(a[r].z, b[j].z, s[r][j]);
+                        s[r][j] = fmaf(a[r].w, b[j].w, s[r][j]);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = s[r][j];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    if (pr == 0 && active && 4 * ab + r < a_valid && 4 * bb + j < b_valid) acc[(4 * ab + r) * ldo + 4 * bb + j] += v;
+                }
+        }
+    }
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -330,14 +381,8 @@ __global__ void __launch_bounds__(kPixTP) lift_bwd_kernel(const LiftK k, long nt
         }
         __syncthreads();
         // ---- phase 2: contract the staged tile over its 256 pixels
-        for (int e = tid; e < k.out_ch * HID; e += kPixTP) {
-            const int c = e / HID, kk = e % HID;
-            accWb[e] += dot_tile(D1 + c * kPixTPP, A0 + kk * kPixTPP);
-        }
-        for (int e = tid; e < HID * CIN; e += kPixTP) {
-            const int kk = e / CIN, ci = e % CIN;
-            accWa[e] += dot_tile(D0 + kk * kPixTPP, IN + ci * kPixTPP);
-        }
+        tile_outer_4x4(D1, OC4 / 4, k.out_ch, A0, HID / 4, HID, accWb, HID);        // dW_b[c][kk] += D1[c] . A0[kk]
+        tile_outer_4x4(D0, HID / 4, HID, IN, CIN / 4, CIN, accWa, CIN);             // dW_a[kk][ci] += D0[kk] . IN[ci]
         if (tid < k.out_ch) accbb[tid] += sum_tile(D1 + tid * kPixTPP);
         else if (tid >= 128 && tid < 128 + HID) accba[tid - 128] += sum_tile(D0 + (tid - 128) * kPixTPP);
         __syncthreads();

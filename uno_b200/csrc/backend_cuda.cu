@@ -2016,9 +2016,8 @@ int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
         const long ntiles = ((long)k.batch * k.g.nraw + kPixTP - 1) / kPixTP;
         const unsigned grid = (unsigned)std::min<long>(ntiles, 148L * 2);     // persistent, two CTAs per SM
         proj_fwd_kernel<CT><<<grid, kPixTP, smem, st>>>(k, ntiles);
-    } else if (k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && !cfg(CFG_PROJ_SIMT) && tc_enabled() &&
-               (CT == 64 || cfg(CFG_EXP1) != 1)) {
-        // (also for fewer than 33 channels -- the 24 of Uno3D_T10: the kernel pads to 64 internally; exp1 = 1 keeps the fp32 kernel there)
+    } else if (k.hid <= kProjHC && k.out_ch == 1 && k.pre_in != nullptr && !cfg(CFG_PROJ_SIMT) && tc_enabled()) {
+        // (also for fewer than 33 channels -- the 24 of Uno3D_T10: the kernel pads to 64 internally; 0.91 -> 0.64 ms per NS-3D step)
         // DEFAULT for the shipped shapes (64 channels, hid <= 32, one output, pre-activations kept by forward):
         // warp-specialised tcgen05 kernel, 1.6 ms at Darcy size against 3.4 ms for the fp32 kernel (switch proj_simt)
         const size_t smem = proj_bwd_tcp_smem(k.hid, k.out_ch);

@@ -700,6 +700,7 @@ def main():
                        "parallelism": f"dp{world} (batch shard, flat-buffer gradient all-reduce)" if world > 1 else "single GPU",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "execution": head["execution"], "graph_error": head["graph_error"],
             "roofline": head["roofline"], "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
             ("strong" if main_mode == "weak" else "weak"): other, "secondary": secondary,
             "kernel_breakdown": head["kernel_breakdown"], "spectral_levels": head["spectral_levels"], "sweep": sweep,

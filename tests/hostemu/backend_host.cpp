@@ -25,6 +25,8 @@ void be_free(void* d) { free(d); }
 int be_memset(void* d, int v, size_t bytes, stream_t) { memset(d, v, bytes); return 0; }
 const char* be_name() { return "host-emulation"; }
 int be_current_device() { return 0; }
+void be_range_push(const char*) {}
+void be_range_pop() {}
 const char* be_error_string(int) { return "host emulation error"; }
 stream_t be_side_stream(int) { return nullptr; }
 int be_fork(stream_t, stream_t) { return 0; }

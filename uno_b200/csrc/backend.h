@@ -46,6 +46,9 @@ void be_profile_scope_begin(const char* label, double bytes, double flops);
 void be_profile_scope_end();
 size_t be_profile_report_scopes(char* buf, size_t cap);
 long be_launch_count();                  // kernels launched by this library since load
+// NVTX ranges: no-ops unless the switch `nvtx` is on
+void be_range_push(const char* label);
+void be_range_pop();
 
 // ---- C[M,N] = A[M,K] * B[K,N]  (fp32, row-major B and C, strided A), optionally batched -----------
 enum GemmEpi {

@@ -11,6 +11,7 @@
 // Everything here is fp32 FMA on the SIMT pipes with fp32 accumulation; the tensor-core variants of
 // the GEMM-shaped stages live in gemm_tc.cuh and are selected by be_gemm when the shape qualifies.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -1521,6 +1522,13 @@ size_t be_profile_report(char* buf, size_t cap) {
 }
 
 long be_launch_count() { return g_launches.load(); }
+
+void be_range_push(const char* label) {
+    if (cfg(CFG_NVTX)) nvtxRangePushA(label);
+}
+void be_range_pop() {
+    if (cfg(CFG_NVTX)) nvtxRangePop();
+}
 
 // ---- side stream + event ring for fork / join -----------------------------------------------------------
 namespace {

@@ -23,6 +23,7 @@ const Entry kEntries[CFG_COUNT] = {
     {"pointwise3d_fixed", "UNO_B200_POINTWISE3D_FIXED", 0, false},
     {"proj_simt", "UNO_B200_PROJ_SIMT", 0, false},
     {"fused_core", "UNO_B200_FUSED_CORE", 1, false},
+    {"nvtx", "UNO_B200_NVTX", 0, false},
     {"exp0", "UNO_B200_EXP0", 0, false},
     {"exp1", "UNO_B200_EXP1", 0, false},
     {"exp2", "UNO_B200_EXP2", 0, false},

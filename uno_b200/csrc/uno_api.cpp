@@ -377,9 +377,10 @@ void corner_geometry(const SpectralPlan* p, int c, long* off, int* q_outer, int*
 // reads / writes on top of the plain layer (forward: the pointwise sum it accumulates onto and, with GELU to a second
 // tensor, that tensor; backward: the input gradient it accumulates onto, when it does).
 struct SpectralProfScope {
-    bool on = false;
+    bool on = false, range = false;
     SpectralProfScope(const uno_conv_desc* d, bool backward, int extra_out_tensors) {
-        if (!be_profile_enabled()) return;
+        range = cfg(CFG_NVTX) != 0;
+        if (!be_profile_enabled() && !range) return;
         const int nd = d->ndim;
         double n_in = 1, n_out = 1, M = 1;
         for (int a = 0; a < nd; ++a) { n_in *= d->in_dim[a]; n_out *= d->out_dim[a]; M *= d->modes[a]; }
@@ -397,10 +398,23 @@ struct SpectralProfScope {
         o += snprintf(label + o, sizeof label - o, "] modes=[");
         for (int a = 0; a < nd; ++a) o += snprintf(label + o, sizeof label - o, "%s%d", a ? "," : "", d->modes[a]);
         snprintf(label + o, sizeof label - o, "]");
-        be_profile_scope_begin(label, bytes, flops);
-        on = true;
+        if (range) be_range_push(label);          // one NVTX range per fused spectral convolution (U-level and direction)
+        if (be_profile_enabled()) {
+            be_profile_scope_begin(label, bytes, flops);
+            on = true;
+        }
     }
-    ~SpectralProfScope() { if (on) be_profile_scope_end(); }
+    ~SpectralProfScope() {
+        if (on) be_profile_scope_end();
+        if (range) be_range_pop();
+    }
+};
+
+// NVTX range around one C-ABI call (switch `nvtx`)
+struct ApiRange {
+    bool on;
+    explicit ApiRange(const char* name) : on(cfg(CFG_NVTX) != 0) { if (on) be_range_push(name); }
+    ~ApiRange() { if (on) be_range_pop(); }
 };
 
 int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, const float* const* w,
@@ -859,6 +873,7 @@ size_t uno_spectral_conv_xhat_elems(const uno_conv_desc* d) {
 
 int uno_spectral_conv_fwd(const uno_conv_desc* d, const float* x, const float* const* w, float* y,
                           float* xhat, void* ws, size_t ws_bytes, void* stream) {
+    ApiRange api_range("uno_spectral_conv_fwd");
     UNO_TRY(check_conv_desc(d, true));
     if (!x || !w || !y) return fail(UNO_EINVAL, "null tensor pointer");
     SpectralPlan* p;
@@ -870,6 +885,7 @@ int uno_spectral_conv_fwd(const uno_conv_desc* d, const float* x, const float* c
 int uno_spectral_conv_bwd(const uno_conv_desc* d, const float* gy, const float* xhat,
                           const float* const* w, float* gx, float* const* gw, int accumulate_gx,
                           void* ws, size_t ws_bytes, void* stream) {
+    ApiRange api_range("uno_spectral_conv_bwd");
     UNO_TRY(check_conv_desc(d, true));
     if (!gy || !xhat || !w) return fail(UNO_EINVAL, "null tensor pointer");
     SpectralPlan* p;
@@ -893,6 +909,7 @@ size_t uno_pointwise_saved_elems(const uno_conv_desc* d) {
 int uno_pointwise_fwd(const uno_conv_desc* d, const float* x, const float* conv_w,
                       const float* conv_b, float* z, float* saved, void* ws, size_t ws_bytes,
                       void* stream) {
+    ApiRange api_range("uno_pointwise_fwd");
     UNO_TRY(check_conv_desc(d, false));
     if (!x || !conv_w || !conv_b || !z) return fail(UNO_EINVAL, "null tensor pointer");
     ResamplePlan* rp;
@@ -904,6 +921,7 @@ int uno_pointwise_fwd(const uno_conv_desc* d, const float* x, const float* conv_
 int uno_pointwise_bwd(const uno_conv_desc* d, const float* gz, const float* x, const float* saved,
                       const float* conv_w, float* gx, float* gconv_w, float* gconv_b, void* ws,
                       size_t ws_bytes, void* stream) {
+    ApiRange api_range("uno_pointwise_bwd");
     UNO_TRY(check_conv_desc(d, false));
     if (!gz || !x || !conv_w) return fail(UNO_EINVAL, "null tensor pointer");
     ResamplePlan* rp;
@@ -921,6 +939,7 @@ int uno_operator_block_fwd(const uno_block_desc* bd, const float* x, const float
                            const float* conv_w, const float* conv_b, const float* gamma,
                            const float* beta, float* y, float* xhat, float* pw_saved, float* pre,
                            float* stats, void* ws, size_t ws_bytes, void* stream) {
+    ApiRange api_range("uno_operator_block_fwd");
     if (!bd) return fail(UNO_EINVAL, "null descriptor");
     const uno_conv_desc* d = &bd->conv;
     UNO_TRY(check_conv_desc(d, true));
@@ -981,6 +1000,7 @@ int uno_operator_block_bwd2(const uno_block_desc* bd, const float* gy, long gy_b
                             const float* pre, const float* stats, const float* const* w, const float* conv_w,
                             const float* gamma, const float* beta, float* gx, float* const* gw, float* gconv_w,
                             float* gconv_b, float* ggamma, float* gbeta, void* ws, size_t ws_bytes, void* stream) {
+    ApiRange api_range("uno_operator_block_bwd2");
     if (!bd) return fail(UNO_EINVAL, "null descriptor");
     const uno_conv_desc* d = &bd->conv;
     UNO_TRY(check_conv_desc(d, true));
@@ -1060,6 +1080,7 @@ int uno_lift_check(const uno_lift_desc* d) { LiftArgs a; return make_lift_args(d
 
 int uno_lift_fwd(const uno_lift_desc* d, const float* a_, const float* grid, const float* w_a,
                  const float* b_a, const float* w_b, const float* b_b, float* h, void* stream) {
+    ApiRange api_range("uno_lift_fwd");
     LiftArgs a;
     UNO_TRY(make_lift_args(d, &a));
     if (!a_ || (!grid && d->grid_ch > 0) || !w_a || !b_a || !w_b || !b_b || !h) return fail(UNO_EINVAL, "null tensor pointer");
@@ -1077,6 +1098,7 @@ int uno_lift_bwd(const uno_lift_desc* d, const float* gh, const float* a_, const
 int uno_lift_bwd2(const uno_lift_desc* d, const float* gh, const float* gh2, const float* a_, const float* grid,
                   const float* w_a, const float* b_a, const float* w_b, const float* b_b, float* ga,
                   float* gw_a, float* gb_a, float* gw_b, float* gb_b, void* stream) {
+    ApiRange api_range("uno_lift_bwd2");
     LiftArgs a;
     UNO_TRY(make_lift_args(d, &a));
     if (!gh || !a_ || (!grid && d->grid_ch > 0) || !w_a || !b_a || !w_b || !b_b || !gw_a || !gb_a || !gw_b || !gb_b)
@@ -1097,6 +1119,7 @@ int uno_project_check(const uno_project_desc* d) { ProjArgs a; return make_proj_
 int uno_project_fwd(const uno_project_desc* d, const float* const* src, const float* w1,
                     const float* b1, const float* w2, const float* b2, float* out, float* hidden_pre,
                     void* stream) {
+    ApiRange api_range("uno_project_fwd");
     ProjArgs a;
     UNO_TRY(make_proj_args(d, &a));
     if (!src || !w1 || !b1 || !w2 || !b2 || !out) return fail(UNO_EINVAL, "null tensor pointer");
@@ -1112,6 +1135,7 @@ int uno_project_fwd(const uno_project_desc* d, const float* const* src, const fl
 int uno_project_bwd(const uno_project_desc* d, const float* gout, const float* const* src,
                     const float* hidden_pre, const float* w1, const float* b1, const float* w2,
                     float* const* gsrc, float* gw1, float* gb1, float* gw2, float* gb2, void* stream) {
+    ApiRange api_range("uno_project_bwd");
     ProjArgs a;
     UNO_TRY(make_proj_args(d, &a));
     if (!gout || !src || !w1 || !b1 || !w2 || !gw1 || !gb1 || !gw2 || !gb2) return fail(UNO_EINVAL, "null tensor pointer");

@@ -206,7 +206,7 @@ int uno_lp_loss_bwd(const float* x, const float* y, const float* norms, const fl
 
 /* ---- run-time switches -------------------------------------------------------------------------------
  * Kernel-selection switches (uno_b200/csrc/config.h: "tc", "mid_tc", "cmm_tc", "kpipe_align", "kpipe_lw16",
- * "rowgemm_epi16", "rowgemm_parity", "norm_big_cluster", "overlap", "pointwise3d_fixed", "proj_simt", "plane2d", "nvtx", ...).
+ * "rowgemm_epi16", "rowgemm_parity", "norm_big_cluster", "overlap", "pointwise3d_fixed", "proj_simt", "nvtx", ...).
  * Their initial values come from the environment ONCE, at first use (UNO_B200_<NAME>); afterwards only these calls change
  * them -- no call path reads the environment.  Every setting computes the same function (parity-tested on B200) except
  * "pointwise3d_fixed", which is documented as deviating from the reference.  uno_config_name(i) enumerates the names

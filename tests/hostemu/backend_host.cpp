@@ -27,9 +27,6 @@ const char* be_name() { return "host-emulation"; }
 int be_current_device() { return 0; }
 void be_range_push(const char*) {}
 void be_range_pop() {}
-int be_plane2d_supported(const Plane2dArgs&, int) { return 0; }   // the emulation always takes the two-stage path
-int be_analysis2d(const Plane2dArgs&, stream_t) { return -1; }
-int be_synthesis2d(const Plane2dArgs&, stream_t) { return -1; }
 const char* be_error_string(int) { return "host emulation error"; }
 stream_t be_side_stream(int) { return nullptr; }
 int be_fork(stream_t, stream_t) { return 0; }

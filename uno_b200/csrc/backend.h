@@ -90,23 +90,6 @@ struct MidArgs {
 };
 int be_mid(const MidArgs& a, stream_t s);
 
-// ---- both transform stages of a 2-D spectral analysis / synthesis on whole planes, one launch (small grids) ------------------------
-//   analysis   xhat[p, j, k] = sum_h mid[j, h] * ( sum_w x[p, h, w] * last[w, (k, re|im)] )      x [P, H, W] -> xhat [P, J, m] complex
-//   synthesis  y[p, h, w] (epi)= sum_c ( sum_j mid[h, j] * yhat[p, j, k] )_(c = (k, re|im)) * last[c, w]   yhat [P, J, m] -> y [P, H, W]
-// last: real row-major ([W x 2m] / [2m x W]); mid: complex interleaved row-major ([J x H] / [H x J]).  be_plane2d_supported
-// returns 0 for shapes the backend does not take (the caller then runs be_gemm + be_mid).
-struct Plane2dArgs {
-    long P = 0;
-    int H = 0, W = 0, J = 0, m = 0;
-    const float* last = nullptr; const float* mid = nullptr;
-    const float* x = nullptr; float* xhat = nullptr;                      // analysis
-    const float* yhat = nullptr; float* y = nullptr; float* y2 = nullptr; // synthesis
-    int epi = EPI_STORE;
-};
-int be_plane2d_supported(const Plane2dArgs& a, int synthesis);
-int be_analysis2d(const Plane2dArgs& a, stream_t s);
-int be_synthesis2d(const Plane2dArgs& a, stream_t s);
-
 // ---- per-mode complex contraction: C[m,n,q] = sum_k opA(A[m,k,q]) * opB(B[k,n,q]) -----------------
 // q = (qo, qi): qi contiguous (length q_inner), qo strided.  All strides in complex elements.
 // Up to four independent problems of identical shape (the spectrum corners weights1..4) run in one launch.

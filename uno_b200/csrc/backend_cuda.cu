@@ -895,7 +895,6 @@ int ensure_smem(K kernel, size_t bytes) {
 #include "pixel_mlp_tc.cuh"
 #include "resample2d.cuh"
 #include "norm_cluster.cuh"
-#include "spectral2d_small.cuh"
 #include "train_ops.cuh"
 
 
@@ -1644,65 +1643,6 @@ int be_gemm_nt_atomic(const GemmNtArgs& a, stream_t s) {
     // (tiling operands wider than 128 channels -- the 192-channel NS-2D levels -- into four tensor-core launches measured no
     // faster than the SIMT kernel below: 0.48 against 0.45 ms per NS-2D call, the operands are a few MB)
     return dispatch_gemm(k, a.batch, S(s));
-}
-
-// ---- whole-plane 2-D analysis / synthesis for small grids (spectral2d_small.cuh) ----------------------------------------------
-namespace {
-// planes per group and shared-memory bytes; PP = 0 when the shape does not fit
-int plane2d_config(const Plane2dArgs& a, int synthesis, size_t* smem) {
-    if (!cfg(CFG_PLANE2D) || a.P < 1 || a.H < 1 || a.W < 1 || a.H > 64 || a.W > 64 || a.J < 1 || a.J > 128 || a.m < 1 || 2 * a.m > 64) return 0;
-    int pp = std::max(1, std::min(8, 128 / a.H));
-    if ((long)pp > a.P) pp = (int)a.P;
-    for (; pp >= 1; --pp) {
-        const Spec2Layout L = synthesis ? spec2_layout_synthesis(a.H, a.W, a.J, a.m, pp) : spec2_layout_analysis(a.H, a.W, a.J, a.m, pp);
-        const size_t bytes = L.total * sizeof(float);
-        if (bytes <= (pp > 1 ? 110 * 1024 : 200 * 1024)) { *smem = bytes; return pp; }     // two CTAs per SM when a group of planes fits
-    }
-    return 0;
-}
-Spec2Small plane2d_params(const Plane2dArgs& a, int pp) {
-    Spec2Small k;
-    k.P = (int)a.P; k.H = a.H; k.W = a.W; k.J = a.J; k.m = a.m; k.PP = pp;
-    k.ldn = s2_round4(2 * a.m); k.ldw = s2_round4(a.W);
-    k.last = a.last; k.mid = a.mid; k.x = a.x; k.xhat = a.xhat; k.yhat = a.yhat; k.y = a.y; k.y2 = a.y2; k.epi = a.epi;
-    return k;
-}
-}  // namespace
-
-int be_plane2d_supported(const Plane2dArgs& a, int synthesis) {
-    size_t smem = 0;
-    return a.P <= 0x7fffffffL && plane2d_config(a, synthesis, &smem) > 0;
-}
-
-int be_analysis2d(const Plane2dArgs& a, stream_t s) {
-    size_t smem = 0;
-    const int pp = plane2d_config(a, 0, &smem);
-    if (pp < 1) return (int)cudaErrorInvalidValue;
-    int rc = ensure_smem(analysis2d_small_kernel, smem);
-    if (rc) return rc;
-    const double hw = (double)a.H * a.W, q = (double)a.J * 2 * a.m;
-    ProfScope ps("dft_plane_analysis", 4.0 * a.P * (hw + q), 2.0 * a.P * (hw * 2 * a.m + q * 2 * a.H), S(s));
-    const long groups = (a.P + pp - 1) / pp;
-    const unsigned grid = (unsigned)std::min<long>(groups, 2L * num_sms());
-    analysis2d_small_kernel<<<grid, 256, smem, S(s)>>>(plane2d_params(a, pp));
-    CU_LAUNCH_CHECK();
-    return 0;
-}
-
-int be_synthesis2d(const Plane2dArgs& a, stream_t s) {
-    size_t smem = 0;
-    const int pp = plane2d_config(a, 1, &smem);
-    if (pp < 1) return (int)cudaErrorInvalidValue;
-    int rc = ensure_smem(synthesis2d_small_kernel, smem);
-    if (rc) return rc;
-    const double hw = (double)a.H * a.W, q = (double)a.J * 2 * a.m;
-    const double outs = 1.0 + (a.epi != EPI_STORE ? 1.0 : 0.0) + (a.epi == EPI_ACCUM_GELU ? 1.0 : 0.0);
-    ProfScope ps("dft_plane_synthesis", 4.0 * a.P * (hw * outs + q), 2.0 * a.P * (hw * 2 * a.m + q * 2 * a.H), S(s));
-    const long groups = (a.P + pp - 1) / pp;
-    const unsigned grid = (unsigned)std::min<long>(groups, 2L * num_sms());
-    synthesis2d_small_kernel<<<grid, 256, smem, S(s)>>>(plane2d_params(a, pp));
-    CU_LAUNCH_CHECK();
-    return 0;
 }
 
 namespace {

@@ -22,7 +22,6 @@ const Entry kEntries[CFG_COUNT] = {
     {"overlap", "UNO_B200_OVERLAP", 1, false},
     {"pointwise3d_fixed", "UNO_B200_POINTWISE3D_FIXED", 0, false},
     {"proj_simt", "UNO_B200_PROJ_SIMT", 0, false},
-    {"plane2d", "UNO_B200_PLANE2D", 1, false},
     {"nvtx", "UNO_B200_NVTX", 0, false},
     {"exp0", "UNO_B200_EXP0", 0, false},
     {"exp1", "UNO_B200_EXP1", 0, false},

@@ -17,7 +17,6 @@ enum CfgKey {
     CFG_OVERLAP,            // fork / join of the two block branches (pointwise / spectral) on a library-owned side stream; default on
     CFG_POINTWISE3D_FIXED,  // NOT the reference's behaviour: band-limited 3-D pointwise resample
     CFG_PROJ_SIMT,          // projection backward on the fp32 kernel instead of the tcgen05 one
-    CFG_PLANE2D,            // small 2-D grids: last-axis + leading-axis transform of whole planes in ONE kernel (spectral2d_small.cuh)
     CFG_NVTX,               // NVTX ranges per C-ABI call and per fused spectral convolution (U-level), for nsys / ncu --nvtx
     CFG_EXP0, CFG_EXP1, CFG_EXP2,   // scratch switches for kernel experiments (0 = shipped behaviour)
     CFG_KPIPE_DEBUG,        // timing probes (tools/kpipe_probe.py): results become garbage

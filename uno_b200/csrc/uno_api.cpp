@@ -154,12 +154,6 @@ size_t analyse_stage_floats(long P, int nmid, const MidOp* mids, int m) {
 
 int analyse(const float* x, long P, int nmid, const MidOp* mids, int n_last, const float* last_mat,
             int m, float* out, float* ws0, float* ws1, stream_t st) {
-    if (nmid == 1) {   // small 2-D grids: both stages on whole planes in one launch
-        Plane2dArgs pa;
-        pa.P = P; pa.H = mids[0].n_in; pa.W = n_last; pa.J = mids[0].n_out; pa.m = m;
-        pa.last = last_mat; pa.mid = mids[0].mat; pa.x = x; pa.xhat = out;
-        if (be_plane2d_supported(pa, 0)) { BE_TRY(be_analysis2d(pa, st)); return 0; }
-    }
     long cur[2] = {1, 1};
     long R = P;
     for (int a = 0; a < nmid; ++a) { cur[a] = mids[a].n_in; R *= cur[a]; }
@@ -205,16 +199,6 @@ size_t synth_stage_floats(long P, int nmid, const MidOp* mids, int m) {
 int synthesise(const float* in, long P, int nmid, const MidOp* mids, int m, const float* last_mat,
                int n_last, float* y, int epi, float* y2, float* ws0, float* ws1, stream_t st,
                stream_t join_side = nullptr) {
-    if (nmid == 1) {   // small 2-D grids: both stages and the fused block epilogue on whole planes in one launch
-        Plane2dArgs pa;
-        pa.P = P; pa.H = mids[0].n_out; pa.W = n_last; pa.J = mids[0].n_in; pa.m = m;
-        pa.last = last_mat; pa.mid = mids[0].mat; pa.yhat = in; pa.y = y; pa.y2 = y2; pa.epi = epi;
-        if (be_plane2d_supported(pa, 1)) {
-            if (join_side) BE_TRY(be_join(st, join_side));
-            BE_TRY(be_synthesis2d(pa, st));
-            return 0;
-        }
-    }
     long cur[2] = {1, 1};
     for (int a = 0; a < nmid; ++a) cur[a] = mids[a].n_in;
     const float* src = in;

@@ -112,8 +112,8 @@ def test_glue_matches_torch_at_darcy_size(cuda_lib):
 
 @pytest.mark.parametrize("name", ["darcy", "tc_two_chunks", "tc_wide", "tc_one_chunk"])
 def test_project_backward_fp32_kernel(name, cuda_lib):
-    """The fp32 projection backward (switch proj_simt) against the fp64 oracle on the shapes whose default is the
-    warp-specialised tcgen05 kernel (which test_project covers), same tolerance."""
+    """The fp32 projection kernels, forward and backward (switch proj_simt), against the fp64 oracle on the shapes whose
+    default is the tcgen05 pair (which test_project covers), same tolerance."""
     from uno_b200 import config
     from uno_b200 import functional as Fn
 
@@ -127,6 +127,7 @@ def test_project_backward_fp32_kernel(name, cuda_lib):
         out = Fn.project(srcs, w1, b1, w2, b2, lo, hi)
         out.backward(_cu(t["gout"]))
         torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu().numpy(), ref["out"]) < FWD_TOL      # the fp32 forward too (default: tcgen05 for > 32 channels)
     for s, r in zip(srcs, ref["gsrcs"]):
         assert rel_err(s.grad.cpu().numpy(), r) < BWD_TOL
     for got, key in ((w1, "gw1"), (b1, "gb1"), (w2, "gw2"), (b2, "gb2")):

@@ -396,3 +396,30 @@ def test_branch_overlap_matches_serial(case, cuda_lib):
     a, b = _with(run, overlap=1), _with(run, overlap=0)
     for u, v in zip(a, b):
         assert np.abs(u - v).max() <= 1e-5 * max(float(np.abs(v).max()), 1e-6), rel_err(u, v)
+
+
+def test_first_call_of_a_new_shape_is_already_correct(cuda_lib):
+    """Constant tables (plan matrices, tensor-core operand images) are built at the first call that needs them and read, in that
+    same call, by kernels on the library's non-blocking side streams.  The upload must be complete for those streams too: with a
+    plain cudaMemcpy from pageable memory the first backward of a new shape intermittently used half-written images once the
+    kernels were resident.  Every iteration uses shapes no earlier test has used; the first call must equal the second."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(11)
+    for i in range(6):
+        idim, odim, modes = (21 + i, 19 + i, 11 + i), (17 + i, 23 - i, 13 + i), (4, 5, 3)
+        blk = ops.OperatorBlock_3D(5, 7, *odim, *modes, Normalize=bool(i & 1)).cuda()
+        x = torch.randn(2, 5, *idim, device="cuda")
+        gy = torch.randn(2, 7, *odim, device="cuda")
+
+        def run():
+            xx = x.clone().requires_grad_(True)
+            blk.zero_grad(set_to_none=True)
+            y = blk(xx, *odim)
+            y.backward(gy)
+            return [y.detach().cpu().numpy(), xx.grad.cpu().numpy()] + [
+                (torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).cpu().numpy() for p in blk.parameters()]
+
+        first, second = run(), run()
+        for u, v in zip(first, second):
+            assert np.abs(u - v).max() <= 1e-5 * max(float(np.abs(v).max()), 1e-6), (i, rel_err(u, v))

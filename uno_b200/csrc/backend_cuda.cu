@@ -79,6 +79,17 @@ struct ProfScope {
         if (_e != cudaSuccess) return (int)_e;     \
     } while (0)
 
+// Host -> device copy of a constant table (plan matrices, operand images), complete on return for EVERY stream.  A plain
+// cudaMemcpy from pageable memory returns once the data sits in the driver's staging buffer; the DMA that follows is ordered
+// only against blocking streams, and the library's side streams (and a caller's capture stream) are non-blocking: the first
+// kernel that read a freshly built image on such a stream could see it half written (found on B200 as an intermittent wrong
+// gradient in the first backward of a new shape when its kernels were already resident).  Tables are built once per shape.
+static cudaError_t upload_sync(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaDeviceSynchronize();
+}
+
 // Exact-erf GELU and its derivative from ONE exponential: with E = exp(-x^2/2) and
 // t = 1/(1 + p|x|/sqrt2), 1 - erf(|x|/sqrt2) = E*t*poly(t) (Abramowitz-Stegun 7.1.26, |eps| <= 1.5e-7); measured in
 // fp32 against fp64: |d gelu| <= 4.3e-7, |d gelu'| <= 3.2e-7, two orders below the parity tolerance, for ~16
@@ -105,11 +116,7 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
            x * 0.39894228040143267794f * expf(-0.5f * x * x);
 }
 #else
-__device__ __forceinline__ float gelu_f(float x) {
-    float a, g;
-    gelu_both(x, a, g);
-    return a;
-}
+__device__ __forceinline__ float gelu_f(float x) { return tc::gelu_fwd_fast(x); }   // forward only: one ex2, no division
 __device__ __forceinline__ float gelu_grad_f(float x) {
     float a, g;
     gelu_both(x, a, g);
@@ -966,7 +973,7 @@ int tc_get_rowgemm_image(const float* B, long ldb, int K, int N, int shifts, TcI
             }
     e = cudaMalloc(&img.dev, h.size() * 4);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    e = upload_sync(img.dev, h.data(), h.size() * 4);
     if (e != cudaSuccess) return (int)e;
     g_tc_images[key] = img;
     *out = img;
@@ -1065,7 +1072,7 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     }
     e = cudaMalloc(&img.dev, h.size() * 4);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    e = upload_sync(img.dev, h.data(), h.size() * 4);
     if (e != cudaSuccess) return (int)e;
     g_tc_kp_images[key] = img;
     *out = img;
@@ -1158,7 +1165,7 @@ int tc_get_mid_image(const float* Mat, int J, int H, TcMidImage* out) {
         }
     e = cudaMalloc(&img.dev, h.size() * 4);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpy(img.dev, h.data(), h.size() * 4, cudaMemcpyHostToDevice);
+    e = upload_sync(img.dev, h.data(), h.size() * 4);
     if (e != cudaSuccess) return (int)e;
     g_tc_mid_images[key] = img;
     *out = img;
@@ -1343,26 +1350,33 @@ int try_tc_conv(const GemmArgs& a, cudaStream_t st) {
     p.tmem_cols = cols;
     int gx = num_sms();
     if ((long)gx > p.n_tiles) gx = (int)p.n_tiles;
-    static DeviceOnce configured;
-    if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        configured.mark();
-    }
-    tc::conv1x1_tc_kernel<<<gx, tc::kCvThreads, tc::conv_tc_smem_bytes(N_t, n_chunks, stages), st>>>(p);
-    CU_LAUNCH_CHECK();
-    return 0;
+    const tc::ConvTcParams& pc = p;
+    const size_t smem = tc::conv_tc_smem_bytes(N_t, n_chunks, stages);
+    auto launch = [&](auto lw) -> int {
+        constexpr int LW = decltype(lw)::value;
+        static DeviceOnce configured;
+        if (!configured.done()) {
+            cudaError_t e = cudaFuncSetAttribute(tc::conv1x1_tc_kernel<LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            configured.mark();
+        }
+        tc::conv1x1_tc_kernel<LW><<<gx, tc::cv_threads(LW), smem, st>>>(pc);
+        CU_LAUNCH_CHECK();
+        return 0;
+    };
+    // 16 loader warps: measured on B200 against 8: 1.63 -> 1.48 ms per Darcy step, 0.79 -> 0.75 ms per NS-3D step
+    return launch(std::integral_constant<int, 16>());
 }
 
-template <bool DBG>
+template <int LW, bool DBG>
 int launch_wgrad(const tc::WgradParams& p, unsigned gx, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::wgrad_tc_kernel<LW, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::wgrad_tc_kernel<DBG><<<gx, tc::kWgThreads, tc::wgrad_smem_bytes(p.stages), st>>>(p);
+    tc::wgrad_tc_kernel<LW, DBG><<<gx, tc::wg_threads(LW), tc::wgrad_smem_bytes(p.stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1384,8 +1398,10 @@ int try_tc_wgrad(const GemmNtArgs& a, cudaStream_t st) {
     if (gx > (p.total_chunks + 3) / 4) gx = (p.total_chunks + 3) / 4;
     if (gx < 1) gx = 1;
     p.debug = cfg(CFG_WGRAD_DEBUG);   // timing probes (tools/wgrad_probe.py)
-    if (p.debug) return launch_wgrad<true>(p, (unsigned)gx, st);
-    return launch_wgrad<false>(p, (unsigned)gx, st);
+    // 16 loader warps: measured on B200 against 8 (a thread then owns 8 rows of a chunk, 168 registers): 1.66 -> 1.27 ms per
+    // Darcy step, 1.14 -> 0.94 ms per NS-3D step
+    if (p.debug) return launch_wgrad<16, true>(p, (unsigned)gx, st);
+    return launch_wgrad<16, false>(p, (unsigned)gx, st);
 }
 
 // returns -1 when the shape does not qualify (caller falls back to the SIMT kernel)
@@ -1591,7 +1607,7 @@ int be_join(stream_t main_stream, stream_t side) { return link_streams(S(side), 
 int be_upload(void** dptr, const void* host, size_t bytes) {
     cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 4);
     if (e != cudaSuccess) return (int)e;
-    e = cudaMemcpy(*dptr, host, bytes, cudaMemcpyHostToDevice);
+    e = upload_sync(*dptr, host, bytes);
     return (int)e;
 }
 void be_free(void* d) {
@@ -2017,7 +2033,25 @@ ProjK proj_k(const ProjArgs& a) {
 
 template <int CT>
 int launch_proj(const ProjK& k, bool bwd, cudaStream_t st) {
-    if (!bwd) {
+    if (!bwd && k.ctot > 32 && k.hid <= 64 && !cfg(CFG_PROJ_SIMT) && tc_enabled()) {
+        // DEFAULT for wide inputs: tcgen05 forward (pixel_mlp_tc.cuh), 1.00 -> 0.74 ms per Darcy step.  The fp32 kernel below
+        // for hid > 64, switch proj_simt, and for at most 32 input channels, where it measured faster (the 24 channels of
+        // Uno3D_T10: 0.23 against 0.27 ms -- the tensor-core kernel stages 64-channel images whatever the real count)
+        const int N_t = std::max(16, (k.hid + 15) & ~15);
+        const size_t smem = proj_fwd_tc_smem(N_t, k.hid, k.out_ch);
+        const long ntiles = ((long)k.batch * k.g.nraw + kPtPix - 1) / kPtPix;
+        const unsigned grid = (unsigned)std::min<long>(ntiles, (long)num_sms());
+        auto go = [&](auto kern) -> int {
+            int rc = ensure_smem(kern, smem);
+            if (rc) return rc;
+            kern<<<grid, kPfThreads, smem, st>>>(k, ntiles, N_t);
+            return 0;
+        };
+        int rc;
+        if (k.out_ch == 1) rc = k.pre_out ? go(proj_fwd_tc_kernel<1, true>) : go(proj_fwd_tc_kernel<1, false>);
+        else rc = k.pre_out ? go(proj_fwd_tc_kernel<4, true>) : go(proj_fwd_tc_kernel<4, false>);
+        if (rc) return rc;
+    } else if (!bwd) {
         const size_t smem = proj_fwd_smem(CT, k.hid, k.out_ch);
         int rc = ensure_smem(proj_fwd_kernel<CT>, smem);
         if (rc) return rc;

@@ -309,3 +309,240 @@ __host__ __device__ inline size_t proj_bwd_tcp_smem(int hid, int out_ch) {
     return 1024 + kPtImgBytes + 2 * kPtA1Bytes + 2 * kPtDBytes + (size_t)2 * kPtWBytes + 64 * kPtPix * 4 + proj_table_bytes(64) +
            sizeof(float) * round4(out_ch * hid) + 64;
 }
+
+// =====================================================================================================
+// Projection FORWARD on tcgen05:   out = W_2 * gelu( W_1 * crop(cat(src..)) + b_1 ) + b_2
+//   PRE[128 pixels, hid] = IN[128 pixels, 64 channels] * W_1^T     UMMA 128 x N_t x 64, 3xTF32 (24 MMAs per tile)
+// The fp32 kernel (pixel_mlp.cuh proj_fwd_kernel) is bound by its FMA / shared-memory instruction stream (ncu: FMA pipe 41 %,
+// 0.31 of HBM); here the product costs the SIMT pipes nothing and what is left per pixel is one load, one tf32 split and a
+// quarter of a 16-byte shared store per input value, and bias + GELU + the fc2 dot product per hidden unit.
+//   warps 0-15  loaders: thread = (pixel of the tile, quarter of the 64 channels); its 16 values of the tiles t+1 and t+2 are in
+//               flight in registers while those of tile t are split into the K-major hi / lo images of stage t % 2
+//   warps 16-23 epilogue: thread = (pixel = TMEM lane, every other 16-column chunk of the hidden units); PRE + b_1 -> optional
+//               pre_out (kept for backward), GELU, partial fc2 sum; the two partial sums of a pixel meet in shared memory
+//               (a first version with four epilogue warps and run-time out_ch / hid predicates in the unrolled loop was bound by
+//               exactly those warps: ncu showed them busy 85 % of the time with the sixteen loader warps spinning on `empty`)
+//   warp  20    one elected lane issues the MMAs of a tile into one of two TMEM accumulators and commits to the mbarriers that
+//               free the operand stage and publish the accumulator
+// Takes: at most 64 input channels, hid <= 64, out_ch <= 4.
+// =====================================================================================================
+constexpr int kPfLoadWarps = 16, kPfEpiWarps = 8;
+constexpr int kPfThreads = (kPfLoadWarps + kPfEpiWarps + 1) * 32;
+constexpr uint32_t kPfImgHalf = 16 * kPtLboA;          // one operand image (hi or lo): 16 channel groups x 128 pixels x 16 B (+ pad)
+constexpr uint32_t kPfStage = 2 * kPfImgHalf;
+
+__host__ __device__ inline size_t proj_fwd_tc_smem(int N_t, int hid, int out_ch) {
+    (void)hid; (void)out_ch;
+    return 1024 + (size_t)2 * kPfStage + (size_t)2 * N_t * 64 * 4 + proj_table_bytes(64) +
+           sizeof(float) * (64 + kProjMaxOut * 64 + 4 + 2 * kPtPix * kProjMaxOut) + 16 * 8;
+}
+
+// NOUT = 1: one output channel (every shipped model); NOUT = 4: out_ch <= 4 at run time.  PRE: pre_out wanted.
+template <int NOUT, bool PRE>
+__global__ void __launch_bounds__(kPfThreads, 1) proj_fwd_tc_kernel(const ProjK k, long ntiles, int N_t) {
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint8_t* IMG = tsm + ((128u - (tc::smem_u32(tsm) & 127u)) & 127u);   // [2 stages][hi | lo]
+    uint8_t* Wimg = IMG + 2 * kPfStage;                                  // [hi | lo] fc1 weights, K-major, N_t rows
+    const uint32_t w_half = (uint32_t)N_t * 64 * 4;
+    const float** sbase = reinterpret_cast<const float**>(Wimg + 2 * w_half);
+    float** gbase = reinterpret_cast<float**>(const_cast<float**>(sbase) + 64);
+    long* sstride = reinterpret_cast<long*>(gbase + 64);
+    float* sb1 = reinterpret_cast<float*>(sstride + 64);      // [64], zero beyond hid
+    float* sW2 = sb1 + 64;                                    // [kProjMaxOut][64], zero beyond hid / out_ch
+    float* sb2 = sW2 + kProjMaxOut * 64;                      // [4]
+    float* osum = sb2 + 4;                                    // [2 stages][128 pixels][kProjMaxOut] partial fc2 sums of the odd chunks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(osum + 2 * kPtPix * kProjMaxOut);
+    uint64_t* full = bars;          // [2] loaders -> mma
+    uint64_t* empty = bars + 2;     // [2] mma -> loaders
+    uint64_t* d_full = bars + 4;    // [2] mma -> epilogue
+    uint64_t* d_empty = bars + 6;   // [2] epilogue -> mma
+    uint64_t* o_full = bars + 8;    // [2] odd-chunk epilogue warps -> even-chunk ones
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    proj_stage_tables<64>(k, sbase, gbase, sstride);
+    for (int i = tid; i < N_t * 64; i += kPfThreads) {
+        const int c = i & 63, n = i >> 6;
+        float hi = 0.f, lo = 0.f;
+        if (n < k.hid && c < k.ctot) {
+            const float v = __ldg(k.w1 + n * k.ctot + c);
+            const uint32_t u = __float_as_uint(v);
+            hi = __uint_as_float((u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u);   // weights: hi rounded to nearest tf32
+            lo = v - hi;
+        }
+        uint8_t* d = Wimg + (uint32_t)(c >> 2) * (uint32_t)(N_t * 16) + (uint32_t)n * 16 + (uint32_t)(c & 3) * 4;
+        *reinterpret_cast<float*>(d) = hi;
+        *reinterpret_cast<float*>(d + w_half) = lo;
+    }
+    for (int i = tid; i < 64; i += kPfThreads) sb1[i] = i < k.hid ? __ldg(k.b1 + i) : 0.f;
+    for (int i = tid; i < kProjMaxOut * 64; i += kPfThreads) {
+        const int u = i >> 6, n = i & 63;
+        sW2[i] = (u < k.out_ch && n < k.hid) ? __ldg(k.w2 + u * k.hid + n) : 0.f;
+    }
+    if (tid < 4) sb2[tid] = tid < k.out_ch ? __ldg(k.b2 + tid) : 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&full[s], kPfLoadWarps * 32);
+            tc::mbar_init(&empty[s], 1);
+            tc::mbar_init(&d_full[s], 1);
+            tc::mbar_init(&d_empty[s], kPfEpiWarps * 32);
+            tc::mbar_init(&o_full[s], kPfEpiWarps * 16);
+        }
+        tc::fence_barrier_init();
+    }
+    constexpr int kMmaWarp = kPfLoadWarps + kPfEpiWarps;
+    constexpr uint32_t kCols = 128;                       // two accumulators of up to 64 columns
+    if (warp == kMmaWarp) tc::tmem_alloc(tmem_slot, kCols);
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const PixGeom g = k.g;
+    const long total = (long)k.batch * g.nraw;
+    const long step_tiles = gridDim.x;
+
+    if (warp < kPfLoadWarps) {
+        // ------------------------------------------------------------------ loaders
+        const int px = tid & 127, qd = tid >> 7;
+        const int c0 = 16 * qd;
+        // all 16 channels of this thread inside one source: one pointer advanced by the plane size
+        const bool contig = c0 + 15 < k.ctot && sbase[c0 + 15] == sbase[c0] + 15 * g.npad && sstride[c0 + 15] == sstride[c0];
+        float ring[3][16];
+        auto issue = [&](long tile, float (&v)[16]) {
+            const long idx = tile * kPtPix + px;
+            const bool valid = tile < ntiles && idx < total;
+            long b = 0, rp = 0, pp = 0;
+            if (valid) raw_to_padded(g, idx, b, rp, pp);
+            if (contig) {
+                const float* src = sbase[c0] + b * sstride[c0] + pp;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = valid ? __ldg(src + (long)j * g.npad) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const bool on = valid && c0 + j < k.ctot;
+                    v[j] = on ? __ldg(sbase[c0 + j] + b * sstride[c0 + j] + pp) : 0.f;
+                }
+            }
+        };
+        long it = 0;
+        auto process = [&](const float (&v)[16]) {
+            const int s = (int)(it & 1);
+            tc::mbar_wait(&empty[s], (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+            uint8_t* d = IMG + (uint32_t)s * kPfStage + (uint32_t)(4 * qd) * kPtLboA + (uint32_t)px * 16;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                float4 hi, lo;
+                tc::split_tf32(v[4 * m + 0], hi.x, lo.x);
+                tc::split_tf32(v[4 * m + 1], hi.y, lo.y);
+                tc::split_tf32(v[4 * m + 2], hi.z, lo.z);
+                tc::split_tf32(v[4 * m + 3], hi.w, lo.w);
+                *reinterpret_cast<float4*>(d + (uint32_t)m * kPtLboA) = hi;
+                *reinterpret_cast<float4*>(d + kPfImgHalf + (uint32_t)m * kPtLboA) = lo;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(&full[s]);
+            ++it;
+        };
+        long tile = blockIdx.x;
+        issue(tile, ring[0]);
+        issue(tile + step_tiles, ring[1]);
+        for (; tile < ntiles; tile += 3 * step_tiles) {
+            issue(tile + 2 * step_tiles, ring[2]);
+            process(ring[0]);
+            if (tile + step_tiles >= ntiles) break;
+            issue(tile + 3 * step_tiles, ring[0]);
+            process(ring[1]);
+            if (tile + 2 * step_tiles >= ntiles) break;
+            issue(tile + 4 * step_tiles, ring[1]);
+            process(ring[2]);
+        }
+    } else if (warp < kMmaWarp) {
+        // ------------------------------------------------------------------ epilogue: thread = (pixel = TMEM lane, chunk parity)
+        const int q = warp & 3, par = (warp - kPfLoadWarps) >> 2;
+        const int px = q * 32 + lane;
+        long it = 0;
+        for (long tile = blockIdx.x; tile < ntiles; tile += step_tiles, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = ((uint32_t)(it >> 1)) & 1u;
+            tc::mbar_wait_relaxed(&d_full[s], ph);
+            tc::tc_fence_after();
+            const long idx = tile * kPtPix + px;
+            const bool valid = idx < total;
+            float o[NOUT];
+#pragma unroll
+            for (int u = 0; u < NOUT; ++u) o[u] = 0.f;
+            const uint32_t t_base = tmem_base + (uint32_t)s * 64u + ((uint32_t)(q * 32) << 16);
+            for (int n0 = 16 * par; n0 < k.hid; n0 += 32) {
+                uint32_t r[16];
+                tc::tmem_ld_32x32b_x16(t_base + (uint32_t)n0, r);
+                tc::tmem_ld_wait();
+                float* pre = PRE ? k.pre_out + (size_t)n0 * total + (valid ? idx : 0) : nullptr;
+                const bool whole = n0 + 16 <= k.hid;          // warp-uniform
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = __uint_as_float(r[j]) + sb1[n0 + j];
+                    if (PRE) {
+                        if (valid && (whole || n0 + j < k.hid)) *pre = v;
+                        pre += total;
+                    }
+                    const float a = gelu_act(v);              // padded units: weights, bias and fc2 row are zero
+#pragma unroll
+                    for (int u = 0; u < NOUT; ++u) o[u] = fmaf(sW2[u * 64 + n0 + j], a, o[u]);
+                }
+            }
+            tc::tc_fence_before();
+            float* os = osum + ((size_t)s * kPtPix + px) * kProjMaxOut;
+            if (par) {
+#pragma unroll
+                for (int u = 0; u < NOUT; ++u) os[u] = o[u];
+                tc::mbar_arrive(&o_full[s]);
+                tc::mbar_arrive(&d_empty[s]);
+            } else {
+                tc::mbar_wait(&o_full[s], ph);
+#pragma unroll
+                for (int u = 0; u < NOUT; ++u) o[u] += os[u] + sb2[u];
+                tc::mbar_arrive(&d_empty[s]);                 // after the read: the odd warps rewrite osum[s] two tiles later
+                if (valid) {
+#pragma unroll
+                    for (int u = 0; u < NOUT; ++u)
+                        if (NOUT == 1 || u < k.out_ch) k.out[idx * k.out_ch + u] = o[u];
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = tc::make_idesc_tf32(128, N_t, 0, 0);
+        const uint32_t lbo_w = (uint32_t)N_t * 16;
+        const uint64_t a0 = tc::make_smem_desc(tc::smem_u32(IMG), kPtLboA, 128);
+        const uint64_t b0 = tc::make_smem_desc(tc::smem_u32(Wimg), lbo_w, 128);
+        const uint32_t a_lo = kPfImgHalf >> 4, b_lo = w_half >> 4, a_step = (2 * kPtLboA) >> 4, b_step = (2 * lbo_w) >> 4;
+        const int nks = (k.ctot + 7) / 8;
+        long it = 0;
+        for (long tile = blockIdx.x; tile < ntiles; tile += step_tiles, ++it) {
+            const int s = (int)(it & 1);
+            const uint32_t ph = ((uint32_t)(it >> 1)) & 1u;
+            tc::mbar_wait(&full[s], ph);
+            tc::mbar_wait(&d_empty[s], ph ^ 1u);
+            tc::tc_fence_after();
+            if (tc::elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)s * 64u;
+                uint64_t da = a0 + (uint64_t)((uint32_t)s * (kPfStage >> 4)), db = b0;
+                for (int ks = 0; ks < nks; ++ks) {
+                    tc::mma_tf32(d_tmem, da, db, idesc, ks ? 1u : 0u);
+                    tc::mma_tf32(d_tmem, da, db + b_lo, idesc, 1u);
+                    tc::mma_tf32(d_tmem, da + a_lo, db, idesc, 1u);
+                    da += a_step;
+                    db += b_step;
+                }
+                tc::tc_commit(&empty[s]);
+                tc::tc_commit(&d_full[s]);
+            }
+            __syncwarp();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tc::tmem_dealloc(tmem_base, kCols);
+}

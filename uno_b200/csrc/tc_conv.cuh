@@ -8,7 +8,7 @@
 // conv_weight_image_kernel (a few KB) right before the main kernel.
 //
 //   * persistent CTAs, tiles = (sample, 128-pixel block), static round-robin
-//   * 8 loader warps stream 32-channel chunks of the tile (float4 along pixels, hi/lo split in registers,
+//   * 16 loader warps stream 32-channel chunks of the tile (float4 along pixels, hi/lo split in registers,
 //     one 16-byte st.shared per value group into the MN-major interleave layout; register ping-pong keeps
 //     two chunks in flight)
 //   * one lane issues 3 MMAs per 8-channel k-step into one of two TMEM accumulators
@@ -38,9 +38,8 @@ constexpr uint32_t kCvSbo = 512;                        // next group of 4 chann
 constexpr uint32_t kCvLbo = (kKC / 4) * kCvSbo;         // next block of 32 pixels (32 channels per stage)
 constexpr uint32_t kCvAHalf = 4 * kCvLbo;               // one A image (hi or lo) per stage: 32 channels x 128 pixels
 constexpr uint32_t kCvLayout = 1;                       // UMMA::LayoutType::SWIZZLE_128B_BASE32B
-constexpr int kCvLoadWarps = 8;
 constexpr int kCvEpiWarps = 8;
-constexpr int kCvThreads = (kCvLoadWarps + kCvEpiWarps + 1) * 32;
+__host__ __device__ constexpr int cv_threads(int LW) { return (LW + kCvEpiWarps + 1) * 32; }
 
 __host__ __device__ inline size_t conv_tc_smem_bytes(int N_t, int n_chunks, int stages) {
     return 1024 + (size_t)2 * N_t * n_chunks * kKC * 4 + (size_t)stages * 2 * kCvAHalf + 32 * 8 + 16;
@@ -64,7 +63,11 @@ __global__ void conv_weight_image_kernel(const float* __restrict__ W, long w_rs,
     }
 }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcParams p) {
+// LW = loader warps (8 or 16): a thread owns 32 / LW channels of every chunk
+template <int LW>
+__global__ void __launch_bounds__(cv_threads(LW), 1) conv1x1_tc_kernel(const ConvTcParams p) {
+    constexpr int kCvLoadWarps = LW;
+    constexpr int CPT = 32 / LW;                   // channels per thread and chunk
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
         int n_my = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_my;
         const long total = (long)n_my * NKC;
-        const long stride8 = 8 * p.npix;
+        const long stride_lw = (long)LW * p.npix;
         int i_tile = blockIdx.x, i_kc = 0;
         const float* i_base = nullptr;                 // X + b*sXb + px of the issue cursor's tile
         bool i_pxok = false;
@@ -186,18 +189,18 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
         if (total > 0) retile();
         int p_s = 0;
         uint32_t p_ph = 0;
-        // swizzled MN-major destination of this thread inside a stage (channel cl = cb + 8*i -> group (cl>>2) = 2*i + (cb>>2), row r4 = cb&3)
+        // swizzled MN-major destination of this thread inside a stage (channel cl = cb + LW*i -> group (cl>>2) = (LW/4)*i + (cb>>2), row r4 = cb&3)
         const uint32_t r4 = (uint32_t)cb & 3u;
         const uint32_t so = (uint32_t)(pg >> 3) * kCvLbo + (uint32_t)(cb >> 2) * kCvSbo + r4 * 128u + ((((uint32_t)(pg & 7) >> 1) ^ r4) << 5) +
                             ((uint32_t)pg & 1u) * 16u;
-        float4 ring[kKpDepth][4];
-        auto issue = [&](float4 (&v)[4]) {
+        float4 ring[kKpDepth][CPT];
+        auto issue = [&](float4 (&v)[CPT]) {
             const int c0 = i_kc * kKC + cb;
             const float* src = i_base + (long)c0 * p.npix;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < CPT; ++i) {
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i_pxok && c0 + 8 * i < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * stride8));
+                if (i_pxok && c0 + LW * i < p.K) v[i] = __ldg(reinterpret_cast<const float4*>(src + i * stride_lw));
             }
             if (++i_kc == NKC) {
                 i_kc = 0;
@@ -205,18 +208,18 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv1x1_tc_kernel(const ConvTcP
                 if (i_tile < n_tiles) retile();
             }
         };
-        auto process = [&](const float4 (&v)[4]) {
+        auto process = [&](const float4 (&v)[CPT]) {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = sA + (size_t)p_s * stage_bytes + so;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < CPT; ++i) {
                 float4 hi, lo;
                 split_tf32(v[i].x, hi.x, lo.x);
                 split_tf32(v[i].y, hi.y, lo.y);
                 split_tf32(v[i].z, hi.z, lo.z);
                 split_tf32(v[i].w, hi.w, lo.w);
-                *reinterpret_cast<float4*>(st + i * 2 * kCvSbo) = hi;
-                *reinterpret_cast<float4*>(st + kCvAHalf + i * 2 * kCvSbo) = lo;
+                *reinterpret_cast<float4*>(st + i * (LW / 4) * kCvSbo) = hi;
+                *reinterpret_cast<float4*>(st + kCvAHalf + i * (LW / 4) * kCvSbo) = lo;
             }
             fence_proxy_async();
             mbar_arrive(&full[p_s]);

@@ -62,9 +62,11 @@ __host__ __device__ inline size_t rowgemm_smem_bytes(int K_pad, int N_t) {
     return b + a + 16 * 8 + 16;
 }
 
-// libm erff here on purpose: the single-exponential form the elementwise kernels use (backend_cuda.cu gelu_both) made the
-// GELU launches of this kernel 6 % SLOWER (3.66 -> 3.88 ms per step): its two MUFU operations per element queue behind the
-// quarter-rate special-function unit in the 8 epilogue warps, while erff is almost all FMA-pipe work
+// libm erff here on purpose.  Measured on B200 per Darcy step (this kernel's launches): erff 3.67 ms; the one-ex2 form the SIMT
+// kernels use (tc_common.cuh gelu_fwd_fast, a third of the instructions) 3.74 ms; the single-exponential Abramowitz-Stegun form of
+// the backward kernels (two MUFU operations per element) 3.88 ms.  The epilogue warps are bound by the latency of their addend
+// loads, not by issue slots, and every special-function operation lengthens the dependent chain of a round, while erff is almost
+// all FMA-pipe work.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // Epilogue of one 128-row tile for one warp: TMEM lane quarter `q`, 16-column chunks c0 = 16*(2*i + half).

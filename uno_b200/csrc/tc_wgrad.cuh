@@ -5,8 +5,9 @@
 // Split-K: the (sample, 32-pixel chunk) sequence is divided evenly over persistent CTAs; each CTA accumulates
 // its whole range in ONE TMEM accumulator (fp32) and flushes it once with atomicAdd -- 148 x M x N atomics in
 // total instead of one per split-K tile.
-//   * 8 loader warps: float4 along pixels, tf32 hi/lo split in registers, K-major interleave layout, 4-deep
+//   * 16 loader warps: float4 along pixels, tf32 hi/lo split in registers, K-major interleave layout, 4-deep
 //     register prefetch ring, rows beyond the real channel count are zeroed once and never touched again
+//     (ncu on the 8-warp form: 14 % of the warp slots occupied, 3.3 long-scoreboard stalls per issue, 0.30 of HBM)
 //   * one lane issues 3 MMAs per 8-pixel k-step; stages are recycled through tcgen05.commit -> mbarrier
 #pragma once
 #include "backend.h"
@@ -29,15 +30,16 @@ struct WgradParams {
                                   // 2 no operand stores, 8 no global loads, 16 no proxy fence, 32 no final flush
 };
 
-constexpr int kWgLoadWarps = 8;
-constexpr int kWgThreads = (kWgLoadWarps + 1) * 32;
+__host__ __device__ constexpr int wg_threads(int LW) { return (LW + 1) * 32; }
 constexpr uint32_t kWgStage = 4 * kKpAHalf;   // A_hi, A_lo, B_hi, B_lo (each 128 rows x 32 k, K-major interleave)
 
 __host__ __device__ inline size_t wgrad_smem_bytes(int stages) { return (size_t)stages * kWgStage + 32 * 8 + 16; }
 
 // DBG = timing-probe instantiation (tools/wgrad_probe.py); the default <false> carries none of the probe branches
-template <bool DBG = false>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradParams p) {
+// LW = loader warps (8 or 16): a thread owns 256 / (4 * LW) rows of every chunk
+template <int LW, bool DBG = false>
+__global__ void __launch_bounds__(wg_threads(LW), 1) wgrad_tc_kernel(const WgradParams p) {
+    constexpr int kWgLoadWarps = LW, kWgThreads = wg_threads(LW);
     const int dbg = DBG ? p.debug : 0;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,7 +121,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
         int i_c = (int)(c_begin - (long)i_b * cpb);
         int p_s = 0;
         uint32_t p_ph = 0;
-        constexpr int RPT = 8;    // up to 8 rows per thread: (M + N) <= 256
+        constexpr int RPT = 64 / LW;          // rows per thread: (M + N) <= 256
+        constexpr int RSTEP = 4 * LW;         // row distance between a thread's rows
         float4 ring[kKpDepth][RPT];
         auto issue = [&](float4 (&v)[RPT]) {
             const long px = (long)i_c * kKC + kq * 4;
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
             const float* xsrc = p.X + (long)i_b * p.sXb + px;
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-                const int r = rbase + 32 * i;
+                const int r = rbase + RSTEP * i;
                 v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pxok && r < rows && !(DBG && (dbg & 8))) {
                     const float* q = (r < p.M) ? gsrc + (long)r * p.npix : xsrc + (long)(r - p.M) * p.npix;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradPara
             uint8_t* st = smem + (size_t)p_s * kWgStage;
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-                const int r = rbase + 32 * i;
+                const int r = rbase + RSTEP * i;
                 if (r < rows && !(DBG && (dbg & 2))) {
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);

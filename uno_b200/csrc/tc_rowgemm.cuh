@@ -73,7 +73,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // All loads of a 32-column group are issued before any store so that they are in flight together; the four
 // row pointers of a thread are formed once per tile (no 64-bit multiplies in the column loop).
 template <int EPI, bool VEC2, int G = 2, int J = 2>
-__device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half, int lane) {
+__device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half, int lane,
+                                                      bool skip_full = false) {
     static_assert(J == 1 || J == 2, "one or two 16-column chunks per round");
     constexpr bool kAccum = (EPI != EPI_STORE);
     const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
@@ -92,6 +93,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
         const int c0a = ci * 16, c0b = (ci + G) * 16;
         const bool has_b = J == 2 && c0b < p.N_t && n_base + c0b < p.N;
         if (n_base + c0a >= p.N) break;
+        if (skip_full && n_base + c0a >= 0 && n_base + c0a + 16 <= p.N) continue;   // done by rowgemm_epilogue_tile_fast
         uint32_t r[2 * J][8];
         tmem_ld_16x256b_x2(t_base + (uint32_t)c0a, r[0]);
         tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)c0a, r[1]);
@@ -140,6 +142,71 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
             }
         }
     }
+}
+
+// Fast path of the epilogue (J = 1, 8-byte aligned pairs, all 128 rows of the tile inside the matrix): the 16-column chunks that
+// lie completely inside the output run without a single bounds predicate -- straight-line 8-byte loads and stores off four row
+// pointers -- and the addend of the warp's NEXT chunk is requested before the current one is combined, so that its latency
+// overlaps the GELU arithmetic and the stores.  Why: ncu (profiles/r02_ncu_full_v51_darcy.txt) has 43 % of this kernel's stall
+// samples on the first use of the addend, and the predicated form spends ~20 control instructions (BSSY / BRA / BSYNC) per load,
+// ~450 per thread and round, before and between those loads; a microbenchmark of the SAME access pattern without them streams
+// 5.65 TB/s from one 512-thread CTA per SM (tools/microbench/epilogue_patterns.cu) against 3.4 - 3.8 TB/s here.  Measured on B200:
+// 3.76 -> 3.58 ms per Darcy step for this kernel's launches, 0.64 of the HBM peak under ncu (0.58 before).  Chunks cut by the
+// matrix edge (and the first chunk of a column-shifted parity tile) are left to the general form above.
+// Returns false (nothing done, accumulator not yet awaited) when the tile does not qualify.
+template <int EPI, int G>
+__device__ __forceinline__ bool rowgemm_epilogue_tile_fast(const RowGemmParams& p, uint32_t t_base, long tile, int q, int n_base, int half,
+                                                           int lane, uint64_t* d_full, uint32_t ph) {
+    constexpr bool kAccum = (EPI != EPI_STORE);
+    if (rowgemm_row(p, tile, 127) >= p.R) return false;                  // warp-uniform: a ragged last tile
+    const int nb = n_base - (p.parity ? (int)(tile & 1) : 0);            // accumulator column c = output column nb + c
+    const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
+    float* rowp[4];                                                      // index hh*2 + rr, as in the general form
+#pragma unroll
+    for (int hr = 0; hr < 4; ++hr)
+        rowp[hr] = p.C + rowgemm_row(p, tile, q * 32 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2)) * p.ldc + nb + 2 * (lane & 3);
+    auto full = [&](int ci) { return ci * 16 < p.N_t && nb + ci * 16 >= 0 && nb + ci * 16 + 16 <= p.N; };
+    auto load = [&](int ci, float2 (&cz)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int hh = e >> 2, rep = (e >> 1) & 1, rr = e & 1;
+            cz[e] = *reinterpret_cast<const float2*>(rowp[hh * 2 + rr] + ci * 16 + rep * 8);
+        }
+    };
+    // the warp's chunks are ci = half, half + G, ...; `cur` walks the full ones
+    int cur = half;
+    while (cur * 16 < p.N_t && !full(cur)) cur += G;
+    float2 cz[8], nz[8];
+    const bool any = cur * 16 < p.N_t;
+    if (kAccum && any) load(cur, cz);                                    // in flight while the MMA of this tile finishes
+    mbar_wait_relaxed(d_full, ph);
+    tc_fence_after();
+    while (cur * 16 < p.N_t) {
+        int nxt = cur + G;
+        while (nxt * 16 < p.N_t && !full(nxt)) nxt += G;
+        uint32_t r[2][8];
+        tmem_ld_16x256b_x2(t_base + (uint32_t)(cur * 16), r[0]);
+        tmem_ld_16x256b_x2(t_base + (16u << 16) + (uint32_t)(cur * 16), r[1]);
+        if (kAccum && nxt * 16 < p.N_t) load(nxt, nz);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int hh = e >> 2, rep = (e >> 1) & 1, rr = e & 1;
+            float2 acc = make_float2(__uint_as_float(r[hh][rep * 4 + rr * 2 + 0]), __uint_as_float(r[hh][rep * 4 + rr * 2 + 1]));
+            if (kAccum) { acc.x += cz[e].x; acc.y += cz[e].y; }
+            float2 act = acc;
+            if (EPI == EPI_ACCUM_GELU || EPI == EPI_ACCUM_GELU_INPLACE) { act.x = gelu_erf(acc.x); act.y = gelu_erf(acc.y); }
+            float* dst = rowp[hh * 2 + rr] + cur * 16 + rep * 8;
+            *reinterpret_cast<float2*>(dst) = (EPI == EPI_ACCUM_GELU_INPLACE) ? act : acc;
+            if (EPI == EPI_ACCUM_GELU) *reinterpret_cast<float2*>(dst + c2_delta) = act;
+        }
+        if (kAccum) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cz[e] = nz[e];
+        }
+        cur = nxt;
+    }
+    return true;
 }
 
 // (A software-pipelined form of this epilogue that loaded the next round's addend before storing the current round was measured
@@ -279,11 +346,16 @@ __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(c
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1;
             const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait_relaxed(&d_full[s], ph);
-            tc_fence_after();
             const uint32_t t_base = tmem_base + (uint32_t)s * buf_cols + ((uint32_t)(q * 32) << 16);
-            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane);
-            else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane);
+            bool fast = false;
+            if (J == 1 && vec2) fast = rowgemm_epilogue_tile_fast<EPI, G>(p, t_base, tile, q, n_base, half, lane, &d_full[s], ph);
+            if (!fast) {
+                mbar_wait_relaxed(&d_full[s], ph);
+                tc_fence_after();
+            }
+            // the general form: the whole tile, or only the chunks the fast path left (those cut by the matrix edge)
+            if (vec2) rowgemm_epilogue_tile<EPI, true, G, J>(p, t_base, tile, q, n_base, half, lane, fast);
+            else rowgemm_epilogue_tile<EPI, false, G, J>(p, t_base, tile, q, n_base, half, lane, fast);
             tc_fence_before();
             mbar_arrive(&d_empty[s]);
         }

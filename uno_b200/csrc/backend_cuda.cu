@@ -1232,6 +1232,16 @@ int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
     p.ms_tiles = (2 * a.N + 127) / 128;
     p.n_chunks = (a.K + 3) / 4;
     p.qg = (a.q_inner + 3) / 4;
+    // split the reduction while the items leave more than half of the SMs idle (tc_cmm4.cuh): a divisor of the k-step count,
+    // at least four k-steps (16 channels) per item
+    p.ksplit = 1;
+    {
+        const long base = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * p.qg;
+        if (!(cfg(CFG_EXP0) & 16))
+            for (int ks = 8; ks >= 2; --ks)
+                if (p.n_chunks % ks == 0 && p.n_chunks / ks >= 4 && base * ks <= (long)num_sms()) { p.ksplit = ks; break; }
+    }
+    p.n_chunks /= p.ksplit;
     int stages = (int)((200 * 1024) / tc::cmm4_stage_bytes(p.N_t));
     if (stages > 4) stages = 4;
     if (stages < 2) return -1;
@@ -1240,7 +1250,7 @@ int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
     while (cols < 2 * tc::kC4Modes * p.N_t) cols *= 2;
     if (cols > 512) return -1;
     p.tmem_cols = cols;
-    p.items = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * p.qg;
+    p.items = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * p.qg * p.ksplit;
     static DeviceOnce configured;
     if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc::cmm_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1249,6 +1259,11 @@ int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
     }
     long gx = num_sms();
     if (gx > p.items) gx = p.items;
+    if (p.ksplit > 1) {
+        const long n = (long)a.M * a.N * a.q_outer * a.q_inner * a.ncorner;
+        tc::cmm_zero_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 4L * num_sms()), 256, 0, st>>>(a);
+        CU_LAUNCH_CHECK();
+    }
     tc::cmm_tc4_kernel<<<(unsigned)gx, tc::kKpThreads, tc::cmm4_smem_bytes(p.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;

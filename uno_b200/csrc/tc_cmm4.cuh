@@ -13,6 +13,11 @@
 //   * the epilogue pairs the (re, im) rows of neighbouring lanes and the four accumulators with two shuffles per sample and
 //     stores 16 bytes per lane: 32 contiguous bytes per (sample, channel).
 // Requires 16-byte friendly operands (all strides and corner offsets even in complex elements); tc_cmm.cuh takes the rest.
+//
+// An item issues 12 MMAs per k-step and each small MMA (128 x N_t x 8) occupies the tensor pipe for ~100 cycles whatever N_t is
+// (the operand fetch from shared memory dominates): 128 input channels are 384 MMAs = ~20 us per item.  Levels with few modes
+// have fewer items than SMs (64 at the inner NS-2D levels), so the launcher splits the reduction of every output tile over
+// `ksplit` items that add into a zeroed C (cmm_zero_kernel): the same MMAs on two to four times as many SMs.
 #pragma once
 #include "backend.h"
 #include "tc_common.cuh"
@@ -26,10 +31,11 @@ struct Cmm4Params {
     int N_t;          // sample columns per tile, multiple of 16, <= 64
     int ns_tiles;     // column tiles over the M samples
     int ms_tiles;     // 128-row tiles over the 2*N rows (n, re|im)
-    int n_chunks;     // ceil(K / 4)
+    int n_chunks;     // k-steps (4 complex k) PER ITEM: ceil(K / 4) / ksplit
+    int ksplit;       // the reduction of one output tile is split over this many items, which then ADD into a pre-zeroed C
     int qg;           // ceil(q_inner / 4) mode groups
     int stages, tmem_cols;
-    long items;       // ms_tiles * ns_tiles * ncorner * q_outer * qg
+    long items;       // ms_tiles * ns_tiles * ncorner * q_outer * qg * ksplit
 };
 
 constexpr int kC4Modes = 4;
@@ -44,10 +50,11 @@ __host__ __device__ inline size_t cmm4_stage_bytes(int N_t) { return (size_t)kC4
 __host__ __device__ inline size_t cmm4_smem_bytes(int N_t, int stages) { return stages * cmm4_stage_bytes(N_t) + 32 * 8 + 16; }
 
 struct Cmm4Item {
-    int ms, ns, corner, qo, qi0;
+    int ms, ns, corner, qo, qi0, kc0;     // kc0: first k-step of this item's share of the reduction
 };
 __device__ __forceinline__ Cmm4Item cmm4_item(const Cmm4Params& p, long w) {
     Cmm4Item it;
+    it.kc0 = (int)(w % p.ksplit) * p.n_chunks; w /= p.ksplit;
     it.qi0 = 4 * (int)(w % p.qg); w /= p.qg;
     it.qo = (int)(w % p.a.q_outer); w /= p.a.q_outer;
     it.corner = (int)(w % p.a.ncorner); w /= p.a.ncorner;
@@ -60,6 +67,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr));
+}
+
+// C = 0 over exactly the elements the contraction writes (the corners are sub-blocks of a larger spectrum tensor)
+__global__ void cmm_zero_kernel(const CmmArgs a) {
+    const long per = (long)a.M * a.N * a.q_outer * a.q_inner;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < per * a.ncorner; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per);
+        long r = i - (long)c * per;
+        const int qi = (int)(r % a.q_inner); r /= a.q_inner;
+        const int qo = (int)(r % a.q_outer); r /= a.q_outer;
+        const int n = (int)(r % a.N);
+        const int m = (int)(r / a.N);
+        reinterpret_cast<float2*>(a.C[c])[(long)m * a.c_sm + (long)n * a.c_sn + (long)qo * a.c_sqo + qi] = make_float2(0.f, 0.f);
+    }
 }
 
 __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params p) {
@@ -163,11 +184,13 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
         const float2* gB = nullptr;       // &B[k = 0, n of this thread, first mode of this thread]
         const float2* gA = nullptr;       // &A[m of this thread, k = 0, first mode of this thread]
         int nmodes = 0;                   // how many of this thread's two modes exist (ragged last group)
+        int i_kc0 = 0;                    // first k-step of the item (split reductions)
         auto seek = [&]() {
             gB = gA = nullptr;
             nmodes = 0;
             if (i_w >= p.items) return;
             const Cmm4Item it = cmm4_item(p, i_w);
+            i_kc0 = it.kc0;
             const int q = it.qi0 + 2 * hf;
             nmodes = min(2, max(0, p.a.q_inner - q));
             if (nmodes == 0) return;
@@ -186,7 +209,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
         Slot ring[kC4Depth];
         auto issue = [&](Slot& v) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int kw = i_kc * 4 + 2 * wkp, kx = i_kc * 4 + 2 * xkp;
+            const int kw = (i_kc0 + i_kc) * 4 + 2 * wkp, kx = (i_kc0 + i_kc) * 4 + 2 * xkp;
             v.w[0] = (gB && kw < p.a.K) ? ld2(gB + (long)kw * p.a.b_sk) : z;
             v.w[1] = (gB && kw + 1 < p.a.K) ? ld2(gB + (long)(kw + 1) * p.a.b_sk) : z;
             v.x[0] = (gA && kx < p.a.K) ? ld2(gA + (long)kx * p.a.a_sk) : z;
@@ -276,7 +299,12 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
                     const int c = c0 + u;
                     if (nok && c < mcols && nst > 0) {
                         float2* dst = crow + (long)(m0 + c) * p.a.c_sm;
-                        if (nst == 2) *reinterpret_cast<float4*>(dst) = out;
+                        if (p.ksplit > 1) {               // partial sum of a split reduction: C was zeroed by the launcher
+                            float* d = reinterpret_cast<float*>(dst);
+                            atomicAdd(d, out.x);
+                            atomicAdd(d + 1, out.y);
+                            if (nst == 2) { atomicAdd(d + 2, out.z); atomicAdd(d + 3, out.w); }
+                        } else if (nst == 2) *reinterpret_cast<float4*>(dst) = out;
                         else *dst = make_float2(out.x, out.y);
                     }
                 }

@@ -24,11 +24,13 @@ elif [[ $STAGES == *bench* ]]; then
     cut -c1-400 gpurun_out/${TAG}_bench_reference.json
 fi
 if [[ $STAGES == *sanitizer* ]]; then
-    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_glue.py -x -q \
+    # memcheck: every kernel variant, the pixel MLPs and the golden parity cases; racecheck (shared-memory hazards, slow): the
+    # golden parity cases, the fan-out / overlap / tensor-core-core variants and the fused lift / projection kernels
+    timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_variants.py tests/test_gpu_glue.py tests/test_gpu_parity.py -x -q \
         > gpurun_out/${TAG}_sanitizer_memcheck.log 2>&1
     echo "memcheck rc=$?" >> gpurun_out/${TAG}_sanitizer_memcheck.log
-    timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -k "golden" \
-        > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1
+    timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_variants.py tests/test_gpu_glue.py -x -q \
+        -k "golden or fanout or overlap or tc_core or test_project or test_lift or first_call" > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1
     echo "racecheck rc=$?" >> gpurun_out/${TAG}_sanitizer_racecheck.log
     tail -4 gpurun_out/${TAG}_sanitizer_memcheck.log gpurun_out/${TAG}_sanitizer_racecheck.log
 fi

@@ -1215,7 +1215,7 @@ int try_tc_mid(const MidArgs& a, cudaStream_t st) {
     }
     int gx = std::max(1, num_sms() / img.n_tiles);
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
-    tc::mid_tc_kernel<<<dim3(gx, img.n_tiles), tc::kKpThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
+    tc::mid_tc_kernel<<<dim3(gx, img.n_tiles), tc::kMidThreads, tc::kpipe_smem_bytes(img.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1263,7 +1263,7 @@ int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
         tc::cmm_zero_kernel<<<(unsigned)std::min<long>((n + 255) / 256, 4L * num_sms()), 256, 0, st>>>(a);
         CU_LAUNCH_CHECK();
     }
-    tc::cmm_tc4_kernel<<<(unsigned)gx, tc::kKpThreads, tc::cmm4_smem_bytes(p.N_t, stages), st>>>(p);
+    tc::cmm_tc4_kernel<<<(unsigned)gx, tc::kC4Threads, tc::cmm4_smem_bytes(p.N_t, stages), st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }

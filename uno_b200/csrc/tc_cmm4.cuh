@@ -39,7 +39,9 @@ struct Cmm4Params {
 };
 
 constexpr int kC4Modes = 4;
-constexpr int kC4Depth = 4;                                  // chunks of global loads in flight per loader thread
+constexpr int kC4LoadWarps = 16;                             // warps 0-7 stage the weight images, 8-15 the sample images
+constexpr int kC4Threads = (kC4LoadWarps + kKpEpiWarps + 1) * 32;
+constexpr int kC4Depth = 4;                                  // chunks of global loads in flight per loader thread (six spill at 80 registers: 0.99 -> 1.19 ms per NS-2D call)
 constexpr uint32_t kC4AHalf = 2 * kLboA;                     // one weight image (hi or lo): two 4-wide k' groups of 128 rows
 constexpr uint32_t kC4AMode = 2 * kC4AHalf;                  // hi + lo
 
@@ -83,7 +85,7 @@ __global__ void cmm_zero_kernel(const CmmArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params p) {
+__global__ void __launch_bounds__(kC4Threads, 1) cmm_tc4_kernel(const Cmm4Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -97,11 +99,11 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
     uint64_t* d_full = bars + 16;     // [2]
     uint64_t* d_empty = bars + 18;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    constexpr int kMmaWarp = kKpLoadWarps + kKpEpiWarps;
+    constexpr int kMmaWarp = kC4LoadWarps + kKpEpiWarps;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], kKpLoadWarps * 32);
+            mbar_init(&full[s], kC4LoadWarps * 32);
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -161,32 +163,38 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
             if (elect_one()) tc_commit(&d_full[buf]);
             __syncwarp();
         }
-    } else if (warp < kKpLoadWarps) {
+    } else if (warp < kC4LoadWarps) {
         // ------------------------------------------------------------------ loaders
-        // Thread pair (2t, 2t+1) shares a task; lane parity `hf` picks the mode half (modes 2hf, 2hf+1): 16 bytes per lane,
-        // one 32-byte sector per pair.  Weight task t: channel row pair wn = t % 64 of the tile, k pair wkp = t / 64.  Sample
-        // task t < 2*N_t: sample xm = t % N_t, k pair xkp = t / N_t.  A task = the elements k, k+1 of its k pair.
-        const int ltid = threadIdx.x;
+        // Warps 0-7 stage the weights, warps 8-15 the samples (one group doing both was bound by its own instruction stream:
+        // ~950 cycles per stage for 24 KB; measured on B200 per NS-2D call: 1.01 -> 0.99 ms -- the kernel is bound by the
+        // latency of one CTA's weight stream, 30 - 40 us per 128-channel item, not by these instructions nor by its MMA count: stacking
+        // the hi / lo sample images along N, 8 instead of 12 MMAs per stage, measured no change).  Thread pair
+        // (2t, 2t+1) shares a task; lane parity `hf` picks the mode half (modes 2hf, 2hf+1): 16 bytes per lane, one 32-byte
+        // sector per pair.  Weight task t: channel row pair wn = t % 64 of the tile, k pair wkp = t / 64.  Sample task
+        // t < 2*N_t: sample xm = t % N_t, k pair xkp = t / N_t.  A task = the elements k, k+1 of its k pair.
+        const bool is_w = warp < 8;                          // warp-uniform role
+        const int ltid = threadIdx.x & 255;
         const int pair = ltid >> 1, hf = ltid & 1;
         const float sa = p.a.conjA ? -1.f : 1.f, sb = p.a.conjB ? -1.f : 1.f;
         long n_my = 0;
         for (long w = blockIdx.x; w < p.items; w += gridDim.x) ++n_my;
         const long total = n_my * NKC;
         const int wn = pair & 63, wkp = pair >> 6;
-        const bool x_task = pair < 2 * p.N_t;
+        const bool x_task = !is_w && pair < 2 * p.N_t;
         const int xkp = x_task ? pair / p.N_t : 0;
         const int xm = pair - xkp * p.N_t;
+        const int kp = is_w ? wkp : xkp;                     // this thread's k pair inside a k-step
         // image offsets of this thread's 16-byte rows inside a stage, for its first mode (the second is one mode image further)
         const uint32_t w_so = (uint32_t)(2 * hf) * kC4AMode + (uint32_t)wkp * kLboA + (uint32_t)(2 * wn) * 16;
         const uint32_t x_so = b_base + (uint32_t)(2 * hf) * b_mode + (uint32_t)xkp * (uint32_t)(p.N_t * 16) + (uint32_t)xm * 16;
         long i_w = blockIdx.x;
         int i_kc = 0;
-        const float2* gB = nullptr;       // &B[k = 0, n of this thread, first mode of this thread]
-        const float2* gA = nullptr;       // &A[m of this thread, k = 0, first mode of this thread]
+        const float2* g0 = nullptr;       // weights: &B[k = 0, n of this thread, first mode]; samples: &A[m of this thread, k = 0, first mode]
+        long g_sk = 0;                    // stride of k in that tensor
         int nmodes = 0;                   // how many of this thread's two modes exist (ragged last group)
         int i_kc0 = 0;                    // first k-step of the item (split reductions)
         auto seek = [&]() {
-            gB = gA = nullptr;
+            g0 = nullptr;
             nmodes = 0;
             if (i_w >= p.items) return;
             const Cmm4Item it = cmm4_item(p, i_w);
@@ -194,26 +202,28 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
             const int q = it.qi0 + 2 * hf;
             nmodes = min(2, max(0, p.a.q_inner - q));
             if (nmodes == 0) return;
-            const int n = it.ms * 64 + wn;
-            if (n < p.a.N) gB = reinterpret_cast<const float2*>(p.a.B[it.corner]) + (long)it.qo * p.a.b_sqo + q + (long)n * p.a.b_sn;
-            const int m = it.ns * p.N_t + xm;
-            if (x_task && m < p.a.M) gA = reinterpret_cast<const float2*>(p.a.A[it.corner]) + (long)it.qo * p.a.a_sqo + q + (long)m * p.a.a_sm;
+            if (is_w) {
+                const int n = it.ms * 64 + wn;
+                if (n < p.a.N) g0 = reinterpret_cast<const float2*>(p.a.B[it.corner]) + (long)it.qo * p.a.b_sqo + q + (long)n * p.a.b_sn;
+            } else {
+                const int m = it.ns * p.N_t + xm;
+                if (x_task && m < p.a.M) g0 = reinterpret_cast<const float2*>(p.a.A[it.corner]) + (long)it.qo * p.a.a_sqo + q + (long)m * p.a.a_sm;
+            }
         };
+        g_sk = is_w ? p.a.b_sk : p.a.a_sk;
         seek();
         auto ld2 = [&](const float2* q) -> float4 {          // modes (q, q+1) of one element; the second may not exist
             if (nmodes == 2) return __ldg(reinterpret_cast<const float4*>(q));
             const float2 e = __ldg(q);
             return make_float4(e.x, e.y, 0.f, 0.f);
         };
-        struct Slot { float4 w[2]; float4 x[2]; };           // [k, k+1] of the k pair, each (re, im) of the thread's two modes
+        struct Slot { float4 e[2]; };                        // [k, k+1] of the k pair, each (re, im) of the thread's two modes
         Slot ring[kC4Depth];
         auto issue = [&](Slot& v) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int kw = (i_kc0 + i_kc) * 4 + 2 * wkp, kx = (i_kc0 + i_kc) * 4 + 2 * xkp;
-            v.w[0] = (gB && kw < p.a.K) ? ld2(gB + (long)kw * p.a.b_sk) : z;
-            v.w[1] = (gB && kw + 1 < p.a.K) ? ld2(gB + (long)(kw + 1) * p.a.b_sk) : z;
-            v.x[0] = (gA && kx < p.a.K) ? ld2(gA + (long)kx * p.a.a_sk) : z;
-            v.x[1] = (gA && kx + 1 < p.a.K) ? ld2(gA + (long)(kx + 1) * p.a.a_sk) : z;
+            const int k = (i_kc0 + i_kc) * 4 + 2 * kp;
+            v.e[0] = (g0 && k < p.a.K) ? ld2(g0 + (long)k * g_sk) : z;
+            v.e[1] = (g0 && k + 1 < p.a.K) ? ld2(g0 + (long)(k + 1) * g_sk) : z;
             if (++i_kc == NKC) { i_kc = 0; i_w += gridDim.x; seek(); }
         };
         auto put = [&](uint8_t* dst, uint32_t lo_off, float4 v) {
@@ -230,9 +240,10 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
         auto process = [&](const Slot& v) {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
-            {   // weight rows (n, re) and (n, im) of both modes: columns (k re, k im, k+1 re, k+1 im).  The odd lane of a pair
+            const float4 e0 = v.e[0], e1 = v.e[1];
+            if (is_w) {
+                // weight rows (n, re) and (n, im) of both modes: columns (k re, k im, k+1 re, k+1 im).  The odd lane of a pair
                 // writes its (n, im) row while the even lane writes its (n, re) row (images two modes apart alias in the banks)
-                const float4 e0 = v.w[0], e1 = v.w[1];
                 uint8_t* d = st + w_so;
                 const float4 re_a = make_float4(e0.x, -sb * e0.y, e1.x, -sb * e1.y), im_a = make_float4(sb * e0.y, e0.x, sb * e1.y, e1.x);
                 const float4 re_b = make_float4(e0.z, -sb * e0.w, e1.z, -sb * e1.w), im_b = make_float4(sb * e0.w, e0.z, sb * e1.w, e1.z);
@@ -241,9 +252,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
                 put(d + o2, kC4AHalf, hf ? re_a : im_a);
                 put(d + kC4AMode + o1, kC4AHalf, hf ? im_b : re_b);
                 put(d + kC4AMode + o2, kC4AHalf, hf ? re_b : im_b);
-            }
-            if (x_task) {
-                const float4 e0 = v.x[0], e1 = v.x[1];
+            } else if (x_task) {
                 uint8_t* d = st + x_so;
                 put(d, b_half, make_float4(e0.x, sa * e0.y, e1.x, sa * e1.y));
                 put(d + b_mode, b_half, make_float4(e0.z, sa * e0.w, e1.z, sa * e1.w));
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) cmm_tc4_kernel(const Cmm4Params
         // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
         // lane pair (2t, 2t+1) holds the (re, im) rows of one channel n in each of the four accumulators; after two exchanges
         // the even lane owns modes 0, 1 and the odd lane modes 2, 3 of (sample, n) as (re, im, re, im): one 16-byte store each
-        const int q = warp - kKpLoadWarps;
+        const int q = warp - kC4LoadWarps;
         const int odd = lane & 1;
         int it = 0;
         for (long w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {

@@ -35,7 +35,12 @@ struct MidTcParams {
     int tmem_cols;
 };
 
-__global__ void __launch_bounds__(kKpThreads, 1) mid_tc_kernel(const MidTcParams p) {
+// LW = loader warps (8 or 16): LW / 4 groups of 128 threads share the eight h pairs of a chunk
+constexpr int kMidLoadWarps = 16;
+constexpr int kMidThreads = (kMidLoadWarps + kKpEpiWarps + 1) * 32;
+__global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParams p) {
+    constexpr int kKpLoadWarps = kMidLoadWarps;          // shadows the analysis kernel's constant
+    constexpr int G = kMidLoadWarps / 4, JP = 8 / G;     // thread groups; h pairs per thread and chunk
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -143,12 +148,12 @@ __global__ void __launch_bounds__(kKpThreads, 1) mid_tc_kernel(const MidTcParams
             } else row_ptr = nullptr;
         };
         seek_row();
-        float4 ring[kKpDepth][4];
-        auto issue = [&](float4 (&v)[4]) {
+        float4 ring[kKpDepth][JP];
+        auto issue = [&](float4 (&v)[JP]) {
             const int h0 = i_kc * (kKC / 2) + 2 * hh;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int h = h0 + 4 * j;
+            for (int j = 0; j < JP; ++j) {
+                const int h = h0 + 2 * G * j;
                 float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
                 if (row_ptr) {
                     const float* q = row_ptr + (long)h * h_stride;
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(kKpThreads, 1) mid_tc_kernel(const MidTcParams
             }
             if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; seek_row(); }
         };
-        auto process = [&](const float4 (&v)[4]) {
+        auto process = [&](const float4 (&v)[JP]) {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
             if (ltid == 0) {
@@ -168,14 +173,14 @@ __global__ void __launch_bounds__(kKpThreads, 1) mid_tc_kernel(const MidTcParams
             }
             st += so;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < JP; ++j) {
                 float4 hi, lo;
                 split_tf32(v[j].x, hi.x, lo.x);
                 split_tf32(v[j].y, hi.y, lo.y);
                 split_tf32(v[j].z, hi.z, lo.z);
                 split_tf32(v[j].w, hi.w, lo.w);
-                *reinterpret_cast<float4*>(st + (uint32_t)(2 * j) * kLboA) = hi;
-                *reinterpret_cast<float4*>(st + kKpAHalf + (uint32_t)(2 * j) * kLboA) = lo;
+                *reinterpret_cast<float4*>(st + (uint32_t)(G * j) * kLboA) = hi;
+                *reinterpret_cast<float4*>(st + kKpAHalf + (uint32_t)(G * j) * kLboA) = lo;
             }
             fence_proxy_async();
             mbar_arrive(&full[p_s]);

@@ -14,10 +14,11 @@
 //     stores 16 bytes per lane: 32 contiguous bytes per (sample, channel).
 // Requires 16-byte friendly operands (all strides and corner offsets even in complex elements); tc_cmm.cuh takes the rest.
 //
-// An item issues 12 MMAs per k-step and each small MMA (128 x N_t x 8) occupies the tensor pipe for ~100 cycles whatever N_t is
-// (the operand fetch from shared memory dominates): 128 input channels are 384 MMAs = ~20 us per item.  Levels with few modes
-// have fewer items than SMs (64 at the inner NS-2D levels), so the launcher splits the reduction of every output tile over
-// `ksplit` items that add into a zeroed C (cmm_zero_kernel): the same MMAs on two to four times as many SMs.
+// An item streams its weights through ONE SM: 128 input channels of four modes are 1 MB and take 30 - 40 us (latency-bound at
+// ~30 GB/s per CTA; neither the loader warps' instruction count nor the MMA count is the limit -- halving either measured no
+// change).  Levels with few modes have fewer items than SMs (32 - 64 at the inner NS-2D levels), so the launcher splits the
+// reduction of every output tile over `ksplit` items that add into a zeroed C (cmm_zero_kernel): the same stream on two to
+// eight times as many SMs.
 #pragma once
 #include "backend.h"
 #include "tc_common.cuh"

@@ -38,7 +38,7 @@ def analysis_ms(layer, x, d, n=8):
     return prof["dft_last_analysis"]["ms"] / n, sum(v["ms"] for v in prof.values()) / n
 
 
-MODES = (0, 1, 2, 8, 15)
+MODES = (0, 1, 2, 8, 15, 31, 47, 143, 191)    # 31 = 15 + no proxy fence, 47 = 15 + plain arrival for commit, 143 = 15 + per-warp arrival, 191 = all
 for name, (B, Ci, Co, S, D, m) in {"481 (4-byte rows)": (32, 32, 64, 481, 240, 18), "240 (16-byte rows)": (32, 64, 128, 240, 120, 8),
                                     "512": (16, 32, 32, 512, 512, 20)}.items():
     torch.manual_seed(0)

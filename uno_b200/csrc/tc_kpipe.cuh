@@ -31,7 +31,7 @@ struct KPipeParams {
     int a_vec_ok;          // rows 16-byte aligned (lda % 4 == 0, base aligned)
     int rclass;            // opt-in (UNO_B200_KPIPE_ALIGN=1) for rows that are NOT 16-byte aligned: see "row classes" below
     int k_valid;           // row-class mode: the real contraction length (K is then k_valid + 3, the longest shifted row)
-    int debug;             // timing probes (UNO_B200_KPIPE_DEBUG, results are garbage): 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads,
+    int debug;             // timing probes (UNO_B200_KPIPE_DEBUG, results are garbage): 1 no MMA, 2 no operand stores, 4 no B copy, 8 no global loads (not in the row-class path), 32 plain arrival instead of tcgen05.commit, 128 one arrival per loader warp,
                            // 16 no proxy fence
 };
 
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], LW * 32 + 1);   // +1: the arrive.expect_tx of the B copy
+            mbar_init(&full[s], ((p.debug & 128) ? LW : LW * 32) + 1);   // +1: the arrive.expect_tx of the B copy (probe bit 128: one arrival per warp)
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -141,7 +141,8 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                             da += a_step;
                             db += b_step;
                         }
-                        tc_commit(&empty[s]);
+                        if (p.debug & 32) mbar_arrive(&empty[s]);      // probe: a plain arrival instead of tcgen05.commit (with bit 1)
+                        else tc_commit(&empty[s]);
                     }
                     acc = 1u;
                     __syncwarp();
@@ -182,7 +183,10 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
         };
         auto stage_epilogue = [&]() {
             if (!(p.debug & 16)) fence_proxy_async();
-            mbar_arrive(&full[p_s]);
+            if (p.debug & 128) {                                  // probe: one arrival per warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[p_s]);
+            } else mbar_arrive(&full[p_s]);
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
             if (++p_kc == NKC) p_kc = 0;
         };

@@ -1079,15 +1079,15 @@ int tc_get_kpipe_image(const float* B, long ldb, int K, int N, TcKpImage* out, i
     return 0;
 }
 
-template <int LW, bool RC>
+template <int LW, bool RC, bool DBG = false>
 int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st) {
     static DeviceOnce configured;
     if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc::kpipe_kernel<LW, RC, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::kpipe_kernel<LW, RC><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    tc::kpipe_kernel<LW, RC, DBG><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }
@@ -1122,6 +1122,7 @@ int try_tc_kpipe(const GemmArgs& a, cudaStream_t st) {
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     const size_t smem = tc::kpipe_smem_bytes(img.N_t, stages);
     // 16 loader warps (default: analysis 2.49 -> 2.19 ms per Darcy step, 2.13 with the row classes) or 8
+    if (p.debug) return rclass ? launch_kpipe<16, true, true>(p, gx, smem, st) : launch_kpipe<16, false, true>(p, gx, smem, st);   // timing probes
     if (cfg(CFG_KPIPE_LW16)) return rclass ? launch_kpipe<16, true>(p, gx, smem, st) : launch_kpipe<16, false>(p, gx, smem, st);
     return rclass ? launch_kpipe<tc::kKpLoadWarps, true>(p, gx, smem, st) : launch_kpipe<tc::kKpLoadWarps, false>(p, gx, smem, st);
 }

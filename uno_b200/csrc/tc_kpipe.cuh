@@ -63,8 +63,10 @@ __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return
 // loaders therefore issue their global loads for TWO consecutive chunks at a time (256 contiguous bytes of every row requested
 // together) and the 16-byte loads carry the L2::256B prefetch hint.  Measured on B200 (Darcy step, all analysis launches):
 // 2.14 ms one chunk at a time, 2.05 with the hint, 1.83 paired, 1.79 both.
-template <int LW = kKpLoadWarps, bool RC = false>
+// DBG = timing-probe instantiation (tools/kpipe_probe.py, switch kpipe_debug); the default <false> carries none of the probe branches
+template <int LW = kKpLoadWarps, bool RC = false, bool DBG = false>
 __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
+    const int dbg = DBG ? p.debug : 0;
     static_assert(LW == 8 || LW == 16, "loader warps");
     constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
     constexpr int RP = 128 / RB;          // 16-byte paths: rows per thread
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], ((p.debug & 128) ? LW : LW * 32) + 1);   // +1: the arrive.expect_tx of the B copy (probe bit 128: one arrival per warp)
+            mbar_init(&full[s], ((dbg & 128) ? LW : LW * 32) + 1);   // +1: the arrive.expect_tx of the B copy (probe bit 128: one arrival per warp)
             mbar_init(&empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < kKC / 8; ++ks) {
-                            if (ks < nks && !(p.debug & 1)) {
+                            if (ks < nks && !(dbg & 1)) {
                                 mma_tf32(d_tmem, da, db, idesc, ks ? 1u : acc);
                                 mma_tf32(d_tmem, da, db + b_lo_off, idesc, 1u);
                                 mma_tf32(d_tmem, da + a_lo_off, db, idesc, 1u);
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                             da += a_step;
                             db += b_step;
                         }
-                        if (p.debug & 32) mbar_arrive(&empty[s]);      // probe: a plain arrival instead of tcgen05.commit (with bit 1)
+                        if (dbg & 32) mbar_arrive(&empty[s]);      // probe: a plain arrival instead of tcgen05.commit (with bit 1)
                         else tc_commit(&empty[s]);
                     }
                     acc = 1u;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             mbar_wait(&empty[p_s], p_ph ^ 1u);
             uint8_t* st = smem + (size_t)p_s * stage_bytes;
             if (ltid == 0) {
-                if (p.debug & 4) mbar_arrive(&full[p_s]);
+                if (dbg & 4) mbar_arrive(&full[p_s]);
                 else {
                     mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
                     bulk_g2s(st + 2 * kKpAHalf, bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
@@ -182,8 +184,8 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             return st;
         };
         auto stage_epilogue = [&]() {
-            if (!(p.debug & 16)) fence_proxy_async();
-            if (p.debug & 128) {                                  // probe: one arrival per warp
+            if (!(dbg & 16)) fence_proxy_async();
+            if (dbg & 128) {                                  // probe: one arrival per warp
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[p_s]);
             } else mbar_arrive(&full[p_s]);
@@ -199,11 +201,17 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             const int k_end = p.k_valid + sh;                 // shifted index k' is real iff sh <= k' < k_end
             const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
             float4 ring[DEPTH][RP];
-            auto issue = [&](float4 (&v)[RP]) {
+            // issue cursor kept incrementally: the loaders' own instruction stream is what bounds this kernel (tools/kpipe_probe.py)
+            const float* src = nullptr;                       // this thread's first row at its 16 bytes of the current chunk
+            int rows_left = 0, k0 = kq * 4;                   // row (4*RB*i) valid iff 4*RB*i < rows_left
+            auto seek = [&]() {
                 const long row0 = (i_tile >> 2) * 512 + 4 * rbase + cls;
-                const int k0 = i_kc * kKC + kq * 4;
-                const float* src = p.A + row0 * p.lda - sh + k0;
-                const long rows_left = p.R - row0;            // row (4*RB*i) valid iff 4*RB*i < rows_left
+                src = p.A + row0 * p.lda - sh + kq * 4;
+                rows_left = (int)max(min(p.R - row0, 1L << 20), 0L);
+                k0 = kq * 4;
+            };
+            seek();
+            auto issue = [&](float4 (&v)[RP]) {
                 if (k0 >= sh && k0 + 4 <= k_end) {
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
@@ -221,7 +229,9 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                         }
                     }
                 }
-                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
+                src += kKC;
+                k0 += kKC;
+                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; seek(); }
             };
             auto process = [&](const float4 (&v)[RP]) {
                 uint8_t* st = stage_prologue() + so;
@@ -259,15 +269,21 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
             const long stride32 = RB * p.lda;
             const uint32_t so = (uint32_t)kq * kLboA + (uint32_t)rbase * 16;
             float4 ring[DEPTH][RP];
-            auto issue = [&](float4 (&v)[RP]) {
+            // issue cursor kept incrementally (see the row-class path)
+            const float* src = nullptr;
+            int rows_left = 0, k0 = kq * 4;                   // row (RB*i) valid iff RB*i < rows_left
+            auto seek = [&]() {
                 const long row0 = i_tile * 128 + rbase;
-                const int k0 = i_kc * kKC + kq * 4;
-                const float* src = p.A + row0 * p.lda + k0;
-                const long rows_left = p.R - row0;            // row (RB*i) valid iff RB*i < rows_left
+                src = p.A + row0 * p.lda + kq * 4;
+                rows_left = (int)max(min(p.R - row0, 1L << 20), 0L);
+                k0 = kq * 4;
+            };
+            seek();
+            auto issue = [&](float4 (&v)[RP]) {
                 if (k0 + 4 <= p.K) {
                     // every chunk but a ragged last one: straight-line predicated 16-byte loads (the loader warps' serial
                     // instruction stream per chunk is what bounds this kernel, tools/kpipe_probe.py)
-                    const long lim = (p.debug & 8) ? 0 : rows_left;
+                    const int lim = (dbg & 8) ? 0 : rows_left;
 #pragma unroll
                     for (int i = 0; i < RP; ++i)
                         v[i] = (RB * i < lim) ? ldg_f4<true>(reinterpret_cast<const float4*>(src + i * stride32)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
 #pragma unroll
                     for (int i = 0; i < RP; ++i) {
                         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (RB * i < rows_left && !(p.debug & 8)) {
+                        if (RB * i < rows_left && !(dbg & 8)) {
                             const float* q = src + i * stride32;
                             if (k0 + 0 < p.K) v[i].x = __ldg(q + 0);
                             if (k0 + 1 < p.K) v[i].y = __ldg(q + 1);
@@ -283,13 +299,15 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                         }
                     }
                 }
-                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
+                src += kKC;
+                k0 += kKC;
+                if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; seek(); }
             };
             auto process = [&](const float4 (&v)[RP]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < RP; ++i) {
-                    if (p.debug & 2) break;
+                    if (dbg & 2) break;
                     float4 hi, lo;
                     split_tf32(v[i].x, hi.x, lo.x);
                     split_tf32(v[i].y, hi.y, lo.y);
@@ -327,14 +345,14 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 const float* src = p.A + row0 * p.lda + k;
                 const long rows_left = (k < p.K) ? (p.R - row0) : 0;   // row (LW*i) valid iff LW*i < rows_left
 #pragma unroll
-                for (int i = 0; i < RP4; ++i) v[i] = (LW * i < rows_left && !(p.debug & 8)) ? __ldg(src + i * stride8) : 0.f;
+                for (int i = 0; i < RP4; ++i) v[i] = (LW * i < rows_left && !(dbg & 8)) ? __ldg(src + i * stride8) : 0.f;
                 if (++i_kc == NKC) { i_kc = 0; i_tile += gridDim.x; }
             };
             auto process = [&](const float (&v)[RP4]) {
                 uint8_t* st = stage_prologue() + so;
 #pragma unroll
                 for (int i = 0; i < RP4; ++i) {
-                    if (p.debug & 2) break;
+                    if (dbg & 2) break;
                     float hi, lo;
                     split_tf32(v[i], hi, lo);
                     *reinterpret_cast<float*>(st + i * (LW * 16)) = hi;

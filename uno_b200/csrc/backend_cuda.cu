@@ -1087,7 +1087,7 @@ int launch_kpipe(const tc::KPipeParams& p, int gx, size_t smem, cudaStream_t st)
         if (e != cudaSuccess) return (int)e;
         configured.mark();
     }
-    tc::kpipe_kernel<LW, RC, DBG><<<gx, (LW + tc::kKpEpiWarps + 1) * 32, smem, st>>>(p);
+    tc::kpipe_kernel<LW, RC, DBG><<<gx, (LW + tc::kKpEpiWarps + 2) * 32, smem, st>>>(p);
     CU_LAUNCH_CHECK();
     return 0;
 }

@@ -65,7 +65,7 @@ __host__ __device__ inline size_t kpipe_smem_bytes(int N_t, int stages) { return
 // 2.14 ms one chunk at a time, 2.05 with the hint, 1.83 paired, 1.79 both.
 // DBG = timing-probe instantiation (tools/kpipe_probe.py, switch kpipe_debug); the default <false> carries none of the probe branches
 template <int LW = kKpLoadWarps, bool RC = false, bool DBG = false>
-__global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(const KPipeParams p) {
+__global__ void __launch_bounds__((LW + kKpEpiWarps + 2) * 32, 1) kpipe_kernel(const KPipeParams p) {
     const int dbg = DBG ? p.debug : 0;
     static_assert(LW == 8 || LW == 16, "loader warps");
     constexpr int RB = LW * 4;            // 16-byte paths: row slots per pass (thread -> row ltid/8 + RB*i)
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
     uint64_t* d_full = bars + 16;     // [2]
     uint64_t* d_empty = bars + 18;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    constexpr int kMmaWarp = LW + kKpEpiWarps;
+    constexpr int kMmaWarp = LW + kKpEpiWarps, kCopyWarp = kMmaWarp + 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -167,21 +167,11 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
         // issue-side cursor (runs DEPTH-1 chunks ahead) and process-side cursor
         long i_tile = blockIdx.x;
         int i_kc = 0;
-        int p_kc = 0, p_s = 0;
+        int p_s = 0;
         uint32_t p_ph = 0;
-        const uint32_t img_chunk_floats = 2 * b_half / 4;
-        const float* bimg = p.Bimg + (RC ? (size_t)(blockIdx.x & 3) * NKC * img_chunk_floats : (size_t)0);
         auto stage_prologue = [&]() -> uint8_t* {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
-            uint8_t* st = smem + (size_t)p_s * stage_bytes;
-            if (ltid == 0) {
-                if (dbg & 4) mbar_arrive(&full[p_s]);
-                else {
-                    mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
-                    bulk_g2s(st + 2 * kKpAHalf, bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
-                }
-            }
-            return st;
+            return smem + (size_t)p_s * stage_bytes;
         };
         auto stage_epilogue = [&]() {
             if (!(dbg & 16)) fence_proxy_async();
@@ -190,7 +180,6 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                 if (lane == 0) mbar_arrive(&full[p_s]);
             } else mbar_arrive(&full[p_s]);
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
-            if (++p_kc == NKC) p_kc = 0;
         };
         if constexpr (RC) {
             // row-class path: 16-byte loads from the 16-byte boundary at or before the row start (see "row classes" above)
@@ -375,6 +364,30 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 1) * 32, 1) kpipe_kernel(c
                     if (g + 2 < total) process(ring[2]);
                     if (g + 3 < total) process(ring[3]);
                 }
+            }
+        }
+    } else if (warp == kCopyWarp) {
+        // ------------------------------------------------------------------ B-chunk copies: one lane issues, per chunk, the bulk copy
+        // of the twiddle image into the stage the MMAs have released.  (It used to be thread 0 of the loaders, inside their
+        // per-chunk loop: the predicate and the reconvergence code around it cost every loader thread ~15 instructions per chunk,
+        // and that instruction stream is what bounds this kernel.)
+        if (lane == 0) {
+            long n_my_tiles = 0;
+            for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) ++n_my_tiles;
+            const long total = n_my_tiles * NKC;
+            const uint32_t img_chunk_floats = 2 * b_half / 4;
+            const float* bimg = p.Bimg + (RC ? (size_t)(blockIdx.x & 3) * NKC * img_chunk_floats : (size_t)0);
+            int s = 0, kc = 0;
+            uint32_t ph = 0;
+            for (long g = 0; g < total; ++g) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                if (dbg & 4) mbar_arrive(&full[s]);
+                else {
+                    mbar_arrive_expect_tx(&full[s], 2 * b_half);
+                    bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kKpAHalf, bimg + (size_t)kc * img_chunk_floats, 2 * b_half, &full[s]);
+                }
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++kc == NKC) kc = 0;
             }
         }
     } else {

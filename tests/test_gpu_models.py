@@ -214,7 +214,9 @@ def test_training_step_is_cuda_graph_capturable(cuda_lib):
     for (k, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
         ga = torch.view_as_real(a.grad) if a.grad.is_complex() else a.grad
         gb = torch.view_as_real(b.grad) if b.grad.is_complex() else b.grad
-        assert float((ga - gb).abs().max()) <= 1e-5 * max(float(gb.abs().max()), 1e-6), k
+        # (same arithmetic, but several reductions finish with atomics -- the weight gradients, the split contraction -- so the
+        # summation order differs from run to run: the bound is the backward tolerance, not bit equality)
+        assert float((ga - gb).abs().max()) <= BWD_TOL * max(float(gb.abs().max()), 1e-6), k
         # Adam turns a gradient into a step of size ~lr whatever its magnitude, so elements whose gradient is at the
         # round-off level (their value depends on the order of the atomics) may legitimately differ by a fraction of lr;
         # the update is compared where the gradient is well above that level, and bounded by lr everywhere

@@ -102,6 +102,9 @@ struct CmmArgs {
     long b_sk = 0, b_sn = 0, b_sqo = 0; int conjB = 0;
     long c_sm = 0, c_sn = 0, c_sqo = 0;
     int M = 0, N = 0, K = 0, q_outer = 1, q_inner = 0;
+    // 1: the result must not depend on the order of atomic additions (forward outputs: repeated calls stay bit-identical);
+    // 0: the backend may split the reduction over several CTAs that add into C (gradients, like the other weight-gradient kernels)
+    int deterministic = 0;
 };
 int be_cmm(const CmmArgs& a, stream_t s);
 

@@ -1238,7 +1238,7 @@ int launch_tc_cmm4(const CmmArgs& a, cudaStream_t st) {
     p.ksplit = 1;
     {
         const long base = (long)p.ms_tiles * p.ns_tiles * a.ncorner * a.q_outer * p.qg;
-        for (int ks = 8; ks >= 2; --ks)
+        for (int ks = a.deterministic ? 0 : 8; ks >= 2; --ks)      // (forward outputs keep a fixed summation order)
                 if (p.n_chunks % ks == 0 && p.n_chunks / ks >= 4 && base * ks <= (long)num_sms()) { p.ksplit = ks; break; }
     }
     p.n_chunks /= p.ksplit;

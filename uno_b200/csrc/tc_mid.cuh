@@ -37,7 +37,7 @@ struct MidTcParams {
 
 // LW = loader warps (8 or 16): LW / 4 groups of 128 threads share the eight h pairs of a chunk
 constexpr int kMidLoadWarps = 16;
-constexpr int kMidThreads = (kMidLoadWarps + kKpEpiWarps + 1) * 32;
+constexpr int kMidThreads = (kMidLoadWarps + kKpEpiWarps + 2) * 32;     // + MMA issuer + B-chunk copy warp
 __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParams p) {
     constexpr int kKpLoadWarps = kMidLoadWarps;          // shadows the analysis kernel's constant
     constexpr int G = kMidLoadWarps / 4, JP = 8 / G;     // thread groups; h pairs per thread and chunk
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParam
     uint64_t* d_full = bars + 16;     // [2]
     uint64_t* d_empty = bars + 18;    // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-    constexpr int kMmaWarp = kKpLoadWarps + kKpEpiWarps;
+    constexpr int kMmaWarp = kKpLoadWarps + kKpEpiWarps, kCopyWarp = kMmaWarp + 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -132,10 +132,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParam
         const long total = n_my_tiles * NKC;
         long i_tile = blockIdx.x;
         int i_kc = 0;
-        int p_kc = 0, p_s = 0;
+        int p_s = 0;
         uint32_t p_ph = 0;
-        const uint32_t img_chunk_floats = 2 * b_half / 4;
-        const float* bimg = p.Bimg + (size_t)nt * NKC * img_chunk_floats;
         const long h_stride = 2L * p.I;                      // floats between X[o, h, i] and X[o, h+1, i]
         const uint32_t so = (uint32_t)hh * kLboA + (uint32_t)rl * 16;
         const float* row_ptr = nullptr;                      // &X[o, 0, i] of this thread's row in tile i_tile (null: row >= R)
@@ -166,12 +164,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParam
         };
         auto process = [&](const float4 (&v)[JP]) {
             mbar_wait(&empty[p_s], p_ph ^ 1u);
-            uint8_t* st = smem + (size_t)p_s * stage_bytes;
-            if (ltid == 0) {
-                mbar_arrive_expect_tx(&full[p_s], 2 * b_half);
-                bulk_g2s(st + 2 * kKpAHalf, bimg + (size_t)p_kc * img_chunk_floats, 2 * b_half, &full[p_s]);
-            }
-            st += so;
+            uint8_t* st = smem + (size_t)p_s * stage_bytes + so;
 #pragma unroll
             for (int j = 0; j < JP; ++j) {
                 float4 hi, lo;
@@ -185,7 +178,6 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParam
             fence_proxy_async();
             mbar_arrive(&full[p_s]);
             if (++p_s == S) { p_s = 0; p_ph ^= 1u; }
-            if (++p_kc == NKC) p_kc = 0;
         };
 #pragma unroll
         for (int d = 0; d < kKpDepth - 1; ++d)
@@ -195,6 +187,25 @@ __global__ void __launch_bounds__(kMidThreads, 1) mid_tc_kernel(const MidTcParam
             for (int d = 0; d < kKpDepth; ++d) {
                 if (g + d + kKpDepth - 1 < total) issue(ring[(d + kKpDepth - 1) % kKpDepth]);
                 if (g + d < total) process(ring[d]);
+            }
+        }
+    } else if (warp == kCopyWarp) {
+        // ------------------------------------------------------------------ B-chunk copies (as tc_kpipe.cuh): one lane issues, per
+        // chunk, the bulk copy of the matrix image into the stage the MMAs have released
+        if (lane == 0) {
+            long n_my_tiles = 0;
+            for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) ++n_my_tiles;
+            const long total = n_my_tiles * NKC;
+            const uint32_t img_chunk_floats = 2 * b_half / 4;
+            const float* bimg = p.Bimg + (size_t)nt * NKC * img_chunk_floats;
+            int s = 0, kc = 0;
+            uint32_t ph = 0;
+            for (long g = 0; g < total; ++g) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[s], 2 * b_half);
+                bulk_g2s(smem + (size_t)s * stage_bytes + 2 * kKpAHalf, bimg + (size_t)kc * img_chunk_floats, 2 * b_half, &full[s]);
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++kc == NKC) kc = 0;
             }
         }
     } else {

@@ -447,6 +447,7 @@ int spectral_fwd_impl(const uno_conv_desc* d, SpectralPlan* p, const float* x, c
         ca.b_sk = (long)d->out_ch * Qw; ca.b_sn = Qw; ca.b_sqo = sqw;
         ca.c_sm = (long)d->out_ch * Q; ca.c_sn = Q; ca.c_sqo = sqx;
         ca.M = d->batch; ca.N = d->out_ch; ca.K = d->in_ch; ca.q_outer = qo; ca.q_inner = qi;
+        ca.deterministic = 1;            // forward: repeated calls give bit-identical outputs
         BE_TRY(be_cmm(ca, st));
     }
     UNO_TRY(synthesise(yhat, Pout, nmid, p->fs, ml, p->s_last.d, d->out_dim[nd - 1], y, epi, y2, ws0, ws1, st, join_side));

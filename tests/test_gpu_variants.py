@@ -423,3 +423,40 @@ def test_first_call_of_a_new_shape_is_already_correct(cuda_lib):
         first, second = run(), run()
         for u, v in zip(first, second):
             assert np.abs(u - v).max() <= 1e-5 * max(float(np.abs(v).max()), 1e-6), (i, rel_err(u, v))
+
+
+# output widths whose row pitch is not a multiple of 8 floats, with at least 128 * nclass output rows so that the row-class tiles are
+# taken: odd pitches (8 classes; 481 and 83 are the Darcy and NS-3D widths), pitches = 2, 6 mod 8 (4 classes), 4 mod 8 (2 classes)
+SECTOR_WIDTHS = [83, 481, 301, 45, 62, 446, 54, 52, 124]
+
+
+@pytest.mark.parametrize("width", SECTOR_WIDTHS)
+@pytest.mark.parametrize("norm,nl", [(False, True), (False, False)])
+def test_synthesis_sector_row_classes(width, norm, nl, cuda_lib):
+    """tc_rowgemm.cuh row classes: a tile holds rows of one residue class and loads a column-shifted twiddle image so that every lane
+    quad covers one whole 32-byte sector (shift up to 7 columns: the first threads of the first column tile own columns left of
+    the row start, which must stay untouched).  Block forward (accumulate + GELU to a second tensor / plain accumulate) and
+    backward (accumulate onto the pointwise gradient) against the oracle, and against the two-class parity tiles."""
+    from uno_b200 import integral_operators as ops
+
+    torch.manual_seed(5)
+    odim = (44, width)
+    modes = (5, min(9, width // 2))
+    blk = ops.OperatorBlock_2D(3, 8, *odim, *modes, Normalize=norm, Non_Lin=nl).cuda()
+    x = torch.randn(4, 3, 30, 40, device="cuda")            # 4 * 8 * 44 = 1408 output rows >= 128 * 8
+    gy = torch.randn(4, 8, *odim, device="cuda")
+
+    def run():
+        xx = x.clone().requires_grad_(True)
+        blk.zero_grad(set_to_none=True)
+        y = blk(xx, *odim)
+        y.backward(gy)
+        return [y.detach().cpu().numpy(), xx.grad.cpu().numpy()]
+
+    a = _with(run, exp0=0)
+    b = _with(run, exp0=32)                                   # exp0 bit 32: parity tiles only (the previous behaviour)
+    assert rel_err(a[0], b[0]) < 1e-6 and rel_err(a[1], b[1]) < 1e-6      # same products, same order per output element
+    p = {k: v.detach().cpu().numpy() for k, v in blk.state_dict().items()}
+    y_or = orc.operator_block_fwd(x.cpu().numpy(), [p["conv.weights1"], p["conv.weights2"]], p["w.conv.weight"], p["w.conv.bias"],
+                                  odim, modes, norm=None, non_lin=nl)
+    assert rel_err(a[0], y_or) < FWD_TOL

@@ -1020,8 +1020,8 @@ int launch_rowgemm_variant(const tc::RowGemmParams& p, size_t smem, cudaStream_t
         configured.mark();
     }
     int gx = num_sms() / p.n_tiles;
-    if (p.parity) gx &= ~1;                 // a CTA must only ever see tiles of one row parity (m_tiles is even too)
-    if (gx < 1 + p.parity) gx = 1 + p.parity;
+    gx &= ~(p.nclass - 1);                  // a CTA must only ever see tiles of one row class (m_tiles is a multiple of nclass too)
+    if (gx < p.nclass) gx = p.nclass;
     if ((long)gx > p.m_tiles) gx = (int)p.m_tiles;
     tc::rowgemm_smallk_kernel<EPI, G, J><<<dim3(gx, p.n_tiles), tc::rowgemm_threads(G), smem, st>>>(p);
     CU_LAUNCH_CHECK();
@@ -1432,15 +1432,22 @@ int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     const bool no_parity = cfg(CFG_ROWGEMM_PARITY) == 0;
     const bool c2_ok = a.epi != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(a.C2) & 7) == 0;
     const int parity = (!no_parity && (a.ldc & 1) && (reinterpret_cast<uintptr_t>(a.C) & 7) == 0 && c2_ok && n_tiles * N_t > a.N) ? 1 : 0;
-    int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, 1 + parity, &img);
+    // row classes (tc_rowgemm.cuh): every lane quad on one whole 32-byte sector when the pitch is not a multiple of 8 floats
+    int nclass = parity ? 2 : 1, shift_mul = 1;
+    {
+        const int g8 = (a.ldc % 8 == 0) ? 8 : (a.ldc % 4 == 0) ? 4 : (a.ldc % 2 == 0) ? 2 : 1;          // gcd(ldc, 8)
+        const bool c32 = (reinterpret_cast<uintptr_t>(a.C) & 31) == 0 && (a.epi != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(a.C2) & 31) == 0);
+        if (!no_parity && !(cfg(CFG_EXP0) & 32) && g8 < 8 && c32 && n_tiles * N_t >= a.N + 7 && a.M >= 128L * (8 / g8)) { nclass = 8 / g8; shift_mul = (int)(a.ldc & 7); }
+    }
+    int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, nclass == 1 ? 1 : (shift_mul == 1 && nclass == 2 ? 2 : 8), &img);
     if (rc) return rc;
     tc::RowGemmParams p;
     p.A = a.A; p.lda = a.a_rs; p.R = a.M;
     p.Bimg = img.dev;
     p.C = a.C; p.C2 = a.C2; p.ldc = a.ldc;
     p.N = a.N; p.K = a.K; p.K_pad = img.K_pad; p.n_tiles = img.n_tiles; p.N_t = img.N_t;
-    p.parity = parity;
-    p.m_tiles = parity ? 2 * (((long)a.M + 255) / 256) : ((long)a.M + 127) / 128;
+    p.nclass = nclass; p.cls_log2 = nclass == 8 ? 3 : nclass == 4 ? 2 : nclass == 2 ? 1 : 0; p.shift_mul = shift_mul;
+    p.m_tiles = (long)nclass * (((long)a.M + 128L * nclass - 1) / (128L * nclass));
     p.epi = a.epi;
     int cols = 32;
     while (cols < 2 * img.N_t) cols *= 2;

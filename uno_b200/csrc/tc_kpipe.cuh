@@ -394,7 +394,7 @@ __global__ void __launch_bounds__((LW + kKpEpiWarps + 2) * 32, 1) kpipe_kernel(c
         // ------------------------------------------------------------------ epilogue: one warp per TMEM lane quarter
         const int q = warp - LW;
         RowGemmParams ep;
-        ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R; ep.parity = 0;
+        ep.C = p.C; ep.C2 = nullptr; ep.ldc = p.ldc; ep.N = p.N; ep.N_t = p.N_t; ep.R = p.R; ep.nclass = 1; ep.cls_log2 = 0; ep.shift_mul = 0;
         const bool vec2 = (p.ldc % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0);
         int it = 0;
         for (long tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {

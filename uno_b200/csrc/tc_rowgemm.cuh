@@ -30,7 +30,9 @@ struct RowGemmParams {
     int epi;
     int tmem_cols;                // power of two >= 2*N_t
     int a_vec_ok;                 // A rows are 16-byte aligned and K % 4 == 0
-    int parity;                   // odd ldc: tiles hold rows of ONE parity and the odd ones use a B image shifted by a column (see below)
+    int nclass;                   // 1, or 2 / 4 / 8 row classes: a tile holds rows of ONE class (row % nclass) and its B image is shifted (see below)
+    int cls_log2;                 // log2(nclass)
+    int shift_mul;                // column shift of class k = (k * shift_mul) & 7
 };
 
 // Odd leading dimension (the 481-wide Darcy grid): every other row of C starts 4 bytes off an 8-byte boundary, so
@@ -39,8 +41,21 @@ struct RowGemmParams {
 // (row = 256*(tile/2) + 2*i + tile%2), a CTA only ever sees one parity (even grid), and the CTAs of the odd rows
 // load a twiddle image whose columns are shifted by one (accumulator column c = output column c-1): the pair a
 // thread owns is then 8-byte aligned in every row and both parities take the float2 path.
+//
+// Row classes generalise this to 32-byte SECTORS: a lane quad owns eight consecutive columns = 32 bytes, which is one whole sector
+// only if the row starts on a 32-byte boundary -- with a pitch of 481 floats the start moves by 4 bytes per row, so seven rows
+// out of eight had every quad straddle two sectors (the 240^2 -> 481^2 forward launch of the Darcy model, which reads one and
+// writes two such tensors, ran at 0.44 of HBM where the aligned 240-wide launches reach 0.65).  With nclass = 8 / gcd(ldc, 8)
+// classes a tile is 128 rows of the same residue (row = 128*nclass*(tile/nclass) + nclass*i + tile%nclass), a CTA only sees one
+// class (grid a multiple of nclass), and class k loads the twiddle image shifted by s_k = (k * ldc) mod 8 columns, so that
+// accumulator column c is output column c - s_k and every quad of every row is exactly one sector.  When the column tiles
+// have no room for a shift of seven (or C is not 32-byte aligned) odd pitches fall back to two classes with shift k.
 __device__ __forceinline__ long rowgemm_row(const RowGemmParams& p, long tile, int i) {
-    return p.parity ? (tile >> 1) * 256 + 2 * i + (tile & 1) : tile * 128 + i;
+    const int cs = p.cls_log2;                           // nclass = 1 << cls_log2
+    return ((tile >> cs) << (7 + cs)) + ((long)i << cs) + (tile & (p.nclass - 1));
+}
+__device__ __forceinline__ int rowgemm_shift(const RowGemmParams& p, long tile) {
+    return p.nclass > 1 ? (int)(((tile & (p.nclass - 1)) * p.shift_mul) & 7) : 0;
 }
 
 // Epilogue warps come in groups of four (one warp per TMEM lane quarter); the G groups split the 16-column chunks of a tile
@@ -80,7 +95,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
     const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
     float* rowp[4];          // index hh*2 + rr
     bool rok[4];
-    n_base -= p.parity ? (int)(tile & 1) : 0;            // accumulator column c of this tile = output column n_base + c
+    n_base -= rowgemm_shift(p, tile);                    // accumulator column c of this tile = output column n_base + c
 #pragma unroll
     for (int hr = 0; hr < 4; ++hr) {
         const long grow = rowgemm_row(p, tile, q * 32 + (hr >> 1) * 16 + (hr & 1) * 8 + (lane >> 2));
@@ -88,7 +103,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
         rowp[hr] = p.C + (rok[hr] ? grow : 0) * p.ldc + n_base + 2 * (lane & 3);
     }
     const int ncol = p.N - n_base - 2 * (lane & 3);     // column c (relative) valid iff cmin <= c < ncol
-    const int cmin = -(n_base + 2 * (lane & 3));        // 1 for the first thread of a shifted first tile, else <= 0
+    const int cmin = -(n_base + 2 * (lane & 3));        // > 0 for the first threads of a column-shifted first tile (shift up to 7), else <= 0
     for (int ci = half; ci * 16 < p.N_t; ci += J * G) {
         const int c0a = ci * 16, c0b = (ci + G) * 16;
         const bool has_b = J == 2 && c0b < p.N_t && n_base + c0b < p.N;
@@ -111,7 +126,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
                 const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
                 const float* q = rowp[hh * 2 + rr] + c;
                 cz[e] = make_float2(0.f, 0.f);
-                const bool in0 = live && c >= cmin && c < ncol, in1 = live && c + 1 < ncol;
+                const bool in0 = live && c >= cmin && c < ncol, in1 = live && c + 1 >= cmin && c + 1 < ncol;
                 // (an L2::256B prefetch hint on these addend loads measured 3.66 against 3.70 ms per Darcy step: not kept)
                 if (VEC2 && in0 && in1) cz[e] = *reinterpret_cast<const float2*>(q);
                 else {
@@ -126,7 +141,7 @@ __device__ __forceinline__ void rowgemm_epilogue_tile(const RowGemmParams& p, ui
             const int j = e >> 3, hh = (e >> 2) & 1, rep = (e >> 1) & 1, rr = e & 1;
             const int c = (j ? c0b : c0a) + rep * 8;
             const bool live = (j == 0 || has_b) && rok[hh * 2 + rr];
-            const bool ok0 = live && c >= cmin && c < ncol, ok1 = live && c + 1 < ncol;
+            const bool ok0 = live && c >= cmin && c < ncol, ok1 = live && c + 1 >= cmin && c + 1 < ncol;
             float* q = rowp[hh * 2 + rr] + c;
             float2 acc = make_float2(__uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 0]), __uint_as_float(r[j * 2 + hh][rep * 4 + rr * 2 + 1]));
             if (kAccum) { acc.x += cz[e].x; acc.y += cz[e].y; }
@@ -159,7 +174,7 @@ __device__ __forceinline__ bool rowgemm_epilogue_tile_fast(const RowGemmParams& 
                                                            int lane, uint64_t* d_full, uint32_t ph) {
     constexpr bool kAccum = (EPI != EPI_STORE);
     if (rowgemm_row(p, tile, 127) >= p.R) return false;                  // warp-uniform: a ragged last tile
-    const int nb = n_base - (p.parity ? (int)(tile & 1) : 0);            // accumulator column c = output column nb + c
+    const int nb = n_base - rowgemm_shift(p, tile);                      // accumulator column c = output column nb + c
     const long c2_delta = (EPI == EPI_ACCUM_GELU) ? (p.C2 - p.C) : 0;
     float* rowp[4];                                                      // index hh*2 + rr, as in the general form
 #pragma unroll
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(c
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             mbar_arrive_expect_tx(b_full, 2 * b_half);
-            const int shifted = p.parity ? (int)(blockIdx.x & 1) : 0;       // gridDim.x is even in parity mode
+            const int shifted = rowgemm_shift(p, blockIdx.x);               // gridDim.x is a multiple of nclass: one class per CTA
             bulk_g2s(sB, p.Bimg + (size_t)(shifted * p.n_tiles + nt) * (2 * b_half / 4), 2 * b_half, b_full);
             mbar_wait(b_full, 0);
             const uint32_t idesc = make_idesc_tf32(128, p.N_t, 0, 0);
@@ -338,7 +353,7 @@ __global__ void __launch_bounds__(rowgemm_threads(G), 1) rowgemm_smallk_kernel(c
         }
     } else {
         // ------------------------------------------------------------------ epilogue: warp e -> TMEM lane quarter e%4, column half e/4
-        const bool vec2 = (p.ldc % 2 == 0 || p.parity) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) &&
+        const bool vec2 = (p.ldc % 2 == 0 || p.nclass > 1) && ((reinterpret_cast<uintptr_t>(p.C) & 7) == 0) &&
                           (EPI != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(p.C2) & 7) == 0);
         const int q = warp & 3, half = warp >> 2;      // half = column group 0 .. G-1
         const int n_base = nt * p.N_t;

@@ -453,8 +453,8 @@ def test_synthesis_sector_row_classes(width, norm, nl, cuda_lib):
         y.backward(gy)
         return [y.detach().cpu().numpy(), xx.grad.cpu().numpy()]
 
-    a = _with(run, exp0=0)
-    b = _with(run, exp0=32)                                   # exp0 bit 32: parity tiles only (the previous behaviour)
+    a = _with(run, rowgemm_parity=1)
+    b = _with(run, rowgemm_parity=2)                          # 2: two-class parity tiles only (the behaviour before the row classes)
     assert rel_err(a[0], b[0]) < 1e-6 and rel_err(a[1], b[1]) < 1e-6      # same products, same order per output element
     p = {k: v.detach().cpu().numpy() for k, v in blk.state_dict().items()}
     y_or = orc.operator_block_fwd(x.cpu().numpy(), [p["conv.weights1"], p["conv.weights2"]], p["w.conv.weight"], p["w.conv.bias"],

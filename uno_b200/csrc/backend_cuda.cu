@@ -1437,7 +1437,7 @@ int try_tc_rowgemm(const GemmArgs& a, cudaStream_t st) {
     {
         const int g8 = (a.ldc % 8 == 0) ? 8 : (a.ldc % 4 == 0) ? 4 : (a.ldc % 2 == 0) ? 2 : 1;          // gcd(ldc, 8)
         const bool c32 = (reinterpret_cast<uintptr_t>(a.C) & 31) == 0 && (a.epi != EPI_ACCUM_GELU || (reinterpret_cast<uintptr_t>(a.C2) & 31) == 0);
-        if (!no_parity && !(cfg(CFG_EXP0) & 32) && g8 < 8 && c32 && n_tiles * N_t >= a.N + 7 && a.M >= 128L * (8 / g8)) { nclass = 8 / g8; shift_mul = (int)(a.ldc & 7); }
+        if (!no_parity && cfg(CFG_ROWGEMM_PARITY) != 2 && g8 < 8 && c32 && n_tiles * N_t >= a.N + 7 && a.M >= 128L * (8 / g8)) { nclass = 8 / g8; shift_mul = (int)(a.ldc & 7); }
     }
     int rc = tc_get_rowgemm_image(a.B, a.ldb, a.K, a.N, nclass == 1 ? 1 : (shift_mul == 1 && nclass == 2 ? 2 : 8), &img);
     if (rc) return rc;

@@ -12,7 +12,7 @@ enum CfgKey {
     CFG_KPIPE_ALIGN,        // analysis kernel: 16-byte row-class loads for rows that are not 16-byte aligned
     CFG_KPIPE_LW16,         // analysis kernel: 16 loader warps
     CFG_ROWGEMM_EPI16,      // synthesis kernel: 16 epilogue warps
-    CFG_ROWGEMM_PARITY,     // synthesis kernel: row-parity tiles for odd row pitch
+    CFG_ROWGEMM_PARITY,     // synthesis kernel: row-class tiles for row pitches that are not multiples of 8 floats (2: two-class parity tiles only, 0: none)
     CFG_NORM_BIG_CLUSTER,   // InstanceNorm cluster kernels with 200 KB per CTA for planes beyond 8 x 72 KB
     CFG_OVERLAP,            // fork / join of the two block branches (pointwise / spectral) on a library-owned side stream; default on
     CFG_POINTWISE3D_FIXED,  // NOT the reference's behaviour: band-limited 3-D pointwise resample

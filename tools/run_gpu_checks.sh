@@ -30,7 +30,7 @@ if [[ $STAGES == *sanitizer* ]]; then
         > gpurun_out/${TAG}_sanitizer_memcheck.log 2>&1
     echo "memcheck rc=$?" >> gpurun_out/${TAG}_sanitizer_memcheck.log
     timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_variants.py tests/test_gpu_glue.py -x -q \
-        -k "golden or fanout or overlap or tc_core or test_project or test_lift or first_call" > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1
+        -k "golden or fanout or overlap or tc_core or test_project or test_lift or first_call or sector" > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1
     echo "racecheck rc=$?" >> gpurun_out/${TAG}_sanitizer_racecheck.log
     tail -n 4 gpurun_out/${TAG}_sanitizer_memcheck.log; tail -n 4 gpurun_out/${TAG}_sanitizer_racecheck.log
 fi

@@ -98,11 +98,11 @@ struct DevBand {
         const BandGroups g = band_groups(b);
         if (!g.ok) return 0;
         G = g.G; W = g.W; ng = g.ng;
-        // rows: the tile height (in groups, <= 16, window <= 128 rows so that two CTAs still share an SM) that wastes the fewest lanes
+        // rows: the tile height (in groups, <= 32, window <= 128 rows so that two CTAs still share an SM) that wastes the fewest lanes
         // when a warp sweeps the window rows.  (Up to 8 groups until round 2: 72-row windows for the 2x down-sampling levels, a
         // third of the lanes of pass A idle in the last sweep; 14 groups give 120-row windows.)
         double best = -1.0;
-        for (int n = std::min(16, ng); n >= 1; --n) {
+        for (int n = std::min(32, ng); n >= 1; --n) {
             const int sp = g.span(n);
             if (sp > 128 && n > 1) continue;
             const double eff = (double)(n * G) / (32.0 * ((sp + 31) / 32));

@@ -18,7 +18,8 @@ ROLES = [
     ("resample2d_kernel", "resample_banded"), ("banded2d_kernel", "resample_banded"), ("banded_kernel", "resample_banded"),
     ("kpipe_kernel", "dft_last_analysis"), ("rowgemm_smallk_kernel", "dft_last_synthesis"),
     ("conv1x1_tc_kernel", "conv1x1"), ("wgrad_tc_kernel", "conv1x1_wgrad"), ("mid2_kernel", "dft_mid"), ("mid_tc_kernel", "dft_mid"), ("cmm_kernel", "mode_contraction"),
-    ("cmm_tc_kernel", "mode_contraction"),
+    ("cmm_tc_kernel", "mode_contraction"), ("cmm_tc4_kernel", "mode_contraction"),
+    ("proj_bwd_tcp_kernel", "project_bwd"), ("proj_fwd_tc_kernel", "project_fwd"),
     ("cmm2_kernel", "mode_contraction"), ("norm_fwd_cluster_kernel", "instnorm_gelu_fwd"), ("norm_bwd_cluster_kernel", "instnorm_gelu_bwd"),
     ("lp_partial_kernel", "lp_loss"), ("lp_finish_kernel", "lp_loss"), ("lp_bwd_kernel", "lp_loss_bwd"),
     ("proj_bwd_kernel", "project_bwd"), ("proj_fwd_kernel", "project_fwd"), ("lift_bwd_kernel", "lift_bwd"), ("lift_fwd_kernel", "lift_fwd"),

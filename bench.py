@@ -351,10 +351,12 @@ def run_workload(ctx, workload, B, steps, warmup, profile=True, breakdown_top=No
 
     # Execution mode.  "graph": the whole step (zero_grad, forward / rollout, loss, backward) captured once in a CUDA graph and
     # replayed (uno_b200/graphed.py); the gradient all-reduce follows the replay.  "eager": autograd drives the C ABI call by
-    # call and the bucketed all-reduce overlaps backward.  Replay wins wherever host work per step rivals the kernel time
-    # (the rollout, strong-scaled shards); a full-batch Darcy step on several GPUs is kernel-bound and keeps the overlap.
+    # call and the bucketed all-reduce overlaps backward.  Replay wins wherever host work per step rivals the kernel time --
+    # since round 2 that is everywhere: the eager Darcy step issues 1820 launches and measured 18.8 ms on 8 GPUs when the
+    # replayed step takes 17.5 ms on one, i.e. the host was the limit; the exposed all-reduce after the replay (65.6 MB, ~0.3 ms
+    # over NVLink) costs less.  `--graph off` keeps the eager path.
     step, reducer, rollout, graph_error = None, None, "eager", None
-    want_graph = graph_mode == "on" or (graph_mode == "auto" and (world == 1 or workload != "darcy" or B < WORKLOADS[workload][5]))
+    want_graph = graph_mode in ("on", "auto")
     if want_graph:
         ok = 1
         try:
@@ -570,7 +572,7 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="replay the step from a CUDA graph (auto: everywhere except the full-batch multi-GPU Darcy step)")
+                    help="replay the step from a CUDA graph (auto / on: every workload at every N, eager fallback if capture fails; off: eager)")
     ap.add_argument("--lean", action="store_true", help="headline workload only (no secondary / reference / sweep legs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
